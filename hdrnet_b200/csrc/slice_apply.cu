@@ -1,0 +1,549 @@
+// slice_apply.cu -- fused BilateralSliceApply for B200 (sm_100a), plus the generic
+// any-shape slice / slice-apply kernel and the cell-index debug kernel.
+//
+// Replaces hdrnet/ops/bilateral_slice_apply.cu.cc:36-126 (BilateralSliceApplyKernel, one
+// thread per OUTPUT ELEMENT, 32 scalar grid loads each, no shared memory) with a design
+// built around what bounds the op on B200: 28 B of HBM traffic per pixel against ~120-150
+// fp32 issue slots per pixel at the HBM roofline.
+//
+// slice_apply_rows_tma_kernel -- persistent, one CTA per resident slot:
+//   * every HBM byte moves through the TMA engine: 1-D bulk copies (cp.async.bulk ->
+//     UBLKCP) bring a row segment's RGB (12 B/px) and guide (4 B/px) into a multi-stage
+//     shared-memory ring, completion on mbarriers; results are written IN PLACE over the
+//     RGB tile and leave with one bulk store per segment.  No LDG/STG address arithmetic
+//     in the math warps, perfectly coalesced traffic whatever the per-thread access shape.
+//   * the grid rows a pixel row touches (gy0, gy0+1: gw*gd*12 floats each) are staged once
+//     by TMA and stay resident while consecutive rows share them; per image row they are
+//     pre-blended along y (wy is constant on a row) into a slab Gy[gx][gz][12], so a pixel
+//     blends 4 corners instead of 8: 48 FMAs -> 24 packed fma.rn.f32x2 (FFMA2) + 9 for
+//     the affine apply.
+//   * one thread owns 4 consecutive pixels: 3 LDS.128 of RGB + 1 LDS.128 of guide, 12
+//     LDS.128 of slab per pixel (conflict-free: the 8 depth cells of one x cell map to
+//     disjoint 4-bank groups), 3 STS.128 of output.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace hdrnet_b200 {
+
+// =========================================================================================
+// Generic kernels: one thread per pixel, any n_in / n_out / alignment / width.
+// =========================================================================================
+
+struct Corners {
+  int off[8];    // float offsets of the 8 corner cells (channel 0) inside this image's grid
+  float w[8];    // trilinear weights, order (y, x, z) as the reference's loops
+};
+
+__device__ __forceinline__ Corners make_corners(const SliceGeom& g, int x, int y, float guide,
+                                                int gc) {
+  const Axis ax = spatial_axis(x, g.scale_x);
+  const Axis ay = spatial_axis(y, g.scale_y);
+  const Axis az = range_axis(guide, static_cast<float>(g.gd));
+  float wz[2];
+  smoothed_weights(az.f, wz[0], wz[1]);
+  const float wx[2] = {1.0f - ax.f, ax.f};
+  const float wy[2] = {1.0f - ay.f, ay.f};
+  Corners c;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const int gyc = clampi(ay.i0 + dy, 0, g.gh - 1);
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int gxc = clampi(ax.i0 + dx, 0, g.gw - 1);
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz) {
+        const int gzc = clampi(az.i0 + dz, 0, g.gd - 1);
+        const int k = dy * 4 + dx * 2 + dz;
+        c.off[k] = ((gyc * g.gw + gxc) * g.gd + gzc) * gc;
+        c.w[k] = wx[dx] * wy[dy] * wz[dz];
+      }
+    }
+  }
+  return c;
+}
+
+__device__ __forceinline__ float sample(const float* __restrict__ grid_b, const Corners& c,
+                                        int ch) {
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s = fmaf(c.w[k], __ldg(grid_b + c.off[k] + ch), s);
+  return s;
+}
+
+// kApply = true : out[p, i] = sum_j sample(i*J + j) * (j < n_in ? input[p, j] : 1)
+// kApply = false: out[p, c] = sample(c), c < gc
+template <bool kApply>
+__global__ void __launch_bounds__(256)
+slice_generic_kernel(const float* __restrict__ grid, const float* __restrict__ guide,
+                     const float* __restrict__ input, float* __restrict__ out, SliceGeom g,
+                     int n_in, int n_out, int J, long long npix) {
+  const int gc = kApply ? n_out * J : J;
+  const long long grid_image = static_cast<long long>(g.gh) * g.gw * g.gd * gc;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
+       p += stride) {
+    const int x = static_cast<int>(p % g.W);
+    const long long row = p / g.W;
+    const int r = static_cast<int>(row % g.rows);
+    const int b = static_cast<int>(row / g.rows);
+    const Corners c = make_corners(g, x, g.y_off + r, __ldg(guide + p), gc);
+    const float* grid_b = grid + b * grid_image;
+    if (kApply) {
+      for (int i = 0; i < n_out; ++i) {
+        float value = 0.0f;
+        for (int j = 0; j < J; ++j) {
+          const float s = sample(grid_b, c, i * J + j);
+          value = (j < n_in) ? fmaf(s, __ldg(input + p * n_in + j), value) : value + s;
+        }
+        out[p * n_out + i] = value;
+      }
+    } else {
+      for (int ch = 0; ch < gc; ++ch) out[p * gc + ch] = sample(grid_b, c, ch);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+slice_indices_kernel(const float* __restrict__ guide, int32_t* __restrict__ idx, SliceGeom g,
+                     long long npix) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
+       p += stride) {
+    const int x = static_cast<int>(p % g.W);
+    const int r = static_cast<int>((p / g.W) % g.rows);
+    idx[3 * p + 0] = spatial_axis(x, g.scale_x).i0;
+    idx[3 * p + 1] = spatial_axis(g.y_off + r, g.scale_y).i0;
+    idx[3 * p + 2] = range_axis(__ldg(guide + p), static_cast<float>(g.gd)).i0;
+  }
+}
+
+// =========================================================================================
+// Persistent TMA row kernel: n_in = 3, n_out = 3, has_offset (gc = 12), W % 4 == 0.
+// =========================================================================================
+
+constexpr int kTmaThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr int kGc = 12;
+
+struct TmaPlan {
+  int ctas;
+  int stages;
+  int nseg;        // segments per row
+  int seg_px;      // pixels per segment (multiple of 4, <= 4 * kTmaThreads)
+  int row_floats;  // gw * gd * 12
+  int smem_bytes;
+  // byte offsets into dynamic shared memory
+  int off_raw, off_slab, off_stage, stage_bytes;
+};
+
+struct TmaArgs {
+  const float* grid;
+  const float* guide;
+  const float* input;
+  float* out;
+  SliceGeom g;
+  TmaPlan p;
+};
+
+__device__ __forceinline__ float4 lerp4(float w0, float4 a, float w1, float4 b) {
+  return make_float4(fmaf(w1, b.x, w0 * a.x), fmaf(w1, b.y, w0 * a.y), fmaf(w1, b.z, w0 * a.z),
+                     fmaf(w1, b.w, w0 * a.w));
+}
+
+// Blend the four (x, z) corners of the y-pre-blended slab for one pixel and apply the
+// 3x4 affine transform to (r, g, b, 1).
+__device__ __forceinline__ void blend_apply(const float* __restrict__ slab, int o00, int o01,
+                                            int o10, int o11, float w00, float w01, float w10,
+                                            float w11, float r, float g, float b, float& out_r,
+                                            float& out_g, float& out_b) {
+  const ulonglong2* v00 = reinterpret_cast<const ulonglong2*>(slab + o00);
+  const ulonglong2* v01 = reinterpret_cast<const ulonglong2*>(slab + o01);
+  const ulonglong2* v10 = reinterpret_cast<const ulonglong2*>(slab + o10);
+  const ulonglong2* v11 = reinterpret_cast<const ulonglong2*>(slab + o11);
+  const unsigned long long W00 = pack2(w00, w00), W01 = pack2(w01, w01);
+  const unsigned long long W10 = pack2(w10, w10), W11 = pack2(w11, w11);
+  unsigned long long acc[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const ulonglong2 a = v00[k], bq = v01[k], c = v10[k], d = v11[k];
+    acc[2 * k] = fma2(W11, d.x, fma2(W10, c.x, fma2(W01, bq.x, mul2(W00, a.x))));
+    acc[2 * k + 1] = fma2(W11, d.y, fma2(W10, c.y, fma2(W01, bq.y, mul2(W00, a.y))));
+  }
+  float a0, a1, a2, a3;
+  unpack2(acc[0], a0, a1);
+  unpack2(acc[1], a2, a3);
+  out_r = fmaf(a2, b, fmaf(a1, g, fmaf(a0, r, a3)));
+  unpack2(acc[2], a0, a1);
+  unpack2(acc[3], a2, a3);
+  out_g = fmaf(a2, b, fmaf(a1, g, fmaf(a0, r, a3)));
+  unpack2(acc[4], a0, a1);
+  unpack2(acc[5], a2, a3);
+  out_b = fmaf(a2, b, fmaf(a1, g, fmaf(a0, r, a3)));
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 2)
+slice_apply_rows_tma_kernel(const TmaArgs args) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SliceGeom& g = args.g;
+  const TmaPlan& pl = args.p;
+  const int tid = threadIdx.x;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // [kMaxStages]
+  uint64_t* gridbar = full + kMaxStages;                      // [1]
+  float* raw0 = reinterpret_cast<float*>(smem + pl.off_raw);
+  float* raw1 = raw0 + pl.row_floats;
+  float* slab = reinterpret_cast<float*>(smem + pl.off_slab);
+  unsigned char* stage_base = smem + pl.off_stage;
+
+  // Contiguous block of buffer rows per CTA (neighbouring rows share grid rows).
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
+  const int nitems = static_cast<int>(r_end - r_begin) * pl.nseg;
+  if (nitems <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < pl.stages; ++s) mbar_init(&full[s], 1);
+    mbar_init(gridbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int NS = pl.stages;
+  const int seg_rgb_bytes_max = pl.seg_px * 12;
+
+  auto stage_rgb = [&](int s) { return stage_base + static_cast<size_t>(s) * pl.stage_bytes; };
+  auto stage_guide = [&](int s) {
+    return stage_base + static_cast<size_t>(s) * pl.stage_bytes + seg_rgb_bytes_max;
+  };
+  // Work item -> (buffer row, first pixel of the segment, pixels in the segment).
+  auto item_span = [&](int item, long long& row, int& x0, int& npx) {
+    const int rr = item / pl.nseg;
+    const int seg = item - rr * pl.nseg;
+    row = r_begin + rr;
+    x0 = seg * pl.seg_px;
+    npx = min(pl.seg_px, g.W - x0);
+  };
+  auto issue_load = [&](int item) {  // thread 0 only
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+    const int s = item % NS;
+    const size_t pix = static_cast<size_t>(row) * g.W + x0;
+    mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * 16u);
+    tma_load_1d(stage_rgb(s), args.input + pix * 3, static_cast<uint32_t>(npx) * 12u, &full[s]);
+    tma_load_1d(stage_guide(s), args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[s]);
+  };
+
+  if (tid == 0) {
+    const int pre = min(NS - 1, nitems);
+    for (int it = 0; it < pre; ++it) issue_load(it);
+  }
+
+  const float gd_f = static_cast<float>(g.gd);
+  const int x_stride = g.gd * kGc;  // floats between neighbouring x cells in the slab
+  int cur_b = -1, cur_gy0 = INT_MIN;
+  uint32_t grid_phase = 0;
+
+  for (int item = 0; item < nitems; ++item) {
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+
+    if (x0 == 0) {
+      // New image row: (re)stage its two grid rows if they changed, then pre-blend in y.
+      // Every thread is past the previous item's post-compute barrier, so raw/slab are idle.
+      const int b = static_cast<int>(row / g.rows);
+      const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
+      const Axis ay = spatial_axis(y, g.scale_y);
+      if (b != cur_b || ay.i0 != cur_gy0) {
+        if (tid == 0) {
+          const int gy0c = clampi(ay.i0, 0, g.gh - 1);
+          const int gy1c = clampi(ay.i0 + 1, 0, g.gh - 1);
+          const float* gb = args.grid + static_cast<size_t>(b) * g.gh * pl.row_floats;
+          const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+          mbar_expect_tx(gridbar, 2u * bytes);
+          tma_load_1d(raw0, gb + static_cast<size_t>(gy0c) * pl.row_floats, bytes, gridbar);
+          tma_load_1d(raw1, gb + static_cast<size_t>(gy1c) * pl.row_floats, bytes, gridbar);
+        }
+        mbar_wait(gridbar, grid_phase);
+        grid_phase ^= 1u;
+        cur_b = b;
+        cur_gy0 = ay.i0;
+      }
+      const float wy1 = ay.f, wy0 = 1.0f - ay.f;
+      const float4* a4 = reinterpret_cast<const float4*>(raw0);
+      const float4* b4 = reinterpret_cast<const float4*>(raw1);
+      float4* s4 = reinterpret_cast<float4*>(slab);
+      for (int e = tid; e < pl.row_floats / 4; e += kTmaThreads) s4[e] = lerp4(wy0, a4[e], wy1, b4[e]);
+      __syncthreads();
+    }
+
+    const int s = item % NS;
+    mbar_wait(&full[s], static_cast<uint32_t>(item / NS) & 1u);
+
+    if (tid * 4 < npx) {
+      float4* rgb4 = reinterpret_cast<float4*>(stage_rgb(s)) + 3 * tid;
+      const float4 gq = reinterpret_cast<const float4*>(stage_guide(s))[tid];
+      const float4 c0 = rgb4[0], c1 = rgb4[1], c2 = rgb4[2];
+      const float pr[4] = {c0.x, c0.w, c1.z, c2.y};
+      const float pg[4] = {c0.y, c1.x, c1.w, c2.z};
+      const float pb[4] = {c0.z, c1.y, c2.x, c2.w};
+      const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+      float o_r[4], o_g[4], o_b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const Axis ax = spatial_axis(x0 + 4 * tid + i, g.scale_x);
+        const Axis az = range_axis(gv[i], gd_f);
+        const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride;
+        const int xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
+        const int zo0 = clampi(az.i0, 0, g.gd - 1) * kGc;
+        const int zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * kGc;
+        float wz0, wz1;
+        smoothed_weights(az.f, wz0, wz1);
+        const float wx1 = ax.f, wx0 = 1.0f - ax.f;
+        blend_apply(slab, xo0 + zo0, xo0 + zo1, xo1 + zo0, xo1 + zo1, wx0 * wz0, wx0 * wz1,
+                    wx1 * wz0, wx1 * wz1, pr[i], pg[i], pb[i], o_r[i], o_g[i], o_b[i]);
+      }
+      rgb4[0] = make_float4(o_r[0], o_g[0], o_b[0], o_r[1]);
+      rgb4[1] = make_float4(o_g[1], o_b[1], o_r[2], o_g[2]);
+      rgb4[2] = make_float4(o_b[2], o_r[3], o_g[3], o_b[3]);
+      fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+      const size_t pix = static_cast<size_t>(row) * g.W + x0;
+      tma_store_1d(args.out + pix * 3, stage_rgb(s), static_cast<uint32_t>(npx) * 12u);
+      tma_store_commit();
+      const int nxt = item + NS - 1;
+      if (nxt < nitems) {
+        tma_store_wait_read<1>();  // the store of item-1 has drained its stage
+        issue_load(nxt);
+      }
+    }
+  }
+  if (tid == 0) tma_store_wait_all<0>();
+}
+
+// =========================================================================================
+// Host side: planning, validation, launch.
+// =========================================================================================
+
+static int device_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+  return sms > 0 ? sms : 148;
+}
+
+static int device_max_smem_optin() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 227 * 1024;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+    return 227 * 1024;
+  return v;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Returns false when the TMA kernel cannot run these shapes.
+static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out) {
+  if (g.W < 4 || (g.W % 4) != 0) return false;
+  TmaPlan p;
+  p.row_floats = g.gw * g.gd * kGc;
+  const int quads = g.W / 4;
+  p.nseg = (quads + kTmaThreads - 1) / kTmaThreads;
+  p.seg_px = 4 * ((quads + p.nseg - 1) / p.nseg);
+  p.stage_bytes = round_up(p.seg_px * 16, 128);
+  p.off_raw = 128;  // barriers: (kMaxStages + 1) * 8 = 72 bytes
+  p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
+  p.off_stage = p.off_slab + round_up(p.row_floats * 4, 128);
+  // Prefer two CTAs per SM with 4 stages each; shrink the ring before giving up residency.
+  const int per_cta_2 = (max_smem + 1024) / 2 - 1024;  // ~113 KB when 227 KB opt-in
+  int stages = 0;
+  for (int ns = 4; ns >= 2; --ns) {
+    if (p.off_stage + ns * p.stage_bytes <= per_cta_2) { stages = ns; break; }
+  }
+  if (stages == 0) {
+    for (int ns = 4; ns >= 2; --ns) {
+      if (p.off_stage + ns * p.stage_bytes <= max_smem) { stages = ns; break; }
+    }
+  }
+  if (stages == 0) return false;
+  p.stages = stages;
+  p.smem_bytes = p.off_stage + stages * p.stage_bytes;
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const int resident = (p.smem_bytes <= per_cta_2) ? 2 : 1;
+  p.ctas = static_cast<int>(std::min<long long>(total_rows, static_cast<long long>(sms) * resident));
+  *out = p;
+  return true;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int validate_common(int B, int H, int W, int gh, int gw, int gd) {
+  if (B < 0 || H < 0 || W < 0) return HDRNET_E_BAD_SHAPE;
+  if (gh < 1 || gw < 1 || gd < 1) return HDRNET_E_BAD_SHAPE;
+  return HDRNET_OK;
+}
+
+static int generic_grid(long long npix, int sms) {
+  const long long blocks = (npix + 255) / 256;
+  return static_cast<int>(std::min<long long>(blocks, static_cast<long long>(sms) * 16));
+}
+
+// Internal launcher shared with the host path (host_path.cu): pixel buffers hold `rows`
+// rows per image starting at image row y_off.
+int launch_slice_apply(const float* grid, const float* guide, const float* input, float* out,
+                       int B, int H, int W, int rows, int y_off, int gh, int gw, int gd,
+                       int n_in, int n_out, int has_offset, int variant, cudaStream_t stream) {
+  int rc = validate_common(B, H, W, gh, gw, gd);
+  if (rc != HDRNET_OK) return rc;
+  if (n_in < 1 || n_out < 1 || rows < 0 || y_off < 0 || y_off + rows > H) return HDRNET_E_BAD_SHAPE;
+  const long long npix = static_cast<long long>(B) * rows * W;
+  if (npix == 0) return HDRNET_OK;
+  if (!grid || !guide || !input || !out) return HDRNET_E_NULL_POINTER;
+  const int J = n_in + (has_offset ? 1 : 0);
+  const long long grid_floats = static_cast<long long>(gh) * gw * gd * n_out * J;
+  if (grid_floats > INT_MAX || static_cast<long long>(rows) * B > INT_MAX / 4) return HDRNET_E_TOO_LARGE;
+
+  const SliceGeom g = make_geom(B, H, W, rows, y_off, gh, gw, gd);
+  const int sms = device_sm_count();
+
+  TmaPlan plan;
+  const bool tma_shape = (n_in == 3 && n_out == 3 && has_offset) &&
+                         make_tma_plan(g, device_max_smem_optin(), sms, &plan) &&
+                         aligned16(grid) && aligned16(guide) && aligned16(input) && aligned16(out);
+  bool use_tma;
+  if (variant == HDRNET_VARIANT_TMA) {
+    if (!tma_shape) return HDRNET_E_UNSUPPORTED;
+    use_tma = true;
+  } else if (variant == HDRNET_VARIANT_GENERIC) {
+    use_tma = false;
+  } else if (variant == HDRNET_VARIANT_AUTO) {
+    use_tma = tma_shape && W >= 128;
+  } else {
+    return HDRNET_E_UNSUPPORTED;
+  }
+
+  if (use_tma) {
+    cudaError_t e = cudaFuncSetAttribute(slice_apply_rows_tma_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         plan.smem_bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    TmaArgs a;
+    a.grid = grid; a.guide = guide; a.input = input; a.out = out; a.g = g; a.p = plan;
+    slice_apply_rows_tma_kernel<<<plan.ctas, kTmaThreads, plan.smem_bytes, stream>>>(a);
+  } else {
+    slice_generic_kernel<true><<<generic_grid(npix, sms), 256, 0, stream>>>(
+        grid, guide, input, out, g, n_in, n_out, J, npix);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_slice(const float* grid, const float* guide, float* out, int B, int H, int W, int rows,
+                 int y_off, int gh, int gw, int gd, int gc, int variant, cudaStream_t stream) {
+  int rc = validate_common(B, H, W, gh, gw, gd);
+  if (rc != HDRNET_OK) return rc;
+  if (gc < 1 || rows < 0 || y_off < 0 || y_off + rows > H) return HDRNET_E_BAD_SHAPE;
+  const long long npix = static_cast<long long>(B) * rows * W;
+  if (npix == 0) return HDRNET_OK;
+  if (!grid || !guide || !out) return HDRNET_E_NULL_POINTER;
+  if (static_cast<long long>(gh) * gw * gd * gc > INT_MAX) return HDRNET_E_TOO_LARGE;
+  if (variant == HDRNET_VARIANT_TMA) return HDRNET_E_UNSUPPORTED;
+  if (variant != HDRNET_VARIANT_AUTO && variant != HDRNET_VARIANT_GENERIC) return HDRNET_E_UNSUPPORTED;
+  const SliceGeom g = make_geom(B, H, W, rows, y_off, gh, gw, gd);
+  slice_generic_kernel<false><<<generic_grid(npix, device_sm_count()), 256, 0, stream>>>(
+      grid, guide, nullptr, out, g, 0, 0, gc, npix);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace hdrnet_b200
+
+// =========================================================================================
+// C-ABI (include/hdrnet_b200.h)
+// =========================================================================================
+using namespace hdrnet_b200;
+
+extern "C" {
+
+int hdrnet_b200_abi_version(void) { return HDRNET_B200_ABI_VERSION; }
+
+const char* hdrnet_b200_error_string(int code) {
+  switch (code) {
+    case HDRNET_OK: return "ok";
+    case HDRNET_E_NULL_POINTER: return "a required pointer is NULL";
+    case HDRNET_E_BAD_SHAPE: return "invalid dimension";
+    case HDRNET_E_BAD_CHANNELS: return "grid channels do not match n_out * (n_in + has_offset)";
+    case HDRNET_E_TOO_LARGE: return "extent exceeds the kernels' 32-bit index range";
+    case HDRNET_E_UNSUPPORTED: return "requested kernel variant cannot run these shapes";
+    case HDRNET_E_BAD_CONTEXT: return "invalid host-path context";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "unknown hdrnet_b200 error";
+}
+
+int hdrnet_slice_apply_f32_variant(const float* grid, const float* guide, const float* input,
+                                   float* out, int B, int H, int W, int gh, int gw, int gd,
+                                   int n_in, int n_out, int has_offset, int variant,
+                                   void* stream) {
+  return launch_slice_apply(grid, guide, input, out, B, H, W, H, 0, gh, gw, gd, n_in, n_out,
+                            has_offset, variant, static_cast<cudaStream_t>(stream));
+}
+
+int hdrnet_slice_apply_f32(const float* grid, const float* guide, const float* input,
+                           float* out, int B, int H, int W, int gh, int gw, int gd, int n_in,
+                           int n_out, int has_offset, void* stream) {
+  return launch_slice_apply(grid, guide, input, out, B, H, W, H, 0, gh, gw, gd, n_in, n_out,
+                            has_offset, HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
+}
+
+int hdrnet_slice_f32_variant(const float* grid, const float* guide, float* out, int B, int H,
+                             int W, int gh, int gw, int gd, int gc, int variant, void* stream) {
+  return launch_slice(grid, guide, out, B, H, W, H, 0, gh, gw, gd, gc, variant,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int hdrnet_slice_f32(const float* grid, const float* guide, float* out, int B, int H, int W,
+                     int gh, int gw, int gd, int gc, void* stream) {
+  return launch_slice(grid, guide, out, B, H, W, H, 0, gh, gw, gd, gc, HDRNET_VARIANT_AUTO,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int hdrnet_slice_indices_i32(const float* guide, int32_t* idx, int B, int H, int W, int gh,
+                             int gw, int gd, void* stream) {
+  int rc = validate_common(B, H, W, gh, gw, gd);
+  if (rc != HDRNET_OK) return rc;
+  const long long npix = static_cast<long long>(B) * H * W;
+  if (npix == 0) return HDRNET_OK;
+  if (!guide || !idx) return HDRNET_E_NULL_POINTER;
+  const SliceGeom g = make_geom(B, H, W, H, 0, gh, gw, gd);
+  slice_indices_kernel<<<generic_grid(npix, device_sm_count()), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(guide, idx, g, npix);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int hdrnet_slice_apply_plan(int B, int H, int W, int gh, int gw, int gd, int n_in, int n_out,
+                            int has_offset, int* variant, int* ctas, int* threads,
+                            int* smem_bytes) {
+  int rc = validate_common(B, H, W, gh, gw, gd);
+  if (rc != HDRNET_OK) return rc;
+  const SliceGeom g = make_geom(B, H, W, H, 0, gh, gw, gd);
+  const int sms = device_sm_count();
+  TmaPlan plan;
+  const bool tma = (n_in == 3 && n_out == 3 && has_offset) && W >= 128 &&
+                   make_tma_plan(g, device_max_smem_optin(), sms, &plan);
+  const long long npix = static_cast<long long>(B) * H * W;
+  if (variant) *variant = tma ? HDRNET_VARIANT_TMA : HDRNET_VARIANT_GENERIC;
+  if (ctas) *ctas = tma ? plan.ctas : generic_grid(npix, sms);
+  if (threads) *threads = tma ? kTmaThreads : 256;
+  if (smem_bytes) *smem_bytes = tma ? plan.smem_bytes : 0;
+  return HDRNET_OK;
+}
+
+}  // extern "C"

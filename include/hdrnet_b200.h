@@ -1,0 +1,134 @@
+/*
+ * hdrnet_b200.h -- C-ABI of libhdrnet_b200.so: the B200 (sm_100a) implementation of
+ * google/hdrnet's bilateral-slice hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / TF types.  Each entry
+ * point cites the reference interface it replaces.  All tensors use the reference op's
+ * layout (TF row-major NHWC, last index fastest; hdrnet/ops/bilateral_slice_apply_op.cc:
+ * 201-227):
+ *
+ *     grid   [B, gh, gw, gd, gc]   float32   gc = n_out * (n_in + has_offset), c = i*J + j
+ *     guide  [B, H, W]             float32   expected in [0, 1], not enforced
+ *     input  [B, H, W, n_in]       float32
+ *     out    [B, H, W, n_out]      float32   (slice-apply)   /  [B, H, W, gc]  (slice)
+ *
+ * Conventions (replacing TF's OpKernel contract):
+ *   - the caller owns and allocates every buffer, including outputs;
+ *   - `*_f32` device entry points take DEVICE pointers valid on the current CUDA device and
+ *     launch asynchronously on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream); they never allocate, never synchronise, and are re-entrant;
+ *   - every function returns 0 on success, a negative HDRNET_E_* code for a contract
+ *     violation (the conditions the reference raises InvalidArgument for), or a positive
+ *     cudaError_t if a launch failed (the reference's Internal("... kernel failed."));
+ *   - empty outputs (B*H*W == 0) succeed without launching (bilateral_slice_apply.cu.cc:
+ *     373-379).
+ */
+#ifndef HDRNET_B200_H_
+#define HDRNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDRNET_B200_ABI_VERSION 1
+
+/* Exported from libhdrnet_b200.so (the library is built with -fvisibility=hidden). */
+#if defined(__GNUC__)
+#define HDRNET_API __attribute__((visibility("default")))
+#else
+#define HDRNET_API
+#endif
+
+/* Contract violations (negative; positive return values are cudaError_t). */
+#define HDRNET_OK 0
+#define HDRNET_E_NULL_POINTER (-1)   /* a required pointer is NULL                         */
+#define HDRNET_E_BAD_SHAPE (-2)      /* a dimension is negative, or gh/gw/gd/gc/n_* is < 1 */
+#define HDRNET_E_BAD_CHANNELS (-3)   /* gc != n_out * (n_in + has_offset)                  */
+#define HDRNET_E_TOO_LARGE (-4)      /* an extent does not fit the kernels' 32-bit indices */
+#define HDRNET_E_UNSUPPORTED (-5)    /* the requested variant cannot run these shapes      */
+#define HDRNET_E_BAD_CONTEXT (-6)    /* invalid / destroyed host-path context              */
+
+/* Kernel selection for the *_variant debug entry points. */
+#define HDRNET_VARIANT_AUTO 0    /* what the plain entry points use                        */
+#define HDRNET_VARIANT_GENERIC 1 /* one thread per pixel, any shape / alignment            */
+#define HDRNET_VARIANT_TMA 2     /* persistent TMA-staged row kernel (needs W % 4 == 0,    */
+                                 /* 16-byte aligned buffers; n_in == 3, n_out == 3,        */
+                                 /* has_offset for slice-apply)                            */
+
+HDRNET_API int hdrnet_b200_abi_version(void);
+
+/* Human-readable text for a return code of this library (static storage). */
+HDRNET_API const char* hdrnet_b200_error_string(int code);
+
+/*
+ * Fused slice + affine apply.  Replaces the BilateralSliceApply op:
+ *   Python   hdrnet/hdrnet_ops.py:31          hdrnet_ops.bilateral_slice_apply
+ *   OpKernel hdrnet/ops/bilateral_slice_apply_op.cc:140-235  (Compute, GpuDevice)
+ *   kernel   hdrnet/ops/bilateral_slice_apply.cu.cc:36-126, launcher :368-382
+ * out[b,y,x,i] = sum_j trilerp(grid[..., i*J + j]) * (j < n_in ? input[b,y,x,j] : 1).
+ */
+HDRNET_API int hdrnet_slice_apply_f32(const float* grid, const float* guide, const float* input,
+                           float* out, int B, int H, int W, int gh, int gw, int gd, int n_in,
+                           int n_out, int has_offset, void* stream);
+
+/* Same, with the kernel variant forced (tests exercise every variant on the same inputs). */
+HDRNET_API int hdrnet_slice_apply_f32_variant(const float* grid, const float* guide, const float* input,
+                                   float* out, int B, int H, int W, int gh, int gw, int gd,
+                                   int n_in, int n_out, int has_offset, int variant,
+                                   void* stream);
+
+/*
+ * Un-fused slice.  Replaces the BilateralSlice op:
+ *   Python   hdrnet/hdrnet_ops.py:30          hdrnet_ops.bilateral_slice
+ *   OpKernel hdrnet/ops/bilateral_slice_op.cc:120-174
+ *   kernel   hdrnet/ops/bilateral_slice.cu.cc:34-91, launcher :230-244
+ * out[b,y,x,c] = trilerp(grid[..., c]) at ((x+.5)*gw/W, (y+.5)*gh/H, guide*gd).
+ */
+HDRNET_API int hdrnet_slice_f32(const float* grid, const float* guide, float* out, int B, int H, int W,
+                     int gh, int gw, int gd, int gc, void* stream);
+
+HDRNET_API int hdrnet_slice_f32_variant(const float* grid, const float* guide, float* out, int B, int H,
+                             int W, int gh, int gw, int gd, int gc, int variant, void* stream);
+
+/*
+ * Debug: the unclamped lower cell indices (gx0, gy0, gz0) the kernels use, written as
+ * idx[b,y,x,0..2] int32.  It runs the same device functions as the slice kernels, so the
+ * bit-exactness of the index arithmetic (bilateral_slice_apply.cu.cc:73-80;
+ * jax/bilateral_slice.py:317-327) can be asserted against the oracle.
+ */
+HDRNET_API int hdrnet_slice_indices_i32(const float* guide, int32_t* idx, int B, int H, int W, int gh,
+                             int gw, int gd, void* stream);
+
+/*
+ * Kernel-introspection for benchmarks: which variant AUTO would pick for these shapes, and
+ * the launch geometry of the TMA kernel (CTAs, threads, dynamic shared memory bytes).
+ */
+HDRNET_API int hdrnet_slice_apply_plan(int B, int H, int W, int gh, int gw, int gd, int n_in, int n_out,
+                            int has_offset, int* variant, int* ctas, int* threads,
+                            int* smem_bytes);
+
+/*
+ * Host-buffer path (what a CPU-tensor caller of the reference op gets: TF copies feeds to
+ * the GPU and fetches back, hdrnet/bin/run.py:185).  A context owns device staging buffers
+ * and streams; the call splits the batch into row bands, and pipelines H2D copy -> kernel
+ * -> D2H copy across streams.  Host buffers should be page-locked for the copies to
+ * overlap (pageable memory works but serialises).  Blocks until `out` is complete.
+ */
+typedef struct hdrnet_host_ctx hdrnet_host_ctx;
+
+/* max_band_pixels: staging capacity per pipeline slot, in pixels (0 = default 4 Mi px). */
+HDRNET_API int hdrnet_host_ctx_create(hdrnet_host_ctx** ctx, size_t max_band_pixels);
+HDRNET_API int hdrnet_host_ctx_destroy(hdrnet_host_ctx* ctx);
+
+HDRNET_API int hdrnet_slice_apply_host_f32(hdrnet_host_ctx* ctx, const float* grid, const float* guide,
+                                const float* input, float* out, int B, int H, int W, int gh,
+                                int gw, int gd, int n_in, int n_out, int has_offset);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* HDRNET_B200_H_ */

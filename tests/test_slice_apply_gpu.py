@@ -1,0 +1,241 @@
+"""GPU parity tests (run on the B200 box): the CUDA kernels, called through the C-ABI, against
+the oracle on the same seeded inputs, against the committed golden fixtures from the
+reference's JAX file, and -- at BASELINE.json's full 4K size -- against the full oracle on
+one frame plus size-independent properties.  Tolerance: 1e-5 relative (tests/util.py);
+cell indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from hdrnet_b200 import _lib, hdrnet_ops, layers
+from util import RTOL, assert_parity, load_golden, rand_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "tma": _lib.VARIANT_TMA}
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run_apply(grid, guide, inp, has_offset, variant="auto"):
+    out = hdrnet_ops.bilateral_slice_apply(cuda(grid), cuda(guide), cuda(inp), has_offset,
+                                           variant=VARIANTS[variant])
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def run_slice(grid, guide):
+    out = hdrnet_ops.bilateral_slice(cuda(grid), cuda(guide))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def checker():
+    """Compiled reference loops when present, else the C restatement."""
+    return oracle.best()
+
+
+# ---- golden fixtures from the reference's jax/bilateral_slice.py ---------------------------
+@pytest.mark.parametrize("name", ["ops_test_extents", "jax_tf2_extents", "interpolate_kat_0",
+                                  "interpolate_kat_1", "interpolate_kat_2", "edge_guides",
+                                  "edge_gd1", "wide_rows"])
+def test_matches_reference_jax_golden(name):
+    g = load_golden(name)
+    assert_parity(run_slice(g["grid"], g["guide"]), g["slice"], what=f"{name}: slice")
+    gh, gw, gd = g["grid"].shape[1:4]
+    idx = hdrnet_ops.slice_indices(cuda(g["guide"]), (gh, gw, gd)).cpu().numpy()
+    assert np.array_equal(idx, g["indices"]), f"{name}: cell indices must be bit-exact"
+    if "apply_offset" in g:
+        for v in ("auto", "generic"):
+            assert_parity(run_apply(g["grid"], g["guide"], g["input"], True, v), g["apply_offset"],
+                          what=f"{name}: apply+offset [{v}]")
+    if "apply_nooffset" in g:
+        assert_parity(run_apply(g["grid"], g["guide"], g["input"], False), g["apply_nooffset"],
+                      what=f"{name}: apply")
+
+
+def test_wide_rows_golden_through_tma_kernel():
+    g = load_golden("wide_rows")
+    assert_parity(run_apply(g["grid"], g["guide"], g["input"], True, "tma"), g["apply_offset"],
+                  what="wide_rows [tma]")
+
+
+@pytest.mark.parametrize("val", [0, 1, 2])
+def test_interpolate_known_answer(val):
+    """hdrnet/test/ops_test.py:61-86, tolerance 5e-4 there."""
+    g = load_golden(f"interpolate_kat_{val}")
+    out = run_slice(g["grid"], g["guide"])
+    assert np.abs(out - val).max() < 5e-4
+
+
+# ---- seeded parity against the oracle, every variant ----------------------------------------
+SHAPES = [
+    # B, H, W, gh, gw, gd
+    (3, 30, 25, 16, 12, 8),     # hdrnet_ops_test.py:91-100 (W % 4 != 0 -> generic only)
+    (3, 8, 5, 6, 3, 7),         # hdrnet_ops_test.py:185-195
+    (4, 48, 64, 16, 12, 8),     # hdrnet_ops_jax_tf2_test.py:28-34, reduced
+    (2, 33, 128, 16, 16, 8),    # narrowest width AUTO sends to the TMA kernel
+    (1, 5, 4, 2, 2, 2),         # a single quad per row
+    (2, 7, 1028, 5, 7, 3),      # two segments per row, ragged second segment
+    (1, 300, 1920, 16, 16, 8),  # 1080p rows: more rows than CTAs
+    (2, 16, 4032, 32, 32, 16),  # 12 MP width, largest grid of the sweep (1 CTA / SM)
+    (1, 9, 512, 1, 1, 1),       # degenerate 1x1x1 grid
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("variant", ["auto", "generic", "tma"])
+def test_slice_apply_matches_oracle(shape, variant):
+    B, H, W, gh, gw, gd = shape
+    if variant == "tma" and W % 4 != 0:
+        pytest.skip("TMA kernel needs W % 4 == 0")
+    grid, guide, inp = rand_case(1234, B, H, W, gh, gw, gd, signed=True)
+    expected = checker().bilateral_slice_apply(grid, guide, inp, True)
+    assert_parity(run_apply(grid, guide, inp, True, variant), expected,
+                  what=f"{shape} [{variant}]")
+
+
+@pytest.mark.parametrize("n_in,n_out,has_offset", [(3, 3, False), (3, 4, True), (1, 1, True),
+                                                   (4, 2, True), (2, 5, False), (3, 9, True)])
+def test_slice_apply_general_channels(n_in, n_out, has_offset):
+    """ops_test.py:345-365 (has_offset False -> gc/n_in outputs) and the GaussianPyrNN
+    n_out = 9 case (models.py:221-223)."""
+    grid, guide, inp = rand_case(7, 2, 21, 36, 5, 4, 6, n_in, n_out, has_offset, signed=True)
+    expected = checker().bilateral_slice_apply(grid, guide, inp, has_offset)
+    got = run_apply(grid, guide, inp, has_offset)
+    assert got.shape == (2, 21, 36, n_out)
+    assert_parity(got, expected)
+
+
+@pytest.mark.parametrize("shape", SHAPES[:6], ids=lambda s: "x".join(map(str, s)))
+def test_slice_matches_oracle(shape):
+    B, H, W, gh, gw, gd = shape
+    rng = np.random.RandomState(3)
+    grid = rng.randn(B, gh, gw, gd, 12).astype(np.float32)
+    guide = rng.rand(B, H, W).astype(np.float32)
+    assert_parity(run_slice(grid, guide), checker().bilateral_slice(grid, guide))
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_cell_indices_bit_exact(shape):
+    B, H, W, gh, gw, gd = shape
+    rng = np.random.RandomState(5)
+    guide = rng.rand(B, H, W).astype(np.float32)
+    # exercise the cell boundaries: guide * gd - 0.5 exactly integral, and just around it
+    k = (np.arange(guide.size) % (gd + 1)).reshape(guide.shape).astype(np.float32)
+    edge = ((k + 0.5) / gd).astype(np.float32)
+    guide = np.where(rng.rand(*guide.shape) < 0.3, edge, guide).astype(np.float32)
+    guide = np.where(rng.rand(*guide.shape) < 0.1, np.nextafter(edge, np.float32(0)), guide)
+    got = hdrnet_ops.slice_indices(cuda(guide), (gh, gw, gd)).cpu().numpy()
+    assert np.array_equal(got, oracle.port().slice_indices(guide, gh, gw, gd))
+
+
+def test_guide_outside_unit_range_clamps_like_reference():
+    grid, guide, inp = rand_case(17, 1, 16, 256, 4, 4, 8, signed=True)
+    guide[0, :, ::3] = -0.75
+    guide[0, :, 1::3] = 1.5
+    guide[0, 0, :4] = [0.0, 1.0, 100.0, -100.0]
+    expected = checker().bilateral_slice_apply(grid, guide, inp, True)
+    for v in ("generic", "tma"):
+        assert_parity(run_apply(grid, guide, inp, True, v), expected, what=v)
+
+
+def test_empty_batch_is_a_no_op():
+    """bilateral_slice_apply.cu.cc:373-379: empty output => no launch."""
+    out = hdrnet_ops.bilateral_slice_apply(torch.zeros(0, 4, 4, 4, 12).cuda(),
+                                           torch.zeros(0, 8, 8).cuda(),
+                                           torch.zeros(0, 8, 8, 3).cuda(), True)
+    assert out.shape == (0, 8, 8, 3)
+
+
+def test_layers_wrappers_on_6d_grid():
+    """hdrnet/layers.py:99-148: 6-D coefficient grids, both packings; fused == slice + apply."""
+    rng = np.random.RandomState(9)
+    B, H, W, gh, gw, gd, n_out, n_in1 = 2, 24, 132, 4, 4, 8, 3, 4
+    coeffs = rng.randn(B, gh, gw, gd, n_out, n_in1).astype(np.float32)
+    guide = rng.rand(B, H, W).astype(np.float32)
+    im = rng.rand(B, H, W, 3).astype(np.float32)
+    fused = layers.bilateral_slice_apply(cuda(coeffs), cuda(guide), cuda(im), has_offset=True)
+    sliced = layers.bilateral_slice(cuda(coeffs), cuda(guide))
+    assert sliced.shape == (B, H, W, n_out, n_in1)
+    unfused = layers.apply(sliced, cuda(im), has_affine_term=True)
+    assert_parity(unfused.cpu().numpy(), fused.cpu().numpy())
+    expected = checker().bilateral_slice_apply(coeffs.reshape(B, gh, gw, gd, 12), guide, im, True)
+    assert_parity(fused.cpu().numpy(), expected)
+
+
+def test_host_buffer_path_matches_device_path():
+    """CPU tensors go through the pipelined host path (row bands, y offsets)."""
+    grid, guide, inp = rand_case(31, 2, 700, 1024, 16, 16, 8, signed=True)
+    dev = run_apply(grid, guide, inp, True)
+    host = hdrnet_ops.bilateral_slice_apply(torch.from_numpy(grid).pin_memory(),
+                                            torch.from_numpy(guide).pin_memory(),
+                                            torch.from_numpy(inp).pin_memory(), True)
+    assert not host.is_cuda
+    assert np.array_equal(host.numpy(), dev)
+    pageable = hdrnet_ops.bilateral_slice_apply(torch.from_numpy(grid), torch.from_numpy(guide),
+                                                torch.from_numpy(inp), True)
+    assert np.array_equal(pageable.numpy(), dev)
+
+
+def test_non_default_stream_and_repeatability():
+    grid, guide, inp = rand_case(41, 2, 64, 640, 8, 8, 8)
+    g, u, i = cuda(grid), cuda(guide), cuda(inp)
+    ref = hdrnet_ops.bilateral_slice_apply(g, u, i, True)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        outs = [hdrnet_ops.bilateral_slice_apply(g, u, i, True) for _ in range(5)]
+    s.synchronize()
+    for o in outs:
+        assert torch.equal(o, ref)
+
+
+# ---- BASELINE.json full size: 4K ------------------------------------------------------------
+def test_4k_frame_against_full_oracle():
+    """One 3840x2160 frame, grid 16x16x8 (config 3's per-image shape), full oracle compare."""
+    grid, guide, inp = rand_case(1234, 1, 2160, 3840, 16, 16, 8)
+    expected = checker().bilateral_slice_apply(grid, guide, inp, True)
+    for v in ("tma", "generic"):
+        got = run_apply(grid, guide, inp, True, v)
+        assert_parity(got, expected, what=f"4K [{v}]")
+    gidx = hdrnet_ops.slice_indices(cuda(guide), (16, 16, 8)).cpu().numpy()
+    assert np.array_equal(gidx, oracle.port().slice_indices(guide, 16, 16, 8))
+
+
+def test_4k_batch8_properties():
+    """Config 3 (8 x 4K) through size-independent properties: the two kernel variants agree,
+    the op is linear in the grid, an identity grid returns in * sum(w) with sum(w) in
+    [0.9999, 1], and image b only depends on grid b."""
+    B, H, W, gh, gw, gd = 8, 2160, 3840, 16, 16, 8
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    grid = torch.rand(B, gh, gw, gd, 12, device="cuda", generator=gen)
+    guide = torch.rand(B, H, W, device="cuda", generator=gen)
+    inp = torch.rand(B, H, W, 3, device="cuda", generator=gen)
+    out = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True)
+    gen_out = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=_lib.VARIANT_GENERIC)
+    scale = out.abs().max().item()
+    assert (out - gen_out).abs().max().item() / scale <= RTOL
+    del gen_out
+    # linearity in the grid
+    grid2 = torch.rand(B, gh, gw, gd, 12, device="cuda", generator=gen)
+    lin = hdrnet_ops.bilateral_slice_apply(2.0 * grid - 0.5 * grid2, guide, inp, True)
+    out2 = hdrnet_ops.bilateral_slice_apply(grid2, guide, inp, True)
+    assert (lin - (2.0 * out - 0.5 * out2)).abs().max().item() / scale <= 4 * RTOL
+    del lin, out2, grid2
+    # identity coefficients
+    ident = torch.zeros(B, gh, gw, gd, 3, 4, device="cuda")
+    for i in range(3):
+        ident[..., i, i] = 1.0
+    ido = hdrnet_ops.bilateral_slice_apply(ident.reshape(B, gh, gw, gd, 12), guide, inp, True)
+    ratio = ido / inp.clamp_min(1e-3)
+    mask = inp > 1e-3
+    assert ratio[mask].max().item() <= 1.0 + 1e-5 and ratio[mask].min().item() >= 0.9999 - 1e-5
+    # batch independence: permuting images permutes outputs
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device="cuda")
+    outp = hdrnet_ops.bilateral_slice_apply(grid[perm].contiguous(), guide[perm].contiguous(),
+                                            inp[perm].contiguous(), True)
+    assert torch.equal(outp, out[perm])

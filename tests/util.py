@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# BASELINE.json north_star: "outputs match the repo's jax/bilateral_slice.py reference to
+# 1e-5 relative fp32".  Relative means relative to the magnitude of the output tensor:
+# a pixel whose terms cancel to ~0 cannot be held to 1e-5 of its own value in float32.
+RTOL = 1e-5
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def rel_err(actual, expected):
+    actual = np.asarray(actual, np.float64)
+    expected = np.asarray(expected, np.float64)
+    scale = max(float(np.abs(expected).max()), 1e-30)
+    return float(np.abs(actual - expected).max()) / scale
+
+
+def assert_parity(actual, expected, rtol=RTOL, what=""):
+    actual = np.asarray(actual)
+    expected = np.asarray(expected)
+    assert actual.shape == expected.shape, f"{what}: shape {actual.shape} != {expected.shape}"
+    assert np.isfinite(actual).all(), f"{what}: non-finite values"
+    err = rel_err(actual, expected)
+    assert err <= rtol, f"{what}: max |diff| / max |ref| = {err:.3e} > {rtol:.1e}"
+
+
+def rand_case(seed, B, H, W, gh, gw, gd, n_in=3, n_out=3, has_offset=True, signed=False):
+    """Seeded inputs as the reference's tests draw them (np.random.rand; hdrnet_ops_test.py:101)."""
+    rng = np.random.RandomState(seed)
+    J = n_in + (1 if has_offset else 0)
+    draw = (lambda *s: rng.randn(*s)) if signed else (lambda *s: rng.rand(*s))
+    grid = draw(B, gh, gw, gd, n_out * J).astype(np.float32)
+    guide = rng.rand(B, H, W).astype(np.float32)
+    inp = draw(B, H, W, n_in).astype(np.float32)
+    return grid, guide, inp

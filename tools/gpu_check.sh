@@ -1,0 +1,20 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, smoke, bench, ncu launch list + full capture of the top kernel.
+# Usage (from the repo root on the GPU box):  bash tools/gpu_check.sh [quick]
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.csv 2>&1
+nproc > gpurun_out/nproc.txt; lscpu | grep -E "Model name|^CPU\(s\)" >> gpurun_out/nproc.txt
+timeout 1500 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
+tail -25 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/smoke.log
+timeout 900 python bench.py --steps 300 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+if [ "${1:-}" != "quick" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
+      --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launches.log 2>&1
+  echo "ncu launches exit $?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:slice_apply_rows_tma -s 3 -c 2 \
+      -f -o gpurun_out/prof_tma python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
+  echo "ncu full exit $?"
+fi
