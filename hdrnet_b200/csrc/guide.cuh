@@ -1,0 +1,62 @@
+// guide.cuh -- per-pixel guidance-map functions, shared by the standalone guide kernels
+// (guide.cu) and the guide-fused slice-apply kernel (slice_apply.cu).
+//
+// Parameters travel BY VALUE in the kernel argument block (constant bank), so every
+// coefficient is a free constant operand of the FMA that uses it: no loads, no shared memory.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace hdrnet_b200 {
+
+constexpr int kCurvePts = 16;     // hdrnet/models.py:147 (npts, hard-coded in the reference)
+constexpr int kMaxGuideFeats = 32;
+
+// HDRNetCurves._guide (hdrnet/models.py:145-190):
+//   t = rgb . ccm + ccm_bias; u_c = sum_k slopes[c][k] * relu(t_c - shifts[c][k]);
+//   guide = clip(sum_c mix[c] * u_c + mix_bias, 0, 1)
+struct CurvesGuideParams {
+  float ccm[3][3];   // [in][out]: t_out = sum_in x_in * ccm[in][out]  (tf.matmul(x, ccm))
+  float ccm_bias[3];
+  float shifts[3][kCurvePts];
+  float slopes[3][kCurvePts];
+  float mix[3];
+  float mix_bias;
+};
+
+// HDRNetPointwiseNNGuide._guide (hdrnet/models.py:199-210) with the batch norm of conv1
+// folded into w1/b1 on the host (inference form, hdrnet/bin/freeze_graph.py:141-142):
+//   h_f = relu(sum_c x_c * w1[c][f] + b1[f]); guide = sigmoid(sum_f h_f * w2[f] + b2)
+struct NNGuideParams {
+  int feats;
+  float w1[3][kMaxGuideFeats];
+  float b1[kMaxGuideFeats];
+  float w2[kMaxGuideFeats];
+  float b2;
+};
+
+__device__ __forceinline__ float curves_guide(const CurvesGuideParams& p, float r, float g,
+                                              float b) {
+  float acc = p.mix_bias;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float t = fmaf(b, p.ccm[2][c], fmaf(g, p.ccm[1][c], fmaf(r, p.ccm[0][c], p.ccm_bias[c])));
+    float u = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kCurvePts; ++k) u = fmaf(p.slopes[c][k], fmaxf(t - p.shifts[c][k], 0.0f), u);
+    acc = fmaf(p.mix[c], u, acc);
+  }
+  return fminf(fmaxf(acc, 0.0f), 1.0f);
+}
+
+__device__ __forceinline__ float nn_guide(const NNGuideParams& p, float r, float g, float b) {
+  float y = p.b2;
+#pragma unroll 8
+  for (int f = 0; f < p.feats; ++f) {
+    const float h = fmaf(b, p.w1[2][f], fmaf(g, p.w1[1][f], fmaf(r, p.w1[0][f], p.b1[f])));
+    y = fmaf(fmaxf(h, 0.0f), p.w2[f], y);
+  }
+  return 1.0f / (1.0f + expf(-y));
+}
+
+}  // namespace hdrnet_b200

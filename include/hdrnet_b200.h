@@ -111,6 +111,32 @@ HDRNET_API int hdrnet_slice_apply_plan(int B, int H, int W, int gh, int gw, int 
                             int* smem_bytes);
 
 /*
+ * Full-resolution guidance maps (input [npix, 3] float32 RGB -> guide [npix] float32).
+ * Coefficient arrays are HOST pointers, read before the call returns (they travel in the
+ * kernel argument block).
+ *
+ * Curves guide.  Replaces HDRNetCurves._guide, hdrnet/models.py:145-190:
+ *   t = rgb . ccm + ccm_bias;  u_c = sum_k slopes[c][k] * relu(t_c - shifts[c][k]);
+ *   guide = clip(sum_c mix[c] * u_c + mix_bias, 0, 1)
+ * ccm[3][3] is indexed [in][out] (tf.matmul(x, ccm), :156); shifts/slopes are [3][16]
+ * (the reference's variables `shifts` [1,1,3,16] and `slopes` [1,1,1,3,16] flattened).
+ */
+HDRNET_API int hdrnet_guide_curves_f32(const float* input, float* guide, long long npix,
+                                       const float* ccm, const float* ccm_bias,
+                                       const float* shifts, const float* slopes,
+                                       const float* mix, float mix_bias, void* stream);
+
+/*
+ * Pointwise-NN guide.  Replaces HDRNetPointwiseNNGuide._guide, hdrnet/models.py:199-210:
+ *   h_f = relu(sum_c x_c * w1[c][f] + b1[f]);  guide = sigmoid(sum_f h_f * w2[f] + b2)
+ * with conv1's batch norm already folded into w1[3][feats] / b1[feats] by the caller
+ * (inference form, hdrnet/bin/freeze_graph.py:141-142).  feats <= 32.
+ */
+HDRNET_API int hdrnet_guide_nn_f32(const float* input, float* guide, long long npix,
+                                   const float* w1, const float* b1, const float* w2, float b2,
+                                   int feats, void* stream);
+
+/*
  * Host-buffer path (what a CPU-tensor caller of the reference op gets: TF copies feeds to
  * the GPU and fetches back, hdrnet/bin/run.py:185).  A context owns device staging buffers
  * and streams; the call splits the batch into row bands, and pipelines H2D copy -> kernel
