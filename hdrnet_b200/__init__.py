@@ -11,6 +11,7 @@ compute is hand-written CUDA in ``csrc/`` reached through the C-ABI in
 from . import _lib  # noqa: F401
 from . import hdrnet_ops  # noqa: F401
 from . import layers  # noqa: F401
+from . import models  # noqa: F401
 
-__all__ = ["hdrnet_ops", "layers", "_lib"]
+__all__ = ["hdrnet_ops", "layers", "models", "_lib"]
 __version__ = "0.1.0"

@@ -1,0 +1,309 @@
+// cnn.cu -- the low-resolution coefficient network: replaces the TF
+// conv / fully_connected layers of HDRNetCurves._coefficients (hdrnet/models.py:62-142,
+// hdrnet/layers.py:25-93) with three hand-written fp32 kernels:
+//
+//   conv2d_nhwc_kernel   k x k (1 or 3), stride 1/2, TF 'SAME' padding (asymmetric for
+//                        stride 2 on even extents), HWIO weights, bias + ReLU epilogue.
+//                        Batch norm is folded into weights/bias on the host (inference form).
+//   fc_kernel            x[B,I] @ W[I,O] + b (+ReLU), weights streamed once for 8 images.
+//   fuse_predict_kernel  fusion relu(local + global) (models.py:122-125), the 1x1 prediction
+//                        conv (:129-132) and the unroll_grid permutation (:134-139) in one
+//                        pass, writing the [B,gh,gw,gd,n_out*n_in] grid slice-apply reads.
+//
+// The whole network is ~83 MFLOP per image: launch-latency bound, not tensor bound (DESIGN.md
+// section 5).  fp32 CUDA-core math keeps the coefficients within float32 round-off of the
+// float64-accumulated oracle, which bf16 / tf32 tensor-core math could not.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "hdrnet_b200.h"
+
+namespace hdrnet_b200 {
+
+constexpr int kConvThreads = 128;  // 32 pixel-pairs x 4 channel groups
+constexpr int kConvPx = 2;         // output pixels per thread
+constexpr int kConvCo = 8;         // output channels per thread
+constexpr int kConvTilePx = 32 * kConvPx;
+constexpr int kConvTileCo = 4 * kConvCo;
+
+struct ConvArgs {
+  const float* in;
+  const float* w;     // [k][k][Cin][Cout]
+  const float* bias;  // [Cout] or nullptr
+  float* out;
+  int B, H, W, Cin, OH, OW, Cout, k, stride, pad_t, pad_l, relu, ci_chunk;
+};
+
+__global__ void __launch_bounds__(kConvThreads)
+conv2d_nhwc_kernel(const ConvArgs a) {
+  extern __shared__ __align__(16) float wsm[];  // [k*k][ci_chunk][kConvTileCo]
+  const int tid = threadIdx.x;
+  const int pg = tid & 31, cg = tid >> 5;
+  const int co0 = blockIdx.y * kConvTileCo;
+  const long long total_px = static_cast<long long>(a.B) * a.OH * a.OW;
+  const long long tile_px0 = static_cast<long long>(blockIdx.x) * kConvTilePx;
+
+  // This thread's output pixels.
+  int pb[kConvPx], py[kConvPx], px[kConvPx];
+  bool pv[kConvPx];
+#pragma unroll
+  for (int p = 0; p < kConvPx; ++p) {
+    const long long q = tile_px0 + pg * kConvPx + p;
+    pv[p] = q < total_px;
+    const long long qq = pv[p] ? q : 0;
+    px[p] = static_cast<int>(qq % a.OW);
+    py[p] = static_cast<int>((qq / a.OW) % a.OH);
+    pb[p] = static_cast<int>(qq / (static_cast<long long>(a.OW) * a.OH));
+  }
+  float acc[kConvPx][kConvCo];
+#pragma unroll
+  for (int p = 0; p < kConvPx; ++p)
+#pragma unroll
+    for (int c = 0; c < kConvCo; ++c) acc[p][c] = 0.0f;
+
+  const int kk = a.k * a.k;
+  const bool vec_in = (a.Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15u) == 0);
+  for (int ci0 = 0; ci0 < a.Cin; ci0 += a.ci_chunk) {
+    const int cn = min(a.ci_chunk, a.Cin - ci0);
+    __syncthreads();
+    // Stage weights [kk][cn][32 co] (zero-fill channels beyond Cout).
+    for (int e = tid; e < kk * cn * kConvTileCo; e += kConvThreads) {
+      const int co = e % kConvTileCo;
+      const int ci = (e / kConvTileCo) % cn;
+      const int t = e / (kConvTileCo * cn);
+      const int gco = co0 + co;
+      wsm[e] = (gco < a.Cout)
+                   ? __ldg(a.w + (static_cast<size_t>(t) * a.Cin + ci0 + ci) * a.Cout + gco)
+                   : 0.0f;
+    }
+    __syncthreads();
+    for (int t = 0; t < kk; ++t) {
+      const int ky = t / a.k, kx = t - ky * a.k;
+      const float* src[kConvPx];
+      bool ok[kConvPx];
+#pragma unroll
+      for (int p = 0; p < kConvPx; ++p) {
+        const int iy = py[p] * a.stride - a.pad_t + ky;
+        const int ix = px[p] * a.stride - a.pad_l + kx;
+        ok[p] = pv[p] && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+        src[p] = a.in + ((static_cast<size_t>(pb[p]) * a.H + (ok[p] ? iy : 0)) * a.W +
+                         (ok[p] ? ix : 0)) * a.Cin + ci0;
+      }
+      const float* wt = wsm + static_cast<size_t>(t) * cn * kConvTileCo + cg * kConvCo;
+      if (vec_in && (cn % 4 == 0)) {
+        for (int ci = 0; ci < cn; ci += 4) {
+          float xin[kConvPx][4];
+#pragma unroll
+          for (int p = 0; p < kConvPx; ++p) {
+            const float4 v = ok[p] ? __ldg(reinterpret_cast<const float4*>(src[p] + ci))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            xin[p][0] = v.x; xin[p][1] = v.y; xin[p][2] = v.z; xin[p][3] = v.w;
+          }
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wt + (ci + d) * kConvTileCo);
+            const float4 w1 = *reinterpret_cast<const float4*>(wt + (ci + d) * kConvTileCo + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int p = 0; p < kConvPx; ++p)
+#pragma unroll
+              for (int c = 0; c < kConvCo; ++c) acc[p][c] = fmaf(xin[p][d], wv[c], acc[p][c]);
+          }
+        }
+      } else {
+        for (int ci = 0; ci < cn; ++ci) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * kConvTileCo);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * kConvTileCo + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int p = 0; p < kConvPx; ++p) {
+            const float x = ok[p] ? __ldg(src[p] + ci) : 0.0f;
+#pragma unroll
+            for (int c = 0; c < kConvCo; ++c) acc[p][c] = fmaf(x, wv[c], acc[p][c]);
+          }
+        }
+      }
+    }
+  }
+
+  // Epilogue: bias, ReLU, store.
+#pragma unroll
+  for (int p = 0; p < kConvPx; ++p) {
+    if (!pv[p]) continue;
+    float* dst = a.out + ((static_cast<size_t>(pb[p]) * a.OH + py[p]) * a.OW + px[p]) * a.Cout;
+#pragma unroll
+    for (int c = 0; c < kConvCo; ++c) {
+      const int gco = co0 + cg * kConvCo + c;
+      if (gco < a.Cout) {
+        float v = acc[p][c] + (a.bias ? __ldg(a.bias + gco) : 0.0f);
+        if (a.relu) v = fmaxf(v, 0.0f);
+        dst[gco] = v;
+      }
+    }
+  }
+}
+
+// ---- fully connected --------------------------------------------------------------------
+constexpr int kFcThreads = 256;   // 64 outputs x 4 k-slices
+constexpr int kFcOut = 64;
+constexpr int kFcSlices = 4;
+constexpr int kFcBatch = 8;       // images per pass (weights streamed once for all of them)
+constexpr int kFcChunk = 512;     // inputs staged per step: 8 x 512 x 4 B = 16 KB
+
+__global__ void __launch_bounds__(kFcThreads)
+fc_kernel(const float* __restrict__ in, const float* __restrict__ w,
+          const float* __restrict__ bias, float* __restrict__ out, int B, int I, int O,
+          int relu) {
+  __shared__ float xs[kFcBatch][kFcChunk];
+  __shared__ float red[kFcSlices][kFcBatch][kFcOut];
+  const int tid = threadIdx.x;
+  const int o = tid % kFcOut, ks = tid / kFcOut;
+  const int go = blockIdx.x * kFcOut + o;
+  const int b0 = blockIdx.y * kFcBatch;
+  const int nb = min(kFcBatch, B - b0);
+  float acc[kFcBatch];
+#pragma unroll
+  for (int b = 0; b < kFcBatch; ++b) acc[b] = 0.0f;
+
+  for (int i0 = 0; i0 < I; i0 += kFcChunk) {
+    const int n = min(kFcChunk, I - i0);
+    __syncthreads();
+    for (int e = tid; e < kFcBatch * kFcChunk; e += kFcThreads) {
+      const int b = e / kFcChunk, i = e % kFcChunk;
+      xs[b][i] = (b < nb && i < n) ? __ldg(in + static_cast<size_t>(b0 + b) * I + i0 + i) : 0.0f;
+    }
+    __syncthreads();
+    if (go < O) {
+      // k-slices interleave so consecutive rows of W stream from consecutive threads' loops
+      for (int i = ks; i < n; i += kFcSlices) {
+        const float wv = __ldg(w + static_cast<size_t>(i0 + i) * O + go);
+#pragma unroll
+        for (int b = 0; b < kFcBatch; ++b) acc[b] = fmaf(xs[b][i], wv, acc[b]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < kFcBatch; ++b) red[ks][b][o] = acc[b];
+  __syncthreads();
+  for (int e = tid; e < kFcBatch * kFcOut; e += kFcThreads) {
+    const int b = e / kFcOut, oo = e % kFcOut;
+    const int goo = blockIdx.x * kFcOut + oo;
+    if (b < nb && goo < O) {
+      float v = ((red[0][b][oo] + red[1][b][oo]) + (red[2][b][oo] + red[3][b][oo])) +
+                (bias ? __ldg(bias + goo) : 0.0f);
+      if (relu) v = fmaxf(v, 0.0f);
+      out[static_cast<size_t>(b0 + b) * O + goo] = v;
+    }
+  }
+}
+
+// ---- fusion + prediction + unroll_grid ----------------------------------------------------
+constexpr int kFpThreads = 256;
+constexpr int kFpCells = 8;  // grid cells per CTA (one warp each)
+
+__global__ void __launch_bounds__(kFpThreads)
+fuse_predict_kernel(const float* __restrict__ local, const float* __restrict__ global_feat,
+                    const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ grid, int B, int cells_per_image, int C, int gd,
+                    int n_out, int n_in) {
+  extern __shared__ __align__(16) float sm[];  // w[C][O] then f[kFpCells][C]
+  const int O = gd * n_out * n_in;
+  float* wsm = sm;
+  float* fsm = sm + static_cast<size_t>(C) * O;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < C * O; e += kFpThreads) wsm[e] = __ldg(w + e);
+  const long long total = static_cast<long long>(B) * cells_per_image;
+  const long long cell = static_cast<long long>(blockIdx.x) * kFpCells + warp;
+  const bool valid = cell < total;
+  if (valid) {
+    const int b = static_cast<int>(cell / cells_per_image);
+    for (int c = lane; c < C; c += 32)
+      fsm[warp * C + c] = fmaxf(__ldg(local + cell * C + c) + __ldg(global_feat + static_cast<size_t>(b) * C + c), 0.0f);
+  }
+  __syncthreads();
+  if (!valid) return;
+  const float* f = fsm + warp * C;
+  for (int o = lane; o < O; o += 32) {
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) acc = fmaf(f[c], wsm[c * O + o], acc);
+    acc += bias ? __ldg(bias + o) : 0.0f;
+    // unroll_grid (models.py:134-139): prediction channel o = (j*n_out + i)*gd + z
+    const int z = o % gd;
+    const int i = (o / gd) % n_out;
+    const int j = o / (gd * n_out);
+    grid[((cell * gd + z) * n_out + i) * n_in + j] = acc;
+  }
+}
+
+static void same_pad(int size, int k, int s, int* out, int* before) {
+  *out = (size + s - 1) / s;
+  int total = (*out - 1) * s + k - size;
+  if (total < 0) total = 0;
+  *before = total / 2;
+}
+
+}  // namespace hdrnet_b200
+
+using namespace hdrnet_b200;
+
+extern "C" {
+
+int hdrnet_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, float* out, int B,
+                           int H, int W, int Cin, int Cout, int k, int stride, int relu,
+                           void* stream) {
+  if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return HDRNET_E_BAD_SHAPE;
+  if ((k != 1 && k != 3) || (stride != 1 && stride != 2)) return HDRNET_E_UNSUPPORTED;
+  if (B == 0) return HDRNET_OK;
+  if (!in || !w || !out) return HDRNET_E_NULL_POINTER;
+  ConvArgs a;
+  a.in = in; a.w = w; a.bias = bias; a.out = out;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = k; a.stride = stride; a.relu = relu;
+  same_pad(H, k, stride, &a.OH, &a.pad_t);
+  same_pad(W, k, stride, &a.OW, &a.pad_l);
+  // weights staged per input-channel chunk: k*k*chunk*32 floats <= 72 KB
+  int chunk = Cin;
+  const int max_chunk = (72 * 1024 / 4) / (k * k * kConvTileCo);
+  if (chunk > max_chunk) chunk = max_chunk / 4 * 4;
+  a.ci_chunk = chunk;
+  const size_t smem = static_cast<size_t>(k) * k * chunk * kConvTileCo * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(conv2d_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const long long total_px = static_cast<long long>(B) * a.OH * a.OW;
+  dim3 grid(static_cast<unsigned>((total_px + kConvTilePx - 1) / kConvTilePx),
+            static_cast<unsigned>((Cout + kConvTileCo - 1) / kConvTileCo));
+  conv2d_nhwc_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out, int B, int I,
+                  int O, int relu, void* stream) {
+  if (B < 0 || I < 1 || O < 1) return HDRNET_E_BAD_SHAPE;
+  if (B == 0) return HDRNET_OK;
+  if (!in || !w || !out) return HDRNET_E_NULL_POINTER;
+  dim3 grid((O + kFcOut - 1) / kFcOut, (B + kFcBatch - 1) / kFcBatch);
+  fc_kernel<<<grid, kFcThreads, 0, static_cast<cudaStream_t>(stream)>>>(in, w, bias, out, B, I, O, relu);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int hdrnet_fuse_predict_f32(const float* local, const float* global_feat, const float* w,
+                            const float* bias, float* grid, int B, int gh, int gw, int C, int gd,
+                            int n_out, int n_in, void* stream) {
+  if (B < 0 || gh < 1 || gw < 1 || C < 1 || gd < 1 || n_out < 1 || n_in < 1) return HDRNET_E_BAD_SHAPE;
+  if (B == 0) return HDRNET_OK;
+  if (!local || !global_feat || !w || !grid) return HDRNET_E_NULL_POINTER;
+  const int O = gd * n_out * n_in;
+  const size_t smem = (static_cast<size_t>(C) * O + static_cast<size_t>(kFpCells) * C) * sizeof(float);
+  if (smem > 200 * 1024) return HDRNET_E_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(fuse_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const long long cells = static_cast<long long>(B) * gh * gw;
+  fuse_predict_kernel<<<static_cast<unsigned>((cells + kFpCells - 1) / kFpCells), kFpThreads, smem,
+                        static_cast<cudaStream_t>(stream)>>>(local, global_feat, w, bias, grid, B,
+                                                             gh * gw, C, gd, n_out, n_in);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -27,6 +27,7 @@
 #include <cstdint>
 
 #include "common.cuh"
+#include "guide.cuh"
 
 namespace hdrnet_b200 {
 
@@ -143,7 +144,8 @@ struct TmaPlan {
 
 struct TmaArgs {
   const float* grid;
-  const float* guide;
+  const float* guide;   // guide input (GuideFromInput), else unused
+  float* guide_out;     // optional guide dump for the fused forms, else nullptr
   const float* input;
   float* out;
   SliceGeom g;
@@ -186,8 +188,33 @@ __device__ __forceinline__ void blend_apply(const float* __restrict__ slab, int 
   out_b = fmaf(a2, b, fmaf(a1, g, fmaf(a0, r, a3)));
 }
 
+// Guide sources.  kFromInput: the op-API form, guide is an input tensor staged by TMA
+// (28 B/px).  The fused forms compute the guide from the pixel's RGB in registers
+// (24 B/px; the guide map never touches HBM) -- the model path of HDRNetCurves /
+// HDRNetPointwiseNNGuide (hdrnet/models.py:43-59).
+struct GuideFromInput {
+  static constexpr bool kFromInput = true;
+  __device__ __forceinline__ float operator()(float, float, float) const { return 0.0f; }
+};
+struct GuideCurves {
+  static constexpr bool kFromInput = false;
+  CurvesGuideParams p;
+  __device__ __forceinline__ float operator()(float r, float g, float b) const {
+    return curves_guide(p, r, g, b);
+  }
+};
+struct GuideNN {
+  static constexpr bool kFromInput = false;
+  NNGuideParams p;
+  __device__ __forceinline__ float operator()(float r, float g, float b) const {
+    return nn_guide(p, r, g, b);
+  }
+};
+
+template <class GuideFn>
 __global__ void __launch_bounds__(kTmaThreads, 2)
-slice_apply_rows_tma_kernel(const TmaArgs args) {
+slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
+  constexpr bool kGuideIn = GuideFn::kFromInput;
   extern __shared__ __align__(128) unsigned char smem[];
   const SliceGeom& g = args.g;
   const TmaPlan& pl = args.p;
@@ -234,9 +261,10 @@ slice_apply_rows_tma_kernel(const TmaArgs args) {
     item_span(item, row, x0, npx);
     const int s = item % NS;
     const size_t pix = static_cast<size_t>(row) * g.W + x0;
-    mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * 16u);
+    mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * (kGuideIn ? 16u : 12u));
     tma_load_1d(stage_rgb(s), args.input + pix * 3, static_cast<uint32_t>(npx) * 12u, &full[s]);
-    tma_load_1d(stage_guide(s), args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[s]);
+    if (kGuideIn)
+      tma_load_1d(stage_guide(s), args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[s]);
   };
 
   if (tid == 0) {
@@ -287,12 +315,22 @@ slice_apply_rows_tma_kernel(const TmaArgs args) {
 
     if (tid * 4 < npx) {
       float4* rgb4 = reinterpret_cast<float4*>(stage_rgb(s)) + 3 * tid;
-      const float4 gq = reinterpret_cast<const float4*>(stage_guide(s))[tid];
       const float4 c0 = rgb4[0], c1 = rgb4[1], c2 = rgb4[2];
       const float pr[4] = {c0.x, c0.w, c1.z, c2.y};
       const float pg[4] = {c0.y, c1.x, c1.w, c2.z};
       const float pb[4] = {c0.z, c1.y, c2.x, c2.w};
-      const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+      float gv[4];
+      if (kGuideIn) {
+        const float4 gq = reinterpret_cast<const float4*>(stage_guide(s))[tid];
+        gv[0] = gq.x; gv[1] = gq.y; gv[2] = gq.z; gv[3] = gq.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gv[i] = guide_fn(pr[i], pg[i], pb[i]);
+        if (args.guide_out != nullptr) {  // optional dump (hdrnet/bin/run.py --debug)
+          const size_t pix = static_cast<size_t>(row) * g.W + x0 + 4 * tid;
+          *reinterpret_cast<float4*>(args.guide_out + pix) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+      }
       float o_r[4], o_g[4], o_b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -396,17 +434,35 @@ static int generic_grid(long long npix, int sms) {
   return static_cast<int>(std::min<long long>(blocks, static_cast<long long>(sms) * 16));
 }
 
-// Internal launcher shared with the host path (host_path.cu): pixel buffers hold `rows`
-// rows per image starting at image row y_off.
-int launch_slice_apply(const float* grid, const float* guide, const float* input, float* out,
-                       int B, int H, int W, int rows, int y_off, int gh, int gw, int gd,
-                       int n_in, int n_out, int has_offset, int variant, cudaStream_t stream) {
+template <class GuideFn>
+static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(slice_apply_rows_tma_kernel<GuideFn>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       a.p.smem_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  slice_apply_rows_tma_kernel<GuideFn><<<a.p.ctas, kTmaThreads, a.p.smem_bytes, stream>>>(a, fn);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Guide source of a launch: an input tensor, or one of the fused per-pixel guide networks.
+struct GuideSpec {
+  int mode;  // 0 = input tensor, 1 = curves, 2 = pointwise NN
+  const float* guide;
+  float* guide_out;
+  const CurvesGuideParams* curves;
+  const NNGuideParams* nn;
+};
+
+static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const float* input,
+                                   float* out, int B, int H, int W, int rows, int y_off, int gh,
+                                   int gw, int gd, int n_in, int n_out, int has_offset,
+                                   int variant, cudaStream_t stream) {
   int rc = validate_common(B, H, W, gh, gw, gd);
   if (rc != HDRNET_OK) return rc;
   if (n_in < 1 || n_out < 1 || rows < 0 || y_off < 0 || y_off + rows > H) return HDRNET_E_BAD_SHAPE;
   const long long npix = static_cast<long long>(B) * rows * W;
   if (npix == 0) return HDRNET_OK;
-  if (!grid || !guide || !input || !out) return HDRNET_E_NULL_POINTER;
+  if (!grid || !input || !out || (gs.mode == 0 && !gs.guide)) return HDRNET_E_NULL_POINTER;
   const int J = n_in + (has_offset ? 1 : 0);
   const long long grid_floats = static_cast<long long>(gh) * gw * gd * n_out * J;
   if (grid_floats > INT_MAX || static_cast<long long>(rows) * B > INT_MAX / 4) return HDRNET_E_TOO_LARGE;
@@ -417,7 +473,9 @@ int launch_slice_apply(const float* grid, const float* guide, const float* input
   TmaPlan plan;
   const bool tma_shape = (n_in == 3 && n_out == 3 && has_offset) &&
                          make_tma_plan(g, device_max_smem_optin(), sms, &plan) &&
-                         aligned16(grid) && aligned16(guide) && aligned16(input) && aligned16(out);
+                         aligned16(grid) && aligned16(input) && aligned16(out) &&
+                         (gs.mode != 0 || aligned16(gs.guide)) &&
+                         (gs.guide_out == nullptr || aligned16(gs.guide_out));
   bool use_tma;
   if (variant == HDRNET_VARIANT_TMA) {
     if (!tma_shape) return HDRNET_E_UNSUPPORTED;
@@ -429,21 +487,39 @@ int launch_slice_apply(const float* grid, const float* guide, const float* input
   } else {
     return HDRNET_E_UNSUPPORTED;
   }
+  // The fused-guide forms exist only in the TMA kernel; other shapes run the standalone
+  // guide kernel first (the caller does that: see hdrnet_slice_apply_{curves,nn}_f32).
+  if (!use_tma && gs.mode != 0) return HDRNET_E_UNSUPPORTED;
 
   if (use_tma) {
-    cudaError_t e = cudaFuncSetAttribute(slice_apply_rows_tma_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         plan.smem_bytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
     TmaArgs a;
-    a.grid = grid; a.guide = guide; a.input = input; a.out = out; a.g = g; a.p = plan;
-    slice_apply_rows_tma_kernel<<<plan.ctas, kTmaThreads, plan.smem_bytes, stream>>>(a);
-  } else {
-    slice_generic_kernel<true><<<generic_grid(npix, sms), 256, 0, stream>>>(
-        grid, guide, input, out, g, n_in, n_out, J, npix);
+    a.grid = grid; a.guide = gs.guide; a.guide_out = gs.guide_out; a.input = input; a.out = out;
+    a.g = g; a.p = plan;
+    if (gs.mode == 0) return launch_tma(a, GuideFromInput{}, stream);
+    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; return launch_tma(a, fn, stream); }
+    GuideNN fn; fn.p = *gs.nn;
+    return launch_tma(a, fn, stream);
   }
+  slice_generic_kernel<true><<<generic_grid(npix, sms), 256, 0, stream>>>(
+      grid, gs.guide, input, out, g, n_in, n_out, J, npix);
   return static_cast<int>(cudaGetLastError());
 }
+
+// Internal launcher shared with the host path (host_path.cu): pixel buffers hold `rows`
+// rows per image starting at image row y_off.
+int launch_slice_apply(const float* grid, const float* guide, const float* input, float* out,
+                       int B, int H, int W, int rows, int y_off, int gh, int gw, int gd,
+                       int n_in, int n_out, int has_offset, int variant, cudaStream_t stream) {
+  GuideSpec gs{0, guide, nullptr, nullptr, nullptr};
+  return launch_slice_apply_impl(grid, gs, input, out, B, H, W, rows, y_off, gh, gw, gd, n_in,
+                                 n_out, has_offset, variant, stream);
+}
+
+int pack_curves_params(CurvesGuideParams* p, const float* ccm, const float* ccm_bias,
+                       const float* shifts, const float* slopes, const float* mix,
+                       float mix_bias);
+int pack_nn_params(NNGuideParams* p, const float* w1, const float* b1, const float* w2, float b2,
+                   int feats);
 
 int launch_slice(const float* grid, const float* guide, float* out, int B, int H, int W, int rows,
                  int y_off, int gh, int gw, int gd, int gc, int variant, cudaStream_t stream) {
@@ -501,6 +577,53 @@ int hdrnet_slice_apply_f32(const float* grid, const float* guide, const float* i
                            int n_out, int has_offset, void* stream) {
   return launch_slice_apply(grid, guide, input, out, B, H, W, H, 0, gh, gw, gd, n_in, n_out,
                             has_offset, HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
+}
+
+// Model-path forms: guide computed per pixel inside the slice-apply kernel (24 B/px).
+// Shapes the TMA kernel cannot take fall back to: standalone guide kernel into `guide_out`
+// (required in that case) followed by the generic slice-apply.
+extern "C" int hdrnet_guide_curves_f32(const float*, float*, long long, const float*, const float*,
+                                       const float*, const float*, const float*, float, void*);
+extern "C" int hdrnet_guide_nn_f32(const float*, float*, long long, const float*, const float*,
+                                   const float*, float, int, void*);
+
+int hdrnet_slice_apply_curves_f32(const float* grid, const float* input, float* out,
+                                  float* guide_out, int B, int H, int W, int gh, int gw, int gd,
+                                  const float* ccm, const float* ccm_bias, const float* shifts,
+                                  const float* slopes, const float* mix, float mix_bias,
+                                  void* stream) {
+  CurvesGuideParams cp;
+  int rc = pack_curves_params(&cp, ccm, ccm_bias, shifts, slopes, mix, mix_bias);
+  if (rc != HDRNET_OK) return rc;
+  GuideSpec gs{1, nullptr, guide_out, &cp, nullptr};
+  rc = launch_slice_apply_impl(grid, gs, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
+                               HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
+  if (rc != HDRNET_E_UNSUPPORTED) return rc;
+  if (!guide_out) return HDRNET_E_NULL_POINTER;
+  rc = hdrnet_guide_curves_f32(input, guide_out, static_cast<long long>(B) * H * W, ccm, ccm_bias,
+                               shifts, slopes, mix, mix_bias, stream);
+  if (rc != HDRNET_OK) return rc;
+  return launch_slice_apply(grid, guide_out, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
+                            HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
+}
+
+int hdrnet_slice_apply_nn_f32(const float* grid, const float* input, float* out, float* guide_out,
+                              int B, int H, int W, int gh, int gw, int gd, const float* w1,
+                              const float* b1, const float* w2, float b2, int feats,
+                              void* stream) {
+  NNGuideParams np;
+  int rc = pack_nn_params(&np, w1, b1, w2, b2, feats);
+  if (rc != HDRNET_OK) return rc;
+  GuideSpec gs{2, nullptr, guide_out, nullptr, &np};
+  rc = launch_slice_apply_impl(grid, gs, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
+                               HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
+  if (rc != HDRNET_E_UNSUPPORTED) return rc;
+  if (!guide_out) return HDRNET_E_NULL_POINTER;
+  rc = hdrnet_guide_nn_f32(input, guide_out, static_cast<long long>(B) * H * W, w1, b1, w2, b2,
+                           feats, stream);
+  if (rc != HDRNET_OK) return rc;
+  return launch_slice_apply(grid, guide_out, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
+                            HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
 }
 
 int hdrnet_slice_f32_variant(const float* grid, const float* guide, float* out, int B, int H,

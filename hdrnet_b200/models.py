@@ -1,0 +1,377 @@
+"""Model graphs: drop-in for the reference's ``hdrnet/models.py`` (inference).
+
+Same class names, classmethods and call signature as the reference
+(hdrnet/models.py:30-210; selected by name in hdrnet/bin/run.py:82-85):
+
+    mdl = getattr(models, params['model_name'])
+    out = mdl.inference(lowres_input, fullres_input, params, is_training=False)
+
+over ``torch.Tensor`` (CUDA, float32, NHWC).  ``params`` carries the reference's model
+hyper-parameters (hdrnet/bin/train.py:224-236): ``luma_bins, channel_multiplier, spatial_bin,
+net_input_size, batch_norm, guide_complexity``.
+
+Where TF keeps variables in the graph (restored from a checkpoint), this module keeps a
+flat dict of numpy arrays keyed by the SAME variable names under ``inference/``
+(``inference/coefficients/splat/conv1/weights`` ...): pass it as ``params['weights']`` or
+install it once with ``set_weights`` / ``load_weights``.  Conv weights are HWIO, FC weights
+[in, out], exactly as TF stores them.
+
+Execution (all hand-written sm_100a kernels through the C-ABI, no torch math on the path):
+  coefficients  4 splat convs, 2 global convs + 3 FCs, 2 local convs (conv2d / fc kernels),
+                then fusion + prediction + unroll_grid in one kernel -> grid [B,gh,gw,gd,12]
+  guide+output  ONE kernel: per-pixel guide (curves or pointwise NN) computed in registers
+                and fed straight into the fused slice-apply (the guide never touches HBM).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, layers
+from .layers import bilateral_slice_apply
+
+__all__ = ["HDRNetCurves", "HDRNetPointwiseNNGuide", "set_weights", "load_weights",
+           "init_weights", "DEFAULT_PARAMS"]
+
+BN_EPS = 1e-3   # tf.contrib.layers.batch_norm default epsilon (hdrnet/layers.py:47-54)
+
+DEFAULT_PARAMS = dict(  # hdrnet/bin/train.py:224-236
+    model_name="HDRNetCurves", net_input_size=256, output_resolution=[512, 512],
+    batch_norm=False, channel_multiplier=1, guide_complexity=16, luma_bins=8, spatial_bin=16)
+
+_weights: dict | None = None
+
+
+def set_weights(weights: dict) -> None:
+    """Install the variable store (reference variable names -> numpy arrays)."""
+    global _weights
+    _weights = {k: np.asarray(v) for k, v in weights.items()}
+    _prepared.clear()
+
+
+def load_weights(path: str) -> dict:
+    """Load a ``.npz`` keyed by the reference's variable names and install it."""
+    with np.load(path) as z:
+        w = {k.replace("__", "/"): z[k] for k in z.files}
+    set_weights(w)
+    return w
+
+
+def _resolve_weights(params) -> dict:
+    w = params.get("weights") if isinstance(params, dict) else None
+    if w is None:
+        w = _weights
+    if w is None:
+        raise ValueError("no weights: pass params['weights'] or call models.set_weights()")
+    return w
+
+
+def init_weights(params, seed: int = 0, model_name: str | None = None) -> dict:
+    """Fresh variables with the reference's initialisers: variance-scaling (fan-in, factor 2,
+    truncated normal) for conv/fc weights and zero biases (hdrnet/layers.py:22-23), identity
+    ccm / linspace shifts / unit first slope / 1/3 mixing for the curves guide
+    (hdrnet/models.py:150-186).  Used for synthetic-weight benchmarks."""
+    rng = np.random.RandomState(seed)
+    gd, cm = params["luma_bins"], params["channel_multiplier"]
+    bn = bool(params["batch_norm"])
+    model_name = model_name or params.get("model_name", "HDRNetCurves")
+    w = {}
+
+    def vs(shape, fan_in):
+        std = math.sqrt(1.3 * 2.0 / fan_in)   # tf.contrib variance_scaling_initializer
+        v = rng.randn(*shape)
+        v = np.clip(v, -2.0, 2.0)             # truncated normal
+        return (v * std).astype(np.float32)
+
+    def post(scope, cout, use_bias, use_bn):
+        if use_bn:
+            w[scope + "/BatchNorm/beta"] = np.zeros(cout, np.float32)
+            w[scope + "/BatchNorm/moving_mean"] = np.zeros(cout, np.float32)
+            w[scope + "/BatchNorm/moving_variance"] = np.ones(cout, np.float32)
+        elif use_bias:
+            w[scope + "/biases"] = np.zeros(cout, np.float32)
+
+    def conv(scope, k, cin, cout, use_bias=True, use_bn=False):
+        w[scope + "/weights"] = vs((k, k, cin, cout), k * k * cin)
+        post(scope, cout, use_bias, use_bn)
+
+    def fc(scope, cin, cout, use_bias=True, use_bn=False):
+        w[scope + "/weights"] = vs((cin, cout), cin)
+        post(scope, cout, use_bias, use_bn)
+
+    p = "inference/coefficients"
+    n_ds = int(np.log2(params["net_input_size"] / params["spatial_bin"]))
+    cin = 3
+    for i in range(n_ds):
+        conv(f"{p}/splat/conv{i + 1}", 3, cin, cm * (2 ** i) * gd, use_bn=bn and i > 0)
+        cin = cm * (2 ** i) * gd
+    c8 = 8 * cm * gd
+    conv(f"{p}/global/conv1", 3, cin, c8, use_bn=bn)
+    conv(f"{p}/global/conv2", 3, c8, c8, use_bn=bn)
+    sb = params["spatial_bin"]
+    flat = int(math.ceil(sb / 4)) ** 2 * c8
+    fc(f"{p}/global/fc1", flat, 32 * cm * gd, use_bn=bn)
+    fc(f"{p}/global/fc2", 32 * cm * gd, 16 * cm * gd, use_bn=bn)
+    fc(f"{p}/global/fc3", 16 * cm * gd, c8)
+    conv(f"{p}/local/conv1", 3, cin, c8, use_bn=bn)
+    conv(f"{p}/local/conv2", 3, c8, c8, use_bias=False)
+    conv(f"{p}/prediction/conv1", 1, c8, gd * 3 * 4)
+    g = "inference/guide"
+    if model_name == "HDRNetCurves":
+        w[g + "/ccm"] = (np.identity(3) + rng.randn(1) * 1e-4).astype(np.float32)
+        w[g + "/ccm_bias"] = np.zeros(3, np.float32)
+        w[g + "/shifts"] = np.tile(np.linspace(0, 1, 16, endpoint=False, dtype=np.float32)
+                                   [None, None, None, :], (1, 1, 3, 1))
+        slopes = np.zeros((1, 1, 1, 3, 16), np.float32)
+        slopes[..., 0] = 1.0
+        w[g + "/slopes"] = slopes
+        w[g + "/channel_mixing/weights"] = np.full((1, 1, 3, 1), 1.0 / 3.0, np.float32)
+        w[g + "/channel_mixing/biases"] = np.zeros(1, np.float32)
+    else:
+        nf = params["guide_complexity"]
+        conv(g + "/conv1", 1, 3, nf, use_bn=True)
+        conv(g + "/conv2", 1, nf, 1)
+    return w
+
+
+# ---- prepared (device-resident, BN-folded) weights ---------------------------------------------
+_prepared: dict = {}
+
+
+def _fold(wts, scope, use_bn, use_bias):
+    """Returns (weights, bias-or-None) as float32 numpy with inference batch norm folded in:
+    y = (conv - mean) / sqrt(var + eps) + beta  (center=True, scale=False; layers.py:47-54;
+    the fold freeze_graph.py:141-142 applies)."""
+    w = np.asarray(wts[scope + "/weights"], np.float32)
+    if use_bn:
+        s = 1.0 / np.sqrt(np.asarray(wts[scope + "/BatchNorm/moving_variance"], np.float64) + BN_EPS)
+        b = np.asarray(wts[scope + "/BatchNorm/beta"], np.float64) - \
+            np.asarray(wts[scope + "/BatchNorm/moving_mean"], np.float64) * s
+        return (w.astype(np.float64) * s).astype(np.float32), b.astype(np.float32)
+    if use_bias:
+        return w, np.asarray(wts[scope + "/biases"], np.float32)
+    return w, None
+
+
+class _Prepared:
+    """Device copies of the coefficient-network weights + host copies of the guide params."""
+
+    def __init__(self, wts, params, device, nn_guide):
+        self.device = device
+        self.source = wts   # keeps the dict alive: the cache is keyed by id(wts)
+        bn = bool(params["batch_norm"])
+        self.layers = {}
+        p = "inference/coefficients"
+        n_ds = int(np.log2(params["net_input_size"] / params["spatial_bin"]))
+        specs = [(f"{p}/splat/conv{i + 1}", bn and i > 0, True) for i in range(n_ds)]
+        specs += [(f"{p}/global/conv1", bn, True), (f"{p}/global/conv2", bn, True),
+                  (f"{p}/global/fc1", bn, True), (f"{p}/global/fc2", bn, True),
+                  (f"{p}/global/fc3", False, True), (f"{p}/local/conv1", bn, True),
+                  (f"{p}/local/conv2", False, False), (f"{p}/prediction/conv1", False, True)]
+        for scope, use_bn, use_bias in specs:
+            w, b = _fold(wts, scope, use_bn, use_bias)
+            self.layers[scope] = (
+                torch.from_numpy(np.ascontiguousarray(w)).to(device),
+                None if b is None else torch.from_numpy(np.ascontiguousarray(b)).to(device))
+        g = "inference/guide"
+        f32 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32))  # noqa: E731
+        if nn_guide:
+            w1, b1 = _fold(wts, g + "/conv1", True, False)
+            self.nn_w1 = f32(w1.reshape(3, -1))
+            self.nn_b1 = f32(b1)
+            self.nn_w2 = f32(np.asarray(wts[g + "/conv2/weights"]).reshape(-1))
+            self.nn_b2 = float(np.asarray(wts[g + "/conv2/biases"]).reshape(-1)[0])
+            self.nn_feats = int(self.nn_w1.shape[1])
+        else:
+            self.ccm = f32(wts[g + "/ccm"])
+            self.ccm_bias = f32(wts[g + "/ccm_bias"])
+            self.shifts = f32(np.asarray(wts[g + "/shifts"]).reshape(3, 16))
+            self.slopes = f32(np.asarray(wts[g + "/slopes"]).reshape(3, 16))
+            self.mix = f32(np.asarray(wts[g + "/channel_mixing/weights"]).reshape(3))
+            self.mix_bias = float(np.asarray(wts[g + "/channel_mixing/biases"]).reshape(-1)[0])
+
+
+def _prepare(wts, params, device, nn_guide) -> _Prepared:
+    key = (id(wts), str(device), bool(nn_guide), bool(params["batch_norm"]),
+           params["net_input_size"], params["spatial_bin"])
+    prep = _prepared.get(key)
+    if prep is None:
+        prep = _Prepared(wts, params, device, nn_guide)
+        _prepared[key] = prep
+    return prep
+
+
+def _hp(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check_input(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or t.dtype != torch.float32 or t.dim() != 4 or t.shape[-1] != 3:
+        raise ValueError(f"{what} must be a float32 tensor [B, H, W, 3]")
+    if t.device.type != "cuda":
+        raise _lib.HdrnetLibraryError(f"{what} must be a CUDA tensor; hdrnet_b200 has no CPU path")
+    return t.contiguous()
+
+
+# ---- layer wrappers (hdrnet/layers.py:25-93 over the C-ABI) ------------------------------------
+def _conv(x: torch.Tensor, wb, stride=1, relu=True) -> torch.Tensor:
+    w, b = wb
+    B, H, W, cin = x.shape
+    k, _, wcin, cout = w.shape
+    if wcin != cin:
+        raise ValueError(f"conv: input has {cin} channels, weights expect {wcin}")
+    oh, ow = -(-H // stride), -(-W // stride)
+    out = torch.empty((B, oh, ow, cout), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    rc = lib.hdrnet_conv2d_nhwc_f32(x.data_ptr(), w.data_ptr(), 0 if b is None else b.data_ptr(),
+                                    out.data_ptr(), B, H, W, cin, cout, k, stride, int(relu),
+                                    torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "conv2d")
+    return out
+
+
+def _fc(x: torch.Tensor, wb, relu=True) -> torch.Tensor:
+    w, b = wb
+    B, I = x.shape
+    if w.shape[0] != I:
+        raise ValueError(f"fc: input has {I} features, weights expect {w.shape[0]}")
+    O = w.shape[1]
+    out = torch.empty((B, O), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    rc = lib.hdrnet_fc_f32(x.data_ptr(), w.data_ptr(), 0 if b is None else b.data_ptr(),
+                           out.data_ptr(), B, I, O, int(relu),
+                           torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "fc")
+    return out
+
+
+class HDRNetCurves(object):
+    """Main model, as submitted in January 2017 (hdrnet/models.py:30-196)."""
+
+    _nn_guide = False
+
+    @classmethod
+    def n_out(cls):
+        return 3
+
+    @classmethod
+    def n_in(cls):
+        return 3 + 1
+
+    @classmethod
+    def inference(cls, lowres_input, fullres_input, params, is_training=False):
+        """models.py:43-59.  lowres_input [B,S,S,3], fullres_input [B,H,W,3] -> [B,H,W,3].
+        With params['debug'] truthy also stores the coefficients and guide on
+        ``cls.last_debug`` (the collections run.py --debug reads, run.py:98-133)."""
+        if is_training:
+            raise NotImplementedError("hdrnet_b200 implements the inference path only")
+        fullres_input = _check_input(fullres_input, "fullres_input")
+        coeffs = cls._coefficients(lowres_input, params, is_training)
+        prep = _prepare(_resolve_weights(params), params, fullres_input.device, cls._nn_guide)
+        B, H, W, _ = fullres_input.shape
+        _, gh, gw, gd = coeffs.shape[:4]
+        out = torch.empty_like(fullres_input)
+        debug = bool(params.get("debug"))
+        need_guide = debug or (W % 4 != 0) or W < 128
+        guide = torch.empty((B, H, W), dtype=torch.float32, device=fullres_input.device) \
+            if need_guide else None
+        lib = _lib.load()
+        with torch.cuda.device(fullres_input.device):
+            stream = torch.cuda.current_stream(fullres_input.device).cuda_stream
+            gptr = 0 if guide is None else guide.data_ptr()
+            if cls._nn_guide:
+                rc = lib.hdrnet_slice_apply_nn_f32(
+                    coeffs.data_ptr(), fullres_input.data_ptr(), out.data_ptr(), gptr, B, H, W,
+                    gh, gw, gd, _hp(prep.nn_w1), _hp(prep.nn_b1), _hp(prep.nn_w2), prep.nn_b2,
+                    prep.nn_feats, stream)
+            else:
+                rc = lib.hdrnet_slice_apply_curves_f32(
+                    coeffs.data_ptr(), fullres_input.data_ptr(), out.data_ptr(), gptr, B, H, W,
+                    gh, gw, gd, _hp(prep.ccm), _hp(prep.ccm_bias), _hp(prep.shifts),
+                    _hp(prep.slopes), _hp(prep.mix), prep.mix_bias, stream)
+        _lib.check(rc, "BilateralSliceApply(fused guide)")
+        if debug:
+            cls.last_debug = {"bilateral_coefficients": coeffs, "guide": guide, "output": out}
+        return out
+
+    @classmethod
+    def _coefficients(cls, input_tensor, params, is_training=False):
+        """models.py:62-142 -> [B, gh, gw, gd, n_out, n_in]."""
+        if is_training:
+            raise NotImplementedError("hdrnet_b200 implements the inference path only")
+        x = _check_input(input_tensor, "lowres_input")
+        prep = _prepare(_resolve_weights(params), params, x.device, cls._nn_guide)
+        L = prep.layers
+        gd = params["luma_bins"]
+        p = "inference/coefficients"
+        n_ds = int(np.log2(params["net_input_size"] / params["spatial_bin"]))
+        bs = x.shape[0]
+        with torch.cuda.device(x.device):
+            for i in range(n_ds):                                   # splat, :69-82
+                x = _conv(x, L[f"{p}/splat/conv{i + 1}"], stride=2)
+            splat = x
+            g = _conv(splat, L[f"{p}/global/conv1"], stride=2)      # global, :86-105
+            g = _conv(g, L[f"{p}/global/conv2"], stride=2)
+            g = g.reshape(bs, -1)                                   # NHWC flatten, :94-95
+            g = _fc(g, L[f"{p}/global/fc1"])
+            g = _fc(g, L[f"{p}/global/fc2"])
+            g = _fc(g, L[f"{p}/global/fc3"], relu=False)
+            loc = _conv(splat, L[f"{p}/local/conv1"])               # local, :109-118
+            loc = _conv(loc, L[f"{p}/local/conv2"], relu=False)
+            wp, bp = L[f"{p}/prediction/conv1"]
+            _, gh, gw, C = loc.shape
+            grid = torch.empty((bs, gh, gw, gd, cls.n_out(), cls.n_in()), dtype=torch.float32,
+                               device=x.device)
+            rc = _lib.load().hdrnet_fuse_predict_f32(           # fusion+prediction+unroll, :122-139
+                loc.data_ptr(), g.data_ptr(), wp.data_ptr(), 0 if bp is None else bp.data_ptr(),
+                grid.data_ptr(), bs, gh, gw, C, gd, cls.n_out(), cls.n_in(),
+                torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc, "fuse_predict")
+        return grid
+
+    @classmethod
+    def _guide(cls, input_tensor, params, is_training=False):
+        """models.py:145-190 as a standalone kernel -> [B, H, W]."""
+        x = _check_input(input_tensor, "fullres_input")
+        prep = _prepare(_resolve_weights(params), params, x.device, False)
+        B, H, W, _ = x.shape
+        guide = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().hdrnet_guide_curves_f32(
+                x.data_ptr(), guide.data_ptr(), B * H * W, _hp(prep.ccm), _hp(prep.ccm_bias),
+                _hp(prep.shifts), _hp(prep.slopes), _hp(prep.mix), prep.mix_bias,
+                torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc, "guide_curves")
+        return guide
+
+    @classmethod
+    def _output(cls, im, guide, coeffs):
+        """models.py:193-196."""
+        return bilateral_slice_apply(coeffs, guide, im, has_offset=True, name="slice")
+
+
+class HDRNetPointwiseNNGuide(HDRNetCurves):
+    """Replaces the pointwise curves in the guide by a pointwise neural net
+    (hdrnet/models.py:199-210)."""
+
+    _nn_guide = True
+
+    @classmethod
+    def _guide(cls, input_tensor, params, is_training=False):
+        x = _check_input(input_tensor, "fullres_input")
+        prep = _prepare(_resolve_weights(params), params, x.device, True)
+        B, H, W, _ = x.shape
+        guide = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().hdrnet_guide_nn_f32(
+                x.data_ptr(), guide.data_ptr(), B * H * W, _hp(prep.nn_w1), _hp(prep.nn_b1),
+                _hp(prep.nn_w2), prep.nn_b2, prep.nn_feats,
+                torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc, "guide_nn")
+        return guide
+
+
+del layers  # imported for the side effect of the public surface only

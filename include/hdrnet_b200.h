@@ -137,6 +137,56 @@ HDRNET_API int hdrnet_guide_nn_f32(const float* input, float* guide, long long n
                                    int feats, void* stream);
 
 /*
+ * Model-path forms of slice-apply: the guide is computed per pixel INSIDE the kernel from the
+ * full-res RGB (the guide map never touches HBM: 24 B/px instead of 28 B/px + a guide pass).
+ * Replaces HDRNetCurves.inference / HDRNetPointwiseNNGuide.inference's `_guide` + `_output`
+ * (hdrnet/models.py:43-59, :145-196, :199-210).  n_in = 3, n_out = 3, has_offset.
+ * guide_out: optional [B,H,W] dump of the guide (run.py --debug); may be NULL when the
+ * shapes suit the fused kernel (W % 4 == 0, W >= 128, 16-byte aligned buffers); other shapes
+ * run guide kernel + generic slice-apply and then REQUIRE guide_out as the intermediate.
+ * Coefficient arrays are host pointers, as for hdrnet_guide_*_f32.
+ */
+HDRNET_API int hdrnet_slice_apply_curves_f32(const float* grid, const float* input, float* out,
+                                             float* guide_out, int B, int H, int W, int gh,
+                                             int gw, int gd, const float* ccm,
+                                             const float* ccm_bias, const float* shifts,
+                                             const float* slopes, const float* mix,
+                                             float mix_bias, void* stream);
+
+HDRNET_API int hdrnet_slice_apply_nn_f32(const float* grid, const float* input, float* out,
+                                         float* guide_out, int B, int H, int W, int gh, int gw,
+                                         int gd, const float* w1, const float* b1,
+                                         const float* w2, float b2, int feats, void* stream);
+
+/*
+ * Coefficient network layers (device pointers; activations NHWC, float32).  Replace the TF
+ * layers of HDRNetCurves._coefficients, hdrnet/models.py:62-142 / hdrnet/layers.py:25-93.
+ * Batch norm (inference) is folded into w / bias by the caller.
+ *
+ * conv2d: k in {1, 3}, stride in {1, 2}, TF 'SAME' padding (total = max((ceil(in/s)-1)*s +
+ * k - in, 0), floor(total/2) before, rest after), weights HWIO [k][k][Cin][Cout], optional
+ * bias (NULL = none), optional ReLU.  out is [B, ceil(H/s), ceil(W/s), Cout].
+ */
+HDRNET_API int hdrnet_conv2d_nhwc_f32(const float* in, const float* w, const float* bias,
+                                      float* out, int B, int H, int W, int Cin, int Cout, int k,
+                                      int stride, int relu, void* stream);
+
+/* fully_connected: out[B,O] = in[B,I] @ w[I,O] + bias (+ReLU). */
+HDRNET_API int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out,
+                             int B, int I, int O, int relu, void* stream);
+
+/*
+ * Fusion + prediction + unroll_grid (models.py:122-139) in one pass:
+ *   f = relu(local[b,y,x,:] + global[b,:]);  p[o] = sum_c f[c] * w[c][o] + bias[o]
+ *   grid[b,y,x,z,i,j] = p[(j*n_out + i)*gd + z]        (n_in counts the offset column)
+ * local [B,gh,gw,C], global [B,C], w [C][gd*n_out*n_in], grid [B,gh,gw,gd,n_out*n_in].
+ */
+HDRNET_API int hdrnet_fuse_predict_f32(const float* local, const float* global_feat,
+                                       const float* w, const float* bias, float* grid, int B,
+                                       int gh, int gw, int C, int gd, int n_out, int n_in,
+                                       void* stream);
+
+/*
  * Host-buffer path (what a CPU-tensor caller of the reference op gets: TF copies feeds to
  * the GPU and fetches back, hdrnet/bin/run.py:185).  A context owns device staging buffers
  * and streams; the call splits the batch into row bands, and pipelines H2D copy -> kernel
