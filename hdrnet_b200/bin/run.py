@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Inference CLI: drop-in for the reference's ``hdrnet/bin/run.py`` (same positional
+arguments and flags, hdrnet/bin/run.py:219-238):
+
+    python -m hdrnet_b200.bin.run <checkpoint_dir> <input> <output> [--lowres_input X]
+                                  [--hdrp] [--debug] [--limit N]
+
+``checkpoint_dir`` holds ``weights.npz`` (reference variable names, '/' written as '__') and
+``params.json`` (the model_params the reference stores as graph constants, train.py:60-63,
+read back by utils.get_model_params) instead of a TF checkpoint + meta graph.
+
+Host-side pre/post processing follows the reference (run.py:139-190):
+  cv2.imread(-1) -> drop alpha -> BGR->RGB -> img_as_float (u8 /255, u16 /65535; --hdrp
+  scales by 32767 white level first, run.py:156-160) -> nearest-neighbour S x S lowres
+  (skimage.transform.resize(order=0), run.py:168-169) -> model -> uint8(255 * clip(out, 0, 1))
+  (truncating cast, run.py:95) -> PNG.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import logging
+import os
+import re
+
+import numpy as np
+import torch
+
+from hdrnet_b200 import models
+
+logging.basicConfig(format="[%(process)d] %(levelname)s %(filename)s:%(lineno)s | %(message)s")
+log = logging.getLogger("run")
+log.setLevel(logging.INFO)
+
+
+def get_input_list(path):
+    """hdrnet/bin/run.py:42-58: a .txt file list, a directory of images, or one image."""
+    regex = re.compile(r".*\.(png|jpeg|jpg|tif|tiff)$", re.IGNORECASE)
+    if os.path.isdir(path):
+        return sorted(os.path.join(path, f) for f in os.listdir(path) if regex.match(f))
+    if os.path.splitext(path)[-1] == ".txt":
+        dirname = os.path.dirname(path)
+        with open(path) as fid:
+            return [os.path.join(dirname, "input", line.strip()) for line in fid if line.strip()]
+    return [path]
+
+
+def img_as_float(im: np.ndarray) -> np.ndarray:
+    """skimage.img_as_float for the dtypes run.py feeds it (run.py:162/164)."""
+    if im.dtype == np.uint8:
+        return im.astype(np.float32) / np.float32(255.0)
+    if im.dtype == np.uint16:
+        return im.astype(np.float32) / np.float32(65535.0)
+    return im.astype(np.float32)
+
+
+def nearest_resize(im: np.ndarray, size: int) -> np.ndarray:
+    """skimage.transform.resize(im, [S, S], order=0) without anti-aliasing: output sample i
+    reads input round((i + 0.5) * H / S - 0.5) (run.py:168-169)."""
+    H, W = im.shape[:2]
+    ys = np.clip(np.floor((np.arange(size) + 0.5) * H / size).astype(np.int64), 0, H - 1)
+    xs = np.clip(np.floor((np.arange(size) + 0.5) * W / size).astype(np.int64), 0, W - 1)
+    return im[ys][:, xs]
+
+
+def load_checkpoint(checkpoint_dir):
+    with open(os.path.join(checkpoint_dir, "params.json")) as f:
+        params = json.load(f)
+    weights = models.load_weights(os.path.join(checkpoint_dir, "weights.npz"))
+    return params, weights
+
+
+def save_checkpoint(checkpoint_dir, params, weights):
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    with open(os.path.join(checkpoint_dir, "params.json"), "w") as f:
+        json.dump({k: v for k, v in params.items() if k != "weights"}, f)
+    np.savez(os.path.join(checkpoint_dir, "weights.npz"),
+             **{k.replace("/", "__"): np.asarray(v) for k, v in weights.items()})
+
+
+def process(mdl, params, im_u: np.ndarray, lowres_u: np.ndarray | None = None, hdrp=False):
+    """One image through the model; returns uint8 HxWx3 (and the float output)."""
+    if im_u.ndim == 2:
+        im_u = np.repeat(im_u[..., None], 3, axis=2)
+    if im_u.shape[2] > 3:
+        im_u = im_u[:, :, :3]                                      # run.py:146-148
+    src = lowres_u if lowres_u is not None else im_u
+    if hdrp:                                                        # run.py:156-160
+        im = np.minimum(im_u.astype(np.float32) / 32767.0, 1.0).astype(np.float32)
+        src = np.minimum(src.astype(np.float32) / 32767.0, 1.0).astype(np.float32)
+    else:
+        im = img_as_float(im_u)
+        src = img_as_float(src)
+    S = int(params["net_input_size"])
+    low = nearest_resize(src, S)
+    full_t = torch.from_numpy(np.ascontiguousarray(im[None])).cuda()
+    low_t = torch.from_numpy(np.ascontiguousarray(low[None])).cuda()
+    out = mdl.inference(low_t, full_t, params, is_training=False)
+    out8 = (255.0 * out.clamp(0.0, 1.0)).to(torch.uint8)[0].cpu().numpy()   # run.py:95
+    return out8, out
+
+
+def main(args):
+    import cv2
+    params, _ = load_checkpoint(args.checkpoint_dir)
+    mdl = getattr(models, params["model_name"])                     # run.py:82-85
+    params["debug"] = bool(args.debug)
+    paths = get_input_list(args.input)
+    if args.limit is not None:
+        paths = paths[:args.limit]
+    os.makedirs(args.output, exist_ok=True)
+    for i, path in enumerate(paths):
+        log.info("Processing %s (%d/%d)", path, i + 1, len(paths))
+        bgr = cv2.imread(path, -1)
+        if bgr is None:
+            log.warning("could not read %s", path)
+            continue
+        rgb = bgr[:, :, :3][:, :, ::-1] if bgr.ndim == 3 else bgr   # run.py:150
+        low_u = None
+        if args.lowres_input is not None:
+            lp = os.path.join(args.lowres_input, os.path.basename(path))
+            lb = cv2.imread(lp, -1)
+            low_u = lb[:, :, :3][:, :, ::-1] if lb is not None and lb.ndim == 3 else lb
+        out8, _ = process(mdl, params, np.ascontiguousarray(rgb), low_u, hdrp=args.hdrp)
+        name = os.path.splitext(os.path.basename(path))[0]
+        cv2.imwrite(os.path.join(args.output, name + ".png"), out8[:, :, ::-1])
+        if args.debug:                                              # run.py:192-215
+            dbg = mdl.last_debug
+            np.save(os.path.join(args.output, name + "_guide.npy"), dbg["guide"][0].cpu().numpy())
+            np.save(os.path.join(args.output, name + "_coefficients.npy"),
+                    dbg["bilateral_coefficients"][0].cpu().numpy())
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("checkpoint_dir", type=str, help="directory with weights.npz + params.json")
+    parser.add_argument("input", type=str, help="image, directory of images, or filelist.txt")
+    parser.add_argument("output", type=str, help="output directory")
+    parser.add_argument("--lowres_input", default=None, type=str)
+    parser.add_argument("--hdrp", dest="hdrp", action="store_true")
+    parser.add_argument("--debug", dest="debug", action="store_true")
+    parser.add_argument("--limit", type=int)
+    parser.set_defaults(hdrp=False, debug=False)
+    main(parser.parse_args())

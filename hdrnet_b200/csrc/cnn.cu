@@ -21,11 +21,7 @@
 
 namespace hdrnet_b200 {
 
-constexpr int kConvThreads = 128;  // 32 pixel-pairs x 4 channel groups
-constexpr int kConvPx = 2;         // output pixels per thread
-constexpr int kConvCo = 8;         // output channels per thread
-constexpr int kConvTilePx = 32 * kConvPx;
-constexpr int kConvTileCo = 4 * kConvCo;
+constexpr int kConvThreads = 128;  // 32 pixel groups x 4 channel groups
 
 struct ConvArgs {
   const float* in;
@@ -33,10 +29,18 @@ struct ConvArgs {
   const float* bias;  // [Cout] or nullptr
   float* out;
   int B, H, W, Cin, OH, OW, Cout, k, stride, pad_t, pad_l, relu, ci_chunk;
+  int w_vec;  // Cout % 4 == 0 and 16-byte aligned weights: cp.async staging
 };
 
+// Register tile per thread: kConvPx output pixels x kConvCo output channels.  <2, 8> is the
+// throughput shape (64 px x 32 channels per CTA); <1, 4> quadruples the CTA count for the
+// tiny late layers at batch 1, which are otherwise a handful of CTAs on 148 SMs.
+template <int kConvPx, int kConvCo>
 __global__ void __launch_bounds__(kConvThreads)
 conv2d_nhwc_kernel(const ConvArgs a) {
+  constexpr int kConvTilePx = 32 * kConvPx;
+  constexpr int kConvTileCo = 4 * kConvCo;
+  static_assert(kConvCo == 4 || kConvCo == 8, "channel tile is one or two float4");
   extern __shared__ __align__(16) float wsm[];  // [k*k][ci_chunk][kConvTileCo]
   const int tid = threadIdx.x;
   const int pg = tid & 31, cg = tid >> 5;
@@ -67,15 +71,36 @@ conv2d_nhwc_kernel(const ConvArgs a) {
   for (int ci0 = 0; ci0 < a.Cin; ci0 += a.ci_chunk) {
     const int cn = min(a.ci_chunk, a.Cin - ci0);
     __syncthreads();
-    // Stage weights [kk][cn][32 co] (zero-fill channels beyond Cout).
-    for (int e = tid; e < kk * cn * kConvTileCo; e += kConvThreads) {
-      const int co = e % kConvTileCo;
-      const int ci = (e / kConvTileCo) % cn;
-      const int t = e / (kConvTileCo * cn);
-      const int gco = co0 + co;
-      wsm[e] = (gco < a.Cout)
-                   ? __ldg(a.w + (static_cast<size_t>(t) * a.Cin + ci0 + ci) * a.Cout + gco)
-                   : 0.0f;
+    // Stage weights [kk][cn][32 co] (zero-fill channels beyond Cout).  16-byte cp.async
+    // (LDGSTS) keeps every copy of the tile in flight at once: the tile is up to 72 KB and a
+    // register-staged loop would serialise on global-load latency.
+    if (a.w_vec) {
+      for (int e4 = tid; e4 < kk * cn * (kConvTileCo / 4); e4 += kConvThreads) {
+        const int co = (e4 % (kConvTileCo / 4)) * 4;
+        const int ci = (e4 / (kConvTileCo / 4)) % cn;
+        const int t = e4 / ((kConvTileCo / 4) * cn);
+        float* dst = wsm + static_cast<size_t>(e4) * 4;
+        if (co0 + co < a.Cout) {
+          const float* src = a.w + (static_cast<size_t>(t) * a.Cin + ci0 + ci) * a.Cout + co0 + co;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                           static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                       "l"(src)
+                       : "memory");
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    } else {
+      for (int e = tid; e < kk * cn * kConvTileCo; e += kConvThreads) {
+        const int co = e % kConvTileCo;
+        const int ci = (e / kConvTileCo) % cn;
+        const int t = e / (kConvTileCo * cn);
+        const int gco = co0 + co;
+        wsm[e] = (gco < a.Cout)
+                     ? __ldg(a.w + (static_cast<size_t>(t) * a.Cin + ci0 + ci) * a.Cout + gco)
+                     : 0.0f;
+      }
     }
     __syncthreads();
     for (int t = 0; t < kk; ++t) {
@@ -103,7 +128,9 @@ conv2d_nhwc_kernel(const ConvArgs a) {
 #pragma unroll
           for (int d = 0; d < 4; ++d) {
             const float4 w0 = *reinterpret_cast<const float4*>(wt + (ci + d) * kConvTileCo);
-            const float4 w1 = *reinterpret_cast<const float4*>(wt + (ci + d) * kConvTileCo + 4);
+            const float4 w1 = (kConvCo == 8)
+                                  ? *reinterpret_cast<const float4*>(wt + (ci + d) * kConvTileCo + 4)
+                                  : w0;
             const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int p = 0; p < kConvPx; ++p)
@@ -114,7 +141,9 @@ conv2d_nhwc_kernel(const ConvArgs a) {
       } else {
         for (int ci = 0; ci < cn; ++ci) {
           const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * kConvTileCo);
-          const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * kConvTileCo + 4);
+          const float4 w1 = (kConvCo == 8)
+                                ? *reinterpret_cast<const float4*>(wt + ci * kConvTileCo + 4)
+                                : w0;
           const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int p = 0; p < kConvPx; ++p) {
@@ -176,6 +205,7 @@ fc_kernel(const float* __restrict__ in, const float* __restrict__ w,
     __syncthreads();
     if (go < O) {
       // k-slices interleave so consecutive rows of W stream from consecutive threads' loops
+#pragma unroll 8
       for (int i = ks; i < n; i += kFcSlices) {
         const float wv = __ldg(w + static_cast<size_t>(i0 + i) * O + go);
 #pragma unroll
@@ -243,6 +273,26 @@ static void same_pad(int size, int k, int s, int* out, int* before) {
   *before = total / 2;
 }
 
+template <int kPx, int kCo>
+static int launch_conv(ConvArgs a, cudaStream_t stream) {
+  constexpr int kTilePx = 32 * kPx, kTileCo = 4 * kCo;
+  // weights staged per input-channel chunk: k*k*chunk*kTileCo floats <= 72 KB
+  int chunk = a.Cin;
+  const int max_chunk = (72 * 1024 / 4) / (a.k * a.k * kTileCo);
+  if (chunk > max_chunk) chunk = max_chunk / 4 * 4;
+  a.ci_chunk = chunk;
+  const size_t smem = static_cast<size_t>(a.k) * a.k * chunk * kTileCo * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(conv2d_nhwc_kernel<kPx, kCo>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const long long total_px = static_cast<long long>(a.B) * a.OH * a.OW;
+  dim3 grid(static_cast<unsigned>((total_px + kTilePx - 1) / kTilePx),
+            static_cast<unsigned>((a.Cout + kTileCo - 1) / kTileCo));
+  conv2d_nhwc_kernel<kPx, kCo><<<grid, kConvThreads, smem, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace hdrnet_b200
 
 using namespace hdrnet_b200;
@@ -261,20 +311,14 @@ int hdrnet_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, f
   a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = k; a.stride = stride; a.relu = relu;
   same_pad(H, k, stride, &a.OH, &a.pad_t);
   same_pad(W, k, stride, &a.OW, &a.pad_l);
-  // weights staged per input-channel chunk: k*k*chunk*32 floats <= 72 KB
-  int chunk = Cin;
-  const int max_chunk = (72 * 1024 / 4) / (k * k * kConvTileCo);
-  if (chunk > max_chunk) chunk = max_chunk / 4 * 4;
-  a.ci_chunk = chunk;
-  const size_t smem = static_cast<size_t>(k) * k * chunk * kConvTileCo * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(conv2d_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return static_cast<int>(e);
+  a.w_vec = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
   const long long total_px = static_cast<long long>(B) * a.OH * a.OW;
-  dim3 grid(static_cast<unsigned>((total_px + kConvTilePx - 1) / kConvTilePx),
-            static_cast<unsigned>((Cout + kConvTileCo - 1) / kConvTileCo));
-  conv2d_nhwc_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  return static_cast<int>(cudaGetLastError());
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long big_ctas = ((total_px + 63) / 64) * ((Cout + 31) / 32);
+  return (big_ctas >= 2LL * sms) ? launch_conv<2, 8>(a, static_cast<cudaStream_t>(stream))
+                                 : launch_conv<1, 4>(a, static_cast<cudaStream_t>(stream));
 }
 
 int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out, int B, int I,

@@ -1,0 +1,106 @@
+"""Multi-GPU plumbing for the batch-sharded path.
+
+The hot path has no per-frame exchange: every output pixel depends only on its own image's
+grid / guide / input (hdrnet/ops/bilateral_slice_apply.cu.cc:67-125 -- the batch index only
+selects slabs), and the coefficient network is per-image (hdrnet/models.py:63, :95).  So the
+design is one process per GPU, images sharded over ranks, and exactly ONE collective: a
+broadcast of the flat coefficient-network weight buffer (~1.93 MB) at init over NCCL
+(NVLink 5 / NVSwitch); "nccl" on GPUs, "gloo" in the CPU tests.  The reference itself has no
+distributed code at all.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["init_distributed", "shard_batch", "shard_rows", "broadcast_weights",
+           "max_over_ranks", "finalize"]
+
+
+def init_distributed(backend: str | None = None):
+    """Join the process group described by torchrun's environment (RANK, WORLD_SIZE,
+    LOCAL_RANK, MASTER_ADDR, MASTER_PORT).  Returns (rank, world, local_rank).  With
+    WORLD_SIZE unset or 1 nothing is initialised."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kwargs["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, local_rank
+
+
+def shard_batch(n_images: int, rank: int, world: int):
+    """Contiguous, balanced image range [start, end) of rank `rank` (earlier ranks take the
+    remainder).  Ranks beyond the image count get an empty range: use shard_rows then."""
+    base, rem = divmod(n_images, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_rows(height: int, rank: int, world: int):
+    """Row band [y0, y1) of ONE image for rank `rank`: the fallback when there are fewer
+    images than GPUs.  Every band needs the whole (98 KB) grid; no halo is needed because the
+    gather is pointwise in x, y (the kernels take the band's y offset and the full height)."""
+    return shard_batch(height, rank, world)
+
+
+def broadcast_weights(weights: dict | None, src: int = 0, device=None) -> dict:
+    """One collective at init: rank `src` holds the weight dict (reference variable names ->
+    numpy arrays); every rank returns an identical dict.  The arrays travel as ONE flat
+    float32 buffer (a single broadcast: latency-bound, ~2 MB), preceded by a broadcast of the
+    name/shape manifest."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        if weights is None:
+            raise ValueError("broadcast_weights: no process group and no weights")
+        return weights
+    rank = dist.get_rank()
+    manifest = [None]
+    if rank == src:
+        if weights is None:
+            raise ValueError("broadcast_weights: the source rank must provide the weights")
+        manifest[0] = [(k, tuple(np.asarray(weights[k]).shape)) for k in sorted(weights)]
+    dist.broadcast_object_list(manifest, src=src)
+    manifest = manifest[0]
+    total = int(sum(int(np.prod(s)) for _, s in manifest))
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) \
+            if dist.get_backend() == "nccl" else torch.device("cpu")
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    if rank == src:
+        host = np.concatenate([np.asarray(weights[k], np.float32).reshape(-1) for k, _ in manifest])
+        flat.copy_(torch.from_numpy(host))
+    dist.broadcast(flat, src=src)
+    host = flat.cpu().numpy()
+    out, off = {}, 0
+    for k, shape in manifest:
+        n = int(np.prod(shape))
+        out[k] = host[off:off + n].reshape(shape).copy()
+        off += n
+    return out
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Device-side timing aggregation: the job takes as long as its slowest rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) \
+            if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def finalize():
+    if dist.is_initialized():
+        dist.destroy_process_group()

@@ -169,3 +169,38 @@ def test_full_inference_matches_oracle(name, H, W):
     # same call without the debug dump takes the guide-fused kernel when W allows it
     got2 = cls.inference(cuda(low), cuda(full), dict(p, weights=wts))
     assert torch.equal(got2, got)
+
+
+# ---- run.py pre/post (row a11) -----------------------------------------------------------------
+def test_run_py_host_preprocessing():
+    from hdrnet_b200.bin import run
+    u8 = np.arange(2 * 3 * 3, dtype=np.uint8).reshape(2, 3, 3)
+    assert run.img_as_float(u8).dtype == np.float32 and run.img_as_float(u8).max() == np.float32(17 / 255)
+    assert run.img_as_float(np.array([[65535]], np.uint16))[0, 0] == 1.0
+    im = np.arange(8 * 6 * 3, dtype=np.float32).reshape(8, 6, 3)
+    low = run.nearest_resize(im, 4)
+    assert low.shape == (4, 4, 3)
+    assert np.array_equal(low[:, :, 0], im[[1, 3, 5, 7]][:, [0, 2, 3, 5], 0])   # centres of 2x1.5 boxes
+
+
+@pytest.mark.gpu
+def test_run_py_identity_sample_plumbing(tmp_path):
+    """BASELINE.json config 1 (plumbing): default-initialised model on a 256x256 image through
+    the CLI's process(): checkpoint round trip, u8 -> float, nearest lowres, model, u8 out; and
+    the float output equals the oracle's."""
+    from hdrnet_b200.bin import run
+    p = dict(M.DEFAULT_PARAMS)
+    wts = models.init_weights(p, seed=0)
+    run.save_checkpoint(str(tmp_path), p, wts)
+    params, loaded = run.load_checkpoint(str(tmp_path))
+    assert sorted(loaded) == sorted(wts) and params["model_name"] == "HDRNetCurves"
+    rng = np.random.RandomState(0)
+    im8 = rng.randint(0, 256, size=(256, 256, 3)).astype(np.uint8)
+    out8, out = run.process(models.HDRNetCurves, params, im8)
+    assert out8.shape == (256, 256, 3) and out8.dtype == np.uint8
+    im = run.img_as_float(im8)[None]
+    low = run.nearest_resize(im[0], 256)[None]
+    ref, _, _ = M.inference(low, im, loaded, params, oracle.best().bilateral_slice_apply)
+    assert_parity(out.cpu().numpy(), ref, rtol=1e-4)
+    ref8 = (255.0 * np.clip(ref, 0, 1)).astype(np.uint8)[0]
+    assert np.abs(out8.astype(int) - ref8.astype(int)).max() <= 1
