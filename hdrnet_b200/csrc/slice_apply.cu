@@ -434,6 +434,16 @@ static int generic_grid(long long npix, int sms) {
   return static_cast<int>(std::min<long long>(blocks, static_cast<long long>(sms) * 16));
 }
 
+// z-bucketed variant (slice_apply_zsort.cu)
+struct ZsPlan {
+  int ctas, stages, nseg, seg_px, row_floats, smem_bytes;
+  int pieces;
+  int off_raw, off_slab, off_rec, off_cnt, off_stage, stage_bytes;
+};
+bool make_zsort_plan(const SliceGeom& g, int max_smem, int sms, ZsPlan* out);
+int launch_zsort(const float* grid, const float* guide, const float* input, float* out,
+                 const SliceGeom& g, const ZsPlan& plan, cudaStream_t stream);
+
 template <class GuideFn>
 static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(slice_apply_rows_tma_kernel<GuideFn>,
@@ -476,6 +486,12 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
                          aligned16(grid) && aligned16(input) && aligned16(out) &&
                          (gs.mode != 0 || aligned16(gs.guide)) &&
                          (gs.guide_out == nullptr || aligned16(gs.guide_out));
+  if (variant == HDRNET_VARIANT_ZSORT) {
+    ZsPlan zp;
+    if (!tma_shape || gs.mode != 0 || !make_zsort_plan(g, device_max_smem_optin(), sms, &zp))
+      return HDRNET_E_UNSUPPORTED;
+    return launch_zsort(grid, gs.guide, input, out, g, zp, stream);
+  }
   bool use_tma;
   if (variant == HDRNET_VARIANT_TMA) {
     if (!tma_shape) return HDRNET_E_UNSUPPORTED;

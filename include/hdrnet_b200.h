@@ -57,6 +57,10 @@ extern "C" {
 #define HDRNET_VARIANT_TMA 2     /* persistent TMA-staged row kernel (needs W % 4 == 0,    */
                                  /* 16-byte aligned buffers; n_in == 3, n_out == 3,        */
                                  /* has_offset for slice-apply)                            */
+#define HDRNET_VARIANT_ZSORT 3   /* z-bucketed TMA kernel: pixels of a row segment are     */
+                                 /* counting-sorted by (x cell, depth cell) so one load    */
+                                 /* of the corner vectors serves 4 pixels (same shape      */
+                                 /* limits as TMA, plus (gd + 1) * cells-per-segment <= 64)*/
 
 HDRNET_API int hdrnet_b200_abi_version(void);
 

@@ -13,7 +13,8 @@ from util import RTOL, assert_parity, load_golden, rand_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "tma": _lib.VARIANT_TMA}
+VARIANTS = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "tma": _lib.VARIANT_TMA,
+            "zsort": _lib.VARIANT_ZSORT}
 
 
 def cuda(a):
@@ -74,6 +75,10 @@ def test_interpolate_known_answer(val):
 # ---- seeded parity against the oracle, every variant ----------------------------------------
 SHAPES = [
     # B, H, W, gh, gw, gd
+    (1, 40, 3840, 16, 16, 8),   # 4K rows: the z-bucketed kernel's home shape (5 x cells / segment)
+    (2, 11, 2048, 8, 8, 8),     # 2 segments, 4-5 x cells each
+    (1, 6, 1920, 16, 16, 4),    # few depth buckets
+    (1, 5, 4000, 16, 12, 15),   # gd + 1 = 16 depth buckets, ragged segments
     (3, 30, 25, 16, 12, 8),     # hdrnet_ops_test.py:91-100 (W % 4 != 0 -> generic only)
     (3, 8, 5, 6, 3, 7),         # hdrnet_ops_test.py:185-195
     (4, 48, 64, 16, 12, 8),     # hdrnet_ops_jax_tf2_test.py:28-34, reduced
@@ -87,15 +92,20 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("variant", ["auto", "generic", "tma"])
+@pytest.mark.parametrize("variant", ["auto", "generic", "tma", "zsort"])
 def test_slice_apply_matches_oracle(shape, variant):
     B, H, W, gh, gw, gd = shape
-    if variant == "tma" and W % 4 != 0:
-        pytest.skip("TMA kernel needs W % 4 == 0")
+    if variant in ("tma", "zsort") and W % 4 != 0:
+        pytest.skip("TMA kernels need W % 4 == 0")
     grid, guide, inp = rand_case(1234, B, H, W, gh, gw, gd, signed=True)
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
-    assert_parity(run_apply(grid, guide, inp, True, variant), expected,
-                  what=f"{shape} [{variant}]")
+    try:
+        got = run_apply(grid, guide, inp, True, variant)
+    except ValueError as e:
+        if variant == "zsort" and "cannot run these shapes" in str(e):
+            pytest.skip("z-bucketed kernel does not take this grid / width")
+        raise
+    assert_parity(got, expected, what=f"{shape} [{variant}]")
 
 
 @pytest.mark.parametrize("n_in,n_out,has_offset", [(3, 3, False), (3, 4, True), (1, 1, True),
@@ -141,6 +151,28 @@ def test_guide_outside_unit_range_clamps_like_reference():
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
     for v in ("generic", "tma"):
         assert_parity(run_apply(grid, guide, inp, True, v), expected, what=v)
+    grid, guide, inp = rand_case(18, 1, 9, 1920, 8, 16, 8, signed=True)
+    guide[0, :, ::3] = -0.75
+    guide[0, :, 1::3] = 1.5
+    guide[0, 0, :4] = [0.0, 1.0, 100.0, -100.0]
+    expected = checker().bilateral_slice_apply(grid, guide, inp, True)
+    assert_parity(run_apply(grid, guide, inp, True, "zsort"), expected, what="zsort")
+
+
+def test_zsort_is_bitwise_equal_to_row_kernel():
+    """Same per-pixel arithmetic in a different order: results must be identical bits."""
+    grid, guide, inp = rand_case(77, 2, 64, 3840, 16, 16, 8, signed=True)
+    a = run_apply(grid, guide, inp, True, "tma")
+    b = run_apply(grid, guide, inp, True, "zsort")
+    assert np.array_equal(a, b)
+    # smooth (image-like) guide: long runs of equal depth cells, heavily unbalanced buckets
+    yy, xx = np.mgrid[0:64, 0:3840]
+    guide2 = np.stack([(0.5 + 0.5 * np.sin(xx / 700.0 + yy / 30.0)).astype(np.float32)] * 2)
+    assert np.array_equal(run_apply(grid, guide2, inp, True, "tma"),
+                          run_apply(grid, guide2, inp, True, "zsort"))
+    const = np.full_like(guide, 0.3)       # every pixel in ONE depth bucket
+    assert np.array_equal(run_apply(grid, const, inp, True, "tma"),
+                          run_apply(grid, const, inp, True, "zsort"))
 
 
 def test_empty_batch_is_a_no_op():
@@ -199,7 +231,7 @@ def test_4k_frame_against_full_oracle():
     """One 3840x2160 frame, grid 16x16x8 (config 3's per-image shape), full oracle compare."""
     grid, guide, inp = rand_case(1234, 1, 2160, 3840, 16, 16, 8)
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
-    for v in ("tma", "generic"):
+    for v in ("tma", "generic", "zsort"):
         got = run_apply(grid, guide, inp, True, v)
         assert_parity(got, expected, what=f"4K [{v}]")
     gidx = hdrnet_ops.slice_indices(cuda(guide), (16, 16, 8)).cpu().numpy()
