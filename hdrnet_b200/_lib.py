@@ -20,7 +20,7 @@ HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "include", "hdrnet_b200
 OK = 0
 E_NULL_POINTER, E_BAD_SHAPE, E_BAD_CHANNELS, E_TOO_LARGE, E_UNSUPPORTED, E_BAD_CONTEXT = (
     -1, -2, -3, -4, -5, -6)
-VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_ZSORT = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_ZSORT, VARIANT_TEX = 0, 1, 2, 3, 4
 
 _c_int = ctypes.c_int
 _vp = ctypes.c_void_p
@@ -32,6 +32,8 @@ SIGNATURES = {
     "hdrnet_b200_error_string": (ctypes.c_char_p, [_c_int]),
     "hdrnet_slice_apply_f32": (_c_int, [_vp] * 4 + [_c_int] * 9 + [_vp]),
     "hdrnet_slice_apply_f32_variant": (_c_int, [_vp] * 4 + [_c_int] * 10 + [_vp]),
+    "hdrnet_slice_apply_workspace_bytes": (ctypes.c_size_t, [_c_int] * 4),
+    "hdrnet_slice_apply_f32_ws": (_c_int, [_vp] * 4 + [_c_int] * 10 + [_vp, ctypes.c_size_t, _vp]),
     "hdrnet_slice_f32": (_c_int, [_vp] * 3 + [_c_int] * 7 + [_vp]),
     "hdrnet_slice_f32_variant": (_c_int, [_vp] * 3 + [_c_int] * 8 + [_vp]),
     "hdrnet_slice_indices_i32": (_c_int, [_vp] * 2 + [_c_int] * 6 + [_vp]),

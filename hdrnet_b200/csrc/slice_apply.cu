@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <mutex>
 
 #include "common.cuh"
 #include "guide.cuh"
@@ -148,6 +149,8 @@ struct TmaArgs {
   float* guide_out;     // optional guide dump for the fused forms, else nullptr
   const float* input;
   float* out;
+  cudaTextureObject_t slab_tex;  // kTexChunks > 0: float4 view of the y-pre-blended slab rows
+  const float* yslab;            // kTexChunks > 0: [B * rows][gw * gd * 12] slab rows (workspace)
   SliceGeom g;
   TmaPlan p;
 };
@@ -157,35 +160,64 @@ __device__ __forceinline__ float4 lerp4(float w0, float4 a, float w1, float4 b) 
                      fmaf(w1, b.w, w0 * a.w));
 }
 
+// One 16-byte chunk (4 coefficients) of a corner vector: from the shared-memory slab through
+// the LSU, or -- for the last kTexChunks of the 12 chunks a pixel needs -- from the same slab
+// row in global memory through the TEXTURE pipe, the one on-chip gather path that does not
+// share the LSU crossbar (tools/ubench/gather_paths.cu: LDS.128 + tex float4 overlap fully).
+template <int kTexChunks, int kChunkId>
+__device__ __forceinline__ ulonglong2 corner_chunk(const float* __restrict__ slab,
+                                                   cudaTextureObject_t tex, int tex_row, int off) {
+  if constexpr (kChunkId >= 12 - kTexChunks) {
+    const float4 v = tex1Dfetch<float4>(tex, tex_row + (off >> 2) + (kChunkId % 3));
+    ulonglong2 r;
+    r.x = pack2(v.x, v.y);
+    r.y = pack2(v.z, v.w);
+    return r;
+  } else {
+    return reinterpret_cast<const ulonglong2*>(slab + off)[kChunkId % 3];
+  }
+}
+
 // Blend the four (x, z) corners of the y-pre-blended slab for one pixel and apply the
 // 3x4 affine transform to (r, g, b, 1).
-__device__ __forceinline__ void blend_apply(const float* __restrict__ slab, int o00, int o01,
-                                            int o10, int o11, float w00, float w01, float w10,
-                                            float w11, float r, float g, float b, float& out_r,
-                                            float& out_g, float& out_b) {
-  const ulonglong2* v00 = reinterpret_cast<const ulonglong2*>(slab + o00);
-  const ulonglong2* v01 = reinterpret_cast<const ulonglong2*>(slab + o01);
-  const ulonglong2* v10 = reinterpret_cast<const ulonglong2*>(slab + o10);
-  const ulonglong2* v11 = reinterpret_cast<const ulonglong2*>(slab + o11);
+template <int kTexChunks>
+__device__ __forceinline__ void blend_apply(const float* __restrict__ slab,
+                                            cudaTextureObject_t tex, int tex_row, int o00,
+                                            int o01, int o10, int o11, float w00, float w01,
+                                            float w10, float w11, float r, float g, float b,
+                                            float& out_r, float& out_g, float& out_b) {
   const unsigned long long W00 = pack2(w00, w00), W01 = pack2(w01, w01);
   const unsigned long long W10 = pack2(w10, w10), W11 = pack2(w11, w11);
+  // chunk ids: v00 -> 0..2, v01 -> 3..5, v10 -> 6..8, v11 -> 9..11
+  const ulonglong2 a0 = corner_chunk<kTexChunks, 0>(slab, tex, tex_row, o00);
+  const ulonglong2 a1 = corner_chunk<kTexChunks, 1>(slab, tex, tex_row, o00);
+  const ulonglong2 a2 = corner_chunk<kTexChunks, 2>(slab, tex, tex_row, o00);
+  const ulonglong2 b0 = corner_chunk<kTexChunks, 3>(slab, tex, tex_row, o01);
+  const ulonglong2 b1 = corner_chunk<kTexChunks, 4>(slab, tex, tex_row, o01);
+  const ulonglong2 b2 = corner_chunk<kTexChunks, 5>(slab, tex, tex_row, o01);
+  const ulonglong2 c0 = corner_chunk<kTexChunks, 6>(slab, tex, tex_row, o10);
+  const ulonglong2 c1 = corner_chunk<kTexChunks, 7>(slab, tex, tex_row, o10);
+  const ulonglong2 c2 = corner_chunk<kTexChunks, 8>(slab, tex, tex_row, o10);
+  const ulonglong2 d0 = corner_chunk<kTexChunks, 9>(slab, tex, tex_row, o11);
+  const ulonglong2 d1 = corner_chunk<kTexChunks, 10>(slab, tex, tex_row, o11);
+  const ulonglong2 d2 = corner_chunk<kTexChunks, 11>(slab, tex, tex_row, o11);
   unsigned long long acc[6];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const ulonglong2 a = v00[k], bq = v01[k], c = v10[k], d = v11[k];
-    acc[2 * k] = fma2(W11, d.x, fma2(W10, c.x, fma2(W01, bq.x, mul2(W00, a.x))));
-    acc[2 * k + 1] = fma2(W11, d.y, fma2(W10, c.y, fma2(W01, bq.y, mul2(W00, a.y))));
-  }
-  float a0, a1, a2, a3;
-  unpack2(acc[0], a0, a1);
-  unpack2(acc[1], a2, a3);
-  out_r = fmaf(a2, b, fmaf(a1, g, fmaf(a0, r, a3)));
-  unpack2(acc[2], a0, a1);
-  unpack2(acc[3], a2, a3);
-  out_g = fmaf(a2, b, fmaf(a1, g, fmaf(a0, r, a3)));
-  unpack2(acc[4], a0, a1);
-  unpack2(acc[5], a2, a3);
-  out_b = fmaf(a2, b, fmaf(a1, g, fmaf(a0, r, a3)));
+  acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
+  acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
+  acc[2] = fma2(W11, d1.x, fma2(W10, c1.x, fma2(W01, b1.x, mul2(W00, a1.x))));
+  acc[3] = fma2(W11, d1.y, fma2(W10, c1.y, fma2(W01, b1.y, mul2(W00, a1.y))));
+  acc[4] = fma2(W11, d2.x, fma2(W10, c2.x, fma2(W01, b2.x, mul2(W00, a2.x))));
+  acc[5] = fma2(W11, d2.y, fma2(W10, c2.y, fma2(W01, b2.y, mul2(W00, a2.y))));
+  float a0f, a1f, a2f, a3f;
+  unpack2(acc[0], a0f, a1f);
+  unpack2(acc[1], a2f, a3f);
+  out_r = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[2], a0f, a1f);
+  unpack2(acc[3], a2f, a3f);
+  out_g = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[4], a0f, a1f);
+  unpack2(acc[5], a2f, a3f);
+  out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
 }
 
 // Guide sources.  kFromInput: the op-API form, guide is an input tensor staged by TMA
@@ -211,7 +243,7 @@ struct GuideNN {
   }
 };
 
-template <class GuideFn>
+template <class GuideFn, int kTexChunks>
 __global__ void __launch_bounds__(kTmaThreads, 2)
 slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
   constexpr bool kGuideIn = GuideFn::kFromInput;
@@ -221,10 +253,11 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
   const int tid = threadIdx.x;
 
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // [kMaxStages]
-  uint64_t* gridbar = full + kMaxStages;                      // [1]
+  uint64_t* gridbar = full + kMaxStages;                      // [2]
   float* raw0 = reinterpret_cast<float*>(smem + pl.off_raw);
   float* raw1 = raw0 + pl.row_floats;
   float* slab = reinterpret_cast<float*>(smem + pl.off_slab);
+  int tex_row = 0;
   unsigned char* stage_base = smem + pl.off_stage;
 
   // Contiguous block of buffer rows per CTA (neighbouring rows share grid rows).
@@ -236,7 +269,8 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
 
   if (tid == 0) {
     for (int s = 0; s < pl.stages; ++s) mbar_init(&full[s], 1);
-    mbar_init(gridbar, 1);
+    mbar_init(&gridbar[0], 1);
+    mbar_init(&gridbar[1], 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -268,6 +302,11 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
   };
 
   if (tid == 0) {
+    if constexpr (kTexChunks > 0) {  // slab of the first row
+      const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+      mbar_expect_tx(&gridbar[0], bytes);
+      tma_load_1d(raw0, args.yslab + static_cast<size_t>(r_begin) * pl.row_floats, bytes, &gridbar[0]);
+    }
     const int pre = min(NS - 1, nitems);
     for (int it = 0; it < pre; ++it) issue_load(it);
   }
@@ -282,6 +321,24 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
     item_span(item, row, x0, npx);
 
     if (x0 == 0) {
+      if constexpr (kTexChunks > 0) {
+        // Texture-assisted form: the y-pre-blended slab rows were produced by a pre-pass
+        // (yblend_rows_kernel) into a global workspace, so that the texture pipe may read
+        // them (texture reads of data written by the SAME kernel are not coherent).  The
+        // row's slab arrives by one TMA copy, double-buffered one row ahead in raw0 / raw1.
+        const int rowk = item / pl.nseg;
+        const int cur = rowk & 1;
+        slab = raw0 + cur * pl.row_floats;
+        mbar_wait(&gridbar[cur], static_cast<uint32_t>(rowk >> 1) & 1u);
+        if (tid == 0 && row + 1 < r_end) {
+          const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+          mbar_expect_tx(&gridbar[cur ^ 1], bytes);
+          tma_load_1d(raw0 + (cur ^ 1) * pl.row_floats,
+                      args.yslab + static_cast<size_t>(row + 1) * pl.row_floats, bytes,
+                      &gridbar[cur ^ 1]);
+        }
+        tex_row = static_cast<int>(row) * (pl.row_floats / 4);
+      } else {
       // New image row: (re)stage its two grid rows if they changed, then pre-blend in y.
       // Every thread is past the previous item's post-compute barrier, so raw/slab are idle.
       const int b = static_cast<int>(row / g.rows);
@@ -308,6 +365,7 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
       float4* s4 = reinterpret_cast<float4*>(slab);
       for (int e = tid; e < pl.row_floats / 4; e += kTmaThreads) s4[e] = lerp4(wy0, a4[e], wy1, b4[e]);
       __syncthreads();
+      }
     }
 
     const int s = item % NS;
@@ -343,8 +401,9 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
         float wz0, wz1;
         smoothed_weights(az.f, wz0, wz1);
         const float wx1 = ax.f, wx0 = 1.0f - ax.f;
-        blend_apply(slab, xo0 + zo0, xo0 + zo1, xo1 + zo0, xo1 + zo1, wx0 * wz0, wx0 * wz1,
-                    wx1 * wz0, wx1 * wz1, pr[i], pg[i], pb[i], o_r[i], o_g[i], o_b[i]);
+        blend_apply<kTexChunks>(slab, args.slab_tex, tex_row, xo0 + zo0, xo0 + zo1, xo1 + zo0,
+                                xo1 + zo1, wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i],
+                                pg[i], pb[i], o_r[i], o_g[i], o_b[i]);
       }
       rgb4[0] = make_float4(o_r[0], o_g[0], o_b[0], o_r[1]);
       rgb4[1] = make_float4(o_g[1], o_b[1], o_r[2], o_g[2]);
@@ -365,6 +424,24 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
     }
   }
   if (tid == 0) tma_store_wait_all<0>();
+}
+
+// Pre-pass of the texture-assisted form: yslab[r] = (1 - fy) * G[b][gy0] + fy * G[b][gy1] for
+// every buffer row r = (b, y) -- the same y pre-blend the row kernel does in shared memory,
+// materialised once (gw*gd*48 B per image row: +11 % HBM traffic at 4K / 16x16x8).
+__global__ void __launch_bounds__(128)
+yblend_rows_kernel(const float* __restrict__ grid, float* __restrict__ yslab, SliceGeom g,
+                   int row_floats) {
+  const long long row = blockIdx.x;
+  const int b = static_cast<int>(row / g.rows);
+  const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
+  const Axis ay = spatial_axis(y, g.scale_y);
+  const float wy1 = ay.f, wy0 = 1.0f - ay.f;
+  const float* gb = grid + static_cast<size_t>(b) * g.gh * row_floats;
+  const float4* a4 = reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * row_floats);
+  const float4* b4 = reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * row_floats);
+  float4* o4 = reinterpret_cast<float4*>(yslab + static_cast<size_t>(row) * row_floats);
+  for (int e = threadIdx.x; e < row_floats / 4; e += blockDim.x) o4[e] = lerp4(wy0, __ldg(a4 + e), wy1, __ldg(b4 + e));
 }
 
 // =========================================================================================
@@ -444,14 +521,46 @@ bool make_zsort_plan(const SliceGeom& g, int max_smem, int sms, ZsPlan* out);
 int launch_zsort(const float* grid, const float* guide, const float* input, float* out,
                  const SliceGeom& g, const ZsPlan& plan, cudaStream_t stream);
 
-template <class GuideFn>
+template <class GuideFn, int kTexChunks = 0>
 static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(slice_apply_rows_tma_kernel<GuideFn>,
+  cudaError_t e = cudaFuncSetAttribute(slice_apply_rows_tma_kernel<GuideFn, kTexChunks>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  slice_apply_rows_tma_kernel<GuideFn><<<a.p.ctas, kTmaThreads, a.p.smem_bytes, stream>>>(a, fn);
+  slice_apply_rows_tma_kernel<GuideFn, kTexChunks>
+      <<<a.p.ctas, kTmaThreads, a.p.smem_bytes, stream>>>(a, fn);
   return static_cast<int>(cudaGetLastError());
+}
+
+// Texture objects over caller workspaces, cached by (pointer, bytes): creating one is a
+// host-side driver call that should not sit inside a timed loop.
+struct TexCacheEntry { const void* ptr; size_t bytes; int dev; cudaTextureObject_t tex; };
+static std::mutex g_tex_mutex;
+static TexCacheEntry g_tex_cache[8];
+static int g_tex_next = 0;
+
+static int get_slab_texture(const float* ws, size_t bytes, cudaTextureObject_t* out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_tex_mutex);
+  for (auto& e : g_tex_cache)
+    if (e.ptr == ws && e.bytes == bytes && e.dev == dev && e.tex) { *out = e.tex; return 0; }
+  cudaResourceDesc rd = {};
+  rd.resType = cudaResourceTypeLinear;
+  rd.res.linear.devPtr = const_cast<float*>(ws);
+  rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+  rd.res.linear.sizeInBytes = bytes;
+  cudaTextureDesc td = {};
+  td.readMode = cudaReadModeElementType;
+  cudaTextureObject_t tex = 0;
+  cudaError_t err = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+  if (err != cudaSuccess) return static_cast<int>(err);
+  TexCacheEntry& slot = g_tex_cache[g_tex_next];
+  g_tex_next = (g_tex_next + 1) % 8;
+  if (slot.tex) cudaDestroyTextureObject(slot.tex);
+  slot = TexCacheEntry{ws, bytes, dev, tex};
+  *out = tex;
+  return 0;
 }
 
 // Guide source of a launch: an input tensor, or one of the fused per-pixel guide networks.
@@ -461,7 +570,11 @@ struct GuideSpec {
   float* guide_out;
   const CurvesGuideParams* curves;
   const NNGuideParams* nn;
+  float* workspace = nullptr;  // HDRNET_VARIANT_TEX: slab rows, B * rows * gw * gd * 48 bytes
+  size_t workspace_bytes = 0;
 };
+
+constexpr int kTexChunksDefault = 4;
 
 static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const float* input,
                                    float* out, int B, int H, int W, int rows, int y_off, int gh,
@@ -492,6 +605,20 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       return HDRNET_E_UNSUPPORTED;
     return launch_zsort(grid, gs.guide, input, out, g, zp, stream);
   }
+  if (variant == HDRNET_VARIANT_TEX) {
+    const size_t need = static_cast<size_t>(B) * rows * plan.row_floats * sizeof(float);
+    if (!tma_shape || gs.mode != 0 || !gs.workspace || gs.workspace_bytes < need ||
+        !aligned16(gs.workspace) || need / 16 > (1u << 27))
+      return HDRNET_E_UNSUPPORTED;
+    TmaArgs a;
+    a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr; a.input = input; a.out = out;
+    a.g = g; a.p = plan; a.yslab = gs.workspace;
+    rc = get_slab_texture(gs.workspace, need, &a.slab_tex);
+    if (rc != 0) return rc;
+    yblend_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows), 128, 0, stream>>>(
+        grid, gs.workspace, g, plan.row_floats);
+    return launch_tma<GuideFromInput, kTexChunksDefault>(a, GuideFromInput{}, stream);
+  }
   bool use_tma;
   if (variant == HDRNET_VARIANT_TMA) {
     if (!tma_shape) return HDRNET_E_UNSUPPORTED;
@@ -510,7 +637,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   if (use_tma) {
     TmaArgs a;
     a.grid = grid; a.guide = gs.guide; a.guide_out = gs.guide_out; a.input = input; a.out = out;
-    a.g = g; a.p = plan;
+    a.g = g; a.p = plan; a.slab_tex = 0; a.yslab = nullptr;
     if (gs.mode == 0) return launch_tma(a, GuideFromInput{}, stream);
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; return launch_tma(a, fn, stream); }
     GuideNN fn; fn.p = *gs.nn;
@@ -586,6 +713,22 @@ int hdrnet_slice_apply_f32_variant(const float* grid, const float* guide, const 
                                    void* stream) {
   return launch_slice_apply(grid, guide, input, out, B, H, W, H, 0, gh, gw, gd, n_in, n_out,
                             has_offset, variant, static_cast<cudaStream_t>(stream));
+}
+
+size_t hdrnet_slice_apply_workspace_bytes(int B, int H, int gw, int gd) {
+  if (B < 0 || H < 0 || gw < 1 || gd < 1) return 0;
+  return static_cast<size_t>(B) * H * gw * gd * kGc * sizeof(float);
+}
+
+int hdrnet_slice_apply_f32_ws(const float* grid, const float* guide, const float* input,
+                              float* out, int B, int H, int W, int gh, int gw, int gd, int n_in,
+                              int n_out, int has_offset, int variant, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  GuideSpec gs{0, guide, nullptr, nullptr, nullptr};
+  gs.workspace = static_cast<float*>(workspace);
+  gs.workspace_bytes = workspace_bytes;
+  return launch_slice_apply_impl(grid, gs, input, out, B, H, W, H, 0, gh, gw, gd, n_in, n_out,
+                                 has_offset, variant, static_cast<cudaStream_t>(stream));
 }
 
 int hdrnet_slice_apply_f32(const float* grid, const float* guide, const float* input,

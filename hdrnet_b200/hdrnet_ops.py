@@ -67,6 +67,17 @@ def _host_context(device_index: int):
         return ctx
 
 
+_ws_cache = {}  # device -> float32 workspace tensor (grown on demand)
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    ws = _ws_cache.get(dev)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty((max(int(nbytes), 16) + 3) // 4, dtype=torch.float32, device=dev)
+        _ws_cache[dev] = ws
+    return ws
+
+
 def _check_slice_args(grid, guide, grid_msg):
     if grid.dim() != 5:
         raise ValueError(grid_msg)
@@ -150,9 +161,17 @@ def bilateral_slice_apply(grid: torch.Tensor, guide: torch.Tensor, input: torch.
             out = torch.empty(shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.hdrnet_slice_apply_f32_variant(
-                grid.data_ptr(), guide.data_ptr(), input.data_ptr(), out.data_ptr(), B, H, W, gh,
-                gw, gd, n_in, n_out, int(has_offset), int(variant), stream)
+            if int(variant) == _lib.VARIANT_TEX:
+                # caller-side workspace (torch's caching allocator): y-pre-blended slab rows
+                ws = _workspace(dev, lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))
+                rc = lib.hdrnet_slice_apply_f32_ws(
+                    grid.data_ptr(), guide.data_ptr(), input.data_ptr(), out.data_ptr(), B, H, W,
+                    gh, gw, gd, n_in, n_out, int(has_offset), int(variant), ws.data_ptr(),
+                    ws.numel() * 4, stream)
+            else:
+                rc = lib.hdrnet_slice_apply_f32_variant(
+                    grid.data_ptr(), guide.data_ptr(), input.data_ptr(), out.data_ptr(), B, H, W,
+                    gh, gw, gd, n_in, n_out, int(has_offset), int(variant), stream)
         _lib.check(rc, "BilateralSliceApply")
         return out
 

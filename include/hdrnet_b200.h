@@ -61,6 +61,11 @@ extern "C" {
                                  /* counting-sorted by (x cell, depth cell) so one load    */
                                  /* of the corner vectors serves 4 pixels (same shape      */
                                  /* limits as TMA, plus (gd + 1) * cells-per-segment <= 64)*/
+#define HDRNET_VARIANT_TEX 4     /* texture-assisted TMA kernel: a pre-pass writes the      */
+                                 /* y-pre-blended slab rows to a caller workspace; the row  */
+                                 /* kernel then fetches part of each pixel's corner data    */
+                                 /* through the texture pipe, which does not share the      */
+                                 /* shared-memory crossbar.  Needs hdrnet_slice_apply_f32_ws*/
 
 HDRNET_API int hdrnet_b200_abi_version(void);
 
@@ -83,6 +88,18 @@ HDRNET_API int hdrnet_slice_apply_f32_variant(const float* grid, const float* gu
                                    float* out, int B, int H, int W, int gh, int gw, int gd,
                                    int n_in, int n_out, int has_offset, int variant,
                                    void* stream);
+
+/*
+ * Same op with a caller-provided device workspace (the library itself never allocates):
+ * required by HDRNET_VARIANT_TEX, ignored by the other variants.
+ * hdrnet_slice_apply_workspace_bytes() = B * H * gw * gd * 48.
+ */
+HDRNET_API size_t hdrnet_slice_apply_workspace_bytes(int B, int H, int gw, int gd);
+HDRNET_API int hdrnet_slice_apply_f32_ws(const float* grid, const float* guide,
+                                         const float* input, float* out, int B, int H, int W,
+                                         int gh, int gw, int gd, int n_in, int n_out,
+                                         int has_offset, int variant, void* workspace,
+                                         size_t workspace_bytes, void* stream);
 
 /*
  * Un-fused slice.  Replaces the BilateralSlice op:
