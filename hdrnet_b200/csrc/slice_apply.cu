@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -605,11 +606,16 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       return HDRNET_E_UNSUPPORTED;
     return launch_zsort(grid, gs.guide, input, out, g, zp, stream);
   }
+  // Texture-assisted form: possible when the caller lent a workspace for the slab rows.
+  const size_t tex_need = tma_shape ? static_cast<size_t>(B) * rows * plan.row_floats * sizeof(float) : 0;
+  const bool tex_ok = tma_shape && gs.mode == 0 && gs.workspace && gs.workspace_bytes >= tex_need &&
+                      aligned16(gs.workspace) && tex_need / 16 <= (1u << 27);
+  // AUTO prefers it once the image is large enough to amortise the pre-pass launch.
+  if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21))
+    variant = HDRNET_VARIANT_TEX;
   if (variant == HDRNET_VARIANT_TEX) {
-    const size_t need = static_cast<size_t>(B) * rows * plan.row_floats * sizeof(float);
-    if (!tma_shape || gs.mode != 0 || !gs.workspace || gs.workspace_bytes < need ||
-        !aligned16(gs.workspace) || need / 16 > (1u << 27))
-      return HDRNET_E_UNSUPPORTED;
+    const size_t need = tex_need;
+    if (!tex_ok) return HDRNET_E_UNSUPPORTED;
     TmaArgs a;
     a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr; a.input = input; a.out = out;
     a.g = g; a.p = plan; a.yslab = gs.workspace;
@@ -617,7 +623,15 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     if (rc != 0) return rc;
     yblend_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows), 128, 0, stream>>>(
         grid, gs.workspace, g, plan.row_floats);
-    return launch_tma<GuideFromInput, kTexChunksDefault>(a, GuideFromInput{}, stream);
+    int chunks = kTexChunksDefault;
+    if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);  // tuning knob
+    switch (chunks) {
+      case 2: return launch_tma<GuideFromInput, 2>(a, GuideFromInput{}, stream);
+      case 3: return launch_tma<GuideFromInput, 3>(a, GuideFromInput{}, stream);
+      case 5: return launch_tma<GuideFromInput, 5>(a, GuideFromInput{}, stream);
+      case 6: return launch_tma<GuideFromInput, 6>(a, GuideFromInput{}, stream);
+      default: return launch_tma<GuideFromInput, kTexChunksDefault>(a, GuideFromInput{}, stream);
+    }
   }
   bool use_tma;
   if (variant == HDRNET_VARIANT_TMA) {
@@ -813,6 +827,7 @@ int hdrnet_slice_indices_i32(const float* guide, int32_t* idx, int B, int H, int
 int hdrnet_slice_apply_plan(int B, int H, int W, int gh, int gw, int gd, int n_in, int n_out,
                             int has_offset, int* variant, int* ctas, int* threads,
                             int* smem_bytes) {
+  // (reports the no-workspace choice; with a workspace AUTO upgrades TMA to TEX for >= 2 Mi px)
   int rc = validate_common(B, H, W, gh, gw, gd);
   if (rc != HDRNET_OK) return rc;
   const SliceGeom g = make_geom(B, H, W, H, 0, gh, gw, gd);

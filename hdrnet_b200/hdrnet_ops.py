@@ -161,17 +161,16 @@ def bilateral_slice_apply(grid: torch.Tensor, guide: torch.Tensor, input: torch.
             out = torch.empty(shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            if int(variant) == _lib.VARIANT_TEX:
-                # caller-side workspace (torch's caching allocator): y-pre-blended slab rows
+            # A workspace from torch's caching allocator (the library never allocates) lets AUTO
+            # pick the texture-assisted kernel for large images (>= 2 Mi px, W % 4 == 0).
+            ws_ptr, ws_bytes = 0, 0
+            if int(variant) in (_lib.VARIANT_AUTO, _lib.VARIANT_TEX) and n_in == 3 and n_out == 3 \
+                    and has_offset and W % 4 == 0 and (int(variant) == _lib.VARIANT_TEX or B * H * W >= (1 << 21)):
                 ws = _workspace(dev, lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))
-                rc = lib.hdrnet_slice_apply_f32_ws(
-                    grid.data_ptr(), guide.data_ptr(), input.data_ptr(), out.data_ptr(), B, H, W,
-                    gh, gw, gd, n_in, n_out, int(has_offset), int(variant), ws.data_ptr(),
-                    ws.numel() * 4, stream)
-            else:
-                rc = lib.hdrnet_slice_apply_f32_variant(
-                    grid.data_ptr(), guide.data_ptr(), input.data_ptr(), out.data_ptr(), B, H, W,
-                    gh, gw, gd, n_in, n_out, int(has_offset), int(variant), stream)
+                ws_ptr, ws_bytes = ws.data_ptr(), ws.numel() * 4
+            rc = lib.hdrnet_slice_apply_f32_ws(
+                grid.data_ptr(), guide.data_ptr(), input.data_ptr(), out.data_ptr(), B, H, W, gh,
+                gw, gd, n_in, n_out, int(has_offset), int(variant), ws_ptr, ws_bytes, stream)
         _lib.check(rc, "BilateralSliceApply")
         return out
 
