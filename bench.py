@@ -117,6 +117,10 @@ class ClockSampler(threading.Thread):
 # CPU arm (reference's own loops on the host cores)
 # ------------------------------------------------------------------------------------------
 def cpu_checker():
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the
+    # host threads it can, so undo that before libgomp is initialised by the oracle library.
+    if os.environ.get("OMP_NUM_THREADS") in (None, "1"):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import oracle
     if not oracle.have_ref() or not os.path.exists(os.path.join(ROOT, "oracle", "_build",
                                                                 "libhdrnet_oracle.so")):
@@ -334,7 +338,7 @@ def run_b200_arm(args):
                     "path": "hdrnet_ops.bilateral_slice_apply on pinned CPU tensors -> "
                             "hdrnet_slice_apply_host_f32 (row-band H2D/kernel/D2H pipeline)",
                     "matches_device_result": e2e_ok},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 2 * args.steps * world,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -36,6 +36,8 @@ SIGNATURES = {
     "hdrnet_slice_apply_f32_ws": (_c_int, [_vp] * 4 + [_c_int] * 10 + [_vp, ctypes.c_size_t, _vp]),
     "hdrnet_slice_f32": (_c_int, [_vp] * 3 + [_c_int] * 7 + [_vp]),
     "hdrnet_slice_f32_variant": (_c_int, [_vp] * 3 + [_c_int] * 8 + [_vp]),
+    "hdrnet_slice_apply_grad_f32": (_c_int, [_vp] * 7 + [_c_int] * 9 + [_vp]),
+    "hdrnet_slice_grad_f32": (_c_int, [_vp] * 5 + [_c_int] * 7 + [_vp]),
     "hdrnet_slice_indices_i32": (_c_int, [_vp] * 2 + [_c_int] * 6 + [_vp]),
     "hdrnet_slice_apply_plan": (_c_int, [_c_int] * 9 + [ctypes.POINTER(_c_int)] * 4),
     "hdrnet_guide_curves_f32": (_c_int, [_vp, _vp, ctypes.c_longlong] + [_vp] * 5 + [ctypes.c_float, _vp]),

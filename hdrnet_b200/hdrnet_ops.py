@@ -87,6 +87,61 @@ def _check_slice_args(grid, guide, grid_msg):
         raise ValueError("Batch sizes should match.")
 
 
+class _SliceFn(torch.autograd.Function):
+    """Gradient registration of BilateralSlice (hdrnet/hdrnet_ops.py:34-38)."""
+
+    @staticmethod
+    def forward(ctx, grid, guide):
+        ctx.save_for_backward(grid, guide)
+        with torch.no_grad():
+            return bilateral_slice(grid, guide)
+
+    @staticmethod
+    def backward(ctx, grad):
+        grid, guide = ctx.saved_tensors
+        grad = grad.contiguous()
+        B, gh, gw, gd, gc = grid.shape
+        _, H, W = guide.shape
+        gv, uv = torch.empty_like(grid), torch.empty_like(guide)
+        with torch.cuda.device(grid.device):
+            rc = _lib.load().hdrnet_slice_grad_f32(
+                grid.data_ptr(), guide.data_ptr(), grad.data_ptr(), gv.data_ptr(), uv.data_ptr(),
+                B, H, W, gh, gw, gd, gc, torch.cuda.current_stream(grid.device).cuda_stream)
+        _lib.check(rc, "BilateralSliceGrad")
+        return gv, uv
+
+
+class _SliceApplyFn(torch.autograd.Function):
+    """Gradient registration of BilateralSliceApply (hdrnet/hdrnet_ops.py:41-48)."""
+
+    @staticmethod
+    def forward(ctx, grid, guide, input, has_offset):  # noqa: A002
+        ctx.save_for_backward(grid, guide, input)
+        ctx.has_offset = bool(has_offset)
+        with torch.no_grad():
+            return bilateral_slice_apply(grid, guide, input, has_offset)
+
+    @staticmethod
+    def backward(ctx, grad):
+        grid, guide, input = ctx.saved_tensors  # noqa: A001
+        grad = grad.contiguous()
+        B, gh, gw, gd, gc = grid.shape
+        _, H, W, n_in = input.shape
+        n_out = gc // (n_in + int(ctx.has_offset))
+        gv, uv, iv = torch.empty_like(grid), torch.empty_like(guide), torch.empty_like(input)
+        with torch.cuda.device(grid.device):
+            rc = _lib.load().hdrnet_slice_apply_grad_f32(
+                grid.data_ptr(), guide.data_ptr(), input.data_ptr(), grad.data_ptr(), gv.data_ptr(),
+                uv.data_ptr(), iv.data_ptr(), B, H, W, gh, gw, gd, n_in, n_out,
+                int(ctx.has_offset), torch.cuda.current_stream(grid.device).cuda_stream)
+        _lib.check(rc, "BilateralSliceApplyGrad")
+        return gv, uv, iv, None
+
+
+def _wants_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t.requires_grad for t in ts)
+
+
 def bilateral_slice(grid: torch.Tensor, guide: torch.Tensor, name=None) -> torch.Tensor:
     """Slices a bilateral grid with a guide image (reference op ``BilateralSlice``,
     hdrnet/ops/bilateral_slice_op.cc:120-174, :274-290)."""
@@ -100,6 +155,8 @@ def bilateral_slice(grid: torch.Tensor, guide: torch.Tensor, name=None) -> torch
     dev = _same_device(grid, guide)
     B, gh, gw, gd, gc = grid.shape
     _, H, W = guide.shape
+    if dev.type == "cuda" and _wants_grad(grid, guide):
+        return _SliceFn.apply(grid, guide)
     if dev.type != "cuda":
         raise _lib.HdrnetLibraryError("bilateral_slice: tensors must be CUDA tensors "
                                       "(only bilateral_slice_apply has a host-buffer path)")
@@ -155,6 +212,9 @@ def bilateral_slice_apply(grid: torch.Tensor, guide: torch.Tensor, input: torch.
         if tuple(out.shape) != shape or out.dtype != torch.float32 or out.device != dev \
                 or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous float32 tensor of shape {shape} on {dev}")
+
+    if dev.type == "cuda" and out is None and _wants_grad(grid, guide, input):
+        return _SliceApplyFn.apply(grid, guide, input, has_offset)
 
     if dev.type == "cuda":
         if out is None:

@@ -115,6 +115,27 @@ HDRNET_API int hdrnet_slice_f32_variant(const float* grid, const float* guide, f
                              int W, int gh, int gw, int gd, int gc, int variant, void* stream);
 
 /*
+ * Vector-Jacobian products (training).  Replace the BilateralSliceApplyGrad / BilateralSliceGrad
+ * ops: Python registration hdrnet/hdrnet_ops.py:34-48; OpKernels
+ * hdrnet/ops/bilateral_slice_apply_op.cc:249-362 and bilateral_slice_op.cc:183-256; kernels
+ * hdrnet/ops/bilateral_slice_apply.cu.cc:128-364 (+ launcher :384-417) and
+ * bilateral_slice.cu.cc:93-227 (+ :246-272).  codomain_tangent has the forward output's shape;
+ * grid_vjp / guide_vjp / input_vjp have the shapes of grid / guide / input.  Semantics follow
+ * the reference exactly (mirror boundary of the grid-VJP footprint, wz = 1 at the depth
+ * borders, dwz = gd * SmoothedLerpWeightGrad); results are deterministic (no atomics).
+ */
+HDRNET_API int hdrnet_slice_apply_grad_f32(const float* grid, const float* guide,
+                                           const float* input, const float* codomain_tangent,
+                                           float* grid_vjp, float* guide_vjp, float* input_vjp,
+                                           int B, int H, int W, int gh, int gw, int gd, int n_in,
+                                           int n_out, int has_offset, void* stream);
+
+HDRNET_API int hdrnet_slice_grad_f32(const float* grid, const float* guide,
+                                     const float* codomain_tangent, float* grid_vjp,
+                                     float* guide_vjp, int B, int H, int W, int gh, int gw,
+                                     int gd, int gc, void* stream);
+
+/*
  * Debug: the unclamped lower cell indices (gx0, gy0, gz0) the kernels use, written as
  * idx[b,y,x,0..2] int32.  It runs the same device functions as the slice kernels, so the
  * bit-exactness of the index arithmetic (bilateral_slice_apply.cu.cc:73-80;

@@ -1,0 +1,105 @@
+"""GPU tests of the VJP kernels against the compiled reference loops
+(oracle/_ref: hdrnet/ops/bilateral_slice_apply.cc:84-259, bilateral_slice.cc:72-168) or their
+bit-exact C restatement, plus the reference's own numeric-vs-analytic criterion through
+torch.autograd (hdrnet/hdrnet_ops_test.py:173-180, :361-408)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from hdrnet_b200 import hdrnet_ops
+from util import assert_parity, rand_case
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.requires_grad_(grad)
+
+
+# (B, H, W, gh, gw, gd, n_in, n_out, has_offset)
+APPLY_CASES = [
+    (3, 8, 5, 6, 3, 7, 3, 4, True),      # hdrnet_ops_test.py:185-195 (generic grid-VJP path: gc=16)
+    (3, 30, 25, 16, 12, 8, 3, 3, True),  # default test extents: fast column kernel (gd<=8, gc<=12)
+    (2, 40, 64, 4, 4, 8, 3, 3, True),    # several pixels per cell, mirror boundary on all sides
+    (2, 33, 47, 5, 3, 4, 3, 4, False),   # no offset
+    (1, 16, 16, 2, 2, 1, 1, 1, True),    # gd = 1: both depth borders at once
+]
+
+
+@pytest.mark.parametrize("case", APPLY_CASES, ids=str)
+def test_slice_apply_vjps_match_reference(case):
+    B, H, W, gh, gw, gd, n_in, n_out, ho = case
+    grid, guide, inp = rand_case(5, B, H, W, gh, gw, gd, n_in, n_out, ho, signed=True)
+    rng = np.random.RandomState(6)
+    ct = rng.randn(B, H, W, n_out).astype(np.float32)
+    want = oracle.port().bilateral_slice_apply_grad(grid, guide, inp, ct, ho)
+    g, u, i = cuda(grid, True), cuda(guide, True), cuda(inp, True)
+    out = hdrnet_ops.bilateral_slice_apply(g, u, i, ho)
+    out.backward(cuda(ct))
+    for got, ref, name in zip((g.grad, u.grad, i.grad), want, ("grid", "guide", "input")):
+        assert_parity(got.cpu().numpy(), ref, rtol=2e-5, what=f"{case} {name} VJP")
+
+
+@pytest.mark.parametrize("case", [(3, 30, 25, 16, 12, 8, 12), (2, 21, 36, 5, 4, 6, 2), (1, 9, 7, 3, 3, 9, 5)],
+                         ids=str)
+def test_slice_vjps_match_reference(case):
+    B, H, W, gh, gw, gd, gc = case
+    rng = np.random.RandomState(7)
+    grid = rng.randn(B, gh, gw, gd, gc).astype(np.float32)
+    guide = rng.rand(B, H, W).astype(np.float32)
+    ct = rng.randn(B, H, W, gc).astype(np.float32)
+    want = oracle.port().bilateral_slice_grad(grid, guide, ct)
+    g, u = cuda(grid, True), cuda(guide, True)
+    hdrnet_ops.bilateral_slice(g, u).backward(cuda(ct))
+    assert_parity(g.grad.cpu().numpy(), want[0], rtol=2e-5, what="grid VJP")
+    assert_parity(u.grad.cpu().numpy(), want[1], rtol=2e-5, what="guide VJP")
+
+
+def test_grad_shapes_follow_reference_contract():
+    """hdrnet_ops_test.py:125-135, :304-315 (test_grad_shape)."""
+    grid, guide, inp = rand_case(1, 3, 30, 25, 16, 12, 8)
+    g, u, i = cuda(grid, True), cuda(guide, True), cuda(inp, True)
+    hdrnet_ops.bilateral_slice_apply(g, u, i, True).sum().backward()
+    assert g.grad.shape == g.shape and u.grad.shape == u.shape and i.grad.shape == i.shape
+
+
+def test_analytic_vs_numeric_gradient_error():
+    """The reference's criterion (compute_gradient_error <= 1e-2, hdrnet_ops_test.py:361-363):
+    central differences of the CUDA forward vs the CUDA VJPs, for grid and input (the forward is
+    piecewise linear in both, so float32 differences are accurate)."""
+    grid, guide, inp = rand_case(3, 1, 12, 10, 3, 3, 4, 3, 3, True)
+    guide = (0.1 + 0.8 * guide).astype(np.float32)
+    rng = np.random.RandomState(4)
+    ct = rng.rand(1, 12, 10, 3).astype(np.float32)
+    g, u, i = cuda(grid, True), cuda(guide, True), cuda(inp, True)
+    hdrnet_ops.bilateral_slice_apply(g, u, i, True).backward(cuda(ct))
+
+    def loss(gg, ii):
+        with torch.no_grad():
+            o = hdrnet_ops.bilateral_slice_apply(cuda(gg), cuda(guide), cuda(ii), True)
+        return float((o.double() * cuda(ct).double()).sum())
+
+    eps = 1e-2
+    for arr, grad, which in ((grid, g.grad, 0), (inp, i.grad, 1)):
+        gflat = grad.cpu().numpy().reshape(-1)
+        for k in rng.choice(arr.size, 10, replace=False):
+            hi, lo = arr.copy(), arr.copy()
+            hi.reshape(-1)[k] += eps
+            lo.reshape(-1)[k] -= eps
+            num = (loss(hi, inp) - loss(lo, inp)) / (2 * eps) if which == 0 else \
+                  (loss(grid, hi) - loss(grid, lo)) / (2 * eps)
+            assert abs(num - gflat[k]) <= 1e-2 * max(1.0, abs(num))
+
+
+def test_backward_is_deterministic():
+    grid, guide, inp = rand_case(9, 2, 64, 96, 8, 8, 8)
+    ct = np.random.RandomState(1).rand(2, 64, 96, 3).astype(np.float32)
+    grads = []
+    for _ in range(2):
+        g, u, i = cuda(grid, True), cuda(guide, True), cuda(inp, True)
+        hdrnet_ops.bilateral_slice_apply(g, u, i, True).backward(cuda(ct))
+        grads.append((g.grad.clone(), u.grad.clone(), i.grad.clone()))
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
