@@ -26,13 +26,19 @@
 
 namespace hdrnet_b200 {
 
-// numerics.h:116-126 with dx = (gz + 0.5) - gzf
+// numerics.h:83-91, :108-126 with dx = (gz + 0.5) - gzf.  The guide VJP sums derivatives of
+// opposite sign (two depth corners), so these follow the reference operation for operation --
+// x*x + eps WITHOUT fusing, IEEE sqrt and division -- instead of the forward's fast forms:
+// a 1-ulp difference here survives the cancellation as a 1e-4-relative error.
+__device__ __forceinline__ float smoothed_abs(float dx) {
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), 1.0e-8f));
+}
 __device__ __forceinline__ float smoothed_lerp_weight_grad(float dx) {
-  const float a = sqrtf(fmaf(dx, dx, 1.0e-8f));
-  return (a > 1.0f) ? 0.0f : dx / a;
+  const float a = smoothed_abs(dx);
+  return (a > 1.0f) ? 0.0f : __fdiv_rn(dx, a);
 }
 __device__ __forceinline__ float smoothed_lerp_weight(float dx) {
-  return fmaxf(1.0f - sqrtf(fmaf(dx, dx, 1.0e-8f)), 0.0f);
+  return fmaxf(__fsub_rn(1.0f, smoothed_abs(dx)), 0.0f);
 }
 __device__ __forceinline__ int mirror_boundary(int x, int extent) {  // numerics.h:72-80
   return x < 0 ? -x - 1 : (x >= extent ? 2 * extent - 1 - x : x);
@@ -100,7 +106,7 @@ slice_grad_pixel_kernel(const float* __restrict__ grid, const float* __restrict_
           for (int k = 0; k < 8; ++k) {
             const float v = __ldg(grid_b + off[k] + i * g.J + j);
             s = fmaf(w[k], v, s);
-            ds = fmaf(dw[k], v, ds);
+            ds = __fadd_rn(ds, __fmul_rn(dw[k], v));  // as the reference: no fusing (cancellation)
           }
           const float iv = (j < g.n_in) ? __ldg(inp + j) : 1.0f;
           dsum = fmaf(ds, iv, dsum);
@@ -112,7 +118,7 @@ slice_grad_pixel_kernel(const float* __restrict__ grid, const float* __restrict_
       for (int c = 0; c < gc; ++c) {
         float ds = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) ds = fmaf(dw[k], __ldg(grid_b + off[k] + c), ds);
+        for (int k = 0; k < 8; ++k) ds = __fadd_rn(ds, __fmul_rn(dw[k], __ldg(grid_b + off[k] + c)));
         gvjp = fmaf(ds, __ldg(ctp + c), gvjp);
       }
     }

@@ -39,6 +39,13 @@ def test_slice_apply_vjps_match_reference(case):
     out = hdrnet_ops.bilateral_slice_apply(g, u, i, ho)
     out.backward(cuda(ct))
     for got, ref, name in zip((g.grad, u.grad, i.grad), want, ("grid", "guide", "input")):
+        if name == "guide" and gd == 1:
+            # Degenerate: both depth corners clamp to cell 0, the two derivative terms cancel
+            # and the reference's own result is float32 rounding noise (|vjp| ~ 1e-7 of the
+            # terms).  Bound it against the scale of the TERMS instead of the cancelled sum.
+            scale = float(np.abs(grid).max() * np.abs(ct).max() * np.abs(inp).max() * gd * 4)
+            assert np.abs(got.cpu().numpy() - ref).max() <= 1e-6 * scale
+            continue
         assert_parity(got.cpu().numpy(), ref, rtol=2e-5, what=f"{case} {name} VJP")
 
 
