@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "hdrnet_b200.h"
 
@@ -266,6 +267,11 @@ fuse_predict_kernel(const float* __restrict__ local, const float* __restrict__ g
   }
 }
 
+// conv_tcgen05.cu: tensor-core (tcgen05 / TMEM, 3xTF32) implicit-GEMM form of the same layer.
+int launch_conv_tcgen05(const float* in, const float* w, const float* bias, float* out, int B,
+                        int H, int W, int Cin, int Cout, int k, int stride, int relu, int OH,
+                        int OW, int pad_t, int pad_l, cudaStream_t stream);
+
 static void same_pad(int size, int k, int s, int* out, int* before) {
   *out = (size + s - 1) / s;
   int total = (*out - 1) * s + k - size;
@@ -312,6 +318,15 @@ int hdrnet_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, f
   same_pad(H, k, stride, &a.OH, &a.pad_t);
   same_pad(W, k, stride, &a.OW, &a.pad_l);
   a.w_vec = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
+  {  // opt-in tensor-core path (see conv_tcgen05.cu); falls through when the shapes do not suit
+    const char* e = std::getenv("HDRNET_CONV_TCGEN05");
+    if (e && e[0] == '1') {
+      const int rc = launch_conv_tcgen05(in, w, bias, out, B, H, W, Cin, Cout, k, stride, relu,
+                                         a.OH, a.OW, a.pad_t, a.pad_l,
+                                         static_cast<cudaStream_t>(stream));
+      if (rc != HDRNET_E_UNSUPPORTED) return rc;
+    }
+  }
   const long long total_px = static_cast<long long>(B) * a.OH * a.OW;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -204,3 +204,43 @@ def test_run_py_identity_sample_plumbing(tmp_path):
     assert_parity(out.cpu().numpy(), ref, rtol=1e-4)
     ref8 = (255.0 * np.clip(ref, 0, 1)).astype(np.uint8)[0]
     assert np.abs(out8.astype(int) - ref8.astype(int)).max() <= 1
+
+
+# ---- tcgen05 (tensor-core, 3xTF32) form of the conv layers ------------------------------------
+@pytest.fixture
+def tcgen05_convs(monkeypatch):
+    monkeypatch.setenv("HDRNET_CONV_TCGEN05", "1")
+    yield
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,cin,cout,k,stride,relu,bias", [
+    (8, 16, 16, 64, 64, 3, 1, True, True),     # local conv1 (models.py:109-113)
+    (1, 16, 16, 64, 64, 3, 1, False, False),   # local conv2 at batch 1: 2 tiles
+    (2, 32, 32, 32, 64, 3, 2, True, True),     # splat conv4, stride 2, SAME pad 0/1
+    (3, 16, 16, 64, 96, 1, 1, False, True),    # 1x1 prediction, N = 96
+    (1, 9, 7, 8, 16, 3, 1, True, True),        # ragged tile (63 px), K = 72 (partial last chunk)
+])
+def test_conv2d_tcgen05_matches_oracle(tcgen05_convs, B, H, W, cin, cout, k, stride, relu, bias):
+    """3xTF32 on tcgen05 keeps float32-grade accuracy: 1e-5 of the tensor's range (a plain
+    TF32 product would be ~1e-3)."""
+    rng = np.random.RandomState(11)
+    x = rng.randn(B, H, W, cin).astype(np.float32)
+    w = (rng.randn(k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rng.randn(cout).astype(np.float32) if bias else None
+    ref = M.conv2d_same(x, w, stride) + (0 if b is None else b)
+    if relu:
+        ref = np.maximum(ref, 0)
+    got = models._conv(cuda(x), (cuda(w), None if b is None else cuda(b)), stride=stride, relu=relu)
+    torch.cuda.synchronize()
+    assert_parity(got.cpu().numpy(), ref.astype(np.float32), rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_coefficients_with_tcgen05_convs(tcgen05_convs):
+    p = PARAM_SETS["default"]
+    wts = M.make_weights(p, seed=3)
+    low = np.random.RandomState(4).rand(2, 256, 256, 3).astype(np.float32)
+    ref = M.coefficients(low, wts, p)
+    got = models.HDRNetCurves._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
+    assert_parity(got, ref, rtol=5e-5, what="coefficients via tcgen05 convs")
