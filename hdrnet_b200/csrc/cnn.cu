@@ -318,9 +318,13 @@ int hdrnet_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, f
   same_pad(H, k, stride, &a.OH, &a.pad_t);
   same_pad(W, k, stride, &a.OW, &a.pad_l);
   a.w_vec = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
-  {  // opt-in tensor-core path (see conv_tcgen05.cu); falls through when the shapes do not suit
+  {  // Tensor-core path (conv_tcgen05.cu).  Each 128-pixel tile runs a fixed-latency chunk loop,
+     // so it wins once there are about as many tiles as SMs (measured on B200: 2x faster at 128
+     // tiles, 3x slower at 2); HDRNET_CONV_TCGEN05=1 / =0 forces it on / off.
     const char* e = std::getenv("HDRNET_CONV_TCGEN05");
-    if (e && e[0] == '1') {
+    const long long tiles = (static_cast<long long>(B) * a.OH * a.OW + 127) / 128;
+    const bool want = e ? (e[0] == '1') : (tiles >= 96);
+    if (want) {
       const int rc = launch_conv_tcgen05(in, w, bias, out, B, H, W, Cin, Cout, k, stride, relu,
                                          a.OH, a.OW, a.pad_t, a.pad_l,
                                          static_cast<cudaStream_t>(stream));
