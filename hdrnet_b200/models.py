@@ -33,7 +33,7 @@ import torch
 from . import _lib, layers
 from .layers import bilateral_slice_apply
 
-__all__ = ["HDRNetCurves", "HDRNetPointwiseNNGuide", "set_weights", "load_weights",
+__all__ = ["HDRNetCurves", "HDRNetPointwiseNNGuide", "HDRNetGaussianPyrNN", "set_weights", "load_weights",
            "init_weights", "DEFAULT_PARAMS"]
 
 BN_EPS = 1e-3   # tf.contrib.layers.batch_norm default epsilon (hdrnet/layers.py:47-54)
@@ -118,9 +118,15 @@ def init_weights(params, seed: int = 0, model_name: str | None = None) -> dict:
     fc(f"{p}/global/fc3", 16 * cm * gd, c8)
     conv(f"{p}/local/conv1", 3, cin, c8, use_bn=bn)
     conv(f"{p}/local/conv2", 3, c8, c8, use_bias=False)
-    conv(f"{p}/prediction/conv1", 1, c8, gd * 3 * 4)
+    n_out = 9 if model_name == "HDRNetGaussianPyrNN" else 3
+    conv(f"{p}/prediction/conv1", 1, c8, gd * n_out * 4)
     g = "inference/guide"
-    if model_name == "HDRNetCurves":
+    if model_name == "HDRNetGaussianPyrNN":
+        nf = params["guide_complexity"]
+        for lvl in range(3):
+            conv(f"{g}/level_{lvl}/conv1", 1, 3, nf, use_bn=True)
+            conv(f"{g}/level_{lvl}/conv2", 1, nf, 1)
+    elif model_name == "HDRNetCurves":
         w[g + "/ccm"] = (np.identity(3) + rng.randn(1) * 1e-4).astype(np.float32)
         w[g + "/ccm_bias"] = np.zeros(3, np.float32)
         w[g + "/shifts"] = np.tile(np.linspace(0, 1, 16, endpoint=False, dtype=np.float32)
@@ -178,13 +184,17 @@ class _Prepared:
                 None if b is None else torch.from_numpy(np.ascontiguousarray(b)).to(device))
         g = "inference/guide"
         f32 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32))  # noqa: E731
-        if nn_guide:
-            w1, b1 = _fold(wts, g + "/conv1", True, False)
-            self.nn_w1 = f32(w1.reshape(3, -1))
-            self.nn_b1 = f32(b1)
-            self.nn_w2 = f32(np.asarray(wts[g + "/conv2/weights"]).reshape(-1))
-            self.nn_b2 = float(np.asarray(wts[g + "/conv2/biases"]).reshape(-1)[0])
-            self.nn_feats = int(self.nn_w1.shape[1])
+
+        def nn_params(scope):
+            w1, b1 = _fold(wts, scope + "/conv1", True, False)
+            w1 = f32(w1.reshape(3, -1))
+            return (w1, f32(b1), f32(np.asarray(wts[scope + "/conv2/weights"]).reshape(-1)),
+                    float(np.asarray(wts[scope + "/conv2/biases"]).reshape(-1)[0]), int(w1.shape[1]))
+
+        if nn_guide == "pyramid":     # HDRNetGaussianPyrNN: one pointwise NN per level
+            self.nn_levels = [nn_params(f"{g}/level_{lvl}") for lvl in range(3)]
+        elif nn_guide:
+            self.nn_w1, self.nn_b1, self.nn_w2, self.nn_b2, self.nn_feats = nn_params(g)
         else:
             self.ccm = f32(wts[g + "/ccm"])
             self.ccm_bias = f32(wts[g + "/ccm_bias"])
@@ -195,7 +205,7 @@ class _Prepared:
 
 
 def _prepare(wts, params, device, nn_guide) -> _Prepared:
-    key = (id(wts), str(device), bool(nn_guide), bool(params["batch_norm"]),
+    key = (id(wts), str(device), str(nn_guide), bool(params["batch_norm"]),
            params["net_input_size"], params["spatial_bin"])
     prep = _prepared.get(key)
     if prep is None:
@@ -372,6 +382,111 @@ class HDRNetPointwiseNNGuide(HDRNetCurves):
                 torch.cuda.current_stream(x.device).cuda_stream)
         _lib.check(rc, "guide_nn")
         return guide
+
+
+def _resize(x: torch.Tensor, oh: int, ow: int, add: torch.Tensor | None = None) -> torch.Tensor:
+    """tf.image.resize_images(x, [oh, ow], BILINEAR, align_corners=True) (+ fused add)."""
+    B, H, W, C = x.shape
+    out = torch.empty((B, oh, ow, C), dtype=torch.float32, device=x.device)
+    rc = _lib.load().hdrnet_resize_bilinear_f32(
+        x.data_ptr(), 0 if add is None else add.data_ptr(), out.data_ptr(), B, H, W, C, oh, ow,
+        torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "resize_bilinear")
+    return out
+
+
+class HDRNetGaussianPyrNN(HDRNetPointwiseNNGuide):
+    """Replace input to the affine model by a pyramid (hdrnet/models.py:213-289): 3-level
+    bilinear (align_corners) pyramid of the full-res image, one pointwise-NN guide per level,
+    one slice-apply per level with its own 3 of the 9 output rows of the coefficient grid,
+    coarse-to-fine upsample-and-add.  The reference file is Python-2 only here
+    (`reversed(zip(...))`, :278); the semantics restated: the COARSEST level uses output rows
+    0..2, the finest rows 6..8."""
+
+    _nn_guide = "pyramid"
+
+    @classmethod
+    def n_scales(cls):
+        return 3
+
+    @classmethod
+    def n_out(cls):
+        return 3 * cls.n_scales()
+
+    @classmethod
+    def n_in(cls):
+        return 3 + 1
+
+    @classmethod
+    def inference(cls, lowres_input, fullres_input, params, is_training=False):
+        if is_training:
+            raise NotImplementedError("hdrnet_b200 implements the inference path only")
+        fullres_input = _check_input(fullres_input, "fullres_input")
+        coeffs = cls._coefficients(lowres_input, params, is_training)       # [B,gh,gw,gd,9,4]
+        with torch.cuda.device(fullres_input.device):
+            multiscale = cls._multiscale_input(fullres_input)
+            guides = cls._guide(multiscale, params, is_training) if params.get("debug") else None
+            out = cls._output(multiscale, guides, coeffs, params)
+        if params.get("debug"):
+            cls.last_debug = {"bilateral_coefficients": coeffs, "guide": guides,
+                              "multiscale": multiscale, "output": out}
+        return out
+
+    @classmethod
+    def _multiscale_input(cls, fullres_input):
+        """models.py:249-262: each level is the previous one resized to floor(size / 2)."""
+        lvls = [fullres_input]
+        h, w = fullres_input.shape[1:3]
+        for _ in range(cls.n_scales() - 1):
+            h, w = h // 2, w // 2
+            lvls.append(_resize(lvls[-1], h, w))
+        return lvls
+
+    @classmethod
+    def _guide(cls, multiscale, params, is_training=False):
+        """models.py:264-272: HDRNetPointwiseNNGuide._guide per level (scope level_{il})."""
+        prep = _prepare(_resolve_weights(params), params, multiscale[0].device, "pyramid")
+        lib = _lib.load()
+        guides = []
+        for lvl, (w1, b1, w2, b2, feats) in zip(multiscale, prep.nn_levels):
+            B, H, W, _ = lvl.shape
+            g = torch.empty((B, H, W), dtype=torch.float32, device=lvl.device)
+            rc = lib.hdrnet_guide_nn_f32(lvl.data_ptr(), g.data_ptr(), B * H * W, _hp(w1), _hp(b1),
+                                         _hp(w2), b2, feats,
+                                         torch.cuda.current_stream(lvl.device).cuda_stream)
+            _lib.check(rc, "guide_nn")
+            guides.append(g)
+        return guides
+
+    @classmethod
+    def _output(cls, lvls, guide_lvls, coeffs, params=None):
+        """models.py:274-289, coarse to fine.  With guide_lvls=None (the fast path) each level's
+        guide is computed inside its slice-apply kernel."""
+        prep = _prepare(_resolve_weights(params), params, lvls[0].device, "pyramid") \
+            if guide_lvls is None else None
+        lib = _lib.load()
+        B, gh, gw, gd = coeffs.shape[:4]
+        current = None
+        for il in range(cls.n_scales()):
+            src = cls.n_scales() - 1 - il                       # reversed(zip(lvls, guides))
+            lvl = lvls[src]
+            c = coeffs[:, :, :, :, il * 3:(il + 1) * 3, :].contiguous().reshape(B, gh, gw, gd, 12)
+            _, H, W, _ = lvl.shape
+            if guide_lvls is not None:
+                out_lvl = bilateral_slice_apply(c, guide_lvls[src], lvl, has_offset=True)
+            else:
+                w1, b1, w2, b2, feats = prep.nn_levels[src]
+                out_lvl = torch.empty_like(lvl)
+                need_guide = (W % 4 != 0) or W < 128
+                scratch = torch.empty((B, H, W), dtype=torch.float32, device=lvl.device) \
+                    if need_guide else None
+                rc = lib.hdrnet_slice_apply_nn_f32(
+                    c.data_ptr(), lvl.data_ptr(), out_lvl.data_ptr(),
+                    0 if scratch is None else scratch.data_ptr(), B, H, W, gh, gw, gd, _hp(w1),
+                    _hp(b1), _hp(w2), b2, feats, torch.cuda.current_stream(lvl.device).cuda_stream)
+                _lib.check(rc, "BilateralSliceApply(fused NN guide)")
+            current = out_lvl if il == 0 else _resize(current, H, W, add=out_lvl)
+        return current
 
 
 del layers  # imported for the side effect of the public surface only

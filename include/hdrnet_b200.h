@@ -229,6 +229,14 @@ HDRNET_API int hdrnet_fuse_predict_f32(const float* local, const float* global_f
                                        void* stream);
 
 /*
+ * Bilinear resize, align_corners=True, NHWC, with an optional fused add (`add` has the output's
+ * shape, or NULL).  Replaces tf.image.resize_images(BILINEAR, align_corners=True) in
+ * HDRNetGaussianPyrNN._multiscale_input / ._output (hdrnet/models.py:249-289).
+ */
+HDRNET_API int hdrnet_resize_bilinear_f32(const float* in, const float* add, float* out, int B,
+                                          int H, int W, int C, int OH, int OW, void* stream);
+
+/*
  * Host-buffer path (what a CPU-tensor caller of the reference op gets: TF copies feeds to
  * the GPU and fetches back, hdrnet/bin/run.py:185).  A context owns device staging buffers
  * and streams; the call splits the batch into row bands, and pipelines H2D copy -> kernel

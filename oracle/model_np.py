@@ -91,7 +91,7 @@ def fc(x, wts, scope, use_bias=True, batch_norm=False, relu=True):
 
 
 # ---- model graphs ----------------------------------------------------------------------------
-def coefficients(lowres, wts, params, prefix="inference/coefficients"):
+def coefficients(lowres, wts, params, prefix="inference/coefficients", n_out=N_OUT):
     """HDRNetCurves._coefficients, hdrnet/models.py:62-142.  lowres [B,S,S,3] ->
     [B, sb, sb, gd, n_out, n_in] (sb = spatial_bin)."""
     gd = params["luma_bins"]
@@ -115,7 +115,7 @@ def coefficients(lowres, wts, params, prefix="inference/coefficients"):
     pred = conv(fusion, wts, f"{prefix}/prediction/conv1", relu=False)        # 1x1, :129-132
     # unroll_grid, :134-139: channel (j*n_out + i)*gd + z -> [b, y, x, z, i, j]
     B, sh, sw, _ = pred.shape
-    return np.ascontiguousarray(pred.reshape(B, sh, sw, N_IN, N_OUT, gd).transpose(0, 1, 2, 5, 4, 3))
+    return np.ascontiguousarray(pred.reshape(B, sh, sw, N_IN, n_out, gd).transpose(0, 1, 2, 5, 4, 3))
 
 
 def guide_curves(fullres, wts, prefix="inference/guide"):
@@ -141,6 +141,47 @@ def guide_nn(fullres, wts, prefix="inference/guide"):
 
 
 # ---- synthetic weights (local_laplacian_sample is not in the tree) ---------------------------
+def resize_bilinear_ac(x, oh, ow):
+    """tf.image.resize_images(..., BILINEAR, align_corners=True), TF1 legacy kernel semantics."""
+    x = np.asarray(x, np.float64)
+    B, H, W, C = x.shape
+    sy = (H - 1) / (oh - 1) if oh > 1 else 0.0
+    sx = (W - 1) / (ow - 1) if ow > 1 else 0.0
+    ys = np.arange(oh) * np.float32(sy)
+    xs = np.arange(ow) * np.float32(sx)
+    ys = ys.astype(np.float32).astype(np.float64)
+    xs = xs.astype(np.float32).astype(np.float64)
+    y0 = np.floor(ys).astype(int); x0 = np.floor(xs).astype(int)
+    y1 = np.minimum(y0 + 1, H - 1); x1 = np.minimum(x0 + 1, W - 1)
+    fy = (ys - y0)[None, :, None, None]; fx = (xs - x0)[None, None, :, None]
+    top = x[:, y0][:, :, x0] + (x[:, y0][:, :, x1] - x[:, y0][:, :, x0]) * fx
+    bot = x[:, y1][:, :, x0] + (x[:, y1][:, :, x1] - x[:, y1][:, :, x0]) * fx
+    return (top + (bot - top) * fy).astype(np.float32)
+
+
+def gaussian_pyr_inference(lowres, fullres, wts, params, slice_apply):
+    """HDRNetGaussianPyrNN.inference, hdrnet/models.py:213-289 (Python-2 `reversed(zip())`
+    restated: coarsest level first, using output rows 0..2)."""
+    coeffs = coefficients(lowres, wts, params, n_out=9)           # [B,gh,gw,gd,9,4]
+    lvls = [np.asarray(fullres, np.float32)]
+    h, w = lvls[0].shape[1:3]
+    for _ in range(2):
+        h, w = h // 2, w // 2
+        lvls.append(resize_bilinear_ac(lvls[-1], h, w))
+    guides = [guide_nn(lvl, wts, f"inference/guide/level_{i}") for i, lvl in enumerate(lvls)]
+    B, gh, gw, gd = coeffs.shape[:4]
+    current = None
+    for il in range(3):
+        src = 2 - il
+        c = np.ascontiguousarray(coeffs[:, :, :, :, il * 3:(il + 1) * 3, :]).reshape(B, gh, gw, gd, 12)
+        out_lvl = slice_apply(c, guides[src], lvls[src], True)
+        if il == 0:
+            current = out_lvl
+        else:
+            current = resize_bilinear_ac(current, out_lvl.shape[1], out_lvl.shape[2]) + out_lvl
+    return current.astype(np.float32), coeffs, guides
+
+
 def make_weights(params, seed=0, model_name=None, trained_like=True):
     """Seeded random weights with the reference's variable names and shapes.
     ``trained_like`` perturbs the guide parameters away from their identity init so the test
@@ -188,10 +229,16 @@ def make_weights(params, seed=0, model_name=None, trained_like=True):
     add_fc(f"{p}/global/fc3", 16 * cm * gd, c8)
     add_conv(f"{p}/local/conv1", 3, splat_c, c8, use_bn=bn)
     add_conv(f"{p}/local/conv2", 3, c8, c8, use_bias=False)
-    add_conv(f"{p}/prediction/conv1", 1, c8, gd * N_OUT * N_IN)
+    n_out = 9 if model_name == "HDRNetGaussianPyrNN" else N_OUT
+    add_conv(f"{p}/prediction/conv1", 1, c8, gd * n_out * N_IN)
 
     g = "inference/guide"
-    if model_name == "HDRNetCurves":
+    if model_name == "HDRNetGaussianPyrNN":
+        nf = params["guide_complexity"]
+        for lvl in range(3):
+            add_conv(f"{g}/level_{lvl}/conv1", 1, 3, nf, use_bn=True)
+            add_conv(f"{g}/level_{lvl}/conv2", 1, nf, 1)
+    elif model_name == "HDRNetCurves":
         npts = 16
         ccm = np.identity(3, dtype=np.float32)
         shifts = np.tile(np.linspace(0, 1, npts, endpoint=False, dtype=np.float32)[None, None, None, :],

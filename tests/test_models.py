@@ -21,6 +21,8 @@ PARAM_SETS = {
     "cm2": dict(M.DEFAULT_PARAMS, channel_multiplier=2, net_input_size=128, spatial_bin=16),
     "nn_guide": dict(M.DEFAULT_PARAMS, model_name="HDRNetPointwiseNNGuide", batch_norm=True,
                      net_input_size=128, spatial_bin=16),
+    "pyramid": dict(M.DEFAULT_PARAMS, model_name="HDRNetGaussianPyrNN", net_input_size=128,
+                    spatial_bin=16),
 }
 
 
@@ -40,6 +42,7 @@ def test_init_weights_has_reference_variable_names_and_shapes(name):
 
 
 def test_model_surface_mirrors_reference():
+    assert models.HDRNetGaussianPyrNN.n_out() == 9 and models.HDRNetGaussianPyrNN.n_scales() == 3
     for cls in (models.HDRNetCurves, models.HDRNetPointwiseNNGuide):     # models.py:23-27
         assert cls.n_out() == 3 and cls.n_in() == 4
         for m in ("inference", "_coefficients", "_guide", "_output"):
@@ -120,10 +123,10 @@ def test_coefficients_match_oracle(name):
     rng = np.random.RandomState(4)
     S = p["net_input_size"]
     low = rng.rand(3, S, S, 3).astype(np.float32)
-    ref = M.coefficients(low, wts, p)
     cls = getattr(models, p["model_name"])
+    ref = M.coefficients(low, wts, p, n_out=cls.n_out())
     got = cls._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
-    assert got.shape == ref.shape == (3, p["spatial_bin"], p["spatial_bin"], p["luma_bins"], 3, 4)
+    assert got.shape == ref.shape == (3, p["spatial_bin"], p["spatial_bin"], p["luma_bins"], cls.n_out(), 4)
     # 9-11 float32 layers deep; the oracle rounds each activation to float32 once
     assert_parity(got, ref, rtol=2e-5, what=name)
 
@@ -244,3 +247,38 @@ def test_coefficients_with_tcgen05_convs(tcgen05_convs):
     ref = M.coefficients(low, wts, p)
     got = models.HDRNetCurves._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
     assert_parity(got, ref, rtol=5e-5, what="coefficients via tcgen05 convs")
+
+
+# ---- HDRNetGaussianPyrNN (row f-2) -------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,oh,ow", [(2, 64, 96, 32, 48), (1, 33, 50, 16, 25), (1, 16, 24, 33, 50),
+                                         (1, 5, 7, 1, 1)])
+def test_resize_bilinear_align_corners(B, H, W, oh, ow):
+    x = np.random.RandomState(0).rand(B, H, W, 3).astype(np.float32)
+    got = models._resize(cuda(x), oh, ow).cpu().numpy()
+    assert np.abs(got - M.resize_bilinear_ac(x, oh, ow)).max() < 2e-6
+    add = np.random.RandomState(1).rand(B, oh, ow, 3).astype(np.float32)
+    got = models._resize(cuda(x), oh, ow, add=cuda(add)).cpu().numpy()
+    assert np.abs(got - (M.resize_bilinear_ac(x, oh, ow) + add)).max() < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W", [(256, 512), (70, 90)])
+def test_gaussian_pyramid_model_matches_oracle(H, W):
+    """models.py:213-289: pyramid, per-level NN guides, per-level slice-apply on rows
+    il*3..il*3+2 of the 9-row grid (coarsest first), upsample-add."""
+    p = PARAM_SETS["pyramid"]
+    wts = M.make_weights(p, seed=12)
+    rng = np.random.RandomState(13)
+    low = rng.rand(2, p["net_input_size"], p["net_input_size"], 3).astype(np.float32)
+    full = rng.rand(2, H, W, 3).astype(np.float32)
+    ref, ref_coeffs, ref_guides = M.gaussian_pyr_inference(low, full, wts, p,
+                                                           oracle.best().bilateral_slice_apply)
+    got = models.HDRNetGaussianPyrNN.inference(cuda(low), cuda(full), dict(p, weights=wts, debug=True))
+    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what="pyramid output")
+    dbg = models.HDRNetGaussianPyrNN.last_debug
+    assert_parity(dbg["bilateral_coefficients"].cpu().numpy(), ref_coeffs, rtol=2e-5)
+    for g, r in zip(dbg["guide"], ref_guides):
+        assert np.abs(g.cpu().numpy() - r).max() < 2e-6
+    fast = models.HDRNetGaussianPyrNN.inference(cuda(low), cuda(full), dict(p, weights=wts))
+    assert_parity(fast.cpu().numpy(), ref, rtol=1e-4, what="pyramid output (guide-fused)")
