@@ -133,6 +133,8 @@ constexpr int kTmaThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kGc = 12;
 
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
 struct TmaPlan {
   int ctas;
   int stages;
@@ -427,6 +429,204 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
   if (tid == 0) tma_store_wait_all<0>();
 }
 
+
+// =========================================================================================
+// Un-fused slice, persistent TMA row kernel (gc = 12, W % 4 == 0): out[b,y,x,0..11].
+// =========================================================================================
+// Same organisation as the fused kernel, but the op is WRITE-bound (4 B in, 48 B out per pixel):
+// the guide arrives through a deep ring of small TMA copies, each thread blends the 4 slab
+// corners of its pixels (24 FFMA2 per pixel, no apply) and writes the 12 coefficients into one of
+// kSliceOutBufs shared-memory output tiles that leave by TMA bulk stores; an mbarrier per
+// output tile (armed by the store-issuing thread after cp.async.bulk.wait_group.read) gates
+// its reuse.  Thread t owns pixels t and t + 256 of a 512-pixel segment: 48-byte stride between
+// lanes keeps the 3 x STS.128 per pixel conflict-free.
+constexpr int kSliceThreads = 256;
+constexpr int kSliceSegPx = 512;
+constexpr int kSliceOutBufs = 3;
+constexpr int kSliceGuideStages = 8;
+
+struct SlicePlan {
+  int ctas, nseg, seg_px, row_floats, smem_bytes;
+  int off_raw, off_slab, off_guide, off_out, out_bytes;
+};
+
+struct SliceArgs {
+  const float* grid;
+  const float* guide;
+  float* out;
+  SliceGeom g;
+  SlicePlan p;
+};
+
+__global__ void __launch_bounds__(kSliceThreads, 2)
+slice_rows_tma_kernel(const SliceArgs args) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SliceGeom& g = args.g;
+  const SlicePlan& pl = args.p;
+  const int tid = threadIdx.x;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kSliceGuideStages]
+  uint64_t* out_free = full + kSliceGuideStages;         // [kSliceOutBufs]
+  uint64_t* gridbar = out_free + kSliceOutBufs;          // [1]
+  float* raw0 = reinterpret_cast<float*>(smem + pl.off_raw);
+  float* raw1 = raw0 + pl.row_floats;
+  float* slab = reinterpret_cast<float*>(smem + pl.off_slab);
+  float* guide_ring = reinterpret_cast<float*>(smem + pl.off_guide);  // [stages][seg_px]
+  unsigned char* out_base = smem + pl.off_out;
+
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
+  const int nitems = static_cast<int>(r_end - r_begin) * pl.nseg;
+  if (nitems <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < kSliceGuideStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < kSliceOutBufs; ++s) mbar_init(&out_free[s], 1);
+    mbar_init(gridbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto item_span = [&](int item, long long& row, int& x0, int& npx) {
+    const int rr = item / pl.nseg;
+    const int seg = item - rr * pl.nseg;
+    row = r_begin + rr;
+    x0 = seg * pl.seg_px;
+    npx = min(pl.seg_px, g.W - x0);
+  };
+  auto issue_load = [&](int item) {  // thread 0 only
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+    const int s = item % kSliceGuideStages;
+    mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * 4u);
+    tma_load_1d(guide_ring + static_cast<size_t>(s) * pl.seg_px,
+                args.guide + static_cast<size_t>(row) * g.W + x0, static_cast<uint32_t>(npx) * 4u,
+                &full[s]);
+  };
+  if (tid == 0) {
+    // every output tile starts free: one arrival completes phase 0 of its barrier
+    for (int s = 0; s < kSliceOutBufs; ++s)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&out_free[s])) : "memory");
+    const int pre = min(kSliceGuideStages - 1, nitems);
+    for (int it = 0; it < pre; ++it) issue_load(it);
+  }
+
+  const float gd_f = static_cast<float>(g.gd);
+  const int x_stride = g.gd * kGc;
+  int cur_b = -1, cur_gy0 = INT_MIN;
+  uint32_t grid_phase = 0;
+
+  for (int item = 0; item < nitems; ++item) {
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+
+    if (x0 == 0) {  // new image row: grid rows + y pre-blend, as in the fused kernel
+      const int b = static_cast<int>(row / g.rows);
+      const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
+      const Axis ay = spatial_axis(y, g.scale_y);
+      if (b != cur_b || ay.i0 != cur_gy0) {
+        if (tid == 0) {
+          const int gy0c = clampi(ay.i0, 0, g.gh - 1);
+          const int gy1c = clampi(ay.i0 + 1, 0, g.gh - 1);
+          const float* gb = args.grid + static_cast<size_t>(b) * g.gh * pl.row_floats;
+          const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+          mbar_expect_tx(gridbar, 2u * bytes);
+          tma_load_1d(raw0, gb + static_cast<size_t>(gy0c) * pl.row_floats, bytes, gridbar);
+          tma_load_1d(raw1, gb + static_cast<size_t>(gy1c) * pl.row_floats, bytes, gridbar);
+        }
+        mbar_wait(gridbar, grid_phase);
+        grid_phase ^= 1u;
+        cur_b = b;
+        cur_gy0 = ay.i0;
+      }
+      const float wy1 = ay.f, wy0 = 1.0f - ay.f;
+      const float4* a4 = reinterpret_cast<const float4*>(raw0);
+      const float4* b4 = reinterpret_cast<const float4*>(raw1);
+      float4* s4 = reinterpret_cast<float4*>(slab);
+      for (int e = tid; e < pl.row_floats / 4; e += kSliceThreads) s4[e] = lerp4(wy0, a4[e], wy1, b4[e]);
+      __syncthreads();
+    }
+
+    const int s = item % kSliceGuideStages;
+    const int ob = item % kSliceOutBufs;
+    mbar_wait(&full[s], static_cast<uint32_t>(item / kSliceGuideStages) & 1u);
+    mbar_wait(&out_free[ob], static_cast<uint32_t>(item / kSliceOutBufs) & 1u);
+    const float* gseg = guide_ring + static_cast<size_t>(s) * pl.seg_px;
+    float* otile = reinterpret_cast<float*>(out_base + static_cast<size_t>(ob) * pl.out_bytes);
+#pragma unroll
+    for (int h = 0; h < kSliceSegPx / kSliceThreads; ++h) {
+      const int px = tid + h * kSliceThreads;
+      if (px < npx) {
+        const Axis ax = spatial_axis(x0 + px, g.scale_x);
+        const Axis az = range_axis(gseg[px], gd_f);
+        const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride;
+        const int xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
+        const int zo0 = clampi(az.i0, 0, g.gd - 1) * kGc;
+        const int zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * kGc;
+        float wz0, wz1;
+        smoothed_weights(az.f, wz0, wz1);
+        const float wx1 = ax.f, wx0 = 1.0f - ax.f;
+        const unsigned long long W00 = pack2(wx0 * wz0, wx0 * wz0), W01 = pack2(wx0 * wz1, wx0 * wz1);
+        const unsigned long long W10 = pack2(wx1 * wz0, wx1 * wz0), W11 = pack2(wx1 * wz1, wx1 * wz1);
+        const ulonglong2* v00 = reinterpret_cast<const ulonglong2*>(slab + xo0 + zo0);
+        const ulonglong2* v01 = reinterpret_cast<const ulonglong2*>(slab + xo0 + zo1);
+        const ulonglong2* v10 = reinterpret_cast<const ulonglong2*>(slab + xo1 + zo0);
+        const ulonglong2* v11 = reinterpret_cast<const ulonglong2*>(slab + xo1 + zo1);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(otile + static_cast<size_t>(px) * kGc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const ulonglong2 a = v00[k], bq = v01[k], c = v10[k], d = v11[k];
+          ulonglong2 r;
+          r.x = fma2(W11, d.x, fma2(W10, c.x, fma2(W01, bq.x, mul2(W00, a.x))));
+          r.y = fma2(W11, d.y, fma2(W10, c.y, fma2(W01, bq.y, mul2(W00, a.y))));
+          dst[k] = r;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (tid == 0) {
+      const size_t pix = static_cast<size_t>(row) * g.W + x0;
+      tma_store_1d(args.out + pix * kGc, otile, static_cast<uint32_t>(npx) * (kGc * 4u));
+      tma_store_commit();
+      // the tile the NEXT item writes is free once all but the newest (kSliceOutBufs-1) stores
+      // have finished reading shared memory
+      tma_store_wait_read<kSliceOutBufs - 1>();
+      if (item + 1 >= kSliceOutBufs)  // first uses were released by the initial arrivals
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
+                         smem_u32(&out_free[(item + 1) % kSliceOutBufs]))
+                     : "memory");
+      const int nxt = item + kSliceGuideStages - 1;
+      if (nxt < nitems) issue_load(nxt);
+    }
+  }
+  if (tid == 0) tma_store_wait_all<0>();
+}
+
+static bool make_slice_plan(const SliceGeom& g, int max_smem, int sms, SlicePlan* out) {
+  if (g.W < 4 || (g.W % 4) != 0) return false;
+  SlicePlan p;
+  p.row_floats = g.gw * g.gd * kGc;
+  const int quads = g.W / 4;
+  const int max_quads = kSliceSegPx / 4;
+  p.nseg = (quads + max_quads - 1) / max_quads;
+  p.seg_px = 4 * ((quads + p.nseg - 1) / p.nseg);
+  p.out_bytes = round_up(p.seg_px * kGc * 4, 128);
+  p.off_raw = 128;  // (8 + 3 + 1) barriers = 96 bytes
+  p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
+  p.off_guide = p.off_slab + round_up(p.row_floats * 4, 128);
+  p.off_out = p.off_guide + round_up(kSliceGuideStages * p.seg_px * 4, 128);
+  p.smem_bytes = p.off_out + kSliceOutBufs * p.out_bytes;
+  if (p.smem_bytes > max_smem) return false;
+  const int resident = (p.smem_bytes <= (max_smem + 1024) / 2 - 1024) ? 2 : 1;
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  p.ctas = static_cast<int>(std::min<long long>(total_rows, static_cast<long long>(sms) * resident));
+  *out = p;
+  return true;
+}
+
 // Pre-pass of the texture-assisted form: yslab[r] = (1 - fy) * G[b][gy0] + fy * G[b][gy1] for
 // every buffer row r = (b, y) -- the same y pre-blend the row kernel does in shared memory,
 // materialised once (gw*gd*48 B per image row: +11 % HBM traffic at 4K / 16x16x8).
@@ -464,7 +664,6 @@ static int device_max_smem_optin() {
   return v;
 }
 
-static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Returns false when the TMA kernel cannot run these shapes.
 static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out) {
@@ -687,11 +886,29 @@ int launch_slice(const float* grid, const float* guide, float* out, int B, int H
   if (npix == 0) return HDRNET_OK;
   if (!grid || !guide || !out) return HDRNET_E_NULL_POINTER;
   if (static_cast<long long>(gh) * gw * gd * gc > INT_MAX) return HDRNET_E_TOO_LARGE;
-  if (variant == HDRNET_VARIANT_TMA) return HDRNET_E_UNSUPPORTED;
-  if (variant != HDRNET_VARIANT_AUTO && variant != HDRNET_VARIANT_GENERIC) return HDRNET_E_UNSUPPORTED;
+  if (variant != HDRNET_VARIANT_AUTO && variant != HDRNET_VARIANT_GENERIC &&
+      variant != HDRNET_VARIANT_TMA)
+    return HDRNET_E_UNSUPPORTED;
   const SliceGeom g = make_geom(B, H, W, rows, y_off, gh, gw, gd);
-  slice_generic_kernel<false><<<generic_grid(npix, device_sm_count()), 256, 0, stream>>>(
-      grid, guide, nullptr, out, g, 0, 0, gc, npix);
+  const int sms = device_sm_count();
+  SlicePlan plan;
+  const bool tma_shape = gc == kGc && make_slice_plan(g, device_max_smem_optin(), sms, &plan) &&
+                         aligned16(grid) && aligned16(guide) && aligned16(out);
+  if (variant == HDRNET_VARIANT_TMA && !tma_shape) return HDRNET_E_UNSUPPORTED;
+  const bool use_tma = tma_shape && (variant == HDRNET_VARIANT_TMA ||
+                                     (variant == HDRNET_VARIANT_AUTO && W >= 128));
+  if (use_tma) {
+    cudaError_t e = cudaFuncSetAttribute(slice_rows_tma_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         plan.smem_bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    SliceArgs a;
+    a.grid = grid; a.guide = guide; a.out = out; a.g = g; a.p = plan;
+    slice_rows_tma_kernel<<<plan.ctas, kSliceThreads, plan.smem_bytes, stream>>>(a);
+  } else {
+    slice_generic_kernel<false><<<generic_grid(npix, sms), 256, 0, stream>>>(
+        grid, guide, nullptr, out, g, 0, 0, gc, npix);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

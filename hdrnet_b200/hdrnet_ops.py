@@ -142,9 +142,10 @@ def _wants_grad(*ts) -> bool:
     return torch.is_grad_enabled() and any(t.requires_grad for t in ts)
 
 
-def bilateral_slice(grid: torch.Tensor, guide: torch.Tensor, name=None) -> torch.Tensor:
+def bilateral_slice(grid: torch.Tensor, guide: torch.Tensor, name=None, *,
+                    variant: int = _lib.VARIANT_AUTO) -> torch.Tensor:
     """Slices a bilateral grid with a guide image (reference op ``BilateralSlice``,
-    hdrnet/ops/bilateral_slice_op.cc:120-174, :274-290)."""
+    hdrnet/ops/bilateral_slice_op.cc:120-174, :274-290).  ``variant`` forces a kernel for tests."""
     del name
     lib = _lib.load()
     grid = _f32c(grid, "grid")
@@ -164,8 +165,8 @@ def bilateral_slice(grid: torch.Tensor, guide: torch.Tensor, name=None) -> torch
     out = torch.empty((B, H, W, gc), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.hdrnet_slice_f32(grid.data_ptr(), guide.data_ptr(), out.data_ptr(), B, H, W, gh,
-                                  gw, gd, gc, stream)
+        rc = lib.hdrnet_slice_f32_variant(grid.data_ptr(), guide.data_ptr(), out.data_ptr(), B, H, W,
+                                          gh, gw, gd, gc, int(variant), stream)
     _lib.check(rc, "BilateralSlice")
     return out
 

@@ -28,8 +28,8 @@ def run_apply(grid, guide, inp, has_offset, variant="auto"):
     return out.cpu().numpy()
 
 
-def run_slice(grid, guide):
-    out = hdrnet_ops.bilateral_slice(cuda(grid), cuda(guide))
+def run_slice(grid, guide, variant="auto"):
+    out = hdrnet_ops.bilateral_slice(cuda(grid), cuda(guide), variant=VARIANTS[variant])
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -120,13 +120,27 @@ def test_slice_apply_general_channels(n_in, n_out, has_offset):
     assert_parity(got, expected)
 
 
-@pytest.mark.parametrize("shape", SHAPES[:6], ids=lambda s: "x".join(map(str, s)))
-def test_slice_matches_oracle(shape):
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("variant", ["auto", "generic", "tma"])
+def test_slice_matches_oracle(shape, variant):
     B, H, W, gh, gw, gd = shape
+    if variant == "tma" and W % 4 != 0:
+        pytest.skip("TMA kernel needs W % 4 == 0")
     rng = np.random.RandomState(3)
     grid = rng.randn(B, gh, gw, gd, 12).astype(np.float32)
     guide = rng.rand(B, H, W).astype(np.float32)
+    assert_parity(run_slice(grid, guide, variant), checker().bilateral_slice(grid, guide),
+                  what=f"{shape} [{variant}]")
+
+
+def test_slice_other_channel_counts_use_generic_kernel():
+    """hdrnet_ops_jax_tf2_test.py:28-34 uses gc = 2; the TMA kernel is specialised for gc = 12."""
+    rng = np.random.RandomState(4)
+    grid = rng.randn(2, 16, 12, 8, 2).astype(np.float32)
+    guide = rng.rand(2, 48, 640).astype(np.float32)
     assert_parity(run_slice(grid, guide), checker().bilateral_slice(grid, guide))
+    with pytest.raises(ValueError):
+        run_slice(grid, guide, "tma")
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))

@@ -49,6 +49,18 @@ def slice_apply_case(name, B, H, W, gh, gw, gd, iters=50, variant=_lib.VARIANT_A
                       "frac_of_measured_hbm": round(gbs / PEAK, 4)}), flush=True)
 
 
+def slice_case(name, B, H, W, gh, gw, gd, iters=30, variant=_lib.VARIANT_AUTO):
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    grid = torch.rand(B, gh, gw, gd, 12, device="cuda", generator=gen)
+    guide = torch.rand(B, H, W, device="cuda", generator=gen)
+    ms = timeit(lambda: hdrnet_ops.bilateral_slice(grid, guide, variant=variant), iters=iters)
+    npx = B * H * W
+    gbs = (npx * 52 + grid.numel() * 4) / ms / 1e6
+    print(json.dumps({"case": name, "shape": [B, H, W], "grid": [gh, gw, gd], "ms": round(ms, 4),
+                      "MP/s": round(npx / ms / 1e3, 1), "GB/s_at_52B_per_px": round(gbs, 1),
+                      "frac_of_measured_hbm": round(gbs / PEAK, 4)}), flush=True)
+
+
 def model_case(name, model_name, B, H, W, iters=30):
     p = dict(models.DEFAULT_PARAMS, model_name=model_name)
     wts = models.init_weights(p, seed=0, model_name=model_name)
@@ -98,6 +110,9 @@ def main():
     slice_apply_case("C4 12MP x8 (one GPU's share of batch 64)", 8, 3024, 4032, 16, 16, 8, iters=20)
     for gh, gw, gd in [(8, 8, 4), (16, 16, 4), (16, 16, 8), (32, 32, 8), (32, 32, 16)]:
         slice_apply_case(f"C5 sweep 4K x8 grid {gh}x{gw}x{gd}", 8, 2160, 3840, gh, gw, gd, iters=20)
+    slice_case("un-fused bilateral_slice 4K x8 (TMA kernel)", 8, 2160, 3840, 16, 16, 8)
+    slice_case("un-fused bilateral_slice 4K x8 (generic kernel)", 8, 2160, 3840, 16, 16, 8, iters=5,
+               variant=_lib.VARIANT_GENERIC)
     model_case("C2 model 1080p x1", "HDRNetCurves", 1, 1080, 1920)
     model_case("model 4K x8", "HDRNetCurves", 8, 2160, 3840, iters=10)
     if not quick:
