@@ -77,6 +77,14 @@ int pack_curves_params(CurvesGuideParams* p, const float* ccm, const float* ccm_
   std::memcpy(p->slopes, slopes, sizeof(p->slopes));
   std::memcpy(p->mix, mix, sizeof(p->mix));
   p->mix_bias = mix_bias;
+  double folded = mix_bias;
+  for (int c = 0; c < 3; ++c) {
+    double cs = 0.0;
+    for (int k = 0; k < kCurvePts; ++k)
+      cs += static_cast<double>(slopes[c * kCurvePts + k]) * static_cast<double>(shifts[c * kCurvePts + k]);
+    folded -= static_cast<double>(mix[c]) * cs;
+  }
+  p->folded_bias = static_cast<float>(folded);
   return HDRNET_OK;
 }
 

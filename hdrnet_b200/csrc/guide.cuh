@@ -7,6 +7,8 @@
 
 #include <cuda_runtime.h>
 
+#include "common.cuh"
+
 namespace hdrnet_b200 {
 
 constexpr int kCurvePts = 16;     // hdrnet/models.py:147 (npts, hard-coded in the reference)
@@ -22,6 +24,10 @@ struct CurvesGuideParams {
   float slopes[3][kCurvePts];
   float mix[3];
   float mix_bias;
+  // Folded by pack_curves_params():  slope * relu(t - s) = slope * max(t, s) - slope * s, so
+  //   sum_c mix_c * u_c + mix_bias = sum_c mix_c * sum_k slope_ck * max(t_c, s_ck) + folded_bias
+  // with folded_bias = mix_bias - sum_c mix_c * sum_k slope_ck * s_ck (computed in double).
+  float folded_bias;
 };
 
 // HDRNetPointwiseNNGuide._guide (hdrnet/models.py:199-210) with the batch norm of conv1
@@ -37,14 +43,20 @@ struct NNGuideParams {
 
 __device__ __forceinline__ float curves_guide(const CurvesGuideParams& p, float r, float g,
                                               float b) {
-  float acc = p.mix_bias;
+  // One FMNMX per knot and one packed FFMA2 per two knots (vs FADD + FMNMX + FFMA each).
+  float acc = p.folded_bias;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float t = fmaf(b, p.ccm[2][c], fmaf(g, p.ccm[1][c], fmaf(r, p.ccm[0][c], p.ccm_bias[c])));
-    float u = 0.0f;
+    unsigned long long u2 = 0ull;  // (0.0f, 0.0f)
 #pragma unroll
-    for (int k = 0; k < kCurvePts; ++k) u = fmaf(p.slopes[c][k], fmaxf(t - p.shifts[c][k], 0.0f), u);
-    acc = fmaf(p.mix[c], u, acc);
+    for (int k = 0; k < kCurvePts; k += 2) {
+      const unsigned long long m2 = pack2(fmaxf(t, p.shifts[c][k]), fmaxf(t, p.shifts[c][k + 1]));
+      u2 = fma2(pack2(p.slopes[c][k], p.slopes[c][k + 1]), m2, u2);
+    }
+    float u0, u1;
+    unpack2(u2, u0, u1);
+    acc = fmaf(p.mix[c], u0 + u1, acc);
   }
   return fminf(fmaxf(acc, 0.0f), 1.0f);
 }

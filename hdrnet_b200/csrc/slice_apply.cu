@@ -137,6 +137,7 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct TmaPlan {
   int ctas;
+  int resident;    // CTAs per SM the plan was sized for (1, 2 or 3)
   int stages;
   int nseg;        // segments per row
   int seg_px;      // pixels per segment (multiple of 4, <= 4 * kTmaThreads)
@@ -246,8 +247,8 @@ struct GuideNN {
   }
 };
 
-template <class GuideFn, int kTexChunks>
-__global__ void __launch_bounds__(kTmaThreads, 2)
+template <class GuideFn, int kTexChunks, int kMinBlocks = 2>
+__global__ void __launch_bounds__(kTmaThreads, kMinBlocks)
 slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
   constexpr bool kGuideIn = GuideFn::kFromInput;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -677,22 +678,31 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
   p.off_raw = 128;  // barriers: (kMaxStages + 1) * 8 = 72 bytes
   p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
   p.off_stage = p.off_slab + round_up(p.row_floats * 4, 128);
-  // Prefer two CTAs per SM with 4 stages each; shrink the ring before giving up residency.
+  // Residency: HDRNET_TMA_OCC=3 asks for three CTAs per SM (3-stage ring, 85 registers) when
+  // the shared memory allows; default two CTAs with 4 stages; shrink the ring before giving up
+  // residency.
+  int want_occ = 2;
+  if (const char* e = std::getenv("HDRNET_TMA_OCC")) want_occ = std::atoi(e);
+  const int per_cta_3 = (max_smem + 1024) / 3 - 1024;
   const int per_cta_2 = (max_smem + 1024) / 2 - 1024;  // ~113 KB when 227 KB opt-in
-  int stages = 0;
-  for (int ns = 4; ns >= 2; --ns) {
-    if (p.off_stage + ns * p.stage_bytes <= per_cta_2) { stages = ns; break; }
+  int stages = 0, resident = 0;
+  if (want_occ == 3) {
+    for (int ns = 3; ns >= 2; --ns)
+      if (p.off_stage + ns * p.stage_bytes <= per_cta_3) { stages = ns; resident = 3; break; }
   }
   if (stages == 0) {
-    for (int ns = 4; ns >= 2; --ns) {
-      if (p.off_stage + ns * p.stage_bytes <= max_smem) { stages = ns; break; }
-    }
+    for (int ns = 4; ns >= 2; --ns)
+      if (p.off_stage + ns * p.stage_bytes <= per_cta_2) { stages = ns; resident = 2; break; }
+  }
+  if (stages == 0) {
+    for (int ns = 4; ns >= 2; --ns)
+      if (p.off_stage + ns * p.stage_bytes <= max_smem) { stages = ns; resident = 1; break; }
   }
   if (stages == 0) return false;
   p.stages = stages;
+  p.resident = resident;
   p.smem_bytes = p.off_stage + stages * p.stage_bytes;
   const long long total_rows = static_cast<long long>(g.B) * g.rows;
-  const int resident = (p.smem_bytes <= per_cta_2) ? 2 : 1;
   p.ctas = static_cast<int>(std::min<long long>(total_rows, static_cast<long long>(sms) * resident));
   *out = p;
   return true;
@@ -721,15 +731,21 @@ bool make_zsort_plan(const SliceGeom& g, int max_smem, int sms, ZsPlan* out);
 int launch_zsort(const float* grid, const float* guide, const float* input, float* out,
                  const SliceGeom& g, const ZsPlan& plan, cudaStream_t stream);
 
-template <class GuideFn, int kTexChunks = 0>
-static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(slice_apply_rows_tma_kernel<GuideFn, kTexChunks>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <class GuideFn, int kTexChunks = 0, int kMinBlocks = 2>
+static int launch_tma_occ(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
+  auto kern = slice_apply_rows_tma_kernel<GuideFn, kTexChunks, kMinBlocks>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  slice_apply_rows_tma_kernel<GuideFn, kTexChunks>
-      <<<a.p.ctas, kTmaThreads, a.p.smem_bytes, stream>>>(a, fn);
+  kern<<<a.p.ctas, kTmaThreads, a.p.smem_bytes, stream>>>(a, fn);
   return static_cast<int>(cudaGetLastError());
+}
+
+template <class GuideFn, int kTexChunks = 0>
+static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
+  // plan.resident == 3: three CTAs per SM (3-stage ring, registers capped at 85 per thread)
+  if (a.p.resident == 3) return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
+  return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
 // Texture objects over caller workspaces, cached by (pointer, bytes): creating one is a
