@@ -13,6 +13,7 @@
 // The whole network is ~83 MFLOP per image: launch-latency bound, not tensor bound (DESIGN.md
 // section 5).  fp32 CUDA-core math keeps the coefficients within float32 round-off of the
 // float64-accumulated oracle, which bf16 / tf32 tensor-core math could not.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -229,6 +230,89 @@ fc_kernel(const float* __restrict__ in, const float* __restrict__ w,
   }
 }
 
+
+// ---- fully connected, split-K over a thread-block cluster ----------------------------------------
+// At batch <= 8 a fully connected layer is a weight stream (fc1: 1 MB) that a handful of CTAs
+// cannot pull fast enough (52 us measured with 4 CTAs).  Here the K dimension is split over the
+// CTAs of a cluster (up to 8): every CTA streams its slice of W with 128-bit loads (16 rows x 16
+// float4 columns in flight per pass), reduces its 16 row-lanes in shared memory, and the
+// cluster's rank 0 sums the per-CTA partials through DISTRIBUTED SHARED MEMORY in a fixed order
+// (deterministic; no atomics), then applies bias / ReLU.
+constexpr int kFcCThreads = 256;
+constexpr int kFcCOut = 64;       // outputs per cluster (16 float4 columns)
+constexpr int kFcCRows = 16;      // k rows streamed in parallel
+constexpr int kFcCMaxSlice = 256; // inputs per CTA staged in shared memory (static smem <= 48 KB)
+
+__global__ void __launch_bounds__(kFcCThreads)
+fc_cluster_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ out, int B, int I, int O,
+                  int relu, int slice) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float xs[kFcBatch][kFcCMaxSlice];
+  __shared__ float red[kFcCRows][kFcBatch][kFcCOut];   // 32 KB
+  __shared__ float partial[kFcBatch][kFcCOut];
+  const int tid = threadIdx.x;
+  const int col = tid % 16, krow = tid / 16;
+  const int o0 = blockIdx.x * kFcCOut + col * 4;
+  const int b0 = blockIdx.z * kFcBatch;
+  const int nb = min(kFcBatch, B - b0);
+  const unsigned rank = cluster.block_rank();
+  const int k0 = static_cast<int>(rank) * slice;
+  const int kn = max(0, min(slice, I - k0));
+
+  for (int e = tid; e < kFcBatch * slice; e += kFcCThreads) {
+    const int b = e / slice, i = e % slice;
+    xs[b][i] = (b < nb && i < kn) ? __ldg(in + static_cast<size_t>(b0 + b) * I + k0 + i) : 0.0f;
+  }
+  __syncthreads();
+
+  float acc[kFcBatch][4];
+#pragma unroll
+  for (int b = 0; b < kFcBatch; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0f;
+  if (o0 < O) {
+#pragma unroll 4
+    for (int i = krow; i < kn; i += kFcCRows) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(k0 + i) * O + o0));
+#pragma unroll
+      for (int b = 0; b < kFcBatch; ++b) {
+        const float x = xs[b][i];
+        acc[b][0] = fmaf(x, wv.x, acc[b][0]);
+        acc[b][1] = fmaf(x, wv.y, acc[b][1]);
+        acc[b][2] = fmaf(x, wv.z, acc[b][2]);
+        acc[b][3] = fmaf(x, wv.w, acc[b][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < kFcBatch; ++b)
+    *reinterpret_cast<float4*>(&red[krow][b][col * 4]) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+  __syncthreads();
+  for (int e = tid; e < kFcBatch * kFcCOut; e += kFcCThreads) {
+    const int b = e / kFcCOut, o = e % kFcCOut;
+    float s = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kFcCRows; ++r) s += red[r][b][o];
+    partial[b][o] = s;
+  }
+  cluster.sync();  // every CTA's partial is complete and visible cluster-wide
+  if (rank == 0) {
+    const unsigned nranks = cluster.num_blocks();
+    for (int e = tid; e < kFcBatch * kFcCOut; e += kFcCThreads) {
+      const int b = e / kFcCOut, o = e % kFcCOut;
+      const int go = blockIdx.x * kFcCOut + o;
+      if (b < nb && go < O) {
+        float s = 0.0f;
+        for (unsigned r = 0; r < nranks; ++r)
+          s += cluster.map_shared_rank(&partial[0][0], r)[b * kFcCOut + o];
+        s += bias ? __ldg(bias + go) : 0.0f;
+        out[static_cast<size_t>(b0 + b) * O + go] = relu ? fmaxf(s, 0.0f) : s;
+      }
+    }
+  }
+  cluster.sync();  // keep the remote shared memory alive until rank 0 has read it
+}
+
 // ---- fusion + prediction + unroll_grid ----------------------------------------------------
 constexpr int kFpThreads = 256;
 constexpr int kFpCells = 8;  // grid cells per CTA (one warp each)
@@ -345,8 +429,32 @@ int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out
   if (B < 0 || I < 1 || O < 1) return HDRNET_E_BAD_SHAPE;
   if (B == 0) return HDRNET_OK;
   if (!in || !w || !out) return HDRNET_E_NULL_POINTER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Cluster split-K form: needs float4 rows of W (O % 4 == 0, aligned) and a K worth splitting.
+  int ksplit = 1;
+  while (ksplit < 8 && I / (ksplit * 2) >= 64) ksplit *= 2;
+  const int slice = (I + ksplit - 1) / ksplit;
+  const char* env = std::getenv("HDRNET_FC_CLUSTER");
+  const bool allow = !(env && env[0] == '0');
+  if (allow && O % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15u) == 0 && ksplit >= 2 &&
+      slice <= kFcCMaxSlice) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((O + kFcCOut - 1) / kFcCOut, ksplit, (B + kFcBatch - 1) / kFcBatch);
+    cfg.blockDim = dim3(kFcCThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = ksplit;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fc_cluster_kernel, in, w, bias, out, B, I, O, relu, slice);
+    return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
+  }
   dim3 grid((O + kFcOut - 1) / kFcOut, (B + kFcBatch - 1) / kFcBatch);
-  fc_kernel<<<grid, kFcThreads, 0, static_cast<cudaStream_t>(stream)>>>(in, w, bias, out, B, I, O, relu);
+  fc_kernel<<<grid, kFcThreads, 0, st>>>(in, w, bias, out, B, I, O, relu);
   return static_cast<int>(cudaGetLastError());
 }
 

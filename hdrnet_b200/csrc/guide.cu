@@ -93,7 +93,7 @@ int pack_nn_params(NNGuideParams* p, const float* w1, const float* b1, const flo
   if (!w1 || !b1 || !w2) return HDRNET_E_NULL_POINTER;
   if (feats < 1 || feats > kMaxGuideFeats) return HDRNET_E_UNSUPPORTED;
   std::memset(p, 0, sizeof(*p));
-  p->feats = feats;
+  p->feats = (feats + 1) & ~1;  // processed in pairs; the pad feature has zero weights
   for (int c = 0; c < 3; ++c)
     for (int f = 0; f < feats; ++f) p->w1[c][f] = w1[c * feats + f];
   std::memcpy(p->b1, b1, sizeof(float) * feats);

@@ -62,13 +62,23 @@ __device__ __forceinline__ float curves_guide(const CurvesGuideParams& p, float 
 }
 
 __device__ __forceinline__ float nn_guide(const NNGuideParams& p, float r, float g, float b) {
-  float y = p.b2;
-#pragma unroll 8
-  for (int f = 0; f < p.feats; ++f) {
-    const float h = fmaf(b, p.w1[2][f], fmaf(g, p.w1[1][f], fmaf(r, p.w1[0][f], p.b1[f])));
-    y = fmaf(fmaxf(h, 0.0f), p.w2[f], y);
+  // Two features per packed FFMA2 (w1/b1/w2 are zero-padded to an even count by
+  // pack_nn_params); sigmoid through ex2.approx / rcp.approx: ~3e-7 absolute on the guide.
+  const unsigned long long r2 = pack2(r, r), g2 = pack2(g, g), b2v = pack2(b, b);
+  unsigned long long y2 = 0ull;
+#pragma unroll 4
+  for (int f = 0; f < p.feats; f += 2) {
+    unsigned long long h2 = fma2(r2, pack2(p.w1[0][f], p.w1[0][f + 1]), pack2(p.b1[f], p.b1[f + 1]));
+    h2 = fma2(g2, pack2(p.w1[1][f], p.w1[1][f + 1]), h2);
+    h2 = fma2(b2v, pack2(p.w1[2][f], p.w1[2][f + 1]), h2);
+    float h0, h1;
+    unpack2(h2, h0, h1);
+    y2 = fma2(pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), pack2(p.w2[f], p.w2[f + 1]), y2);
   }
-  return 1.0f / (1.0f + expf(-y));
+  float y0, y1;
+  unpack2(y2, y0, y1);
+  const float y = (y0 + y1) + p.b2;
+  return __fdividef(1.0f, 1.0f + __expf(-y));
 }
 
 }  // namespace hdrnet_b200
