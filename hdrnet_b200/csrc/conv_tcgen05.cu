@@ -20,8 +20,12 @@
 //     and a tcgen05.commit onto an mbarrier that gates the next chunk's overwrite;
 //   * epilogue: tcgen05.ld 32x32b (each warp its 32 TMEM lanes = 32 pixels), bias + ReLU,
 //     float4 stores.
-// This first version is deliberately unpipelined (one chunk in flight): the tensor pipe idles
-// while threads gather.  It is opt-in (HDRNET_CONV_TCGEN05=1) until it is double-buffered.
+// Two kernels: conv2d_tcgen05_kernel gathers the weights itself, one chunk in flight (any HWIO
+// weight buffer); conv2d_tcgen05_packed_kernel takes weights PRE-PACKED per 32-k chunk into the
+// canonical layout, already split hi/lo (hdrnet_conv2d_tc_pack_f32, once per model), so that a
+// chunk's B operand is ONE TMA bulk copy, and runs a 3-stage ring: the im2col gather of chunk
+// c+1 is prefetched into registers while chunk c's MMAs run asynchronously, each stage being
+// recycled on the mbarrier its tcgen05.commit arrives on.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -217,6 +221,212 @@ conv2d_tcgen05_kernel(const TcConvArgs a) {
   }
 }
 
+
+// =========================================================================================
+// Pipelined form with pre-packed weights
+// =========================================================================================
+constexpr int kTcStages = 3;
+
+// packed[chunk][half: hi, lo][kchunk 0..7][n 0..N-1][4]: chunk c's B operand (both halves) is one
+// contiguous block of 2 * N * 32 floats in exactly the shared-memory layout the MMA reads.
+__global__ void __launch_bounds__(256)
+conv_tc_pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int K, int N,
+                    int nchunks) {
+  const long long total = static_cast<long long>(nchunks) * 8 * N;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(e % N);
+    const int c = static_cast<int>((e / N) % 8);
+    const int ch = static_cast<int>(e / (static_cast<long long>(N) * 8));
+    float4 h, l;
+    float* hp = reinterpret_cast<float*>(&h);
+    float* lp = reinterpret_cast<float*>(&l);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = ch * kTcKc + 4 * c + j;
+      const float v = (kk < K) ? __ldg(w + static_cast<size_t>(kk) * N + n) : 0.0f;
+      split_tf32(v, hp[j], lp[j]);
+    }
+    float* base = packed + static_cast<size_t>(ch) * 2 * N * kTcKc;
+    const int off = c * (N * 4) + (n >> 3) * 32 + (n & 7) * 4;
+    *reinterpret_cast<float4*>(base + off) = h;
+    *reinterpret_cast<float4*>(base + N * kTcKc + off) = l;
+  }
+}
+
+struct TcPackedArgs {
+  const float* in;
+  const float* packed;  // conv_tc_pack_kernel output
+  const float* bias;
+  float* out;
+  int B, H, W, Cin, OH, OW, Cout, k, stride, pad_t, pad_l, relu, ncols;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t b_full[kTcStages];    // TMA: weights of the stage have landed
+  __shared__ uint64_t mma_done[kTcStages];  // tcgen05.commit: the stage's operands were consumed
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int N = a.Cout;
+  const int a_floats = kTcM * kTcKc;         // one half (hi or lo) of the A stage
+  const int b_floats = N * kTcKc;
+  const int stage_floats = 2 * a_floats + 2 * b_floats;
+  float* ring = reinterpret_cast<float*>(smem);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_smem)),
+                 "r"(static_cast<uint32_t>(a.ncols)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&mma_done[s], 1); }
+    fence_mbar_init();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const long long total_px = static_cast<long long>(a.B) * a.OH * a.OW;
+  const long long q = static_cast<long long>(blockIdx.x) * kTcM + tid;
+  const bool pv = q < total_px;
+  const long long qq = pv ? q : 0;
+  const int ox = static_cast<int>(qq % a.OW);
+  const int oy = static_cast<int>((qq / a.OW) % a.OH);
+  const int ob = static_cast<int>(qq / (static_cast<long long>(a.OW) * a.OH));
+  const int K = a.k * a.k * a.Cin;
+  const int nchunks = (K + kTcKc - 1) / kTcKc;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+                         (static_cast<uint32_t>(kTcM >> 4) << 24);
+  const uint32_t a_lbo = kTcM * 16, b_lbo = static_cast<uint32_t>(N) * 16, sbo = 128;
+  const uint32_t b_bytes = static_cast<uint32_t>(2 * b_floats) * 4u;
+
+  // im2col gather of this thread's row for one chunk, into registers
+  auto gather = [&](int ch, float4 (&v)[kTcKc / 4]) {
+#pragma unroll
+    for (int c = 0; c < kTcKc / 4; ++c) {
+      const int kk = ch * kTcKc + 4 * c;
+      v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pv && kk < K) {
+        const int t = kk / a.Cin, ci = kk - t * a.Cin;
+        const int ky = t / a.k, kx = t - ky * a.k;
+        const int iy = oy * a.stride - a.pad_t + ky, ix = ox * a.stride - a.pad_l + kx;
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+          v[c] = __ldg(reinterpret_cast<const float4*>(
+              a.in + ((static_cast<size_t>(ob) * a.H + iy) * a.W + ix) * a.Cin + ci));
+      }
+    }
+  };
+
+  float4 cur[kTcKc / 4], nxt[kTcKc / 4];
+  gather(0, cur);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int s = ch % kTcStages;
+    const uint32_t use = static_cast<uint32_t>(ch / kTcStages);
+    float* a_hi = ring + static_cast<size_t>(s) * stage_floats;
+    float* a_lo = a_hi + a_floats;
+    float* b_hi = a_lo + a_floats;   // b_lo follows b_hi (one TMA copy fills both)
+    // the MMAs that read this stage kTcStages chunks ago must have completed
+    if (use > 0) mbar_wait(&mma_done[s], (use - 1) & 1u);
+    if (tid == 0) {
+      mbar_expect_tx(&b_full[s], b_bytes);
+      tma_load_1d(b_hi, a.packed + static_cast<size_t>(ch) * 2 * b_floats, b_bytes, &b_full[s]);
+    }
+    if (ch + 1 < nchunks) gather(ch + 1, nxt);  // loads in flight across the stores + barrier
+#pragma unroll
+    for (int c = 0; c < kTcKc / 4; ++c) {
+      float4 h, l;
+      split_tf32(cur[c].x, h.x, l.x); split_tf32(cur[c].y, h.y, l.y);
+      split_tf32(cur[c].z, h.z, l.z); split_tf32(cur[c].w, h.w, l.w);
+      const int off = c * (kTcM * 4) + (tid >> 3) * 32 + (tid & 7) * 4;
+      *reinterpret_cast<float4*>(a_hi + off) = h;
+      *reinterpret_cast<float4*>(a_lo + off) = l;
+    }
+    fence_proxy_async_smem();
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    if (tid == 0) {
+      mbar_wait(&b_full[s], use & 1u);
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi);
+      const uint32_t bl = bh + static_cast<uint32_t>(b_floats) * 4u;
+#pragma unroll
+      for (int ks = 0; ks < kTcKc / 8; ++ks) {
+        const uint64_t dah = make_kmajor_desc(ah + ks * 2 * a_lbo, a_lbo, sbo);
+        const uint64_t dal = make_kmajor_desc(al + ks * 2 * a_lbo, a_lbo, sbo);
+        const uint64_t dbh = make_kmajor_desc(bh + ks * 2 * b_lbo, b_lbo, sbo);
+        const uint64_t dbl = make_kmajor_desc(bl + ks * 2 * b_lbo, b_lbo, sbo);
+        const uint64_t da[3] = {dah, dah, dal};
+        const uint64_t db[3] = {dbh, dbl, dbh};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t acc = (ch > 0 || ks > 0 || t > 0) ? 1u : 0u;
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+              "}\n" ::"r"(tmem_base),
+              "l"(da[t]), "l"(db[t]), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(&mma_done[s]))
+                   : "memory");
+    }
+#pragma unroll
+    for (int c = 0; c < kTcKc / 4; ++c) cur[c] = nxt[c];
+  }
+  // all MMAs complete when the last chunk's commit has arrived (commits are ordered)
+  {
+    const int last = nchunks - 1;
+    mbar_wait(&mma_done[last % kTcStages], static_cast<uint32_t>(last / kTcStages) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+  }
+
+  float* dst = a.out + static_cast<size_t>(qq) * a.Cout;
+  for (int n0 = 0; n0 < N; n0 += 16) {
+    uint32_t r[16];
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + n0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (pv) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 o;
+        float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v = __uint_as_float(r[j + e]) + (a.bias ? __ldg(a.bias + n0 + j + e) : 0.0f);
+          op[e] = a.relu ? fmaxf(v, 0.0f) : v;
+        }
+        *reinterpret_cast<float4*>(dst + n0 + j) = o;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(a.ncols)));
+  }
+}
+
+static bool tc_shape_ok(int Cin, int Cout) {
+  return Cin % 4 == 0 && Cout % 16 == 0 && Cout <= kTcMaxN && Cout >= 16;
+}
+
 // Returns HDRNET_E_UNSUPPORTED when the shapes do not suit this path (the caller then runs the
 // CUDA-core kernel in cnn.cu).
 int launch_conv_tcgen05(const float* in, const float* w, const float* bias, float* out, int B,
@@ -244,3 +454,60 @@ int launch_conv_tcgen05(const float* in, const float* w, const float* bias, floa
 }
 
 }  // namespace hdrnet_b200
+
+using namespace hdrnet_b200;
+
+extern "C" {
+
+size_t hdrnet_conv2d_tc_packed_bytes(int k, int Cin, int Cout) {
+  if ((k != 1 && k != 3) || !tc_shape_ok(Cin, Cout)) return 0;
+  const int K = k * k * Cin;
+  const size_t nchunks = (K + kTcKc - 1) / kTcKc;
+  return nchunks * 2 * static_cast<size_t>(Cout) * kTcKc * sizeof(float);
+}
+
+int hdrnet_conv2d_tc_pack_f32(const float* w, float* packed, int k, int Cin, int Cout,
+                              void* stream) {
+  if (hdrnet_conv2d_tc_packed_bytes(k, Cin, Cout) == 0) return HDRNET_E_UNSUPPORTED;
+  if (!w || !packed) return HDRNET_E_NULL_POINTER;
+  const int K = k * k * Cin, nchunks = (K + kTcKc - 1) / kTcKc;
+  const long long total = static_cast<long long>(nchunks) * 8 * Cout;
+  conv_tc_pack_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(w, packed, K, Cout, nchunks);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int hdrnet_conv2d_nhwc_tc_f32(const float* in, const float* packed_w, const float* bias,
+                              float* out, int B, int H, int W, int Cin, int Cout, int k,
+                              int stride, int relu, void* stream) {
+  if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return HDRNET_E_BAD_SHAPE;
+  if ((k != 1 && k != 3) || (stride != 1 && stride != 2) || !tc_shape_ok(Cin, Cout))
+    return HDRNET_E_UNSUPPORTED;
+  if (B == 0) return HDRNET_OK;
+  if (!in || !packed_w || !out) return HDRNET_E_NULL_POINTER;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u) ||
+      (reinterpret_cast<uintptr_t>(packed_w) & 15u))
+    return HDRNET_E_UNSUPPORTED;
+  TcPackedArgs a;
+  a.in = in; a.packed = packed_w; a.bias = bias; a.out = out;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = k; a.stride = stride; a.relu = relu;
+  a.OH = (H + stride - 1) / stride;
+  a.OW = (W + stride - 1) / stride;
+  int tot = (a.OH - 1) * stride + k - H; if (tot < 0) tot = 0; a.pad_t = tot / 2;
+  tot = (a.OW - 1) * stride + k - W; if (tot < 0) tot = 0; a.pad_l = tot / 2;
+  int ncols = 32;
+  while (ncols < Cout) ncols <<= 1;
+  a.ncols = ncols;
+  const size_t smem = static_cast<size_t>(kTcStages) * 2 * (kTcM + Cout) * kTcKc * sizeof(float);
+  if (smem > 200 * 1024) return HDRNET_E_UNSUPPORTED;  // Cout > 128: use the unpacked kernel
+  cudaError_t e = cudaFuncSetAttribute(conv2d_tcgen05_packed_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const long long total_px = static_cast<long long>(B) * a.OH * a.OW;
+  conv2d_tcgen05_packed_kernel<<<static_cast<unsigned>((total_px + kTcM - 1) / kTcM), kTcThreads,
+                                 smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

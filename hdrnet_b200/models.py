@@ -179,9 +179,10 @@ class _Prepared:
                   (f"{p}/local/conv2", False, False), (f"{p}/prediction/conv1", False, True)]
         for scope, use_bn, use_bias in specs:
             w, b = _fold(wts, scope, use_bn, use_bias)
-            self.layers[scope] = (
-                torch.from_numpy(np.ascontiguousarray(w)).to(device),
-                None if b is None else torch.from_numpy(np.ascontiguousarray(b)).to(device))
+            wd = torch.from_numpy(np.ascontiguousarray(w)).to(device)
+            bd = None if b is None else torch.from_numpy(np.ascontiguousarray(b)).to(device)
+            packed = pack_conv_weights(wd) if (wd.dim() == 4 and device.type == "cuda") else None
+            self.layers[scope] = (wd, bd, packed)
         g = "inference/guide"
         f32 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32))  # noqa: E731
 
@@ -227,8 +228,35 @@ def _check_input(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 # ---- layer wrappers (hdrnet/layers.py:25-93 over the C-ABI) ------------------------------------
+def pack_conv_weights(w: torch.Tensor):
+    """Pre-pack HWIO conv weights for the pipelined tcgen05 kernel (once per model); returns a
+    device buffer, or None when the layer's shape does not suit that kernel."""
+    lib = _lib.load()
+    k, _, cin, cout = w.shape
+    nbytes = int(lib.hdrnet_conv2d_tc_packed_bytes(k, cin, cout))
+    if nbytes == 0 or cout > 128:
+        return None
+    packed = torch.empty(nbytes // 4, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = lib.hdrnet_conv2d_tc_pack_f32(w.data_ptr(), packed.data_ptr(), k, cin, cout,
+                                           torch.cuda.current_stream(w.device).cuda_stream)
+    _lib.check(rc, "conv weight packing")
+    return packed
+
+
+def _use_packed_tc() -> bool:
+    """HDRNET_CONV_TCGEN05: '1' = pipelined tensor-core convs wherever weights were packed,
+    '0' = never; default: see DESIGN.md section 6 (measured crossover)."""
+    import os
+    return os.environ.get("HDRNET_CONV_TCGEN05", _TC_DEFAULT) == "1"
+
+
+_TC_DEFAULT = "0"
+
+
 def _conv(x: torch.Tensor, wb, stride=1, relu=True) -> torch.Tensor:
-    w, b = wb
+    w, b = wb[0], wb[1]
+    packed = wb[2] if len(wb) > 2 else None
     B, H, W, cin = x.shape
     k, _, wcin, cout = w.shape
     if wcin != cin:
@@ -236,6 +264,14 @@ def _conv(x: torch.Tensor, wb, stride=1, relu=True) -> torch.Tensor:
     oh, ow = -(-H // stride), -(-W // stride)
     out = torch.empty((B, oh, ow, cout), dtype=torch.float32, device=x.device)
     lib = _lib.load()
+    if packed is not None and _use_packed_tc():
+        rc = lib.hdrnet_conv2d_nhwc_tc_f32(x.data_ptr(), packed.data_ptr(),
+                                           0 if b is None else b.data_ptr(), out.data_ptr(), B, H,
+                                           W, cin, cout, k, stride, int(relu),
+                                           torch.cuda.current_stream(x.device).cuda_stream)
+        if rc != _lib.E_UNSUPPORTED:
+            _lib.check(rc, "conv2d(tcgen05)")
+            return out
     rc = lib.hdrnet_conv2d_nhwc_f32(x.data_ptr(), w.data_ptr(), 0 if b is None else b.data_ptr(),
                                     out.data_ptr(), B, H, W, cin, cout, k, stride, int(relu),
                                     torch.cuda.current_stream(x.device).cuda_stream)
@@ -244,7 +280,7 @@ def _conv(x: torch.Tensor, wb, stride=1, relu=True) -> torch.Tensor:
 
 
 def _fc(x: torch.Tensor, wb, relu=True) -> torch.Tensor:
-    w, b = wb
+    w, b = wb[0], wb[1]
     B, I = x.shape
     if w.shape[0] != I:
         raise ValueError(f"fc: input has {I} features, weights expect {w.shape[0]}")
@@ -331,7 +367,7 @@ class HDRNetCurves(object):
             g = _fc(g, L[f"{p}/global/fc3"], relu=False)
             loc = _conv(splat, L[f"{p}/local/conv1"])               # local, :109-118
             loc = _conv(loc, L[f"{p}/local/conv2"], relu=False)
-            wp, bp = L[f"{p}/prediction/conv1"]
+            wp, bp = L[f"{p}/prediction/conv1"][:2]
             _, gh, gw, C = loc.shape
             grid = torch.empty((bs, gh, gw, gd, cls.n_out(), cls.n_in()), dtype=torch.float32,
                                device=x.device)

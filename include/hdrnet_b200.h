@@ -213,6 +213,21 @@ HDRNET_API int hdrnet_conv2d_nhwc_f32(const float* in, const float* w, const flo
                                       float* out, int B, int H, int W, int Cin, int Cout, int k,
                                       int stride, int relu, void* stream);
 
+/*
+ * Tensor-core form of conv2d (tcgen05.mma kind::tf32 with 3xTF32 operand splitting, accumulator
+ * in TMEM; float32-grade results).  Weights are packed ONCE per model into per-chunk hi/lo tiles
+ * in the MMA's shared-memory layout (hdrnet_conv2d_tc_packed_bytes() bytes, device memory owned
+ * by the caller); the layer call then needs Cin % 4 == 0, Cout % 16 == 0, 16 <= Cout <= 128.
+ * hdrnet_conv2d_nhwc_f32 also reaches an unpacked tensor-core kernel on its own when the layer
+ * has >= 96 tiles of 128 pixels (HDRNET_CONV_TCGEN05=0/1 overrides).
+ */
+HDRNET_API size_t hdrnet_conv2d_tc_packed_bytes(int k, int Cin, int Cout);
+HDRNET_API int hdrnet_conv2d_tc_pack_f32(const float* w, float* packed, int k, int Cin, int Cout,
+                                         void* stream);
+HDRNET_API int hdrnet_conv2d_nhwc_tc_f32(const float* in, const float* packed_w, const float* bias,
+                                         float* out, int B, int H, int W, int Cin, int Cout,
+                                         int k, int stride, int relu, void* stream);
+
 /* fully_connected: out[B,O] = in[B,I] @ w[I,O] + bias (+ReLU). */
 HDRNET_API int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out,
                              int B, int I, int O, int relu, void* stream);

@@ -237,6 +237,14 @@ def test_conv2d_tcgen05_matches_oracle(tcgen05_convs, B, H, W, cin, cout, k, str
     got = models._conv(cuda(x), (cuda(w), None if b is None else cuda(b)), stride=stride, relu=relu)
     torch.cuda.synchronize()
     assert_parity(got.cpu().numpy(), ref.astype(np.float32), rtol=1e-5)
+    # pipelined kernel with pre-packed hi/lo weight tiles (3-stage ring, one TMA copy per chunk)
+    wd = cuda(w)
+    packed = models.pack_conv_weights(wd)
+    if cout <= 128:
+        assert packed is not None
+        got2 = models._conv(cuda(x), (wd, None if b is None else cuda(b), packed), stride=stride, relu=relu)
+        torch.cuda.synchronize()
+        assert_parity(got2.cpu().numpy(), ref.astype(np.float32), rtol=1e-5, what="packed/pipelined")
 
 
 @pytest.mark.gpu
