@@ -322,6 +322,17 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
     }
   };
 
+  auto stage_b = [&](int st) { return ring + static_cast<size_t>(st) * stage_floats + 2 * a_floats; };
+  auto issue_b = [&](int ch) {  // thread 0: weights of chunk `ch` -> its stage, one TMA bulk copy
+    const int st = ch % kTcStages;
+    mbar_expect_tx(&b_full[st], b_bytes);
+    tma_load_1d(stage_b(st), a.packed + static_cast<size_t>(ch) * 2 * b_floats, b_bytes, &b_full[st]);
+  };
+  // Weights run two chunks ahead of the MMAs, the im2col gather one chunk ahead (in registers).
+  if (tid == 0) {
+    issue_b(0);
+    if (nchunks > 1) issue_b(1);
+  }
   float4 cur[kTcKc / 4], nxt[kTcKc / 4];
   gather(0, cur);
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -329,13 +340,8 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
     const uint32_t use = static_cast<uint32_t>(ch / kTcStages);
     float* a_hi = ring + static_cast<size_t>(s) * stage_floats;
     float* a_lo = a_hi + a_floats;
-    float* b_hi = a_lo + a_floats;   // b_lo follows b_hi (one TMA copy fills both)
     // the MMAs that read this stage kTcStages chunks ago must have completed
     if (use > 0) mbar_wait(&mma_done[s], (use - 1) & 1u);
-    if (tid == 0) {
-      mbar_expect_tx(&b_full[s], b_bytes);
-      tma_load_1d(b_hi, a.packed + static_cast<size_t>(ch) * 2 * b_floats, b_bytes, &b_full[s]);
-    }
     if (ch + 1 < nchunks) gather(ch + 1, nxt);  // loads in flight across the stores + barrier
 #pragma unroll
     for (int c = 0; c < kTcKc / 4; ++c) {
@@ -352,7 +358,7 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (tid == 0) {
       mbar_wait(&b_full[s], use & 1u);
-      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi);
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(stage_b(s));
       const uint32_t bl = bh + static_cast<uint32_t>(b_floats) * 4u;
 #pragma unroll
       for (int ks = 0; ks < kTcKc / 8; ++ks) {
@@ -378,6 +384,14 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                        smem_u32(&mma_done[s]))
                    : "memory");
+      // refill the stage chunk ch+2 will use: its last reader was chunk ch-1
+      if (ch + 2 < nchunks) {
+        if (ch >= 1) {
+          const int pc = ch - 1;
+          mbar_wait(&mma_done[pc % kTcStages], static_cast<uint32_t>(pc / kTcStages) & 1u);
+        }
+        issue_b(ch + 2);
+      }
     }
 #pragma unroll
     for (int c = 0; c < kTcKc / 4; ++c) cur[c] = nxt[c];
