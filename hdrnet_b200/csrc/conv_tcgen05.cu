@@ -304,20 +304,26 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
                          (static_cast<uint32_t>(kTcM >> 4) << 24);
   const uint32_t a_lbo = kTcM * 16, b_lbo = static_cast<uint32_t>(N) * 16, sbo = 128;
   const uint32_t b_bytes = static_cast<uint32_t>(2 * b_floats) * 4u;
+  const uint32_t acc_stride = static_cast<uint32_t>(a.ncols) / 4u;  // columns between accumulators
 
-  // im2col gather of this thread's row for one chunk, into registers
-  auto gather = [&](int ch, float4 (&v)[kTcKc / 4]) {
+  // im2col gather of this thread's row for the NEXT chunk in sequence, into registers.  The
+  // (ky, kx, ci) position advances incrementally -- 4 channels per 16-byte k-chunk -- because
+  // runtime integer divisions here cost ~900 instructions per warp per chunk (ncu).
+  int g_ky = 0, g_kx = 0, g_ci = 0;
+  const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
+  const float* in_b = a.in + static_cast<size_t>(ob) * a.H * a.W * a.Cin;
+  auto gather = [&](float4 (&v)[kTcKc / 4]) {
 #pragma unroll
     for (int c = 0; c < kTcKc / 4; ++c) {
-      const int kk = ch * kTcKc + 4 * c;
       v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pv && kk < K) {
-        const int t = kk / a.Cin, ci = kk - t * a.Cin;
-        const int ky = t / a.k, kx = t - ky * a.k;
-        const int iy = oy * a.stride - a.pad_t + ky, ix = ox * a.stride - a.pad_l + kx;
-        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-          v[c] = __ldg(reinterpret_cast<const float4*>(
-              a.in + ((static_cast<size_t>(ob) * a.H + iy) * a.W + ix) * a.Cin + ci));
+      const int iy = iy0 + g_ky, ix = ix0 + g_kx;
+      if (pv && g_ky < a.k && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+        v[c] = __ldg(reinterpret_cast<const float4*>(
+            in_b + (static_cast<size_t>(iy) * a.W + ix) * a.Cin + g_ci));
+      g_ci += 4;
+      if (g_ci >= a.Cin) {
+        g_ci = 0;
+        if (++g_kx == a.k) { g_kx = 0; ++g_ky; }  // g_ky == k: past K, zero-fill
       }
     }
   };
@@ -334,7 +340,7 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
     if (nchunks > 1) issue_b(1);
   }
   float4 cur[kTcKc / 4], nxt[kTcKc / 4];
-  gather(0, cur);
+  gather(cur);
   for (int ch = 0; ch < nchunks; ++ch) {
     const int s = ch % kTcStages;
     const uint32_t use = static_cast<uint32_t>(ch / kTcStages);
@@ -342,7 +348,7 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
     float* a_lo = a_hi + a_floats;
     // the MMAs that read this stage kTcStages chunks ago must have completed
     if (use > 0) mbar_wait(&mma_done[s], (use - 1) & 1u);
-    if (ch + 1 < nchunks) gather(ch + 1, nxt);  // loads in flight across the stores + barrier
+    if (ch + 1 < nchunks) gather(nxt);  // loads in flight across the stores + barrier
 #pragma unroll
     for (int c = 0; c < kTcKc / 4; ++c) {
       float4 h, l;
@@ -370,13 +376,15 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
         const uint64_t db[3] = {dbh, dbl, dbh};
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint32_t acc = (ch > 0 || ks > 0 || t > 0) ? 1u : 0u;
+          // hi*hi, hi*lo and lo*hi go to THREE accumulators (TMEM columns t*acc_stride..):
+          // into one accumulator every MMA would wait for the previous one (~128 clk each).
+          const uint32_t acc = (ch > 0 || ks > 0) ? 1u : 0u;
           asm volatile(
               "{\n\t"
               ".reg .pred p;\n\t"
               "setp.ne.b32 p, %4, 0;\n\t"
               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-              "}\n" ::"r"(tmem_base),
+              "}\n" ::"r"(tmem_base + static_cast<uint32_t>(t) * acc_stride),
               "l"(da[t]), "l"(db[t]), "r"(idesc), "r"(acc)
               : "memory");
         }
@@ -405,16 +413,23 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
 
   float* dst = a.out + static_cast<size_t>(qq) * a.Cout;
   for (int n0 = 0; n0 < N; n0 += 16) {
-    uint32_t r[16];
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + n0;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-          "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float sum[16];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) +
+                             static_cast<uint32_t>(t) * acc_stride + n0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+            "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sum[e] = (t == 0) ? __uint_as_float(r[e]) : sum[e] + __uint_as_float(r[e]);
+    }
     if (pv) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
@@ -422,7 +437,7 @@ conv2d_tcgen05_packed_kernel(const TcPackedArgs a) {
         float* op = reinterpret_cast<float*>(&o);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float v = __uint_as_float(r[j + e]) + (a.bias ? __ldg(a.bias + n0 + j + e) : 0.0f);
+          float v = sum[j + e] + (a.bias ? __ldg(a.bias + n0 + j + e) : 0.0f);
           op[e] = a.relu ? fmaxf(v, 0.0f) : v;
         }
         *reinterpret_cast<float4*>(dst + n0 + j) = o;
@@ -511,7 +526,7 @@ int hdrnet_conv2d_nhwc_tc_f32(const float* in, const float* packed_w, const floa
   tot = (a.OW - 1) * stride + k - W; if (tot < 0) tot = 0; a.pad_l = tot / 2;
   int ncols = 32;
   while (ncols < Cout) ncols <<= 1;
-  a.ncols = ncols;
+  a.ncols = 4 * ncols;  // three accumulators at a power-of-two stride (<= 512 columns: Cout <= 128)
   const size_t smem = static_cast<size_t>(kTcStages) * 2 * (kTcM + Cout) * kTcKc * sizeof(float);
   if (smem > 200 * 1024) return HDRNET_E_UNSUPPORTED;  // Cout > 128: use the unpacked kernel
   cudaError_t e = cudaFuncSetAttribute(conv2d_tcgen05_packed_kernel,
