@@ -244,14 +244,16 @@ def pack_conv_weights(w: torch.Tensor):
     return packed
 
 
-def _use_packed_tc() -> bool:
-    """HDRNET_CONV_TCGEN05: '1' = pipelined tensor-core convs wherever weights were packed,
-    '0' = never; default: see DESIGN.md section 6 (measured crossover)."""
+def _use_packed_tc(tiles: int) -> bool:
+    """HDRNET_CONV_TCGEN05: '1' = tensor-core convs wherever weights were packed, '0' = never.
+    Default: from 8 tiles of 128 output pixels up -- the measured crossover on B200
+    (profiles/r01_conv_tcgen05_vs_cudacore.txt: slower than the CUDA-core kernel at 2 tiles,
+    faster from batch 8, 5x faster at batch 64)."""
     import os
-    return os.environ.get("HDRNET_CONV_TCGEN05", _TC_DEFAULT) == "1"
-
-
-_TC_DEFAULT = "0"
+    flag = os.environ.get("HDRNET_CONV_TCGEN05")
+    if flag is not None:
+        return flag == "1"
+    return tiles >= 8
 
 
 def _conv(x: torch.Tensor, wb, stride=1, relu=True) -> torch.Tensor:
@@ -264,7 +266,7 @@ def _conv(x: torch.Tensor, wb, stride=1, relu=True) -> torch.Tensor:
     oh, ow = -(-H // stride), -(-W // stride)
     out = torch.empty((B, oh, ow, cout), dtype=torch.float32, device=x.device)
     lib = _lib.load()
-    if packed is not None and _use_packed_tc():
+    if packed is not None and _use_packed_tc((B * oh * ow + 127) // 128):
         rc = lib.hdrnet_conv2d_nhwc_tc_f32(x.data_ptr(), packed.data_ptr(),
                                            0 if b is None else b.data_ptr(), out.data_ptr(), B, H,
                                            W, cin, cout, k, stride, int(relu),
