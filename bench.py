@@ -306,8 +306,8 @@ def run_b200_arm(args):
         peak, peak_src = measured_peaks()
         achieved = algo_bytes / (own_launch_ms * 1e-3) / 1e9
         variant, ctas, threads, smem = (ctypes.c_int() for _ in range(4))
-        lib.hdrnet_slice_apply_plan(B, H, W, GH, GW, GD, N_IN, N_OUT, 1, ctypes.byref(variant),
-                                    ctypes.byref(ctas), ctypes.byref(threads), ctypes.byref(smem))
+        lib.hdrnet_slice_apply_plan_ws(B, H, W, GH, GW, GD, N_IN, N_OUT, 1, 1, ctypes.byref(variant),
+                                       ctypes.byref(ctas), ctypes.byref(threads), ctypes.byref(smem))
         line = {
             "metric": METRIC,
             "value": round(world * npix * args.steps / (elapsed_max_ms * 1e-3) / 1e6, 1),

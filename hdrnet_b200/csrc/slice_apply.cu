@@ -667,7 +667,10 @@ static int device_max_smem_optin() {
 
 
 // Returns false when the TMA kernel cannot run these shapes.
-static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out) {
+// tex_mode: the texture-assisted form double-buffers whole slab rows in raw0 / raw1 and needs no
+// separate slab region (lets 32x32x16 grids keep two CTAs per SM).
+static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out,
+                          bool tex_mode = false) {
   if (g.W < 4 || (g.W % 4) != 0) return false;
   TmaPlan p;
   p.row_floats = g.gw * g.gd * kGc;
@@ -677,7 +680,7 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
   p.stage_bytes = round_up(p.seg_px * 16, 128);
   p.off_raw = 128;  // barriers: (kMaxStages + 1) * 8 = 72 bytes
   p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
-  p.off_stage = p.off_slab + round_up(p.row_floats * 4, 128);
+  p.off_stage = p.off_slab + (tex_mode ? 0 : round_up(p.row_floats * 4, 128));
   // Residency: HDRNET_TMA_OCC=3 asks for three CTAs per SM (3-stage ring, 85 registers) when
   // the shared memory allows; default two CTAs with 4 stages; shrink the ring before giving up
   // residency.
@@ -831,9 +834,11 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   if (variant == HDRNET_VARIANT_TEX) {
     const size_t need = tex_need;
     if (!tex_ok) return HDRNET_E_UNSUPPORTED;
+    TmaPlan tplan;
+    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true)) tplan = plan;
     TmaArgs a;
     a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr; a.input = input; a.out = out;
-    a.g = g; a.p = plan; a.yslab = gs.workspace;
+    a.g = g; a.p = tplan; a.yslab = gs.workspace;
     rc = get_slab_texture(gs.workspace, need, &a.slab_tex);
     if (rc != 0) return rc;
     yblend_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows), 128, 0, stream>>>(
@@ -1057,23 +1062,30 @@ int hdrnet_slice_indices_i32(const float* guide, int32_t* idx, int B, int H, int
   return static_cast<int>(cudaGetLastError());
 }
 
-int hdrnet_slice_apply_plan(int B, int H, int W, int gh, int gw, int gd, int n_in, int n_out,
-                            int has_offset, int* variant, int* ctas, int* threads,
-                            int* smem_bytes) {
-  // (reports the no-workspace choice; with a workspace AUTO upgrades TMA to TEX for >= 2 Mi px)
+int hdrnet_slice_apply_plan_ws(int B, int H, int W, int gh, int gw, int gd, int n_in, int n_out,
+                               int has_offset, int with_workspace, int* variant, int* ctas,
+                               int* threads, int* smem_bytes) {
   int rc = validate_common(B, H, W, gh, gw, gd);
   if (rc != HDRNET_OK) return rc;
   const SliceGeom g = make_geom(B, H, W, H, 0, gh, gw, gd);
   const int sms = device_sm_count();
+  const long long npix = static_cast<long long>(B) * H * W;
+  const bool tex = with_workspace && npix >= (1LL << 21);
   TmaPlan plan;
   const bool tma = (n_in == 3 && n_out == 3 && has_offset) && W >= 128 &&
-                   make_tma_plan(g, device_max_smem_optin(), sms, &plan);
-  const long long npix = static_cast<long long>(B) * H * W;
-  if (variant) *variant = tma ? HDRNET_VARIANT_TMA : HDRNET_VARIANT_GENERIC;
+                   make_tma_plan(g, device_max_smem_optin(), sms, &plan, tex);
+  if (variant) *variant = tma ? (tex ? HDRNET_VARIANT_TEX : HDRNET_VARIANT_TMA) : HDRNET_VARIANT_GENERIC;
   if (ctas) *ctas = tma ? plan.ctas : generic_grid(npix, sms);
   if (threads) *threads = tma ? kTmaThreads : 256;
   if (smem_bytes) *smem_bytes = tma ? plan.smem_bytes : 0;
   return HDRNET_OK;
+}
+
+int hdrnet_slice_apply_plan(int B, int H, int W, int gh, int gw, int gd, int n_in, int n_out,
+                            int has_offset, int* variant, int* ctas, int* threads,
+                            int* smem_bytes) {
+  return hdrnet_slice_apply_plan_ws(B, H, W, gh, gw, gd, n_in, n_out, has_offset, 0, variant, ctas,
+                                    threads, smem_bytes);
 }
 
 }  // extern "C"

@@ -151,6 +151,10 @@ HDRNET_API int hdrnet_slice_indices_i32(const float* guide, int32_t* idx, int B,
 HDRNET_API int hdrnet_slice_apply_plan(int B, int H, int W, int gh, int gw, int gd, int n_in, int n_out,
                             int has_offset, int* variant, int* ctas, int* threads,
                             int* smem_bytes);
+/* Same, for a call that lends a workspace (hdrnet_slice_apply_f32_ws). */
+HDRNET_API int hdrnet_slice_apply_plan_ws(int B, int H, int W, int gh, int gw, int gd, int n_in,
+                                          int n_out, int has_offset, int with_workspace,
+                                          int* variant, int* ctas, int* threads, int* smem_bytes);
 
 /*
  * Full-resolution guidance maps (input [npix, 3] float32 RGB -> guide [npix] float32).
