@@ -18,8 +18,14 @@
 //     blends 4 corners instead of 8: 48 FMAs -> 24 packed fma.rn.f32x2 (FFMA2) + 9 for
 //     the affine apply.
 //   * one thread owns 4 consecutive pixels: 3 LDS.128 of RGB + 1 LDS.128 of guide, 12
-//     LDS.128 of slab per pixel (conflict-free: the 8 depth cells of one x cell map to
+//     16-byte slab chunks per pixel (conflict-free within an x cell: its 8 depth cells map to
 //     disjoint 4-bank groups), 3 STS.128 of output.
+//   * the kernel is bound by the shared-memory data pipe (ncu), so its texture-assisted form
+//     (template parameter kTexChunks, HDRNET_VARIANT_TEX) reads the y-pre-blended slab rows
+//     from a pre-pass workspace and serves 4 of the 12 chunks through the texture pipe -- the
+//     only on-chip gather path that does not share the LSU crossbar.
+//   * template parameter GuideFn fuses the curves / pointwise-NN guide (model path, 24 B/px).
+// slice_rows_tma_kernel is the un-fused bilateral_slice on the same plan (write-bound).
 #include <cuda_runtime.h>
 
 #include <algorithm>
