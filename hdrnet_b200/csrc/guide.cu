@@ -20,10 +20,11 @@ struct CurvesFn {
     return curves_guide(p, r, g, b);
   }
 };
+template <int kFeats>
 struct NNFn {
   NNGuideParams p;
   __device__ __forceinline__ float operator()(float r, float g, float b) const {
-    return nn_guide(p, r, g, b);
+    return nn_guide<kFeats>(p, r, g, b);
   }
 };
 
@@ -119,9 +120,14 @@ int hdrnet_guide_curves_f32(const float* input, float* guide, long long npix, co
 
 int hdrnet_guide_nn_f32(const float* input, float* guide, long long npix, const float* w1,
                         const float* b1, const float* w2, float b2, int feats, void* stream) {
-  NNFn fn;
-  const int rc = pack_nn_params(&fn.p, w1, b1, w2, b2, feats);
+  NNGuideParams np;
+  const int rc = pack_nn_params(&np, w1, b1, w2, b2, feats);
   if (rc != HDRNET_OK) return rc;
+  if (np.feats <= 16) {
+    NNFn<16> fn; fn.p = np;
+    return launch_guide(input, guide, npix, fn, static_cast<cudaStream_t>(stream));
+  }
+  NNFn<kMaxGuideFeats> fn; fn.p = np;
   return launch_guide(input, guide, npix, fn, static_cast<cudaStream_t>(stream));
 }
 

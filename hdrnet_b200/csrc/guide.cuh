@@ -61,13 +61,16 @@ __device__ __forceinline__ float curves_guide(const CurvesGuideParams& p, float 
   return fminf(fmaxf(acc, 0.0f), 1.0f);
 }
 
+// kFeats is a compile-time bound (16 or 32): the loop unrolls fully and every weight is a
+// constant-bank operand with a static offset (a runtime feature count costs an indexed LDC per
+// weight).  Weights beyond p.feats are zero (pack_nn_params), so the extra features add 0.
+template <int kFeats>
 __device__ __forceinline__ float nn_guide(const NNGuideParams& p, float r, float g, float b) {
-  // Two features per packed FFMA2 (w1/b1/w2 are zero-padded to an even count by
-  // pack_nn_params); sigmoid through ex2.approx / rcp.approx: ~3e-7 absolute on the guide.
+  // Two features per packed FFMA2; sigmoid through ex2.approx / rcp.approx: ~3e-7 absolute.
   const unsigned long long r2 = pack2(r, r), g2 = pack2(g, g), b2v = pack2(b, b);
   unsigned long long y2 = 0ull;
-#pragma unroll 4
-  for (int f = 0; f < p.feats; f += 2) {
+#pragma unroll
+  for (int f = 0; f < kFeats; f += 2) {
     unsigned long long h2 = fma2(r2, pack2(p.w1[0][f], p.w1[0][f + 1]), pack2(p.b1[f], p.b1[f + 1]));
     h2 = fma2(g2, pack2(p.w1[1][f], p.w1[1][f + 1]), h2);
     h2 = fma2(b2v, pack2(p.w1[2][f], p.w1[2][f + 1]), h2);

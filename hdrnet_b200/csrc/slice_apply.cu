@@ -245,11 +245,12 @@ struct GuideCurves {
     return curves_guide(p, r, g, b);
   }
 };
+template <int kFeats>
 struct GuideNN {
   static constexpr bool kFromInput = false;
   NNGuideParams p;
   __device__ __forceinline__ float operator()(float r, float g, float b) const {
-    return nn_guide(p, r, g, b);
+    return nn_guide<kFeats>(p, r, g, b);
   }
 };
 
@@ -752,8 +753,12 @@ static int launch_tma_occ(const TmaArgs& a, const GuideFn& fn, cudaStream_t stre
 
 template <class GuideFn, int kTexChunks = 0>
 static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  // plan.resident == 3: three CTAs per SM (3-stage ring, registers capped at 85 per thread)
-  if (a.p.resident == 3) return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
+  // plan.resident == 3 (HDRNET_TMA_OCC=3, tuning knob): three CTAs per SM, registers capped at 85
+  // per thread.  Only the guide-from-input form is built that way; the fused-guide forms need
+  // their registers and simply run two of the three planned CTAs.
+  if constexpr (GuideFn::kFromInput) {
+    if (a.p.resident == 3) return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
+  }
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
@@ -880,7 +885,8 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     a.g = g; a.p = plan; a.slab_tex = 0; a.yslab = nullptr;
     if (gs.mode == 0) return launch_tma(a, GuideFromInput{}, stream);
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; return launch_tma(a, fn, stream); }
-    GuideNN fn; fn.p = *gs.nn;
+    if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn; return launch_tma(a, fn, stream); }
+    GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
     return launch_tma(a, fn, stream);
   }
   slice_generic_kernel<true><<<generic_grid(npix, sms), 256, 0, stream>>>(
