@@ -837,7 +837,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   }
   // Texture-assisted form: possible when the caller lent a workspace for the slab rows.
   const size_t tex_need = tma_shape ? static_cast<size_t>(B) * rows * plan.row_floats * sizeof(float) : 0;
-  const bool tex_ok = tma_shape && gs.mode == 0 && gs.workspace && gs.workspace_bytes >= tex_need &&
+  const bool tex_ok = tma_shape && gs.workspace && gs.workspace_bytes >= tex_need &&
                       aligned16(gs.workspace) && tex_need / 16 <= (1u << 27);
   // AUTO prefers it once the image is large enough to amortise the pre-pass launch.
   if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21))
@@ -854,6 +854,14 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     if (rc != 0) return rc;
     yblend_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows), 128, 0, stream>>>(
         grid, gs.workspace, g, plan.row_floats);
+    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
+                        return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream); }
+    if (gs.mode == 2) {
+      a.guide_out = gs.guide_out;
+      if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn; return launch_tma<GuideNN<16>, kTexChunksDefault>(a, fn, stream); }
+      GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
+      return launch_tma<GuideNN<kMaxGuideFeats>, kTexChunksDefault>(a, fn, stream);
+    }
     int chunks = kTexChunksDefault;
     if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);  // tuning knob
     switch (chunks) {
@@ -1010,15 +1018,17 @@ extern "C" int hdrnet_guide_curves_f32(const float*, float*, long long, const fl
 extern "C" int hdrnet_guide_nn_f32(const float*, float*, long long, const float*, const float*,
                                    const float*, float, int, void*);
 
-int hdrnet_slice_apply_curves_f32(const float* grid, const float* input, float* out,
-                                  float* guide_out, int B, int H, int W, int gh, int gw, int gd,
-                                  const float* ccm, const float* ccm_bias, const float* shifts,
-                                  const float* slopes, const float* mix, float mix_bias,
-                                  void* stream) {
+int hdrnet_slice_apply_curves_f32_ws(const float* grid, const float* input, float* out,
+                                     float* guide_out, int B, int H, int W, int gh, int gw, int gd,
+                                     const float* ccm, const float* ccm_bias, const float* shifts,
+                                     const float* slopes, const float* mix, float mix_bias,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   CurvesGuideParams cp;
   int rc = pack_curves_params(&cp, ccm, ccm_bias, shifts, slopes, mix, mix_bias);
   if (rc != HDRNET_OK) return rc;
   GuideSpec gs{1, nullptr, guide_out, &cp, nullptr};
+  gs.workspace = static_cast<float*>(workspace);
+  gs.workspace_bytes = workspace_bytes;
   rc = launch_slice_apply_impl(grid, gs, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
                                HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
   if (rc != HDRNET_E_UNSUPPORTED) return rc;
@@ -1030,14 +1040,26 @@ int hdrnet_slice_apply_curves_f32(const float* grid, const float* input, float* 
                             HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
 }
 
-int hdrnet_slice_apply_nn_f32(const float* grid, const float* input, float* out, float* guide_out,
-                              int B, int H, int W, int gh, int gw, int gd, const float* w1,
-                              const float* b1, const float* w2, float b2, int feats,
-                              void* stream) {
+int hdrnet_slice_apply_curves_f32(const float* grid, const float* input, float* out,
+                                  float* guide_out, int B, int H, int W, int gh, int gw, int gd,
+                                  const float* ccm, const float* ccm_bias, const float* shifts,
+                                  const float* slopes, const float* mix, float mix_bias,
+                                  void* stream) {
+  return hdrnet_slice_apply_curves_f32_ws(grid, input, out, guide_out, B, H, W, gh, gw, gd, ccm,
+                                          ccm_bias, shifts, slopes, mix, mix_bias, nullptr, 0,
+                                          stream);
+}
+
+int hdrnet_slice_apply_nn_f32_ws(const float* grid, const float* input, float* out,
+                                 float* guide_out, int B, int H, int W, int gh, int gw, int gd,
+                                 const float* w1, const float* b1, const float* w2, float b2,
+                                 int feats, void* workspace, size_t workspace_bytes, void* stream) {
   NNGuideParams np;
   int rc = pack_nn_params(&np, w1, b1, w2, b2, feats);
   if (rc != HDRNET_OK) return rc;
   GuideSpec gs{2, nullptr, guide_out, nullptr, &np};
+  gs.workspace = static_cast<float*>(workspace);
+  gs.workspace_bytes = workspace_bytes;
   rc = launch_slice_apply_impl(grid, gs, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
                                HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
   if (rc != HDRNET_E_UNSUPPORTED) return rc;
@@ -1047,6 +1069,14 @@ int hdrnet_slice_apply_nn_f32(const float* grid, const float* input, float* out,
   if (rc != HDRNET_OK) return rc;
   return launch_slice_apply(grid, guide_out, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
                             HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
+}
+
+int hdrnet_slice_apply_nn_f32(const float* grid, const float* input, float* out, float* guide_out,
+                              int B, int H, int W, int gh, int gw, int gd, const float* w1,
+                              const float* b1, const float* w2, float b2, int feats,
+                              void* stream) {
+  return hdrnet_slice_apply_nn_f32_ws(grid, input, out, guide_out, B, H, W, gh, gw, gd, w1, b1, w2,
+                                      b2, feats, nullptr, 0, stream);
 }
 
 int hdrnet_slice_f32_variant(const float* grid, const float* guide, float* out, int B, int H,

@@ -330,16 +330,24 @@ class HDRNetCurves(object):
         with torch.cuda.device(fullres_input.device):
             stream = torch.cuda.current_stream(fullres_input.device).cuda_stream
             gptr = 0 if guide is None else guide.data_ptr()
+            # workspace lent to the library (it never allocates): texture-assisted kernel for
+            # large images, exactly as hdrnet_ops.bilateral_slice_apply does
+            ws_ptr, ws_bytes = 0, 0
+            if B * H * W >= (1 << 21) and W % 4 == 0:
+                from .hdrnet_ops import _workspace
+                ws = _workspace(fullres_input.device,
+                                lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))
+                ws_ptr, ws_bytes = ws.data_ptr(), ws.numel() * 4
             if cls._nn_guide:
-                rc = lib.hdrnet_slice_apply_nn_f32(
+                rc = lib.hdrnet_slice_apply_nn_f32_ws(
                     coeffs.data_ptr(), fullres_input.data_ptr(), out.data_ptr(), gptr, B, H, W,
                     gh, gw, gd, _hp(prep.nn_w1), _hp(prep.nn_b1), _hp(prep.nn_w2), prep.nn_b2,
-                    prep.nn_feats, stream)
+                    prep.nn_feats, ws_ptr, ws_bytes, stream)
             else:
-                rc = lib.hdrnet_slice_apply_curves_f32(
+                rc = lib.hdrnet_slice_apply_curves_f32_ws(
                     coeffs.data_ptr(), fullres_input.data_ptr(), out.data_ptr(), gptr, B, H, W,
                     gh, gw, gd, _hp(prep.ccm), _hp(prep.ccm_bias), _hp(prep.shifts),
-                    _hp(prep.slopes), _hp(prep.mix), prep.mix_bias, stream)
+                    _hp(prep.slopes), _hp(prep.mix), prep.mix_bias, ws_ptr, ws_bytes, stream)
         _lib.check(rc, "BilateralSliceApply(fused guide)")
         if debug:
             cls.last_debug = {"bilateral_coefficients": coeffs, "guide": guide, "output": out}

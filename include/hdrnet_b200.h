@@ -255,6 +255,21 @@ HDRNET_API int hdrnet_fuse_predict_f32(const float* local, const float* global_f
 HDRNET_API int hdrnet_resize_bilinear_f32(const float* in, const float* add, float* out, int B,
                                           int H, int W, int C, int OH, int OW, void* stream);
 
+/* The model-path forms with a lent workspace (B*H*gw*gd*48 bytes, as for
+ * hdrnet_slice_apply_f32_ws): large images then run the texture-assisted kernel. */
+HDRNET_API int hdrnet_slice_apply_curves_f32_ws(const float* grid, const float* input, float* out,
+                                                float* guide_out, int B, int H, int W, int gh,
+                                                int gw, int gd, const float* ccm,
+                                                const float* ccm_bias, const float* shifts,
+                                                const float* slopes, const float* mix,
+                                                float mix_bias, void* workspace,
+                                                size_t workspace_bytes, void* stream);
+HDRNET_API int hdrnet_slice_apply_nn_f32_ws(const float* grid, const float* input, float* out,
+                                            float* guide_out, int B, int H, int W, int gh, int gw,
+                                            int gd, const float* w1, const float* b1,
+                                            const float* w2, float b2, int feats, void* workspace,
+                                            size_t workspace_bytes, void* stream);
+
 /*
  * Host-buffer path (what a CPU-tensor caller of the reference op gets: TF copies feeds to
  * the GPU and fetches back, hdrnet/bin/run.py:185).  A context owns device staging buffers

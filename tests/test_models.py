@@ -290,3 +290,20 @@ def test_gaussian_pyramid_model_matches_oracle(H, W):
         assert np.abs(g.cpu().numpy() - r).max() < 2e-6
     fast = models.HDRNetGaussianPyrNN.inference(cuda(low), cuda(full), dict(p, weights=wts))
     assert_parity(fast.cpu().numpy(), ref, rtol=1e-4, what="pyramid output (guide-fused)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["default", "nn_guide"])
+def test_full_inference_large_image_takes_texture_assisted_kernel(name):
+    """>= 2 Mi pixels: models.inference lends a workspace and the library runs the
+    texture-assisted guide-fused kernel; same oracle, same tolerance."""
+    p = PARAM_SETS[name]
+    wts = M.make_weights(p, seed=21)
+    rng = np.random.RandomState(22)
+    S = p["net_input_size"]
+    low = rng.rand(1, S, S, 3).astype(np.float32)
+    full = rng.rand(1, 1024, 2048, 3).astype(np.float32)
+    ref, _, _ = M.inference(low, full, wts, p, oracle.best().bilateral_slice_apply)
+    cls = getattr(models, p["model_name"])
+    got = cls.inference(cuda(low), cuda(full), dict(p, weights=wts))
+    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what=f"{name} 2 MP output")
