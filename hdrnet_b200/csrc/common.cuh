@@ -89,6 +89,18 @@ __device__ __forceinline__ void smoothed_weights(float f, float& w0, float& w1) 
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// One 128-bit shared-memory load that the compiler may not split or rematerialise: under
+// register pressure nvcc turned `float4 g = guide4[tid]` into four LDS.32 issued right before
+// each use -- 4-way bank conflicted (lanes 16 B apart) -- which cost 6.6 % of the kernel's
+// shared-memory wavefronts (ncu source counters, profiles/).
+__device__ __forceinline__ float4 lds128(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))));
+  return v;
+}
+
 // ---- packed fp32x2 math (Blackwell-only: fma.rn.f32x2 -> SASS FFMA2) --------------------
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   unsigned long long r;

@@ -254,6 +254,58 @@ struct GuideNN {
   }
 };
 
+
+// One thread's 4 consecutive pixels (quad `q` of a staged segment): guide (staged, or computed
+// from RGB), bit-exact cell indices, 4-corner blend + affine apply, result written IN PLACE over
+// the RGB tile.  Shared by the block-synchronous and the warp-specialised row kernels.
+template <class GuideFn, int kTexChunks>
+__device__ __forceinline__ void process_quad(const TmaArgs& args, const GuideFn& guide_fn,
+                                             unsigned char* rgb_tile, const unsigned char* guide_tile,
+                                             const float* slab, int tex_row, long long row, int x0,
+                                             int q) {
+  constexpr bool kGuideIn = GuideFn::kFromInput;
+  const SliceGeom& g = args.g;
+  const float gd_f = static_cast<float>(g.gd);
+  const int x_stride = g.gd * kGc;
+  float4* rgb4 = reinterpret_cast<float4*>(rgb_tile) + 3 * q;
+  const float4 c0 = rgb4[0], c1 = rgb4[1], c2 = rgb4[2];
+  const float pr[4] = {c0.x, c0.w, c1.z, c2.y};
+  const float pg[4] = {c0.y, c1.x, c1.w, c2.z};
+  const float pb[4] = {c0.z, c1.y, c2.x, c2.w};
+  float gv[4];
+  if (kGuideIn) {
+    const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
+    gv[0] = gq.x; gv[1] = gq.y; gv[2] = gq.z; gv[3] = gq.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gv[i] = guide_fn(pr[i], pg[i], pb[i]);
+    if (args.guide_out != nullptr) {  // optional dump (hdrnet/bin/run.py --debug)
+      const size_t pix = static_cast<size_t>(row) * g.W + x0 + 4 * q;
+      *reinterpret_cast<float4*>(args.guide_out + pix) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    }
+  }
+  float o_r[4], o_g[4], o_b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const Axis ax = spatial_axis(x0 + 4 * q + i, g.scale_x);
+    const Axis az = range_axis(gv[i], gd_f);
+    const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride;
+    const int xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
+    const int zo0 = clampi(az.i0, 0, g.gd - 1) * kGc;
+    const int zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * kGc;
+    float wz0, wz1;
+    smoothed_weights(az.f, wz0, wz1);
+    const float wx1 = ax.f, wx0 = 1.0f - ax.f;
+    blend_apply<kTexChunks>(slab, args.slab_tex, tex_row, xo0 + zo0, xo0 + zo1, xo1 + zo0,
+                            xo1 + zo1, wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i], pg[i],
+                            pb[i], o_r[i], o_g[i], o_b[i]);
+  }
+  rgb4[0] = make_float4(o_r[0], o_g[0], o_b[0], o_r[1]);
+  rgb4[1] = make_float4(o_g[1], o_b[1], o_r[2], o_g[2]);
+  rgb4[2] = make_float4(o_b[2], o_r[3], o_g[3], o_b[3]);
+  fence_proxy_async_smem();
+}
+
 template <class GuideFn, int kTexChunks, int kMinBlocks = 2>
 __global__ void __launch_bounds__(kTmaThreads, kMinBlocks)
 slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
@@ -322,8 +374,6 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
     for (int it = 0; it < pre; ++it) issue_load(it);
   }
 
-  const float gd_f = static_cast<float>(g.gd);
-  const int x_stride = g.gd * kGc;  // floats between neighbouring x cells in the slab
   int cur_b = -1, cur_gy0 = INT_MIN;
   uint32_t grid_phase = 0;
 
@@ -382,45 +432,9 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
     const int s = item % NS;
     mbar_wait(&full[s], static_cast<uint32_t>(item / NS) & 1u);
 
-    if (tid * 4 < npx) {
-      float4* rgb4 = reinterpret_cast<float4*>(stage_rgb(s)) + 3 * tid;
-      const float4 c0 = rgb4[0], c1 = rgb4[1], c2 = rgb4[2];
-      const float pr[4] = {c0.x, c0.w, c1.z, c2.y};
-      const float pg[4] = {c0.y, c1.x, c1.w, c2.z};
-      const float pb[4] = {c0.z, c1.y, c2.x, c2.w};
-      float gv[4];
-      if (kGuideIn) {
-        const float4 gq = reinterpret_cast<const float4*>(stage_guide(s))[tid];
-        gv[0] = gq.x; gv[1] = gq.y; gv[2] = gq.z; gv[3] = gq.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gv[i] = guide_fn(pr[i], pg[i], pb[i]);
-        if (args.guide_out != nullptr) {  // optional dump (hdrnet/bin/run.py --debug)
-          const size_t pix = static_cast<size_t>(row) * g.W + x0 + 4 * tid;
-          *reinterpret_cast<float4*>(args.guide_out + pix) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-        }
-      }
-      float o_r[4], o_g[4], o_b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const Axis ax = spatial_axis(x0 + 4 * tid + i, g.scale_x);
-        const Axis az = range_axis(gv[i], gd_f);
-        const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride;
-        const int xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
-        const int zo0 = clampi(az.i0, 0, g.gd - 1) * kGc;
-        const int zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * kGc;
-        float wz0, wz1;
-        smoothed_weights(az.f, wz0, wz1);
-        const float wx1 = ax.f, wx0 = 1.0f - ax.f;
-        blend_apply<kTexChunks>(slab, args.slab_tex, tex_row, xo0 + zo0, xo0 + zo1, xo1 + zo0,
-                                xo1 + zo1, wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i],
-                                pg[i], pb[i], o_r[i], o_g[i], o_b[i]);
-      }
-      rgb4[0] = make_float4(o_r[0], o_g[0], o_b[0], o_r[1]);
-      rgb4[1] = make_float4(o_g[1], o_b[1], o_r[2], o_g[2]);
-      rgb4[2] = make_float4(o_b[2], o_r[3], o_g[3], o_b[3]);
-      fence_proxy_async_smem();
-    }
+    if (tid * 4 < npx)
+      process_quad<GuideFn, kTexChunks>(args, guide_fn, stage_rgb(s), stage_guide(s), slab, tex_row,
+                                        row, x0, tid);
     __syncthreads();
 
     if (tid == 0) {
@@ -437,6 +451,136 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
   if (tid == 0) tma_store_wait_all<0>();
 }
 
+
+
+// =========================================================================================
+// Warp-specialised form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_WS).
+// =========================================================================================
+// ncu stall sampling of the block-synchronous kernel: ~20 % of samples sit in synchronisation
+// (the per-item __syncthreads before the bulk store, and all 256 threads spinning on the TMA
+// barrier).  Here nothing is block-synchronous after start-up:
+//   * warp 8 (one lane) is the PRODUCER: it issues every TMA load -- per item the RGB + guide
+//     segment into the stage ring, per image row the y-pre-blended slab row (from the pre-pass
+//     workspace) into one of two slab buffers -- gated by stage_free[] / slab_free[] mbarriers;
+//   * warps 0..7 are CONSUMERS and never wait for each other: a warp waits for its stage
+//     (full[]) and slab (slab_full[]), processes its own 128 pixels in place, issues ITS OWN
+//     bulk store (lane 0), and one item later -- once cp.async.bulk.wait_group.read says the
+//     store has drained the tile -- arrives on stage_free[]; after a row's last item it arrives
+//     on slab_free[].  stage_free / slab_free count kWsConsumerWarps arrivals per phase.
+constexpr int kTexChunksWs = 4;
+constexpr int kWsConsumerWarps = 8;
+constexpr int kWsThreads = (kWsConsumerWarps + 1) * 32;
+
+template <class GuideFn, int kTexChunks>
+__global__ void __launch_bounds__(kWsThreads, 2)
+slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
+  static_assert(kTexChunks > 0, "the warp-specialised kernel reads slab rows from the workspace");
+  constexpr bool kGuideIn = GuideFn::kFromInput;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SliceGeom& g = args.g;
+  const TmaPlan& pl = args.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]  TMA landed
+  uint64_t* stage_free = full + kMaxStages;              // [kMaxStages]  all consumers done + stored
+  uint64_t* slab_full = stage_free + kMaxStages;         // [2]
+  uint64_t* slab_free = slab_full + 2;                   // [2]
+  float* raw0 = reinterpret_cast<float*>(smem + pl.off_raw);
+  unsigned char* stage_base = smem + pl.off_stage;
+
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
+  const int nitems = static_cast<int>(r_end - r_begin) * pl.nseg;
+  if (nitems <= 0) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&stage_free[s], kWsConsumerWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&slab_full[b], 1); mbar_init(&slab_free[b], kWsConsumerWarps); }
+    fence_mbar_init();
+  }
+  __syncthreads();  // the only block-wide barrier
+
+  const int NS = pl.stages;
+  const int seg_rgb_bytes_max = pl.seg_px * 12;
+  const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+  auto stage_rgb = [&](int s) { return stage_base + static_cast<size_t>(s) * pl.stage_bytes; };
+  auto stage_guide = [&](int s) {
+    return stage_base + static_cast<size_t>(s) * pl.stage_bytes + seg_rgb_bytes_max;
+  };
+  auto item_span = [&](int item, long long& row, int& x0, int& npx) {
+    const int rr = item / pl.nseg;
+    const int seg = item - rr * pl.nseg;
+    row = r_begin + rr;
+    x0 = seg * pl.seg_px;
+    npx = min(pl.seg_px, g.W - x0);
+  };
+  auto arrive = [&](uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  };
+
+  if (warp == kWsConsumerWarps) {
+    // ------------------------------- producer ---------------------------------------------
+    if (lane != 0) return;
+    for (int item = 0; item < nitems; ++item) {
+      long long row; int x0, npx;
+      item_span(item, row, x0, npx);
+      const int s = item % NS;
+      const int use = item / NS;
+      if (x0 == 0) {  // first item of an image row: its slab row, two buffers deep
+        const int rowk = item / pl.nseg, rb = rowk & 1, v = rowk >> 1;
+        if (v >= 1) mbar_wait(&slab_free[rb], static_cast<uint32_t>(v - 1) & 1u);
+        mbar_expect_tx(&slab_full[rb], slab_bytes);
+        tma_load_1d(raw0 + rb * pl.row_floats, args.yslab + static_cast<size_t>(row) * pl.row_floats,
+                    slab_bytes, &slab_full[rb]);
+      }
+      if (use >= 1) mbar_wait(&stage_free[s], static_cast<uint32_t>(use - 1) & 1u);
+      const size_t pix = static_cast<size_t>(row) * g.W + x0;
+      mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * (kGuideIn ? 16u : 12u));
+      tma_load_1d(stage_rgb(s), args.input + pix * 3, static_cast<uint32_t>(npx) * 12u, &full[s]);
+      if (kGuideIn)
+        tma_load_1d(stage_guide(s), args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[s]);
+    }
+    return;
+  }
+
+  // --------------------------------- consumers ----------------------------------------------
+  const int px0w = warp * 128;   // this warp's pixels inside a segment
+  const float* slab = raw0;
+  int tex_row = 0;
+  for (int item = 0; item < nitems; ++item) {
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+    const int s = item % NS;
+    const int rowk = item / pl.nseg, rb = rowk & 1;
+    mbar_wait(&full[s], static_cast<uint32_t>(item / NS) & 1u);
+    if (x0 == 0) {
+      mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
+      slab = raw0 + rb * pl.row_floats;
+      tex_row = static_cast<int>(row) * (pl.row_floats / 4);
+    }
+    const int q = (px0w >> 2) + lane;
+    if (q * 4 < npx)
+      process_quad<GuideFn, kTexChunks>(args, guide_fn, stage_rgb(s), stage_guide(s), slab, tex_row,
+                                        row, x0, q);
+    __syncwarp();
+    if (lane == 0) {
+      const int nw = min(128, npx - px0w);
+      if (nw > 0) {
+        const size_t pix = static_cast<size_t>(row) * g.W + x0 + px0w;
+        tma_store_1d(args.out + pix * 3, stage_rgb(s) + static_cast<size_t>(px0w) * 12,
+                     static_cast<uint32_t>(nw) * 12u);
+      }
+      tma_store_commit();            // one (possibly empty) group per item keeps the counting simple
+      if (item >= 1) {
+        tma_store_wait_read<1>();    // this warp's store of item-1 has drained its tile
+        arrive(&stage_free[(item - 1) % NS]);
+      }
+      if (x0 + pl.seg_px >= g.W) arrive(&slab_free[rb]);  // row finished: slab no longer read here
+    }
+  }
+  if (lane == 0) tma_store_wait_all<0>();
+}
 
 // =========================================================================================
 // Un-fused slice, persistent TMA row kernel (gc = 12, W % 4 == 0): out[b,y,x,0..11].
@@ -685,7 +829,7 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
   p.nseg = (quads + kTmaThreads - 1) / kTmaThreads;
   p.seg_px = 4 * ((quads + p.nseg - 1) / p.nseg);
   p.stage_bytes = round_up(p.seg_px * 16, 128);
-  p.off_raw = 128;  // barriers: (kMaxStages + 1) * 8 = 72 bytes
+  p.off_raw = 256;  // barriers: up to 2 * kMaxStages + 4 (warp-specialised form) = 160 bytes
   p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
   p.off_stage = p.off_slab + (tex_mode ? 0 : round_up(p.row_floats * 4, 128));
   // Residency: HDRNET_TMA_OCC=3 asks for three CTAs per SM (3-stage ring, 85 registers) when
@@ -700,8 +844,10 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
     for (int ns = 3; ns >= 2; --ns)
       if (p.off_stage + ns * p.stage_bytes <= per_cta_3) { stages = ns; resident = 3; break; }
   }
+  int max_ns = 4;
+  if (const char* e = std::getenv("HDRNET_TMA_STAGES")) max_ns = std::min(std::max(std::atoi(e), 2), kMaxStages);
   if (stages == 0) {
-    for (int ns = 4; ns >= 2; --ns)
+    for (int ns = max_ns; ns >= 2; --ns)
       if (p.off_stage + ns * p.stage_bytes <= per_cta_2) { stages = ns; resident = 2; break; }
   }
   if (stages == 0) {
@@ -760,6 +906,16 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) 
     if (a.p.resident == 3) return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
   }
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
+}
+
+template <class GuideFn>
+static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
+  auto kern = slice_apply_rows_ws_kernel<GuideFn, kTexChunksWs>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       a.p.smem_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  kern<<<a.p.ctas, kWsThreads, a.p.smem_bytes, stream>>>(a, fn);
+  return static_cast<int>(cudaGetLastError());
 }
 
 // Texture objects over caller workspaces, cached by (pointer, bytes): creating one is a
@@ -842,7 +998,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   // AUTO prefers it once the image is large enough to amortise the pre-pass launch.
   if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21))
     variant = HDRNET_VARIANT_TEX;
-  if (variant == HDRNET_VARIANT_TEX) {
+  if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_WS) {
     const size_t need = tex_need;
     if (!tex_ok) return HDRNET_E_UNSUPPORTED;
     TmaPlan tplan;
@@ -854,6 +1010,10 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     if (rc != 0) return rc;
     yblend_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows), 128, 0, stream>>>(
         grid, gs.workspace, g, plan.row_floats);
+    if (variant == HDRNET_VARIANT_TEX_WS) {
+      if (gs.mode != 0 || plan.seg_px > kWsConsumerWarps * 128) return HDRNET_E_UNSUPPORTED;
+      return launch_ws(a, GuideFromInput{}, stream);
+    }
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
                         return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream); }
     if (gs.mode == 2) {

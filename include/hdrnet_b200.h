@@ -66,6 +66,8 @@ extern "C" {
                                  /* kernel then fetches part of each pixel's corner data    */
                                  /* through the texture pipe, which does not share the      */
                                  /* shared-memory crossbar.  Needs hdrnet_slice_apply_f32_ws*/
+#define HDRNET_VARIANT_TEX_WS 5  /* the same, warp-specialised: a producer warp issues all  */
+                                 /* TMA loads, 8 math warps run without block barriers     */
 
 HDRNET_API int hdrnet_b200_abi_version(void);
 
