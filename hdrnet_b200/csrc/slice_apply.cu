@@ -136,6 +136,7 @@ slice_indices_kernel(const float* __restrict__ guide, int32_t* __restrict__ idx,
 // =========================================================================================
 
 constexpr int kTmaThreads = 256;
+constexpr int kTmaThreadsDefault = 256;  // 512 = 64-register form (HDRNET_TMA_THREADS)
 constexpr int kMaxStages = 8;
 constexpr int kGc = 12;
 
@@ -143,6 +144,7 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct TmaPlan {
   int ctas;
+  int threads;     // threads per CTA (256, or 512 = the 64-register / 32-warps-per-SM form)
   int resident;    // CTAs per SM the plan was sized for (1, 2 or 3)
   int stages;
   int nseg;        // segments per row
@@ -306,8 +308,8 @@ __device__ __forceinline__ void process_quad(const TmaArgs& args, const GuideFn&
   fence_proxy_async_smem();
 }
 
-template <class GuideFn, int kTexChunks, int kMinBlocks = 2>
-__global__ void __launch_bounds__(kTmaThreads, kMinBlocks)
+template <class GuideFn, int kTexChunks, int kMinBlocks = 2, int kThreads = kTmaThreads>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
   constexpr bool kGuideIn = GuideFn::kFromInput;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -424,7 +426,7 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
       const float4* a4 = reinterpret_cast<const float4*>(raw0);
       const float4* b4 = reinterpret_cast<const float4*>(raw1);
       float4* s4 = reinterpret_cast<float4*>(slab);
-      for (int e = tid; e < pl.row_floats / 4; e += kTmaThreads) s4[e] = lerp4(wy0, a4[e], wy1, b4[e]);
+      for (int e = tid; e < pl.row_floats / 4; e += kThreads) s4[e] = lerp4(wy0, a4[e], wy1, b4[e]);
       __syncthreads();
       }
     }
@@ -821,12 +823,13 @@ static int device_max_smem_optin() {
 // tex_mode: the texture-assisted form double-buffers whole slab rows in raw0 / raw1 and needs no
 // separate slab region (lets 32x32x16 grids keep two CTAs per SM).
 static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out,
-                          bool tex_mode = false) {
+                          bool tex_mode = false, int threads = kTmaThreads) {
   if (g.W < 4 || (g.W % 4) != 0) return false;
   TmaPlan p;
+  p.threads = threads;
   p.row_floats = g.gw * g.gd * kGc;
   const int quads = g.W / 4;
-  p.nseg = (quads + kTmaThreads - 1) / kTmaThreads;
+  p.nseg = (quads + threads - 1) / threads;
   p.seg_px = 4 * ((quads + p.nseg - 1) / p.nseg);
   p.stage_bytes = round_up(p.seg_px * 16, 128);
   p.off_raw = 256;  // barriers: up to 2 * kMaxStages + 4 (warp-specialised form) = 160 bytes
@@ -887,13 +890,13 @@ bool make_zsort_plan(const SliceGeom& g, int max_smem, int sms, ZsPlan* out);
 int launch_zsort(const float* grid, const float* guide, const float* input, float* out,
                  const SliceGeom& g, const ZsPlan& plan, cudaStream_t stream);
 
-template <class GuideFn, int kTexChunks = 0, int kMinBlocks = 2>
+template <class GuideFn, int kTexChunks = 0, int kMinBlocks = 2, int kThreads = kTmaThreads>
 static int launch_tma_occ(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  auto kern = slice_apply_rows_tma_kernel<GuideFn, kTexChunks, kMinBlocks>;
+  auto kern = slice_apply_rows_tma_kernel<GuideFn, kTexChunks, kMinBlocks, kThreads>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<a.p.ctas, kTmaThreads, a.p.smem_bytes, stream>>>(a, fn);
+  kern<<<a.p.ctas, kThreads, a.p.smem_bytes, stream>>>(a, fn);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -903,7 +906,10 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) 
   // per thread.  Only the guide-from-input form is built that way; the fused-guide forms need
   // their registers and simply run two of the three planned CTAs.
   if constexpr (GuideFn::kFromInput) {
-    if (a.p.resident == 3) return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
+    if (a.p.resident == 3 && a.p.threads == kTmaThreads)
+      return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
+    // 512 threads x 2 CTAs: 64 registers per thread (no spills), 32 warps per SM
+    if (a.p.threads == 512) return launch_tma_occ<GuideFn, kTexChunks, 2, 512>(a, fn, stream);
   }
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
@@ -978,10 +984,13 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
 
   const SliceGeom g = make_geom(B, H, W, rows, y_off, gh, gw, gd);
   const int sms = device_sm_count();
+  int tma_threads = kTmaThreadsDefault;
+  if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tma_threads = (std::atoi(e) == 512) ? 512 : 256;
+  if (gs.mode != 0) tma_threads = kTmaThreads;  // fused-guide forms are built for 256 threads
 
   TmaPlan plan;
   const bool tma_shape = (n_in == 3 && n_out == 3 && has_offset) &&
-                         make_tma_plan(g, device_max_smem_optin(), sms, &plan) &&
+                         make_tma_plan(g, device_max_smem_optin(), sms, &plan, false, tma_threads) &&
                          aligned16(grid) && aligned16(input) && aligned16(out) &&
                          (gs.mode != 0 || aligned16(gs.guide)) &&
                          (gs.guide_out == nullptr || aligned16(gs.guide_out));
@@ -1002,7 +1011,9 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     const size_t need = tex_need;
     if (!tex_ok) return HDRNET_E_UNSUPPORTED;
     TmaPlan tplan;
-    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true)) tplan = plan;
+    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true,
+                       variant == HDRNET_VARIANT_TEX_WS ? kTmaThreads : tma_threads))
+      tplan = plan;
     TmaArgs a;
     a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr; a.input = input; a.out = out;
     a.g = g; a.p = tplan; a.yslab = gs.workspace;

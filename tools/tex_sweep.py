@@ -22,7 +22,15 @@ for ns in ("4", "5", "6"):
     os.environ["HDRNET_TMA_STAGES"] = ns
     print("stages", ns, "tex", round(t(_lib.VARIANT_TEX), 4), "tex_ws", round(t(_lib.VARIANT_TEX_WS), 4))
 os.environ["HDRNET_TMA_STAGES"] = "4"
-for c in (2, 3, 4, 5, 6):
+for thr in ("256", "512"):
+    os.environ["HDRNET_TMA_THREADS"] = thr
+    os.environ["HDRNET_TEX_CHUNKS"] = "4"
+    print("threads", thr, "tma", round(t(_lib.VARIANT_TMA), 4), "tex", round(t(_lib.VARIANT_TEX), 4))
+    for c in (5, 6):
+        os.environ["HDRNET_TEX_CHUNKS"] = str(c)
+        print("   threads", thr, "tex chunks", c, round(t(_lib.VARIANT_TEX), 4))
+os.environ["HDRNET_TMA_THREADS"] = "256"
+for c in ():
     os.environ["HDRNET_TEX_CHUNKS"] = str(c)
     ms = t(_lib.VARIANT_TEX)
     print("tex chunks", c, round(ms, 4), "ms", round(8*2160*3840*28/ms/1e6/6577.4, 4), "frac")
