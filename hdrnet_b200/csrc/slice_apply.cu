@@ -136,7 +136,8 @@ slice_indices_kernel(const float* __restrict__ guide, int32_t* __restrict__ idx,
 // =========================================================================================
 
 constexpr int kTmaThreads = 256;
-constexpr int kTmaThreadsDefault = 256;  // 512 = 64-register form (HDRNET_TMA_THREADS)
+constexpr int kTmaThreadsDefault = 256;  // all-LSU form; 512 = 64-register form (HDRNET_TMA_THREADS)
+constexpr int kTexThreadsDefault = 512;  // texture-assisted form: measured 7 % faster at 512
 constexpr int kMaxStages = 8;
 constexpr int kGc = 12;
 
@@ -470,11 +471,9 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
 //     store has drained the tile -- arrives on stage_free[]; after a row's last item it arrives
 //     on slab_free[].  stage_free / slab_free count kWsConsumerWarps arrivals per phase.
 constexpr int kTexChunksWs = 4;
-constexpr int kWsConsumerWarps = 8;
-constexpr int kWsThreads = (kWsConsumerWarps + 1) * 32;
 
-template <class GuideFn, int kTexChunks>
-__global__ void __launch_bounds__(kWsThreads, 2)
+template <class GuideFn, int kTexChunks, int kWsConsumerWarps>
+__global__ void __launch_bounds__((kWsConsumerWarps + 1) * 32, 2)
 slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
   static_assert(kTexChunks > 0, "the warp-specialised kernel reads slab rows from the workspace");
   constexpr bool kGuideIn = GuideFn::kFromInput;
@@ -914,14 +913,21 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) 
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
-template <class GuideFn>
-static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  auto kern = slice_apply_rows_ws_kernel<GuideFn, kTexChunksWs>;
+template <class GuideFn, int kConsumerWarps>
+static int launch_ws_n(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
+  auto kern = slice_apply_rows_ws_kernel<GuideFn, kTexChunksWs, kConsumerWarps>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<a.p.ctas, kWsThreads, a.p.smem_bytes, stream>>>(a, fn);
+  kern<<<a.p.ctas, (kConsumerWarps + 1) * 32, a.p.smem_bytes, stream>>>(a, fn);
   return static_cast<int>(cudaGetLastError());
+}
+
+template <class GuideFn>
+static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
+  // consumer warps = planned threads / 32 (8 for the 256-thread plan, 16 for the 512-thread one)
+  if (a.p.threads == 512) return launch_ws_n<GuideFn, 16>(a, fn, stream);
+  return launch_ws_n<GuideFn, 8>(a, fn, stream);
 }
 
 // Texture objects over caller workspaces, cached by (pointer, bytes): creating one is a
@@ -1011,8 +1017,11 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     const size_t need = tex_need;
     if (!tex_ok) return HDRNET_E_UNSUPPORTED;
     TmaPlan tplan;
-    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true,
-                       variant == HDRNET_VARIANT_TEX_WS ? kTmaThreads : tma_threads))
+    // the texture forms default to the 512-thread / 64-register plan (32 warps per SM)
+    int tex_threads = kTexThreadsDefault;
+    if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tex_threads = (std::atoi(e) == 512) ? 512 : 256;
+    if (gs.mode != 0) tex_threads = kTmaThreads;
+    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true, tex_threads))
       tplan = plan;
     TmaArgs a;
     a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr; a.input = input; a.out = out;
@@ -1022,7 +1031,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     yblend_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows), 128, 0, stream>>>(
         grid, gs.workspace, g, plan.row_floats);
     if (variant == HDRNET_VARIANT_TEX_WS) {
-      if (gs.mode != 0 || plan.seg_px > kWsConsumerWarps * 128) return HDRNET_E_UNSUPPORTED;
+      if (gs.mode != 0 || tplan.seg_px > tplan.threads * 4) return HDRNET_E_UNSUPPORTED;
       return launch_ws(a, GuideFromInput{}, stream);
     }
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
@@ -1286,10 +1295,11 @@ int hdrnet_slice_apply_plan_ws(int B, int H, int W, int gh, int gw, int gd, int 
   const bool tex = with_workspace && npix >= (1LL << 21);
   TmaPlan plan;
   const bool tma = (n_in == 3 && n_out == 3 && has_offset) && W >= 128 &&
-                   make_tma_plan(g, device_max_smem_optin(), sms, &plan, tex);
+                   make_tma_plan(g, device_max_smem_optin(), sms, &plan, tex,
+                                 tex ? kTexThreadsDefault : kTmaThreadsDefault);
   if (variant) *variant = tma ? (tex ? HDRNET_VARIANT_TEX : HDRNET_VARIANT_TMA) : HDRNET_VARIANT_GENERIC;
   if (ctas) *ctas = tma ? plan.ctas : generic_grid(npix, sms);
-  if (threads) *threads = tma ? kTmaThreads : 256;
+  if (threads) *threads = tma ? plan.threads : 256;
   if (smem_bytes) *smem_bytes = tma ? plan.smem_bytes : 0;
   return HDRNET_OK;
 }

@@ -17,15 +17,12 @@ def t(variant, iters=100):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / iters
 print("tma", round(t(_lib.VARIANT_TMA), 4))
-print("tex_ws", round(t(_lib.VARIANT_TEX_WS), 4), "ms", round(8*2160*3840*28/t(_lib.VARIANT_TEX_WS)/1e6/6577.4, 4), "frac")
-for ns in ("4", "5", "6"):
-    os.environ["HDRNET_TMA_STAGES"] = ns
-    print("stages", ns, "tex", round(t(_lib.VARIANT_TEX), 4), "tex_ws", round(t(_lib.VARIANT_TEX_WS), 4))
-os.environ["HDRNET_TMA_STAGES"] = "4"
+print("defaults: tex", round(t(_lib.VARIANT_TEX), 4), "tex_ws", round(t(_lib.VARIANT_TEX_WS), 4), "auto", round(t(_lib.VARIANT_AUTO), 4))
 for thr in ("256", "512"):
     os.environ["HDRNET_TMA_THREADS"] = thr
     os.environ["HDRNET_TEX_CHUNKS"] = "4"
-    print("threads", thr, "tma", round(t(_lib.VARIANT_TMA), 4), "tex", round(t(_lib.VARIANT_TEX), 4))
+    print("threads", thr, "tma", round(t(_lib.VARIANT_TMA), 4), "tex", round(t(_lib.VARIANT_TEX), 4),
+          "tex_ws", round(t(_lib.VARIANT_TEX_WS), 4))
     for c in (5, 6):
         os.environ["HDRNET_TEX_CHUNKS"] = str(c)
         print("   threads", thr, "tex chunks", c, round(t(_lib.VARIANT_TEX), 4))
