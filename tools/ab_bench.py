@@ -1,0 +1,42 @@
+"""Interleaved A/B timing of slice-apply kernel configurations at the headline shape: every
+configuration is timed in short bursts, round-robin, and the median burst is reported (guards
+against clock / thermal drift across a long sweep)."""
+import os, sys, statistics, torch
+sys.path.insert(0, ".")
+from hdrnet_b200 import hdrnet_ops, _lib
+B = 8
+gen = torch.Generator(device="cuda").manual_seed(1234)
+grid = torch.rand(B, 16, 16, 8, 12, device="cuda", generator=gen)
+guide = torch.rand(B, 2160, 3840, device="cuda", generator=gen)
+inp = torch.rand(B, 2160, 3840, 3, device="cuda", generator=gen)
+out = torch.empty_like(inp)
+CONFIGS = {
+    "auto": (dict(), _lib.VARIANT_AUTO),
+    "tex t512 c4": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
+    "tex t512 c5": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="5"), _lib.VARIANT_TEX),
+    "tex t512 c3": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX),
+    "tex t256 c4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
+    "ws  t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TEX_WS),
+    "ws  t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TEX_WS),
+    "tma t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TMA),
+    "tma t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TMA),
+}
+KEYS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC")
+def burst(env, variant, iters=40):
+    for k in KEYS: os.environ.pop(k, None)
+    os.environ.update(env)
+    f = lambda: hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, out=out, variant=variant)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): f()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+res = {k: [] for k in CONFIGS}
+for r in range(7):
+    for k, (env, v) in CONFIGS.items():
+        res[k].append(burst(env, v))
+for k, v in res.items():
+    med = statistics.median(v)
+    print(f"{k:14s} median {med:.4f} ms  min {min(v):.4f}  max {max(v):.4f}  frac {8*2160*3840*28/med/1e6/6577.4:.4f}")
