@@ -37,6 +37,12 @@ res = {k: [] for k in CONFIGS}
 for r in range(7):
     for k, (env, v) in CONFIGS.items():
         res[k].append(burst(env, v))
+lines = []
 for k, v in res.items():
     med = statistics.median(v)
-    print(f"{k:14s} median {med:.4f} ms  min {min(v):.4f}  max {max(v):.4f}  frac {8*2160*3840*28/med/1e6/6577.4:.4f}")
+    lines.append(f"{k:14s} median {med:.4f} ms  min {min(v):.4f}  max {max(v):.4f}  frac {8*2160*3840*28/med/1e6/6577.4:.4f}")
+print("\n".join(lines))
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/ab_bench.txt", "w") as f:
+    f.write("# tools/ab_bench.py: 4K x 8, grid 16x16x8, 7 interleaved bursts of 40 launches per configuration\n")
+    f.write("\n".join(lines) + "\n")

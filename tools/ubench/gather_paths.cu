@@ -51,6 +51,18 @@ __global__ void __launch_bounds__(THREADS) k(const float4* __restrict__ gtab, cu
       const float* t = reinterpret_cast<const float*>(tab) + zz * 12 + (it & 1) * 4;
       acc.x += t[0]; acc.y += t[1]; acc.z += t[2]; acc.w += t[3];
     }
+    if (MODE & 64) {   // second LDS.128 (different chunk)
+      const float4 v = tab[zz * 3 + 2];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (MODE & 128) {  // third LDS.128 (neighbour cell)
+      const float4 v = tab[24 + zz * 3 + (it & 1)];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (MODE & 256) {  // fourth LDS.128
+      const float4 v = tab[24 + zz * 3 + 2];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
     if (MODE & 32) {
       const float4 v = tex1Dfetch<float4>(tex, zz * 3 + (it & 1));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -105,6 +117,12 @@ int main() {
     run<1 | 4>("LDS.128 + LDG.128 (2 lookups/iter)", gtab, tex, zs, out, cyc, c);
     run<1 | 32>("LDS.128 + tex float4 (2 lookups/iter)", gtab, tex, zs, out, cyc, c);
     run<1 | 2 | 32>("LDS.128 + 4xSHFL + tex (3 lookups/iter)", gtab, tex, zs, out, cyc, c);
+    run<1 | 64>("2 x LDS.128 (per iter)", gtab, tex, zs, out, cyc, c);
+    run<1 | 64 | 32>("2 x LDS.128 + tex (per iter)", gtab, tex, zs, out, cyc, c);
+    run<1 | 64 | 128>("3 x LDS.128 (per iter)", gtab, tex, zs, out, cyc, c);
+    run<1 | 64 | 128 | 32>("3 x LDS.128 + tex (per iter)", gtab, tex, zs, out, cyc, c);
+    run<1 | 64 | 128 | 256>("4 x LDS.128 (per iter)", gtab, tex, zs, out, cyc, c);
+    run<1 | 64 | 128 | 256 | 32>("4 x LDS.128 + tex (per iter)", gtab, tex, zs, out, cyc, c);
   }
   return 0;
 }
