@@ -49,6 +49,12 @@ SIGNATURES = {
                                          + [ctypes.c_float, _vp, ctypes.c_size_t, _vp]),
     "hdrnet_slice_apply_nn_f32_ws": (_c_int, [_vp] * 4 + [_c_int] * 6 + [_vp] * 3
                                      + [ctypes.c_float, _c_int, _vp, ctypes.c_size_t, _vp]),
+    # (grid, input, in_fmt, out, out_fmt, guide_out, B,H,W,gh,gw,gd, guide params..., ws, bytes, stream)
+    "hdrnet_slice_apply_curves_px_ws": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp] + [_c_int] * 6
+                                        + [_vp] * 5 + [ctypes.c_float, _vp, ctypes.c_size_t, _vp]),
+    "hdrnet_slice_apply_nn_px_ws": (_c_int, [_vp, _vp, _c_int, _vp, _c_int, _vp] + [_c_int] * 6
+                                    + [_vp] * 3 + [ctypes.c_float, _c_int, _vp, ctypes.c_size_t, _vp]),
+    "hdrnet_lowres_nearest_f32": (_c_int, [_vp, _c_int, _vp] + [_c_int] * 5 + [_vp]),
     "hdrnet_conv2d_nhwc_f32": (_c_int, [_vp] * 4 + [_c_int] * 8 + [_vp]),
     "hdrnet_conv2d_tc_packed_bytes": (ctypes.c_size_t, [_c_int] * 3),
     "hdrnet_conv2d_tc_pack_f32": (_c_int, [_vp, _vp] + [_c_int] * 3 + [_vp]),
@@ -60,6 +66,9 @@ SIGNATURES = {
     "hdrnet_host_ctx_destroy": (_c_int, [_vp]),
     "hdrnet_slice_apply_host_f32": (_c_int, [_vp] * 5 + [_c_int] * 9),
 }
+
+# pixel storage formats (include/hdrnet_b200.h HDRNET_PX_*)
+PX_F32, PX_U8, PX_U16 = 0, 1, 2
 
 _lock = threading.Lock()
 _lib = None

@@ -10,10 +10,11 @@ arguments and flags, hdrnet/bin/run.py:219-238):
 read back by utils.get_model_params) instead of a TF checkpoint + meta graph.
 
 Host-side pre/post processing follows the reference (run.py:139-190):
-  cv2.imread(-1) -> drop alpha -> BGR->RGB -> img_as_float (u8 /255, u16 /65535; --hdrp
-  scales by 32767 white level first, run.py:156-160) -> nearest-neighbour S x S lowres
+  cv2.imread(-1) -> drop alpha -> BGR->RGB -> img_as_float (u8 /255, u16 /65535; --hdrp only
+  logs, both branches of run.py:156-164 call img_as_float) -> nearest-neighbour S x S lowres
   (skimage.transform.resize(order=0), run.py:168-169) -> model -> uint8(255 * clip(out, 0, 1))
-  (truncating cast, run.py:95) -> PNG.
+  (truncating cast, run.py:95) -> PNG.  Everything after the decode runs on the device, on the
+  integer pixels (models.*.inference_image).
 """
 from __future__ import annotations
 
@@ -79,25 +80,34 @@ def save_checkpoint(checkpoint_dir, params, weights):
 
 
 def process(mdl, params, im_u: np.ndarray, lowres_u: np.ndarray | None = None, hdrp=False):
-    """One image through the model; returns uint8 HxWx3 (and the float output)."""
+    """One image through the model; returns uint8 HxWx3 (and the float output when
+    params['debug'] asks for the collections).
+
+    The decoded uint8 / uint16 pixels go to the device as they are (3 or 6 bytes per pixel);
+    img_as_float, the nearest-neighbour network input, the model and the uint8 cast all run
+    there (models.*.inference_image).  ``--hdrp`` only logs a notice in the reference: both of
+    its branches call skimage.img_as_float (run.py:156-164), so it changes nothing here."""
     if im_u.ndim == 2:
         im_u = np.repeat(im_u[..., None], 3, axis=2)
     if im_u.shape[2] > 3:
         im_u = im_u[:, :, :3]                                      # run.py:146-148
-    src = lowres_u if lowres_u is not None else im_u
-    if hdrp:                                                        # run.py:156-160
-        im = np.minimum(im_u.astype(np.float32) / 32767.0, 1.0).astype(np.float32)
-        src = np.minimum(src.astype(np.float32) / 32767.0, 1.0).astype(np.float32)
-    else:
-        im = img_as_float(im_u)
-        src = img_as_float(src)
-    S = int(params["net_input_size"])
-    low = nearest_resize(src, S)
-    full_t = torch.from_numpy(np.ascontiguousarray(im[None])).cuda()
-    low_t = torch.from_numpy(np.ascontiguousarray(low[None])).cuda()
-    out = mdl.inference(low_t, full_t, params, is_training=False)
-    out8 = (255.0 * out.clamp(0.0, 1.0)).to(torch.uint8)[0].cpu().numpy()   # run.py:95
-    return out8, out
+    if hdrp and im_u.dtype == np.uint16:
+        log.info("Using HDR+ hack for uint16 input. Assuming input white level is 32767.")
+
+    def to_dev(a):
+        if a.dtype not in (np.uint8, np.uint16):
+            a = a.astype(np.float32)
+        return torch.from_numpy(np.ascontiguousarray(a[None])).cuda()
+
+    full_t = to_dev(im_u)
+    low_t = None
+    if lowres_u is not None:
+        if lowres_u.ndim == 2:
+            lowres_u = np.repeat(lowres_u[..., None], 3, axis=2)
+        low_t = to_dev(lowres_u[:, :, :3])
+    out8 = mdl.inference_image(full_t, params, lowres_image=low_t)  # run.py:95 cast included
+    out = mdl.last_debug["output"] if params.get("debug") and hasattr(mdl, "last_debug") else None
+    return out8[0].cpu().numpy(), out
 
 
 def main(args):

@@ -53,3 +53,70 @@ extern "C" int hdrnet_resize_bilinear_f32(const float* in, const float* add, flo
       in, add, out, B, H, W, C, OH, OW, sy, sx, total);
   return static_cast<int>(cudaGetLastError());
 }
+
+// ---- nearest-neighbour low-resolution input from the decoded image (row f-3) -----------------
+namespace hdrnet_b200 {
+
+// img_as_float of one code value: bit-exact with float32(float64(v) / D) for every v (one
+// Newton step on v * (1/D); exhaustive check in tests/test_px_gpu.py).
+template <int kFmt>
+__device__ __forceinline__ float code_to_float(const void* image, long long idx) {
+  if constexpr (kFmt == HDRNET_PX_F32) {
+    return __ldg(static_cast<const float*>(image) + idx);
+  } else {
+    constexpr float D = (kFmt == HDRNET_PX_U8) ? 255.0f : 65535.0f;
+    constexpr float R = 1.0f / D;
+    const float f = (kFmt == HDRNET_PX_U8)
+                        ? static_cast<float>(__ldg(static_cast<const unsigned char*>(image) + idx))
+                        : static_cast<float>(__ldg(static_cast<const unsigned short*>(image) + idx));
+    const float q0 = f * R;
+    return fmaf(fmaf(-q0, D, f), R, q0);
+  }
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(256)
+lowres_nearest_kernel(const void* __restrict__ image, float* __restrict__ lowres, int B, int H,
+                      int W, int SH, int SW, long long total) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += stride) {
+    const int c = static_cast<int>(e % 3);
+    const long long px = e / 3;
+    const int ox = static_cast<int>(px % SW);
+    const int oy = static_cast<int>((px / SW) % SH);
+    const long long b = px / (static_cast<long long>(SW) * SH);
+    // floor((o + 0.5) * H / S) in exact integer arithmetic
+    const int iy = min(static_cast<int>((2LL * oy + 1) * H / (2LL * SH)), H - 1);
+    const int ix = min(static_cast<int>((2LL * ox + 1) * W / (2LL * SW)), W - 1);
+    lowres[e] = code_to_float<kFmt>(image, ((b * H + iy) * W + ix) * 3 + c);
+  }
+}
+
+}  // namespace hdrnet_b200
+
+extern "C" int hdrnet_lowres_nearest_f32(const void* image, int fmt, float* lowres, int B, int H,
+                                         int W, int SH, int SW, void* stream) {
+  if (B < 0 || H < 1 || W < 1 || SH < 1 || SW < 1) return HDRNET_E_BAD_SHAPE;
+  const long long total = static_cast<long long>(B) * SH * SW * 3;
+  if (total == 0) return HDRNET_OK;
+  if (!image || !lowres) return HDRNET_E_NULL_POINTER;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned nb = static_cast<unsigned>(blocks);
+  switch (fmt) {
+    case HDRNET_PX_F32:
+      hdrnet_b200::lowres_nearest_kernel<HDRNET_PX_F32><<<nb, 256, 0, st>>>(image, lowres, B, H, W, SH, SW, total);
+      break;
+    case HDRNET_PX_U8:
+      hdrnet_b200::lowres_nearest_kernel<HDRNET_PX_U8><<<nb, 256, 0, st>>>(image, lowres, B, H, W, SH, SW, total);
+      break;
+    case HDRNET_PX_U16:
+      hdrnet_b200::lowres_nearest_kernel<HDRNET_PX_U16><<<nb, 256, 0, st>>>(image, lowres, B, H, W, SH, SW, total);
+      break;
+    default:
+      return HDRNET_E_UNSUPPORTED;
+  }
+  return static_cast<int>(cudaGetLastError());
+}

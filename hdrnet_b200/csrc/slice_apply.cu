@@ -132,12 +132,137 @@ slice_indices_kernel(const float* __restrict__ guide, int32_t* __restrict__ idx,
 }
 
 // =========================================================================================
+// Pixel storage formats of the model-path forms (row f-3): the full-resolution image may stay
+// in the integer format it was decoded to, and the result may leave as the uint8 the reference
+// writes (hdrnet/bin/run.py:145-169 img_as_float; :95 uint8(255 * clip(out, 0, 1))).
+// =========================================================================================
+constexpr int kPxF32 = HDRNET_PX_F32, kPxU8 = HDRNET_PX_U8, kPxU16 = HDRNET_PX_U16;
+
+__host__ __device__ constexpr int px_bytes_per_channel(int fmt) {
+  return fmt == kPxU8 ? 1 : (fmt == kPxU16 ? 2 : 4);
+}
+
+// skimage.img_as_float: v / 255 (uint8) or v / 65535 (uint16), evaluated in float64 and handed
+// to a float32 placeholder.  q0 = v * (1/D) with one Newton correction reproduces that float32
+// for EVERY code value (exhaustive check: tests/test_px_gpu.py) at 3 FMA-pipe instructions.
+template <int kFmt>
+__device__ __forceinline__ float px_to_float(unsigned v) {
+  constexpr float D = (kFmt == kPxU8) ? 255.0f : 65535.0f;
+  constexpr float R = 1.0f / D;
+  const float f = static_cast<float>(v);
+  const float q0 = f * R;
+  return fmaf(fmaf(-q0, D, f), R, q0);
+}
+
+// tf.cast(255.0 * tf.clip_by_value(x, 0, 1), tf.uint8): truncating conversion.
+__device__ __forceinline__ unsigned float_to_u8(float x) {
+  return __float2uint_rz(255.0f * fminf(fmaxf(x, 0.0f), 1.0f));
+}
+
+// One thread's 4 consecutive pixels, from / to a staged tile (shared memory) or global memory.
+template <int kFmt>
+__device__ __forceinline__ void load_quad(const unsigned char* tile, int q, float (&pr)[4],
+                                          float (&pg)[4], float (&pb)[4]) {
+  if constexpr (kFmt == kPxF32) {
+    const float4* rgb4 = reinterpret_cast<const float4*>(tile) + 3 * q;
+    const float4 c0 = rgb4[0], c1 = rgb4[1], c2 = rgb4[2];
+    pr[0] = c0.x; pg[0] = c0.y; pb[0] = c0.z; pr[1] = c0.w;
+    pg[1] = c1.x; pb[1] = c1.y; pr[2] = c1.z; pg[2] = c1.w;
+    pb[2] = c2.x; pr[3] = c2.y; pg[3] = c2.z; pb[3] = c2.w;
+  } else if constexpr (kFmt == kPxU8) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(tile) + 3 * q;  // 12 bytes
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    pr[0] = px_to_float<kPxU8>(w0 & 0xffu);         pg[0] = px_to_float<kPxU8>((w0 >> 8) & 0xffu);
+    pb[0] = px_to_float<kPxU8>((w0 >> 16) & 0xffu); pr[1] = px_to_float<kPxU8>(w0 >> 24);
+    pg[1] = px_to_float<kPxU8>(w1 & 0xffu);         pb[1] = px_to_float<kPxU8>((w1 >> 8) & 0xffu);
+    pr[2] = px_to_float<kPxU8>((w1 >> 16) & 0xffu); pg[2] = px_to_float<kPxU8>(w1 >> 24);
+    pb[2] = px_to_float<kPxU8>(w2 & 0xffu);         pr[3] = px_to_float<kPxU8>((w2 >> 8) & 0xffu);
+    pg[3] = px_to_float<kPxU8>((w2 >> 16) & 0xffu); pb[3] = px_to_float<kPxU8>(w2 >> 24);
+  } else {
+    const uint2* w = reinterpret_cast<const uint2*>(tile) + 3 * q;        // 24 bytes
+    const uint2 w0 = w[0], w1 = w[1], w2 = w[2];
+    pr[0] = px_to_float<kPxU16>(w0.x & 0xffffu); pg[0] = px_to_float<kPxU16>(w0.x >> 16);
+    pb[0] = px_to_float<kPxU16>(w0.y & 0xffffu); pr[1] = px_to_float<kPxU16>(w0.y >> 16);
+    pg[1] = px_to_float<kPxU16>(w1.x & 0xffffu); pb[1] = px_to_float<kPxU16>(w1.x >> 16);
+    pr[2] = px_to_float<kPxU16>(w1.y & 0xffffu); pg[2] = px_to_float<kPxU16>(w1.y >> 16);
+    pb[2] = px_to_float<kPxU16>(w2.x & 0xffffu); pr[3] = px_to_float<kPxU16>(w2.x >> 16);
+    pg[3] = px_to_float<kPxU16>(w2.y & 0xffffu); pb[3] = px_to_float<kPxU16>(w2.y >> 16);
+  }
+}
+
+template <int kFmt>
+__device__ __forceinline__ void store_quad(unsigned char* tile, int q, const float (&o_r)[4],
+                                           const float (&o_g)[4], const float (&o_b)[4]) {
+  if constexpr (kFmt == kPxF32) {
+    float4* rgb4 = reinterpret_cast<float4*>(tile) + 3 * q;
+    rgb4[0] = make_float4(o_r[0], o_g[0], o_b[0], o_r[1]);
+    rgb4[1] = make_float4(o_g[1], o_b[1], o_r[2], o_g[2]);
+    rgb4[2] = make_float4(o_b[2], o_r[3], o_g[3], o_b[3]);
+  } else {
+    static_assert(kFmt == kPxU8, "results leave as float32 or uint8");
+    uint32_t* w = reinterpret_cast<uint32_t*>(tile) + 3 * q;
+    w[0] = float_to_u8(o_r[0]) | (float_to_u8(o_g[0]) << 8) | (float_to_u8(o_b[0]) << 16) | (float_to_u8(o_r[1]) << 24);
+    w[1] = float_to_u8(o_g[1]) | (float_to_u8(o_b[1]) << 8) | (float_to_u8(o_r[2]) << 16) | (float_to_u8(o_g[2]) << 24);
+    w[2] = float_to_u8(o_b[2]) | (float_to_u8(o_r[3]) << 8) | (float_to_u8(o_g[3]) << 16) | (float_to_u8(o_b[3]) << 24);
+  }
+}
+
+// Any-shape fallback of the model-path forms with integer pixel I/O: one thread per pixel, guide
+// computed in registers, 8-corner gather as slice_generic_kernel<true> (same summation order, so
+// its float32 result equals guide kernel + generic kernel bit for bit).
+template <int kFmt>
+__device__ __forceinline__ float load_channel(const unsigned char* base, long long idx) {
+  if constexpr (kFmt == kPxF32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+  else if constexpr (kFmt == kPxU8) return px_to_float<kPxU8>(__ldg(base + idx));
+  else return px_to_float<kPxU16>(__ldg(reinterpret_cast<const unsigned short*>(base) + idx));
+}
+
+template <class GuideFn, int kIn, int kOut>
+__global__ void __launch_bounds__(256)
+slice_apply_px_generic_kernel(const float* __restrict__ grid, const unsigned char* __restrict__ input,
+                              unsigned char* __restrict__ out, float* __restrict__ guide_out,
+                              SliceGeom g, long long npix, const __grid_constant__ GuideFn guide_fn) {
+  const long long grid_image = static_cast<long long>(g.gh) * g.gw * g.gd * 12;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
+       p += stride) {
+    const int x = static_cast<int>(p % g.W);
+    const long long row = p / g.W;
+    const int r = static_cast<int>(row % g.rows);
+    const int b = static_cast<int>(row / g.rows);
+    const float in[3] = {load_channel<kIn>(input, 3 * p), load_channel<kIn>(input, 3 * p + 1),
+                         load_channel<kIn>(input, 3 * p + 2)};
+    const float gv = guide_fn(in[0], in[1], in[2]);
+    if (guide_out != nullptr) guide_out[p] = gv;
+    const Corners c = make_corners(g, x, g.y_off + r, gv, 12);
+    const float* grid_b = grid + b * grid_image;
+    float o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float value = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) value = fmaf(sample(grid_b, c, i * 4 + j), in[j], value);
+      o[i] = value + sample(grid_b, c, i * 4 + 3);
+    }
+    if constexpr (kOut == kPxF32) {
+      float* op = reinterpret_cast<float*>(out) + 3 * p;
+      op[0] = o[0]; op[1] = o[1]; op[2] = o[2];
+    } else {
+      out[3 * p] = static_cast<unsigned char>(float_to_u8(o[0]));
+      out[3 * p + 1] = static_cast<unsigned char>(float_to_u8(o[1]));
+      out[3 * p + 2] = static_cast<unsigned char>(float_to_u8(o[2]));
+    }
+  }
+}
+
+// =========================================================================================
 // Persistent TMA row kernel: n_in = 3, n_out = 3, has_offset (gc = 12), W % 4 == 0.
 // =========================================================================================
 
 constexpr int kTmaThreads = 256;
 constexpr int kTmaThreadsDefault = 256;  // all-LSU form; 512 = 64-register form (HDRNET_TMA_THREADS)
 constexpr int kTexThreadsDefault = 512;  // texture-assisted form: measured 7 % faster at 512
+constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the texture-assisted kernel
 constexpr int kMaxStages = 8;
 constexpr int kGc = 12;
 
@@ -154,14 +279,17 @@ struct TmaPlan {
   int smem_bytes;
   // byte offsets into dynamic shared memory
   int off_raw, off_slab, off_stage, stage_bytes;
+  // pixel formats: bytes per pixel of the staged input / output tiles, and where the guide and
+  // output tiles sit inside a stage (off_out == 0: the result overwrites the input tile)
+  int in_bpp, out_bpp, off_guide, off_out;
 };
 
 struct TmaArgs {
   const float* grid;
   const float* guide;   // guide input (GuideFromInput), else unused
   float* guide_out;     // optional guide dump for the fused forms, else nullptr
-  const float* input;
-  float* out;
+  const unsigned char* input;   // [B * rows][W][3] in the kernel's input pixel format
+  unsigned char* out;           // [B * rows][W][3] in the kernel's output pixel format
   cudaTextureObject_t slab_tex;  // kTexChunks > 0: float4 view of the y-pre-blended slab rows
   const float* yslab;            // kTexChunks > 0: [B * rows][gw * gd * 12] slab rows (workspace)
   SliceGeom g;
@@ -261,20 +389,17 @@ struct GuideNN {
 // One thread's 4 consecutive pixels (quad `q` of a staged segment): guide (staged, or computed
 // from RGB), bit-exact cell indices, 4-corner blend + affine apply, result written IN PLACE over
 // the RGB tile.  Shared by the block-synchronous and the warp-specialised row kernels.
-template <class GuideFn, int kTexChunks>
+template <class GuideFn, int kTexChunks, int kIn = kPxF32, int kOut = kPxF32>
 __device__ __forceinline__ void process_quad(const TmaArgs& args, const GuideFn& guide_fn,
-                                             unsigned char* rgb_tile, const unsigned char* guide_tile,
-                                             const float* slab, int tex_row, long long row, int x0,
-                                             int q) {
+                                             const unsigned char* in_tile, unsigned char* out_tile,
+                                             const unsigned char* guide_tile, const float* slab,
+                                             int tex_row, long long row, int x0, int q) {
   constexpr bool kGuideIn = GuideFn::kFromInput;
   const SliceGeom& g = args.g;
   const float gd_f = static_cast<float>(g.gd);
   const int x_stride = g.gd * kGc;
-  float4* rgb4 = reinterpret_cast<float4*>(rgb_tile) + 3 * q;
-  const float4 c0 = rgb4[0], c1 = rgb4[1], c2 = rgb4[2];
-  const float pr[4] = {c0.x, c0.w, c1.z, c2.y};
-  const float pg[4] = {c0.y, c1.x, c1.w, c2.z};
-  const float pb[4] = {c0.z, c1.y, c2.x, c2.w};
+  float pr[4], pg[4], pb[4];
+  load_quad<kIn>(in_tile, q, pr, pg, pb);
   float gv[4];
   if (kGuideIn) {
     const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
@@ -303,16 +428,16 @@ __device__ __forceinline__ void process_quad(const TmaArgs& args, const GuideFn&
                             xo1 + zo1, wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i], pg[i],
                             pb[i], o_r[i], o_g[i], o_b[i]);
   }
-  rgb4[0] = make_float4(o_r[0], o_g[0], o_b[0], o_r[1]);
-  rgb4[1] = make_float4(o_g[1], o_b[1], o_r[2], o_g[2]);
-  rgb4[2] = make_float4(o_b[2], o_r[3], o_g[3], o_b[3]);
+  store_quad<kOut>(out_tile, q, o_r, o_g, o_b);
   fence_proxy_async_smem();
 }
 
-template <class GuideFn, int kTexChunks, int kMinBlocks = 2, int kThreads = kTmaThreads>
+template <class GuideFn, int kTexChunks, int kMinBlocks = 2, int kThreads = kTmaThreads,
+          int kIn = kPxF32, int kOut = kPxF32>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
   constexpr bool kGuideIn = GuideFn::kFromInput;
+  constexpr uint32_t kInBpp = 3u * px_bytes_per_channel(kIn), kOutBpp = 3u * px_bytes_per_channel(kOut);
   extern __shared__ __align__(128) unsigned char smem[];
   const SliceGeom& g = args.g;
   const TmaPlan& pl = args.p;
@@ -342,12 +467,10 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
   __syncthreads();
 
   const int NS = pl.stages;
-  const int seg_rgb_bytes_max = pl.seg_px * 12;
 
   auto stage_rgb = [&](int s) { return stage_base + static_cast<size_t>(s) * pl.stage_bytes; };
-  auto stage_guide = [&](int s) {
-    return stage_base + static_cast<size_t>(s) * pl.stage_bytes + seg_rgb_bytes_max;
-  };
+  auto stage_guide = [&](int s) { return stage_rgb(s) + pl.off_guide; };
+  auto stage_out = [&](int s) { return stage_rgb(s) + pl.off_out; };  // off_out == 0: in place
   // Work item -> (buffer row, first pixel of the segment, pixels in the segment).
   auto item_span = [&](int item, long long& row, int& x0, int& npx) {
     const int rr = item / pl.nseg;
@@ -361,8 +484,8 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
     item_span(item, row, x0, npx);
     const int s = item % NS;
     const size_t pix = static_cast<size_t>(row) * g.W + x0;
-    mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * (kGuideIn ? 16u : 12u));
-    tma_load_1d(stage_rgb(s), args.input + pix * 3, static_cast<uint32_t>(npx) * 12u, &full[s]);
+    mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * (kInBpp + (kGuideIn ? 4u : 0u)));
+    tma_load_1d(stage_rgb(s), args.input + pix * kInBpp, static_cast<uint32_t>(npx) * kInBpp, &full[s]);
     if (kGuideIn)
       tma_load_1d(stage_guide(s), args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[s]);
   };
@@ -436,13 +559,13 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
     mbar_wait(&full[s], static_cast<uint32_t>(item / NS) & 1u);
 
     if (tid * 4 < npx)
-      process_quad<GuideFn, kTexChunks>(args, guide_fn, stage_rgb(s), stage_guide(s), slab, tex_row,
-                                        row, x0, tid);
+      process_quad<GuideFn, kTexChunks, kIn, kOut>(args, guide_fn, stage_rgb(s), stage_out(s),
+                                                   stage_guide(s), slab, tex_row, row, x0, tid);
     __syncthreads();
 
     if (tid == 0) {
       const size_t pix = static_cast<size_t>(row) * g.W + x0;
-      tma_store_1d(args.out + pix * 3, stage_rgb(s), static_cast<uint32_t>(npx) * 12u);
+      tma_store_1d(args.out + pix * kOutBpp, stage_out(s), static_cast<uint32_t>(npx) * kOutBpp);
       tma_store_commit();
       const int nxt = item + NS - 1;
       if (nxt < nitems) {
@@ -503,12 +626,9 @@ slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn g
   __syncthreads();  // the only block-wide barrier
 
   const int NS = pl.stages;
-  const int seg_rgb_bytes_max = pl.seg_px * 12;
   const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
   auto stage_rgb = [&](int s) { return stage_base + static_cast<size_t>(s) * pl.stage_bytes; };
-  auto stage_guide = [&](int s) {
-    return stage_base + static_cast<size_t>(s) * pl.stage_bytes + seg_rgb_bytes_max;
-  };
+  auto stage_guide = [&](int s) { return stage_rgb(s) + pl.off_guide; };
   auto item_span = [&](int item, long long& row, int& x0, int& npx) {
     const int rr = item / pl.nseg;
     const int seg = item - rr * pl.nseg;
@@ -538,7 +658,7 @@ slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn g
       if (use >= 1) mbar_wait(&stage_free[s], static_cast<uint32_t>(use - 1) & 1u);
       const size_t pix = static_cast<size_t>(row) * g.W + x0;
       mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * (kGuideIn ? 16u : 12u));
-      tma_load_1d(stage_rgb(s), args.input + pix * 3, static_cast<uint32_t>(npx) * 12u, &full[s]);
+      tma_load_1d(stage_rgb(s), args.input + pix * 12, static_cast<uint32_t>(npx) * 12u, &full[s]);
       if (kGuideIn)
         tma_load_1d(stage_guide(s), args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[s]);
     }
@@ -562,14 +682,14 @@ slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn g
     }
     const int q = (px0w >> 2) + lane;
     if (q * 4 < npx)
-      process_quad<GuideFn, kTexChunks>(args, guide_fn, stage_rgb(s), stage_guide(s), slab, tex_row,
-                                        row, x0, q);
+      process_quad<GuideFn, kTexChunks>(args, guide_fn, stage_rgb(s), stage_rgb(s), stage_guide(s),
+                                        slab, tex_row, row, x0, q);
     __syncwarp();
     if (lane == 0) {
       const int nw = min(128, npx - px0w);
       if (nw > 0) {
         const size_t pix = static_cast<size_t>(row) * g.W + x0 + px0w;
-        tma_store_1d(args.out + pix * 3, stage_rgb(s) + static_cast<size_t>(px0w) * 12,
+        tma_store_1d(args.out + pix * 12, stage_rgb(s) + static_cast<size_t>(px0w) * 12,
                      static_cast<uint32_t>(nw) * 12u);
       }
       tma_store_commit();            // one (possibly empty) group per item keeps the counting simple
@@ -822,15 +942,25 @@ static int device_max_smem_optin() {
 // tex_mode: the texture-assisted form double-buffers whole slab rows in raw0 / raw1 and needs no
 // separate slab region (lets 32x32x16 grids keep two CTAs per SM).
 static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out,
-                          bool tex_mode = false, int threads = kTmaThreads) {
-  if (g.W < 4 || (g.W % 4) != 0) return false;
+                          bool tex_mode = false, int threads = kTmaThreads, int in_fmt = kPxF32,
+                          int out_fmt = kPxF32) {
+  // Bulk copies move 16-byte units: a row and every segment must start on one.  float32 pixels
+  // need W % 4 == 0, uint16 W % 8 == 0, uint8 W % 16 == 0 (12 / 6 / 3 bytes per pixel).
+  const int in_bpp = 3 * px_bytes_per_channel(in_fmt), out_bpp = 3 * px_bytes_per_channel(out_fmt);
+  const int gran = std::max(4, std::max(16 / std::__gcd(16, in_bpp), 16 / std::__gcd(16, out_bpp)));
+  if (g.W < gran || (g.W % gran) != 0) return false;
   TmaPlan p;
   p.threads = threads;
   p.row_floats = g.gw * g.gd * kGc;
+  p.in_bpp = in_bpp;
+  p.out_bpp = out_bpp;
   const int quads = g.W / 4;
   p.nseg = (quads + threads - 1) / threads;
-  p.seg_px = 4 * ((quads + p.nseg - 1) / p.nseg);
-  p.stage_bytes = round_up(p.seg_px * 16, 128);
+  p.seg_px = round_up(4 * ((quads + p.nseg - 1) / p.nseg), gran);  // <= 4 * threads (a multiple of 16)
+  // stage = input tile | guide tile (always reserved) | output tile unless it fits in place
+  p.off_guide = round_up(p.seg_px * in_bpp, 16);
+  p.off_out = (out_bpp == in_bpp) ? 0 : p.off_guide + p.seg_px * 4;
+  p.stage_bytes = round_up((p.off_out ? p.off_out + p.seg_px * out_bpp : p.off_guide + p.seg_px * 4), 128);
   p.off_raw = 256;  // barriers: up to 2 * kMaxStages + 4 (warp-specialised form) = 160 bytes
   p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
   p.off_stage = p.off_slab + (tex_mode ? 0 : round_up(p.row_floats * 4, 128));
@@ -889,9 +1019,10 @@ bool make_zsort_plan(const SliceGeom& g, int max_smem, int sms, ZsPlan* out);
 int launch_zsort(const float* grid, const float* guide, const float* input, float* out,
                  const SliceGeom& g, const ZsPlan& plan, cudaStream_t stream);
 
-template <class GuideFn, int kTexChunks = 0, int kMinBlocks = 2, int kThreads = kTmaThreads>
+template <class GuideFn, int kTexChunks = 0, int kMinBlocks = 2, int kThreads = kTmaThreads,
+          int kIn = kPxF32, int kOut = kPxF32>
 static int launch_tma_occ(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  auto kern = slice_apply_rows_tma_kernel<GuideFn, kTexChunks, kMinBlocks, kThreads>;
+  auto kern = slice_apply_rows_tma_kernel<GuideFn, kTexChunks, kMinBlocks, kThreads, kIn, kOut>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -900,16 +1031,24 @@ static int launch_tma_occ(const TmaArgs& a, const GuideFn& fn, cudaStream_t stre
 }
 
 template <class GuideFn, int kTexChunks = 0>
-static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  // plan.resident == 3 (HDRNET_TMA_OCC=3, tuning knob): three CTAs per SM, registers capped at 85
-  // per thread.  Only the guide-from-input form is built that way; the fused-guide forms need
-  // their registers and simply run two of the three planned CTAs.
+static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream, int in_fmt = kPxF32,
+                      int out_fmt = kPxF32) {
   if constexpr (GuideFn::kFromInput) {
+    // plan.resident == 3 (HDRNET_TMA_OCC=3, tuning knob): three CTAs per SM, registers capped at
+    // 85 per thread; plan.threads == 512: 64 registers per thread (no spills), 32 warps per SM.
     if (a.p.resident == 3 && a.p.threads == kTmaThreads)
       return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
-    // 512 threads x 2 CTAs: 64 registers per thread (no spills), 32 warps per SM
     if (a.p.threads == 512) return launch_tma_occ<GuideFn, kTexChunks, 2, 512>(a, fn, stream);
+  } else {
+    // The fused-guide forms are issue-bound and need their registers: 256 threads x 2 CTAs.
+    // Measured at 4K x 8 (tools/ab_fused.py): curves 0.69 ms against 0.71 (256 x 3) and 0.80
+    // (512 x 2); pointwise NN 0.63 / 0.69 / 0.72.  Integer pixel formats exist for them only.
+    if (in_fmt == kPxU8 && out_fmt == kPxU8)
+      return launch_tma_occ<GuideFn, kTexChunks, 2, kTmaThreads, kPxU8, kPxU8>(a, fn, stream);
+    if (in_fmt == kPxU16 && out_fmt == kPxU8)
+      return launch_tma_occ<GuideFn, kTexChunks, 2, kTmaThreads, kPxU16, kPxU8>(a, fn, stream);
   }
+  if (in_fmt != kPxF32 || out_fmt != kPxF32) return HDRNET_E_UNSUPPORTED;
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
@@ -970,14 +1109,47 @@ struct GuideSpec {
   const NNGuideParams* nn;
   float* workspace = nullptr;  // HDRNET_VARIANT_TEX: slab rows, B * rows * gw * gd * 48 bytes
   size_t workspace_bytes = 0;
+  int in_fmt = kPxF32;         // pixel storage of `input` / `out` (fused-guide modes only)
+  int out_fmt = kPxF32;
 };
 
 constexpr int kTexChunksDefault = 4;
 
-static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const float* input,
-                                   float* out, int B, int H, int W, int rows, int y_off, int gh,
+template <class GuideFn>
+static int launch_px_generic(const float* grid, const void* input, void* out, float* guide_out,
+                             const SliceGeom& g, long long npix, int sms, int in_fmt, int out_fmt,
+                             const GuideFn& fn, cudaStream_t stream) {
+  const unsigned char* in = static_cast<const unsigned char*>(input);
+  unsigned char* o = static_cast<unsigned char*>(out);
+  const int blocks = generic_grid(npix, sms);
+#define HDRNET_PX_CASE(I, O)                                                                    \
+  if (in_fmt == I && out_fmt == O) {                                                            \
+    slice_apply_px_generic_kernel<GuideFn, I, O><<<blocks, 256, 0, stream>>>(grid, in, o,       \
+                                                                           guide_out, g, npix, fn); \
+    return static_cast<int>(cudaGetLastError());                                                \
+  }
+  HDRNET_PX_CASE(kPxU8, kPxU8)
+  HDRNET_PX_CASE(kPxU16, kPxU8)
+  HDRNET_PX_CASE(kPxF32, kPxU8)
+  HDRNET_PX_CASE(kPxU8, kPxF32)
+  HDRNET_PX_CASE(kPxU16, kPxF32)
+#undef HDRNET_PX_CASE
+  return HDRNET_E_UNSUPPORTED;
+}
+
+static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const void* input_v,
+                                   void* out_v, int B, int H, int W, int rows, int y_off, int gh,
                                    int gw, int gd, int n_in, int n_out, int has_offset,
                                    int variant, cudaStream_t stream) {
+  const float* input = static_cast<const float*>(input_v);   // float32 forms
+  float* out = static_cast<float*>(out_v);
+  const bool px = gs.in_fmt != kPxF32 || gs.out_fmt != kPxF32;
+  if (px) {  // integer pixel I/O: model-path (fused-guide) forms of the 3 -> 3 affine op only
+    if (gs.mode == 0 || n_in != 3 || n_out != 3 || !has_offset) return HDRNET_E_UNSUPPORTED;
+    if (gs.in_fmt < kPxF32 || gs.in_fmt > kPxU16 || (gs.out_fmt != kPxF32 && gs.out_fmt != kPxU8))
+      return HDRNET_E_UNSUPPORTED;
+    if (variant == HDRNET_VARIANT_ZSORT || variant == HDRNET_VARIANT_TEX_WS) return HDRNET_E_UNSUPPORTED;
+  }
   int rc = validate_common(B, H, W, gh, gw, gd);
   if (rc != HDRNET_OK) return rc;
   if (n_in < 1 || n_out < 1 || rows < 0 || y_off < 0 || y_off + rows > H) return HDRNET_E_BAD_SHAPE;
@@ -992,11 +1164,14 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   const int sms = device_sm_count();
   int tma_threads = kTmaThreadsDefault;
   if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tma_threads = (std::atoi(e) == 512) ? 512 : 256;
-  if (gs.mode != 0) tma_threads = kTmaThreads;  // fused-guide forms are built for 256 threads
+  if (gs.mode != 0) tma_threads = kFusedThreadsDefault;
 
   TmaPlan plan;
   const bool tma_shape = (n_in == 3 && n_out == 3 && has_offset) &&
-                         make_tma_plan(g, device_max_smem_optin(), sms, &plan, false, tma_threads) &&
+                         make_tma_plan(g, device_max_smem_optin(), sms, &plan, false, tma_threads,
+                                       gs.in_fmt, gs.out_fmt) &&
+                         // the row kernel has (u8 | u16) -> u8 and f32 -> f32 pixel forms
+                         (!px || (gs.in_fmt != kPxF32 && gs.out_fmt == kPxU8)) &&
                          aligned16(grid) && aligned16(input) && aligned16(out) &&
                          (gs.mode != 0 || aligned16(gs.guide)) &&
                          (gs.guide_out == nullptr || aligned16(gs.guide_out));
@@ -1020,11 +1195,13 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     // the texture forms default to the 512-thread / 64-register plan (32 warps per SM)
     int tex_threads = kTexThreadsDefault;
     if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tex_threads = (std::atoi(e) == 512) ? 512 : 256;
-    if (gs.mode != 0) tex_threads = kTmaThreads;
-    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true, tex_threads))
+    if (gs.mode != 0) tex_threads = kFusedThreadsDefault;
+    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true, tex_threads,
+                       gs.in_fmt, gs.out_fmt))
       tplan = plan;
     TmaArgs a;
-    a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr; a.input = input; a.out = out;
+    a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr;
+    a.input = static_cast<const unsigned char*>(input_v); a.out = static_cast<unsigned char*>(out_v);
     a.g = g; a.p = tplan; a.yslab = gs.workspace;
     rc = get_slab_texture(gs.workspace, need, &a.slab_tex);
     if (rc != 0) return rc;
@@ -1035,12 +1212,13 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       return launch_ws(a, GuideFromInput{}, stream);
     }
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
-                        return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream); }
+                        return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt); }
     if (gs.mode == 2) {
       a.guide_out = gs.guide_out;
-      if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn; return launch_tma<GuideNN<16>, kTexChunksDefault>(a, fn, stream); }
+      if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn;
+                                return launch_tma<GuideNN<16>, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt); }
       GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
-      return launch_tma<GuideNN<kMaxGuideFeats>, kTexChunksDefault>(a, fn, stream);
+      return launch_tma<GuideNN<kMaxGuideFeats>, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt);
     }
     int chunks = kTexChunksDefault;
     if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);  // tuning knob
@@ -1063,19 +1241,29 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   } else {
     return HDRNET_E_UNSUPPORTED;
   }
-  // The fused-guide forms exist only in the TMA kernel; other shapes run the standalone
+  // Integer pixel I/O on shapes the row kernel cannot take: the per-pixel fused kernel.
+  if (!use_tma && px) {
+    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves;
+                        return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream); }
+    if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn;
+                              return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream); }
+    GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
+    return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream);
+  }
+  // The float32 fused-guide forms exist only in the TMA kernel; other shapes run the standalone
   // guide kernel first (the caller does that: see hdrnet_slice_apply_{curves,nn}_f32).
   if (!use_tma && gs.mode != 0) return HDRNET_E_UNSUPPORTED;
 
   if (use_tma) {
     TmaArgs a;
-    a.grid = grid; a.guide = gs.guide; a.guide_out = gs.guide_out; a.input = input; a.out = out;
+    a.grid = grid; a.guide = gs.guide; a.guide_out = gs.guide_out;
+    a.input = static_cast<const unsigned char*>(input_v); a.out = static_cast<unsigned char*>(out_v);
     a.g = g; a.p = plan; a.slab_tex = 0; a.yslab = nullptr;
     if (gs.mode == 0) return launch_tma(a, GuideFromInput{}, stream);
-    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; return launch_tma(a, fn, stream); }
-    if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn; return launch_tma(a, fn, stream); }
+    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; return launch_tma(a, fn, stream, gs.in_fmt, gs.out_fmt); }
+    if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn; return launch_tma(a, fn, stream, gs.in_fmt, gs.out_fmt); }
     GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
-    return launch_tma(a, fn, stream);
+    return launch_tma(a, fn, stream, gs.in_fmt, gs.out_fmt);
   }
   slice_generic_kernel<true><<<generic_grid(npix, sms), 256, 0, stream>>>(
       grid, gs.guide, input, out, g, n_in, n_out, J, npix);
@@ -1257,6 +1445,49 @@ int hdrnet_slice_apply_nn_f32(const float* grid, const float* input, float* out,
                               void* stream) {
   return hdrnet_slice_apply_nn_f32_ws(grid, input, out, guide_out, B, H, W, gh, gw, gd, w1, b1, w2,
                                       b2, feats, nullptr, 0, stream);
+}
+
+int hdrnet_slice_apply_curves_px_ws(const float* grid, const void* input, int in_fmt, void* out,
+                                    int out_fmt, float* guide_out, int B, int H, int W, int gh,
+                                    int gw, int gd, const float* ccm, const float* ccm_bias,
+                                    const float* shifts, const float* slopes, const float* mix,
+                                    float mix_bias, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  if (in_fmt == HDRNET_PX_F32 && out_fmt == HDRNET_PX_F32)
+    return hdrnet_slice_apply_curves_f32_ws(grid, static_cast<const float*>(input),
+                                            static_cast<float*>(out), guide_out, B, H, W, gh, gw,
+                                            gd, ccm, ccm_bias, shifts, slopes, mix, mix_bias,
+                                            workspace, workspace_bytes, stream);
+  CurvesGuideParams cp;
+  const int rc = pack_curves_params(&cp, ccm, ccm_bias, shifts, slopes, mix, mix_bias);
+  if (rc != HDRNET_OK) return rc;
+  GuideSpec gs{1, nullptr, guide_out, &cp, nullptr};
+  gs.workspace = static_cast<float*>(workspace);
+  gs.workspace_bytes = workspace_bytes;
+  gs.in_fmt = in_fmt;
+  gs.out_fmt = out_fmt;
+  return launch_slice_apply_impl(grid, gs, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
+                                 HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
+}
+
+int hdrnet_slice_apply_nn_px_ws(const float* grid, const void* input, int in_fmt, void* out,
+                                int out_fmt, float* guide_out, int B, int H, int W, int gh, int gw,
+                                int gd, const float* w1, const float* b1, const float* w2, float b2,
+                                int feats, void* workspace, size_t workspace_bytes, void* stream) {
+  if (in_fmt == HDRNET_PX_F32 && out_fmt == HDRNET_PX_F32)
+    return hdrnet_slice_apply_nn_f32_ws(grid, static_cast<const float*>(input),
+                                        static_cast<float*>(out), guide_out, B, H, W, gh, gw, gd,
+                                        w1, b1, w2, b2, feats, workspace, workspace_bytes, stream);
+  NNGuideParams np;
+  const int rc = pack_nn_params(&np, w1, b1, w2, b2, feats);
+  if (rc != HDRNET_OK) return rc;
+  GuideSpec gs{2, nullptr, guide_out, nullptr, &np};
+  gs.workspace = static_cast<float*>(workspace);
+  gs.workspace_bytes = workspace_bytes;
+  gs.in_fmt = in_fmt;
+  gs.out_fmt = out_fmt;
+  return launch_slice_apply_impl(grid, gs, input, out, B, H, W, H, 0, gh, gw, gd, 3, 3, 1,
+                                 HDRNET_VARIANT_AUTO, static_cast<cudaStream_t>(stream));
 }
 
 int hdrnet_slice_f32_variant(const float* grid, const float* guide, float* out, int B, int H,

@@ -228,6 +228,50 @@ def _check_input(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 # ---- layer wrappers (hdrnet/layers.py:25-93 over the C-ABI) ------------------------------------
+_PX_FMT = {torch.float32: _lib.PX_F32, torch.uint8: _lib.PX_U8, torch.uint16: _lib.PX_U16}
+
+
+def _check_image(t: torch.Tensor, what: str) -> torch.Tensor:
+    """A decoded image batch [B,H,W,3], uint8 / uint16 / float32, on a CUDA device."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor")
+    if t.dtype not in _PX_FMT:
+        raise TypeError(f"{what} must be uint8, uint16 or float32, got {t.dtype}")
+    if t.dim() != 4 or t.shape[-1] != 3:
+        raise ValueError(f"{what} must be [B,H,W,3], got {tuple(t.shape)}")
+    if not t.is_cuda:
+        raise _lib.HdrnetLibraryError(f"{what} is on {t.device}: hdrnet_b200 has no CPU path")
+    return t.contiguous()
+
+
+def lowres_from_image(image: torch.Tensor, size: int) -> torch.Tensor:
+    """[B,H,W,3] uint8 / uint16 / float32 -> [B,size,size,3] float32: img_as_float +
+    skimage.transform.resize(order=0) of hdrnet/bin/run.py:156-169 in one gather kernel."""
+    image = _check_image(image, "image")
+    B, H, W, _ = image.shape
+    low = torch.empty((B, size, size, 3), dtype=torch.float32, device=image.device)
+    with torch.cuda.device(image.device):
+        rc = _lib.load().hdrnet_lowres_nearest_f32(
+            image.data_ptr(), _PX_FMT[image.dtype], low.data_ptr(), B, H, W, size, size,
+            torch.cuda.current_stream(image.device).cuda_stream)
+    _lib.check(rc, "lowres_nearest")
+    return low
+
+
+def image_to_float(image: torch.Tensor) -> torch.Tensor:
+    """skimage.img_as_float of a uint8 / uint16 tensor (IEEE division: the same float32)."""
+    if image.dtype == torch.uint8:
+        return image.to(torch.float32) / 255.0
+    if image.dtype == torch.uint16:
+        return image.to(torch.int32).to(torch.float32) / 65535.0
+    return image.to(torch.float32)
+
+
+def quantize_u8(x: torch.Tensor) -> torch.Tensor:
+    """tf.cast(255.0 * tf.clip_by_value(x, 0, 1), tf.uint8) (hdrnet/bin/run.py:95)."""
+    return (255.0 * x.clamp(0.0, 1.0)).to(torch.uint8)
+
+
 def pack_conv_weights(w: torch.Tensor):
     """Pre-pack HWIO conv weights for the pipelined tcgen05 kernel (once per model); returns a
     device buffer, or None when the layer's shape does not suit that kernel."""
@@ -318,12 +362,35 @@ class HDRNetCurves(object):
             raise NotImplementedError("hdrnet_b200 implements the inference path only")
         fullres_input = _check_input(fullres_input, "fullres_input")
         coeffs = cls._coefficients(lowres_input, params, is_training)
+        return cls._fullres(coeffs, fullres_input, params, torch.float32)
+
+    @classmethod
+    def inference_image(cls, image, params, lowres_image=None, out_dtype=torch.uint8):
+        """The reference CLI's per-image path (hdrnet/bin/run.py:145-190) with the decoded image
+        kept in its storage format on the device: ``image`` [B,H,W,3] uint8 / uint16 / float32
+        -> nearest-neighbour S x S float32 network input (img_as_float on the fly, run.py:156-169)
+        -> coefficients -> guide + slice + apply in one full-resolution pass that reads the
+        integer pixels and writes ``uint8(255 * clip(out, 0, 1))`` (run.py:95).  3 + 3 bytes per
+        pixel cross PCIe / HBM instead of 12 + 12.  ``lowres_image`` replaces the resized input
+        (run.py --lowres_input); ``out_dtype=torch.float32`` returns the unquantised prediction."""
+        image = _check_image(image, "image")
+        src = image if lowres_image is None else _check_image(lowres_image, "lowres_image")
+        lowres = lowres_from_image(src, int(params["net_input_size"]))
+        coeffs = cls._coefficients(lowres, params, False)
+        return cls._fullres(coeffs, image, params, out_dtype)
+
+    @classmethod
+    def _fullres(cls, coeffs, fullres_input, params, out_dtype):
+        """Guide + slice + apply over the full-resolution image (models.py:53-58), one kernel."""
         prep = _prepare(_resolve_weights(params), params, fullres_input.device, cls._nn_guide)
         B, H, W, _ = fullres_input.shape
         _, gh, gw, gd = coeffs.shape[:4]
-        out = torch.empty_like(fullres_input)
+        in_fmt, out_fmt = _PX_FMT[fullres_input.dtype], _PX_FMT[out_dtype]
+        out = torch.empty((B, H, W, 3), dtype=out_dtype, device=fullres_input.device)
         debug = bool(params.get("debug"))
-        need_guide = debug or (W % 4 != 0) or W < 128
+        f32 = in_fmt == _lib.PX_F32 and out_fmt == _lib.PX_F32
+        # the float32 form needs the guide buffer for shapes its row kernel cannot take
+        need_guide = debug or (f32 and ((W % 4 != 0) or W < 128))
         guide = torch.empty((B, H, W), dtype=torch.float32, device=fullres_input.device) \
             if need_guide else None
         lib = _lib.load()
@@ -339,14 +406,14 @@ class HDRNetCurves(object):
                                 lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))
                 ws_ptr, ws_bytes = ws.data_ptr(), ws.numel() * 4
             if cls._nn_guide:
-                rc = lib.hdrnet_slice_apply_nn_f32_ws(
-                    coeffs.data_ptr(), fullres_input.data_ptr(), out.data_ptr(), gptr, B, H, W,
-                    gh, gw, gd, _hp(prep.nn_w1), _hp(prep.nn_b1), _hp(prep.nn_w2), prep.nn_b2,
-                    prep.nn_feats, ws_ptr, ws_bytes, stream)
+                rc = lib.hdrnet_slice_apply_nn_px_ws(
+                    coeffs.data_ptr(), fullres_input.data_ptr(), in_fmt, out.data_ptr(), out_fmt,
+                    gptr, B, H, W, gh, gw, gd, _hp(prep.nn_w1), _hp(prep.nn_b1), _hp(prep.nn_w2),
+                    prep.nn_b2, prep.nn_feats, ws_ptr, ws_bytes, stream)
             else:
-                rc = lib.hdrnet_slice_apply_curves_f32_ws(
-                    coeffs.data_ptr(), fullres_input.data_ptr(), out.data_ptr(), gptr, B, H, W,
-                    gh, gw, gd, _hp(prep.ccm), _hp(prep.ccm_bias), _hp(prep.shifts),
+                rc = lib.hdrnet_slice_apply_curves_px_ws(
+                    coeffs.data_ptr(), fullres_input.data_ptr(), in_fmt, out.data_ptr(), out_fmt,
+                    gptr, B, H, W, gh, gw, gd, _hp(prep.ccm), _hp(prep.ccm_bias), _hp(prep.shifts),
                     _hp(prep.slopes), _hp(prep.mix), prep.mix_bias, ws_ptr, ws_bytes, stream)
         _lib.check(rc, "BilateralSliceApply(fused guide)")
         if debug:
@@ -477,6 +544,17 @@ class HDRNetGaussianPyrNN(HDRNetPointwiseNNGuide):
             cls.last_debug = {"bilateral_coefficients": coeffs, "guide": guides,
                               "multiscale": multiscale, "output": out}
         return out
+
+    @classmethod
+    def inference_image(cls, image, params, lowres_image=None, out_dtype=torch.uint8):
+        """Same contract as HDRNetCurves.inference_image.  The pyramid needs the float image at
+        three scales, so only the network input is taken straight from the integer pixels; the
+        full-resolution image is converted once on the device."""
+        image = _check_image(image, "image")
+        src = image if lowres_image is None else _check_image(lowres_image, "lowres_image")
+        lowres = lowres_from_image(src, int(params["net_input_size"]))
+        out = cls.inference(lowres, image_to_float(image), params, False)
+        return quantize_u8(out) if out_dtype == torch.uint8 else out
 
     @classmethod
     def _multiscale_input(cls, fullres_input):

@@ -273,6 +273,48 @@ HDRNET_API int hdrnet_slice_apply_nn_f32_ws(const float* grid, const float* inpu
                                             size_t workspace_bytes, void* stream);
 
 /*
+ * Pixel storage formats of the model-path forms below.  The
+ * reference's CLI decodes an image to uint8 / uint16, converts it on the host with
+ * skimage.img_as_float (v / 255, v / 65535; hdrnet/bin/run.py:156-164), feeds float32 to the
+ * graph and casts the prediction with tf.cast(255 * clip(x, 0, 1), tf.uint8) (run.py:95).  These
+ * entry points keep the full-resolution image in its integer format on both sides: 3 + 3 bytes
+ * per pixel cross PCIe and HBM instead of 12 + 12.
+ */
+#define HDRNET_PX_F32 0 /* float32 [B,H,W,3]                                              */
+#define HDRNET_PX_U8 1  /* uint8   [B,H,W,3]; as input: img_as_float; as output: the cast  */
+#define HDRNET_PX_U16 2 /* uint16  [B,H,W,3]; input only                                  */
+
+/*
+ * hdrnet_slice_apply_{curves,nn}_f32_ws with `input` in in_fmt and `out` in out_fmt
+ * (HDRNET_PX_F32 or HDRNET_PX_U8).  The conversion of a code value is bit-exact with
+ * float32(float64(v) / 255) (resp. 65535); the uint8 cast truncates like tf.cast.  (u8 | u16) ->
+ * u8 with W % 16 == 0 (W % 8 for u16) and 16-byte aligned buffers runs the persistent row kernel;
+ * every other combination runs a one-thread-per-pixel fused kernel.  guide_out (optional)
+ * receives the float32 guide map.  f32 -> f32 is hdrnet_slice_apply_{curves,nn}_f32_ws itself.
+ */
+HDRNET_API int hdrnet_slice_apply_curves_px_ws(const float* grid, const void* input, int in_fmt,
+                                               void* out, int out_fmt, float* guide_out, int B,
+                                               int H, int W, int gh, int gw, int gd,
+                                               const float* ccm, const float* ccm_bias,
+                                               const float* shifts, const float* slopes,
+                                               const float* mix, float mix_bias, void* workspace,
+                                               size_t workspace_bytes, void* stream);
+HDRNET_API int hdrnet_slice_apply_nn_px_ws(const float* grid, const void* input, int in_fmt,
+                                           void* out, int out_fmt, float* guide_out, int B, int H,
+                                           int W, int gh, int gw, int gd, const float* w1,
+                                           const float* b1, const float* w2, float b2, int feats,
+                                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Low-resolution network input straight from the decoded image: nearest-neighbour resize of
+ * image [B,H,W,3] (fmt) to lowres [B,SH,SW,3] float32, img_as_float applied on the fly.
+ * Replaces skimage.transform.resize(im, [S, S], order=0) on the float image (run.py:168-169):
+ * output sample i reads input floor((i + 0.5) * H / SH).
+ */
+HDRNET_API int hdrnet_lowres_nearest_f32(const void* image, int fmt, float* lowres, int B, int H,
+                                         int W, int SH, int SW, void* stream);
+
+/*
  * Host-buffer path (what a CPU-tensor caller of the reference op gets: TF copies feeds to
  * the GPU and fetches back, hdrnet/bin/run.py:185).  A context owns device staging buffers
  * and streams; the call splits the batch into row bands, and pipelines H2D copy -> kernel

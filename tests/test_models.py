@@ -199,8 +199,10 @@ def test_run_py_identity_sample_plumbing(tmp_path):
     assert sorted(loaded) == sorted(wts) and params["model_name"] == "HDRNetCurves"
     rng = np.random.RandomState(0)
     im8 = rng.randint(0, 256, size=(256, 256, 3)).astype(np.uint8)
-    out8, out = run.process(models.HDRNetCurves, params, im8)
+    out8, _ = run.process(models.HDRNetCurves, params, im8)
     assert out8.shape == (256, 256, 3) and out8.dtype == np.uint8
+    out = models.HDRNetCurves.inference_image(torch.from_numpy(im8[None]).cuda(), params,
+                                              out_dtype=torch.float32)
     im = run.img_as_float(im8)[None]
     low = run.nearest_resize(im[0], 256)[None]
     ref, _, _ = M.inference(low, im, loaded, params, oracle.best().bilateral_slice_apply)

@@ -96,6 +96,42 @@ def model_case(name, model_name, B, H, W, iters=30):
           flush=True)
 
 
+def image_case(name, model_name, B, H, W, iters=20):
+    """run.py's per-image path (decode format in, uint8 out): device-resident and end to end from
+    pinned host memory, integer pixels (inference_image) against the float32 feed (inference)."""
+    p = dict(models.DEFAULT_PARAMS, model_name=model_name)
+    p["weights"] = models.init_weights(p, seed=0, model_name=model_name)
+    cls = getattr(models, model_name)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    im8 = torch.randint(0, 256, (B, H, W, 3), device="cuda", generator=gen, dtype=torch.uint8)
+    im8_h = im8.cpu().pin_memory()
+    out8_h = torch.empty_like(im8_h).pin_memory()
+    imf_h = models.image_to_float(im8).cpu().pin_memory()
+    low_h = models.lowres_from_image(im8, 256).cpu().pin_memory()
+    outf_h = torch.empty_like(imf_h).pin_memory()
+
+    def e2e_u8():
+        out8_h.copy_(cls.inference_image(im8_h.cuda(non_blocking=True), p), non_blocking=True)
+
+    def e2e_f32():   # what a float32 feed costs: 12 B/px up (+ lowres), 12 B/px down
+        out = cls.inference(low_h.cuda(non_blocking=True), imf_h.cuda(non_blocking=True), p)
+        outf_h.copy_(out, non_blocking=True)
+
+    t_dev = timeit(lambda: cls.inference_image(im8, p), iters=iters)
+    imf = models.image_to_float(im8)
+    low = models.lowres_from_image(im8, 256)
+    t_dev_f32 = timeit(lambda: cls.inference(low, imf, p), iters=iters)
+    t_e2e = timeit(e2e_u8, warm=2, iters=max(3, iters // 4))
+    t_e2e_f32 = timeit(e2e_f32, warm=2, iters=max(3, iters // 4))
+    npx = B * H * W
+    print(json.dumps({"case": name, "model": model_name, "shape": [B, H, W],
+                      "ms_device_u8_in_u8_out": round(t_dev, 4), "MP/s_device_u8": round(npx / t_dev / 1e3, 1),
+                      "ms_device_f32": round(t_dev_f32, 4), "MP/s_device_f32": round(npx / t_dev_f32 / 1e3, 1),
+                      "ms_e2e_pinned_u8": round(t_e2e, 3), "MP/s_e2e_u8": round(npx / t_e2e / 1e3, 1),
+                      "ms_e2e_pinned_f32": round(t_e2e_f32, 3), "MP/s_e2e_f32": round(npx / t_e2e_f32 / 1e3, 1),
+                      "pcie_bytes_per_px": {"u8": 6, "f32": 24}}), flush=True)
+
+
 def main():
     quick = "--quick" in sys.argv
     torch.cuda.set_device(0)
@@ -115,10 +151,18 @@ def main():
                variant=_lib.VARIANT_GENERIC)
     model_case("C2 model 1080p x1", "HDRNetCurves", 1, 1080, 1920)
     model_case("model 4K x8", "HDRNetCurves", 8, 2160, 3840, iters=10)
+    image_case("image path 4K x8 (u8 in, u8 out)", "HDRNetCurves", 8, 2160, 3840)
+    image_case("image path 1080p x1 (u8 in, u8 out)", "HDRNetCurves", 1, 1080, 1920)
     if not quick:
         model_case("C2 model 1080p x1 (NN guide)", "HDRNetPointwiseNNGuide", 1, 1080, 1920)
         model_case("model 4K x8 (NN guide)", "HDRNetPointwiseNNGuide", 8, 2160, 3840, iters=10)
 
 
 if __name__ == "__main__":
-    main()
+    if "--image-only" in sys.argv:
+        torch.cuda.set_device(0)
+        image_case("image path 4K x8 (u8 in, u8 out)", "HDRNetCurves", 8, 2160, 3840)
+        image_case("image path 4K x8 (u8 in, u8 out, NN guide)", "HDRNetPointwiseNNGuide", 8, 2160, 3840)
+        image_case("image path 1080p x1 (u8 in, u8 out)", "HDRNetCurves", 1, 1080, 1920)
+    else:
+        main()
