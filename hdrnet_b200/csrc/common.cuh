@@ -176,6 +176,10 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// Ask the L2 to fetch a span of global memory (no destination): warms it for later loads.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 // Make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA).
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -290,6 +290,8 @@ struct TmaArgs {
   float* guide_out;     // optional guide dump for the fused forms, else nullptr
   const unsigned char* input;   // [B * rows][W][3] in the kernel's input pixel format
   unsigned char* out;           // [B * rows][W][3] in the kernel's output pixel format
+  cudaTextureObject_t in_tex;    // texture-fed form: float4 views of `input` and `guide`
+  cudaTextureObject_t guide_tex;
   cudaTextureObject_t slab_tex;  // kTexChunks > 0: float4 view of the y-pre-blended slab rows
   const float* yslab;            // kTexChunks > 0: [B * rows][gw * gd * 12] slab rows (workspace)
   SliceGeom g;
@@ -470,7 +472,8 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
 
   auto stage_rgb = [&](int s) { return stage_base + static_cast<size_t>(s) * pl.stage_bytes; };
   auto stage_guide = [&](int s) { return stage_rgb(s) + pl.off_guide; };
-  auto stage_out = [&](int s) { return stage_rgb(s) + pl.off_out; };  // off_out == 0: in place
+  // same pixel size in and out: the result overwrites the input tile (plan.off_out == 0)
+  auto stage_out = [&](int s) { return stage_rgb(s) + (kInBpp == kOutBpp ? 0 : pl.off_out); };
   // Work item -> (buffer row, first pixel of the segment, pixels in the segment).
   auto item_span = [&](int item, long long& row, int& x0, int& npx) {
     const int rr = item / pl.nseg;
@@ -578,6 +581,147 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
 }
 
 
+
+// =========================================================================================
+// Texture-fed form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_IN).
+// =========================================================================================
+// The block-synchronous kernel spends 0.25 of its 1.56 shared-memory wavefronts per pixel on
+// staging the INPUT: the TMA engine writes 16 B/px into the ring and the threads read them back
+// with LDS.128, while the texture pipe idles at 56 %.  Here a thread fetches its 4 pixels (3 RGB
+// texels + 1 guide texel, float4 views of the caller's tensors) through the texture pipe
+// straight into registers -- issued one item ahead, right before the block barrier, when no
+// other value is live -- and shared memory only carries the slab rows and the OUTPUT tiles
+// (3 x STS.128 per thread, one bulk store per segment).  Thread 0 asks the L2 for the segments two
+// items ahead (cp.async.bulk.prefetch.L2) so that the texture fetches are L2 hits.
+// Wavefronts per pixel: 1.29 (LSU) against 1.25 texture-pipe clocks -- the two pipes balanced.
+constexpr int kTexInStages = 3;
+
+template <int kTexChunks, int kThreads>
+__global__ void __launch_bounds__(kThreads, 2)
+slice_apply_rows_texin_kernel(const TmaArgs args) {
+  static_assert(kTexChunks > 0, "slab rows come from the pre-pass workspace");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SliceGeom& g = args.g;
+  const TmaPlan& pl = args.p;
+  const int tid = threadIdx.x;
+
+  uint64_t* gridbar = reinterpret_cast<uint64_t*>(smem);  // [2] slab row landed
+  float* raw0 = reinterpret_cast<float*>(smem + pl.off_raw);
+  unsigned char* stage_base = smem + pl.off_stage;
+
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
+  const int nitems = static_cast<int>(r_end - r_begin) * pl.nseg;
+  if (nitems <= 0) return;
+
+  if (tid == 0) {
+    mbar_init(&gridbar[0], 1);
+    mbar_init(&gridbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto item_span = [&](int item, long long& row, int& x0, int& npx) {
+    const int rr = item / pl.nseg;
+    const int seg = item - rr * pl.nseg;
+    row = r_begin + rr;
+    x0 = seg * pl.seg_px;
+    npx = min(pl.seg_px, g.W - x0);
+  };
+  auto prefetch_l2 = [&](int item) {  // thread 0 only
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+    const size_t pix = static_cast<size_t>(row) * g.W + x0;
+    l2_prefetch_bulk(args.input + pix * 12, static_cast<uint32_t>(npx) * 12u);
+    l2_prefetch_bulk(args.guide + pix, static_cast<uint32_t>(npx) * 4u);
+  };
+  // This thread's quad of item `item`: three RGB texels and one guide texel into registers.
+  float4 c0, c1, c2, gq;
+  auto fetch = [&](int item) {
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+    if (tid * 4 < npx) {
+      const int quad = static_cast<int>((row * g.W + x0) >> 2) + tid;   // pixel quad index
+      c0 = tex1Dfetch<float4>(args.in_tex, 3 * quad);
+      c1 = tex1Dfetch<float4>(args.in_tex, 3 * quad + 1);
+      c2 = tex1Dfetch<float4>(args.in_tex, 3 * quad + 2);
+      gq = tex1Dfetch<float4>(args.guide_tex, quad);
+    }
+  };
+
+  if (tid == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+    mbar_expect_tx(&gridbar[0], bytes);
+    tma_load_1d(raw0, args.yslab + static_cast<size_t>(r_begin) * pl.row_floats, bytes, &gridbar[0]);
+    prefetch_l2(0);
+    if (nitems > 1) prefetch_l2(1);
+    if (nitems > 2) prefetch_l2(2);
+  }
+  fetch(0);
+
+  const float gd_f = static_cast<float>(g.gd);
+  const int x_stride = g.gd * kGc;
+  const float* slab = raw0;
+  int tex_row = 0;
+
+  for (int item = 0; item < nitems; ++item) {
+    long long row; int x0, npx;
+    item_span(item, row, x0, npx);
+    if (x0 == 0) {  // new image row: its slab row (double-buffered one row ahead)
+      const int rowk = item / pl.nseg;
+      const int cur = rowk & 1;
+      slab = raw0 + cur * pl.row_floats;
+      mbar_wait(&gridbar[cur], static_cast<uint32_t>(rowk >> 1) & 1u);
+      if (tid == 0 && row + 1 < r_end) {
+        const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+        mbar_expect_tx(&gridbar[cur ^ 1], bytes);
+        tma_load_1d(raw0 + (cur ^ 1) * pl.row_floats,
+                    args.yslab + static_cast<size_t>(row + 1) * pl.row_floats, bytes, &gridbar[cur ^ 1]);
+      }
+      tex_row = static_cast<int>(row) * (pl.row_floats / 4);
+    }
+    unsigned char* otile = stage_base + static_cast<size_t>(item % kTexInStages) * pl.stage_bytes;
+
+    if (tid * 4 < npx) {
+      const float pr[4] = {c0.x, c0.w, c1.z, c2.y};
+      const float pg[4] = {c0.y, c1.x, c1.w, c2.z};
+      const float pb[4] = {c0.z, c1.y, c2.x, c2.w};
+      const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+      float o_r[4], o_g[4], o_b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const Axis ax = spatial_axis(x0 + 4 * tid + i, g.scale_x);
+        const Axis az = range_axis(gv[i], gd_f);
+        const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride;
+        const int xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
+        const int zo0 = clampi(az.i0, 0, g.gd - 1) * kGc;
+        const int zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * kGc;
+        float wz0, wz1;
+        smoothed_weights(az.f, wz0, wz1);
+        const float wx1 = ax.f, wx0 = 1.0f - ax.f;
+        blend_apply<kTexChunks>(slab, args.slab_tex, tex_row, xo0 + zo0, xo0 + zo1, xo1 + zo0,
+                                xo1 + zo1, wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i], pg[i],
+                                pb[i], o_r[i], o_g[i], o_b[i]);
+      }
+      store_quad<kPxF32>(otile, tid, o_r, o_g, o_b);
+      fence_proxy_async_smem();
+    }
+    // Next item's pixels: issued here, when nothing else is live; they land during the barrier.
+    if (item + 1 < nitems) fetch(item + 1);
+    // Thread 0: the output stage the NEXT item writes must have been drained by its last store.
+    if (tid == 0) tma_store_wait_read<kTexInStages - 2>();
+    __syncthreads();
+
+    if (tid == 0) {
+      const size_t pix = static_cast<size_t>(row) * g.W + x0;
+      tma_store_1d(args.out + pix * 12, otile, static_cast<uint32_t>(npx) * 12u);
+      tma_store_commit();
+      if (item + 3 < nitems) prefetch_l2(item + 3);
+    }
+  }
+  if (tid == 0) tma_store_wait_all<0>();
+}
 
 // =========================================================================================
 // Warp-specialised form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_WS).
@@ -1052,6 +1196,16 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream, 
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
+template <int kTexChunks, int kThreads>
+static int launch_texin(const TmaArgs& a, cudaStream_t stream) {
+  auto kern = slice_apply_rows_texin_kernel<kTexChunks, kThreads>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       a.p.smem_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  kern<<<a.p.ctas, kThreads, a.p.smem_bytes, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <class GuideFn, int kConsumerWarps>
 static int launch_ws_n(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
   auto kern = slice_apply_rows_ws_kernel<GuideFn, kTexChunksWs, kConsumerWarps>;
@@ -1064,8 +1218,9 @@ static int launch_ws_n(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream)
 
 template <class GuideFn>
 static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  // consumer warps = planned threads / 32 (8 for the 256-thread plan, 16 for the 512-thread one)
-  if (a.p.threads == 512) return launch_ws_n<GuideFn, 16>(a, fn, stream);
+  // consumer warps = planned threads / 32 (8 for the 256-thread plan, 15 for the 480-quad one)
+  // 15 consumer warps + the producer warp = 512 threads: 64 registers at two CTAs per SM
+  if (a.p.threads == 480) return launch_ws_n<GuideFn, 15>(a, fn, stream);
   return launch_ws_n<GuideFn, 8>(a, fn, stream);
 }
 
@@ -1188,7 +1343,8 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   // AUTO prefers it once the image is large enough to amortise the pre-pass launch.
   if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21))
     variant = HDRNET_VARIANT_TEX;
-  if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_WS) {
+  if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_WS ||
+      variant == HDRNET_VARIANT_TEX_IN) {
     const size_t need = tex_need;
     if (!tex_ok) return HDRNET_E_UNSUPPORTED;
     TmaPlan tplan;
@@ -1196,6 +1352,8 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     int tex_threads = kTexThreadsDefault;
     if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tex_threads = (std::atoi(e) == 512) ? 512 : 256;
     if (gs.mode != 0) tex_threads = kFusedThreadsDefault;
+    // warp-specialised form: the 512-thread CTA is 15 math warps (480 pixel quads) + the producer
+    if (variant == HDRNET_VARIANT_TEX_WS && tex_threads == 512) tex_threads = 480;
     if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true, tex_threads,
                        gs.in_fmt, gs.out_fmt))
       tplan = plan;
@@ -1210,6 +1368,30 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     if (variant == HDRNET_VARIANT_TEX_WS) {
       if (gs.mode != 0 || tplan.seg_px > tplan.threads * 4) return HDRNET_E_UNSUPPORTED;
       return launch_ws(a, GuideFromInput{}, stream);
+    }
+    if (variant == HDRNET_VARIANT_TEX_IN) {
+      // float32 guide-from-input form only; pixel tensors addressable as 1-D float4 textures
+      const size_t in_bytes = static_cast<size_t>(npix) * 12, guide_bytes = static_cast<size_t>(npix) * 4;
+      if (gs.mode != 0 || px || in_bytes / 16 > (1u << 27)) return HDRNET_E_UNSUPPORTED;
+      // shared memory: two slab rows + kTexInStages output tiles (no input ring)
+      a.p.stage_bytes = round_up(a.p.seg_px * 12, 128);
+      a.p.stages = kTexInStages;
+      a.p.smem_bytes = a.p.off_stage + kTexInStages * a.p.stage_bytes;
+      if (a.p.smem_bytes > (device_max_smem_optin() + 1024) / 2 - 1024) return HDRNET_E_UNSUPPORTED;
+      rc = get_slab_texture(input, in_bytes, &a.in_tex);
+      if (rc != 0) return rc;
+      rc = get_slab_texture(gs.guide, guide_bytes, &a.guide_tex);
+      if (rc != 0) return rc;
+      int chunks = kTexChunksDefault;
+      if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);
+      if (a.p.threads == 512) {
+        switch (chunks) {
+          case 3: return launch_texin<3, 512>(a, stream);
+          case 5: return launch_texin<5, 512>(a, stream);
+          default: return launch_texin<kTexChunksDefault, 512>(a, stream);
+        }
+      }
+      return launch_texin<kTexChunksDefault, kTmaThreads>(a, stream);
     }
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
                         return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt); }

@@ -69,6 +69,10 @@ extern "C" {
 #define HDRNET_VARIANT_TEX_WS 5  /* the same, warp-specialised: a producer warp issues all  */
                                  /* TMA loads, 8 math warps run without block barriers     */
 
+#define HDRNET_VARIANT_TEX_IN 6  /* the texture-assisted kernel with the pixel INPUT fetched     */
+                                 /* through the texture pipe as well (no input staging in    */
+                                 /* shared memory); same requirements as HDRNET_VARIANT_TEX  */
+
 HDRNET_API int hdrnet_b200_abi_version(void);
 
 /* Human-readable text for a return code of this library (static storage). */

@@ -18,6 +18,10 @@ CONFIGS = {
     "tex t256 c4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
     "ws  t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TEX_WS),
     "ws  t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TEX_WS),
+    "texin t512 c4": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX_IN),
+    "texin t512 c3": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX_IN),
+    "texin t512 c5": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="5"), _lib.VARIANT_TEX_IN),
+    "texin t256 c4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX_IN),
     "tma t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TMA),
     "tma t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TMA),
 }
@@ -40,7 +44,7 @@ for r in range(7):
 lines = []
 for k, v in res.items():
     med = statistics.median(v)
-    lines.append(f"{k:14s} median {med:.4f} ms  min {min(v):.4f}  max {max(v):.4f}  frac {8*2160*3840*28/med/1e6/6577.4:.4f}")
+    lines.append(f"{k:15s} median {med:.4f} ms  min {min(v):.4f}  max {max(v):.4f}  frac {8*2160*3840*28/med/1e6/6577.4:.4f}")
 print("\n".join(lines))
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/ab_bench.txt", "w") as f:
