@@ -320,7 +320,7 @@ def run_b200_arm(args):
                        "parallelism": f"batch-shard x{world}, no data-path collective",
                        "l2": "1.86 GB touched per step >> 126 MB L2: no flush between iterations",
                        "kernel": {"variant": "tex (AUTO with workspace): yblend_rows_kernel pre-pass + "
-                                             "slice_apply_rows_tma_kernel<GuideFromInput,4,2,512>, both inside "
+                                             "slice_apply_rows_tma_kernel<GuideFromInput,4,2,512,f32,f32>, both inside "
                                              "every timed step",
                                   "ctas": ctas.value, "threads": threads.value,
                                   "dyn_smem_bytes": smem.value, "workspace_bytes": ws_bytes}},

@@ -596,8 +596,8 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
 // Wavefronts per pixel: 1.29 (LSU) against 1.25 texture-pipe clocks -- the two pipes balanced.
 constexpr int kTexInStages = 3;
 
-template <int kTexChunks, int kThreads>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kTexChunks, int kThreads, int kMinBlocks = 2>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 slice_apply_rows_texin_kernel(const TmaArgs args) {
   static_assert(kTexChunks > 0, "slab rows come from the pre-pass workspace");
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1111,7 +1111,7 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
   // Residency: HDRNET_TMA_OCC=3 asks for three CTAs per SM (3-stage ring, 85 registers) when
   // the shared memory allows; default two CTAs with 4 stages; shrink the ring before giving up
   // residency.
-  int want_occ = 2;
+  int want_occ = (threads == 320) ? 3 : 2;  // 320 threads: three 10-warp CTAs per SM, 64 registers
   if (const char* e = std::getenv("HDRNET_TMA_OCC")) want_occ = std::atoi(e);
   const int per_cta_3 = (max_smem + 1024) / 3 - 1024;
   const int per_cta_2 = (max_smem + 1024) / 2 - 1024;  // ~113 KB when 227 KB opt-in
@@ -1183,6 +1183,10 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream, 
     if (a.p.resident == 3 && a.p.threads == kTmaThreads)
       return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
     if (a.p.threads == 512) return launch_tma_occ<GuideFn, kTexChunks, 2, 512>(a, fn, stream);
+    if (a.p.threads == 320) {
+      if (a.p.resident != 3) return HDRNET_E_UNSUPPORTED;
+      return launch_tma_occ<GuideFn, kTexChunks, 3, 320>(a, fn, stream);
+    }
   } else {
     // The fused-guide forms are issue-bound and need their registers: 256 threads x 2 CTAs.
     // Measured at 4K x 8 (tools/ab_fused.py): curves 0.69 ms against 0.71 (256 x 3) and 0.80
@@ -1196,9 +1200,9 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream, 
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
-template <int kTexChunks, int kThreads>
+template <int kTexChunks, int kThreads, int kMinBlocks = 2>
 static int launch_texin(const TmaArgs& a, cudaStream_t stream) {
-  auto kern = slice_apply_rows_texin_kernel<kTexChunks, kThreads>;
+  auto kern = slice_apply_rows_texin_kernel<kTexChunks, kThreads, kMinBlocks>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -1318,7 +1322,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   const SliceGeom g = make_geom(B, H, W, rows, y_off, gh, gw, gd);
   const int sms = device_sm_count();
   int tma_threads = kTmaThreadsDefault;
-  if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tma_threads = (std::atoi(e) == 512) ? 512 : 256;
+  if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tma_threads = (std::atoi(e) == 512) ? 512 : (std::atoi(e) == 320 ? 320 : 256);
   if (gs.mode != 0) tma_threads = kFusedThreadsDefault;
 
   TmaPlan plan;
@@ -1350,7 +1354,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     TmaPlan tplan;
     // the texture forms default to the 512-thread / 64-register plan (32 warps per SM)
     int tex_threads = kTexThreadsDefault;
-    if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tex_threads = (std::atoi(e) == 512) ? 512 : 256;
+    if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tex_threads = (std::atoi(e) == 512) ? 512 : (std::atoi(e) == 320 ? 320 : 256);
     if (gs.mode != 0) tex_threads = kFusedThreadsDefault;
     // warp-specialised form: the 512-thread CTA is 15 math warps (480 pixel quads) + the producer
     if (variant == HDRNET_VARIANT_TEX_WS && tex_threads == 512) tex_threads = 480;
@@ -1378,6 +1382,15 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       a.p.stages = kTexInStages;
       a.p.smem_bytes = a.p.off_stage + kTexInStages * a.p.stage_bytes;
       if (a.p.smem_bytes > (device_max_smem_optin() + 1024) / 2 - 1024) return HDRNET_E_UNSUPPORTED;
+      // no input ring: the 256-thread form fits three or four CTAs per SM (HDRNET_TEXIN_OCC)
+      int occ = 2;
+      if (const char* e = std::getenv("HDRNET_TEXIN_OCC")) occ = std::atoi(e);
+      if (a.p.threads == kTmaThreads && (occ == 3 || occ == 4) &&
+          a.p.smem_bytes <= (device_max_smem_optin() + 1024) / occ - 1024) {
+        const long long total_rows = static_cast<long long>(B) * rows;
+        a.p.ctas = static_cast<int>(std::min<long long>(total_rows, static_cast<long long>(sms) * occ));
+        a.p.resident = occ;
+      }
       rc = get_slab_texture(input, in_bytes, &a.in_tex);
       if (rc != 0) return rc;
       rc = get_slab_texture(gs.guide, guide_bytes, &a.guide_tex);
@@ -1391,6 +1404,8 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
           default: return launch_texin<kTexChunksDefault, 512>(a, stream);
         }
       }
+      if (a.p.resident == 4) return launch_texin<kTexChunksDefault, kTmaThreads, 4>(a, stream);
+      if (a.p.resident == 3) return launch_texin<kTexChunksDefault, kTmaThreads, 3>(a, stream);
       return launch_texin<kTexChunksDefault, kTmaThreads>(a, stream);
     }
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;

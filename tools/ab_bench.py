@@ -18,14 +18,15 @@ CONFIGS = {
     "tex t256 c4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
     "ws  t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TEX_WS),
     "ws  t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TEX_WS),
+    "tex t320x3 c4": (dict(HDRNET_TMA_THREADS="320", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
     "texin t512 c4": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX_IN),
-    "texin t512 c3": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX_IN),
-    "texin t512 c5": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="5"), _lib.VARIANT_TEX_IN),
     "texin t256 c4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX_IN),
+    "texin t256x3": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEXIN_OCC="3"), _lib.VARIANT_TEX_IN),
+    "texin t256x4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEXIN_OCC="4"), _lib.VARIANT_TEX_IN),
     "tma t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TMA),
     "tma t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TMA),
 }
-KEYS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC")
+KEYS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC")
 def burst(env, variant, iters=40):
     for k in KEYS: os.environ.pop(k, None)
     os.environ.update(env)
