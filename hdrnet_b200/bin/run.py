@@ -65,9 +65,23 @@ def nearest_resize(im: np.ndarray, size: int) -> np.ndarray:
 
 
 def load_checkpoint(checkpoint_dir):
-    with open(os.path.join(checkpoint_dir, "params.json")) as f:
-        params = json.load(f)
-    weights = models.load_weights(os.path.join(checkpoint_dir, "weights.npz"))
+    """``weights.npz`` + ``params.json``; or, like the reference (run.py:70-85, :136-142), a
+    TensorFlow training directory: latest ``model.ckpt-N`` + its ``.meta`` model_params (read by
+    hdrnet_b200.checkpoint, no TensorFlow needed; ``params.json`` there overrides the .meta)."""
+    npz = os.path.join(checkpoint_dir, "weights.npz")
+    pjson = os.path.join(checkpoint_dir, "params.json")
+    if os.path.exists(npz):
+        with open(pjson) as f:
+            params = json.load(f)
+        return params, models.load_weights(npz)
+    from hdrnet_b200 import checkpoint
+    params, weights = checkpoint.import_checkpoint(checkpoint_dir)
+    if os.path.exists(pjson):
+        with open(pjson) as f:
+            params = json.load(f)
+    if params is None:
+        raise FileNotFoundError(f"{checkpoint_dir}: no params.json and no .meta file to read model_params from")
+    models.set_weights(weights)
     return params, weights
 
 
@@ -110,6 +124,26 @@ def process(mdl, params, im_u: np.ndarray, lowres_u: np.ndarray | None = None, h
     return out8[0].cpu().numpy(), out
 
 
+def _to_png(x01: np.ndarray) -> np.ndarray:
+    """A [0, 1] float image as skimage.io.imsave stores it (uint8, round to nearest)."""
+    return np.clip(np.rint(x01 * 255.0), 0, 255).astype(np.uint8)
+
+
+def debug_images(im_rgb: np.ndarray, coeffs: np.ndarray, guides: list) -> dict:
+    """The --debug pictures of the reference (run.py:98-133, :192-215) as {file suffix: image}:
+    the input, the coefficient mosaic ([gh*gd, gw*n_in*n_out], symmetric normalisation
+    (x + m) / 2m with m = max |x|) and one normalised picture per guide map."""
+    out = {"_input.png": np.ascontiguousarray(im_rgb[:, :, ::-1])}
+    gh, gw, gd, no, ni = coeffs.shape
+    c = np.transpose(coeffs, (2, 0, 3, 4, 1)).reshape(gh * gd, gw * ni * no)   # tf.transpose [0,3,1,4,5,2]
+    m = float(np.abs(c).max()) or 1.0
+    out["_coeffs.png"] = _to_png(np.clip((c + m) / (2 * m), 0, 1))
+    for i, g in enumerate(guides):
+        mg = float(np.abs(g).max()) or 1.0
+        out[f"_guide_{i}.png"] = _to_png(np.clip((g + mg) / (2 * mg), 0, 1))
+    return out
+
+
 def main(args):
     import cv2
     params, _ = load_checkpoint(args.checkpoint_dir)
@@ -136,9 +170,12 @@ def main(args):
         cv2.imwrite(os.path.join(args.output, name + ".png"), out8[:, :, ::-1])
         if args.debug:                                              # run.py:192-215
             dbg = mdl.last_debug
-            np.save(os.path.join(args.output, name + "_guide.npy"), dbg["guide"][0].cpu().numpy())
-            np.save(os.path.join(args.output, name + "_coefficients.npy"),
-                    dbg["bilateral_coefficients"][0].cpu().numpy())
+            guides = dbg["guide"] if isinstance(dbg["guide"], (list, tuple)) else [dbg["guide"]]
+            coeffs = dbg["bilateral_coefficients"][0].cpu().numpy()
+            np.save(os.path.join(args.output, name + "_guide.npy"), guides[0][0].cpu().numpy())
+            np.save(os.path.join(args.output, name + "_coefficients.npy"), coeffs)
+            for fname, img in debug_images(rgb, coeffs, [g[0].cpu().numpy() for g in guides]).items():
+                cv2.imwrite(os.path.join(args.output, name + fname), img)
 
 
 if __name__ == "__main__":
