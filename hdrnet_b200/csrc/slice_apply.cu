@@ -263,6 +263,7 @@ constexpr int kTmaThreads = 256;
 constexpr int kTmaThreadsDefault = 256;  // all-LSU form; 512 = 64-register form (HDRNET_TMA_THREADS)
 constexpr int kTexThreadsDefault = 512;  // texture-assisted form: measured 7 % faster at 512
 constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the texture-assisted kernel
+constexpr int kAsyncThreads = 512;        // issuer-warp form: 15 math warps + the issuer
 constexpr int kMaxStages = 8;
 constexpr int kGc = 12;
 
@@ -307,15 +308,18 @@ __device__ __forceinline__ float4 lerp4(float w0, float4 a, float w1, float4 b) 
 // the LSU, or -- for the last kTexChunks of the 12 chunks a pixel needs -- from the same slab
 // row in global memory through the TEXTURE pipe, the one on-chip gather path that does not
 // share the LSU crossbar (tools/ubench/gather_paths.cu: LDS.128 + tex float4 overlap fully).
-template <int kTexChunks, int kChunkId>
+// kBytes: `off` is a BYTE offset into the slab row (the lean index path) instead of a float one.
+template <int kTexChunks, int kChunkId, bool kBytes = false>
 __device__ __forceinline__ ulonglong2 corner_chunk(const float* __restrict__ slab,
                                                    cudaTextureObject_t tex, int tex_row, int off) {
   if constexpr (kChunkId >= 12 - kTexChunks) {
-    const float4 v = tex1Dfetch<float4>(tex, tex_row + (off >> 2) + (kChunkId % 3));
+    const float4 v = tex1Dfetch<float4>(tex, tex_row + (off >> (kBytes ? 4 : 2)) + (kChunkId % 3));
     ulonglong2 r;
     r.x = pack2(v.x, v.y);
     r.y = pack2(v.z, v.w);
     return r;
+  } else if constexpr (kBytes) {
+    return reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(slab) + off)[kChunkId % 3];
   } else {
     return reinterpret_cast<const ulonglong2*>(slab + off)[kChunkId % 3];
   }
@@ -323,7 +327,7 @@ __device__ __forceinline__ ulonglong2 corner_chunk(const float* __restrict__ sla
 
 // Blend the four (x, z) corners of the y-pre-blended slab for one pixel and apply the
 // 3x4 affine transform to (r, g, b, 1).
-template <int kTexChunks>
+template <int kTexChunks, bool kBytes = false>
 __device__ __forceinline__ void blend_apply(const float* __restrict__ slab,
                                             cudaTextureObject_t tex, int tex_row, int o00,
                                             int o01, int o10, int o11, float w00, float w01,
@@ -332,18 +336,18 @@ __device__ __forceinline__ void blend_apply(const float* __restrict__ slab,
   const unsigned long long W00 = pack2(w00, w00), W01 = pack2(w01, w01);
   const unsigned long long W10 = pack2(w10, w10), W11 = pack2(w11, w11);
   // chunk ids: v00 -> 0..2, v01 -> 3..5, v10 -> 6..8, v11 -> 9..11
-  const ulonglong2 a0 = corner_chunk<kTexChunks, 0>(slab, tex, tex_row, o00);
-  const ulonglong2 a1 = corner_chunk<kTexChunks, 1>(slab, tex, tex_row, o00);
-  const ulonglong2 a2 = corner_chunk<kTexChunks, 2>(slab, tex, tex_row, o00);
-  const ulonglong2 b0 = corner_chunk<kTexChunks, 3>(slab, tex, tex_row, o01);
-  const ulonglong2 b1 = corner_chunk<kTexChunks, 4>(slab, tex, tex_row, o01);
-  const ulonglong2 b2 = corner_chunk<kTexChunks, 5>(slab, tex, tex_row, o01);
-  const ulonglong2 c0 = corner_chunk<kTexChunks, 6>(slab, tex, tex_row, o10);
-  const ulonglong2 c1 = corner_chunk<kTexChunks, 7>(slab, tex, tex_row, o10);
-  const ulonglong2 c2 = corner_chunk<kTexChunks, 8>(slab, tex, tex_row, o10);
-  const ulonglong2 d0 = corner_chunk<kTexChunks, 9>(slab, tex, tex_row, o11);
-  const ulonglong2 d1 = corner_chunk<kTexChunks, 10>(slab, tex, tex_row, o11);
-  const ulonglong2 d2 = corner_chunk<kTexChunks, 11>(slab, tex, tex_row, o11);
+  const ulonglong2 a0 = corner_chunk<kTexChunks, 0, kBytes>(slab, tex, tex_row, o00);
+  const ulonglong2 a1 = corner_chunk<kTexChunks, 1, kBytes>(slab, tex, tex_row, o00);
+  const ulonglong2 a2 = corner_chunk<kTexChunks, 2, kBytes>(slab, tex, tex_row, o00);
+  const ulonglong2 b0 = corner_chunk<kTexChunks, 3, kBytes>(slab, tex, tex_row, o01);
+  const ulonglong2 b1 = corner_chunk<kTexChunks, 4, kBytes>(slab, tex, tex_row, o01);
+  const ulonglong2 b2 = corner_chunk<kTexChunks, 5, kBytes>(slab, tex, tex_row, o01);
+  const ulonglong2 c0 = corner_chunk<kTexChunks, 6, kBytes>(slab, tex, tex_row, o10);
+  const ulonglong2 c1 = corner_chunk<kTexChunks, 7, kBytes>(slab, tex, tex_row, o10);
+  const ulonglong2 c2 = corner_chunk<kTexChunks, 8, kBytes>(slab, tex, tex_row, o10);
+  const ulonglong2 d0 = corner_chunk<kTexChunks, 9, kBytes>(slab, tex, tex_row, o11);
+  const ulonglong2 d1 = corner_chunk<kTexChunks, 10, kBytes>(slab, tex, tex_row, o11);
+  const ulonglong2 d2 = corner_chunk<kTexChunks, 11, kBytes>(slab, tex, tex_row, o11);
   unsigned long long acc[6];
   acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
   acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
@@ -848,6 +852,198 @@ slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn g
 }
 
 // =========================================================================================
+// Issuer-warp form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_ASYNC).
+// =========================================================================================
+// What the block-synchronous kernel loses (ncu, profiles/r01_final_ncu_full_summary.txt): 1.8
+// barrier stalls per issue and ~116 warp instructions per item outside the pixel body.  After
+// every segment's __syncthreads thread 0 runs a SERIAL section (bulk store, wait for the previous
+// store, an integer division for the next item, expect_tx, two bulk loads) while its own warp's
+// pixels wait -- so warp 0 reaches the next barrier late by that section and the other fifteen
+// warps wait for it, every item.  The first warp-specialised form (above) moved the loads to a
+// producer warp but left a serial store / wait / arrive section in lane 0 of EVERY math warp.
+//
+// Here the serial work has a warp of its own and nothing else is synchronous:
+//   * warps 0..N-2 are MATH warps.  Per item a warp waits for the stage's TMA barrier (full[s]),
+//     processes its 128 pixels in place, and one lane ARRIVES on done[s] -- an mbarrier arrive
+//     does not block, the warp goes straight on to the next stage.  No __syncthreads, no bulk
+//     copies, no divisions (row / segment are nested loop counters) in a math warp.
+//   * warp N-1 (one lane) is the ISSUER: it waits on done[s], issues the segment's ONE bulk store,
+//     refills the stage freed one item earlier, and after a row's last segment prefetches the slab
+//     row two rows ahead into the buffer that row just released.
+// 512 threads = 15 math warps (480 quads = one 1920-pixel segment, half a 4K row) + the issuer:
+// the 16th warp of the block-synchronous 512-thread form was idle at this width anyway.
+//
+// kLean: index arithmetic per QUAD instead of per pixel where the x cells are at least 4 pixels
+// wide (W >= 4 gw).  floor(t_i) of the quad's pixels is floor(t_0) or floor(t_0) + 1 (t grows by
+// scale_x <= 1/4 per pixel), so one float->int conversion serves four pixels and the cell offsets
+// are one of three precomputed values; the depth cell uses F2I.FLOOR + I2FP (one XU-pipe op)
+// instead of FRND + F2I (two).  t_i, the fractions and every weight are computed by the same
+// rounded operations as spatial_axis / range_axis: results are bitwise those of the other forms.
+template <int kTexChunks>
+__device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const unsigned char* tile,
+                                                  unsigned char* out_tile,
+                                                  const unsigned char* guide_tile,
+                                                  const unsigned char* slab_b, int tex_row, int x0,
+                                                  int q) {
+  const SliceGeom& g = args.g;
+  const float gd_f = static_cast<float>(g.gd);
+  const int xsb = g.gd * (kGc * 4);  // bytes between x cells of the slab row
+  float pr[4], pg[4], pb[4];
+  load_quad<kPxF32>(tile, q, pr, pg, pb);
+  const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
+  const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+
+  // x axis, once per quad: t_i = (x_i + 0.5f) * scale - 0.5f with the reference's roundings
+  // (float(X + i) + 0.5f == float(X) + (i + 0.5f): both exact below 2^22).
+  const float xf = static_cast<float>(x0 + 4 * q);
+  float tx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    tx[i] = __fsub_rn(__fmul_rn(__fadd_rn(xf, static_cast<float>(i) + 0.5f), g.scale_x), 0.5f);
+  const int ix0 = __float2int_rd(tx[0]);
+  const float fl0 = static_cast<float>(ix0), fl1 = fl0 + 1.0f;
+  const int c0 = clampi(ix0, 0, g.gw - 1) * xsb;
+  const int c1 = clampi(ix0 + 1, 0, g.gw - 1) * xsb;
+  const int c2 = clampi(ix0 + 2, 0, g.gw - 1) * xsb;
+
+  float o_r[4], o_g[4], o_b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool step = (i > 0) && (tx[i] >= fl1);     // this pixel sits in the next x cell
+    const float fx = tx[i] - (step ? fl1 : fl0);
+    const int xo0 = step ? c1 : c0;
+    const int xo1 = step ? c2 : c1;
+    // depth axis (range_axis with one conversion)
+    const float tz = __fsub_rn(__fmul_rn(gv[i], gd_f), 0.5f);
+    const int iz = __float2int_rd(tz);
+    const float fz = tz - static_cast<float>(iz);
+    const int zc0 = clampi(iz, 0, g.gd - 1);
+    const int zc1 = clampi(iz + 1, 0, g.gd - 1);
+    float wz0, wz1;
+    smoothed_weights(fz, wz0, wz1);
+    const float wx1 = fx, wx0 = 1.0f - fx;
+    blend_apply<kTexChunks, true>(reinterpret_cast<const float*>(slab_b), args.slab_tex, tex_row,
+                                  zc0 * 48 + xo0, zc1 * 48 + xo0, zc0 * 48 + xo1, zc1 * 48 + xo1,
+                                  wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i], pg[i], pb[i],
+                                  o_r[i], o_g[i], o_b[i]);
+  }
+  store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
+  fence_proxy_async_smem();
+}
+
+template <int kTexChunks, bool kLean, int kThreads = 512>
+__global__ void __launch_bounds__(kThreads, 2)
+slice_apply_rows_async_kernel(const TmaArgs args) {
+  static_assert(kTexChunks > 0, "the issuer-warp kernel reads slab rows from the workspace");
+  constexpr int kMathWarps = kThreads / 32 - 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SliceGeom& g = args.g;
+  const TmaPlan& pl = args.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]  TMA landed
+  uint64_t* done = full + kMaxStages;                    // [kMaxStages]  every math warp has written
+  uint64_t* slab_full = done + kMaxStages;               // [2]
+  unsigned char* raw0 = smem + pl.off_raw;               // two slab rows
+  unsigned char* stage_base = smem + pl.off_stage;
+
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
+  if (r_end <= r_begin) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kMathWarps); }
+    mbar_init(&slab_full[0], 1);
+    mbar_init(&slab_full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();  // the only block-wide barrier
+
+  const int NS = pl.stages;
+  const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+
+  if (warp == kMathWarps) {
+    // ------------------------------- issuer -------------------------------------------------
+    if (lane != 0) return;
+    auto load_slab = [&](long long row) {
+      const int rb = static_cast<int>(row - r_begin) & 1;
+      mbar_expect_tx(&slab_full[rb], slab_bytes);
+      tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
+                  args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes, &slab_full[rb]);
+    };
+    // load cursor: runs NS - 1 items ahead of the store cursor
+    long long l_row = r_begin;
+    int l_x0 = 0, l_s = 0;
+    auto issue_next_load = [&]() {
+      if (l_row >= r_end) return;
+      const int npx = min(pl.seg_px, g.W - l_x0);
+      unsigned char* st = stage_base + static_cast<size_t>(l_s) * pl.stage_bytes;
+      const size_t pix = static_cast<size_t>(l_row) * g.W + l_x0;
+      mbar_expect_tx(&full[l_s], static_cast<uint32_t>(npx) * 16u);
+      tma_load_1d(st, args.input + pix * 12, static_cast<uint32_t>(npx) * 12u, &full[l_s]);
+      tma_load_1d(st + pl.off_guide, args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[l_s]);
+      if (++l_s == NS) l_s = 0;
+      l_x0 += pl.seg_px;
+      if (l_x0 >= g.W) { l_x0 = 0; ++l_row; }
+    };
+    load_slab(r_begin);
+    if (r_begin + 1 < r_end) load_slab(r_begin + 1);
+    for (int i = 0; i < NS - 1; ++i) issue_next_load();
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long row = r_begin; row < r_end; ++row) {
+      for (int x0 = 0; x0 < g.W; x0 += pl.seg_px) {
+        const int npx = min(pl.seg_px, g.W - x0);
+        unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+        mbar_wait(&done[s], ph);  // every math warp has written (and proxy-fenced) its results
+        const size_t pix = static_cast<size_t>(row) * g.W + x0;
+        tma_store_1d(args.out + pix * 12, st, static_cast<uint32_t>(npx) * 12u);
+        tma_store_commit();
+        if (l_row < r_end) {
+          tma_store_wait_read<1>();  // the previous item's store has drained the stage refilled now
+          issue_next_load();
+        }
+        if (++s == NS) { s = 0; ph ^= 1u; }
+      }
+      // the row's slab buffer is free: every math warp arrived after its last read of it
+      if (row + 2 < r_end) load_slab(row + 2);
+    }
+    tma_store_wait_all<0>();
+    return;
+  }
+
+  // --------------------------------- math warps ---------------------------------------------
+  const int q = warp * 32 + lane;  // this thread's quad inside a segment
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long row = r_begin; row < r_end; ++row) {
+    const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
+    mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
+    const unsigned char* slab_b = raw0 + static_cast<size_t>(rb) * slab_bytes;
+    const int tex_row = static_cast<int>(row) * (pl.row_floats / 4);
+    for (int x0 = 0; x0 < g.W; x0 += pl.seg_px) {
+      const int npx = min(pl.seg_px, g.W - x0);
+      unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+      mbar_wait(&full[s], ph);
+      if (q * 4 < npx) {
+        if constexpr (kLean)
+          process_quad_lean<kTexChunks>(args, st, st, st + pl.off_guide, slab_b, tex_row, x0, q);
+        else
+          process_quad<GuideFromInput, kTexChunks>(args, GuideFromInput{}, st, st, st + pl.off_guide,
+                                                   reinterpret_cast<const float*>(slab_b), tex_row,
+                                                   row, x0, q);
+      }
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&done[s])) : "memory");
+      if (++s == NS) { s = 0; ph ^= 1u; }
+    }
+  }
+}
+
+// =========================================================================================
 // Un-fused slice, persistent TMA row kernel (gc = 12, W % 4 == 0): out[b,y,x,0..11].
 // =========================================================================================
 // Same organisation as the fused kernel, but the op is WRITE-bound (4 B in, 48 B out per pixel):
@@ -1228,6 +1424,16 @@ static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
   return launch_ws_n<GuideFn, 8>(a, fn, stream);
 }
 
+template <int kTexChunks, bool kLean>
+static int launch_async(const TmaArgs& a, cudaStream_t stream) {
+  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kAsyncThreads>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       a.p.smem_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  kern<<<a.p.ctas, kAsyncThreads, a.p.smem_bytes, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // Texture objects over caller workspaces, cached by (pointer, bytes): creating one is a
 // host-side driver call that should not sit inside a timed loop.
 struct TexCacheEntry { const void* ptr; size_t bytes; int dev; cudaTextureObject_t tex; };
@@ -1348,7 +1554,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21))
     variant = HDRNET_VARIANT_TEX;
   if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_WS ||
-      variant == HDRNET_VARIANT_TEX_IN) {
+      variant == HDRNET_VARIANT_TEX_IN || variant == HDRNET_VARIANT_TEX_ASYNC) {
     const size_t need = tex_need;
     if (!tex_ok) return HDRNET_E_UNSUPPORTED;
     TmaPlan tplan;
@@ -1358,6 +1564,8 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     if (gs.mode != 0) tex_threads = kFusedThreadsDefault;
     // warp-specialised form: the 512-thread CTA is 15 math warps (480 pixel quads) + the producer
     if (variant == HDRNET_VARIANT_TEX_WS && tex_threads == 512) tex_threads = 480;
+    // issuer-warp form: the plan covers the math warps only (segments of <= 4 * 480 pixels)
+    if (variant == HDRNET_VARIANT_TEX_ASYNC) tex_threads = kAsyncThreads - 32;
     if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true, tex_threads,
                        gs.in_fmt, gs.out_fmt))
       tplan = plan;
@@ -1372,6 +1580,29 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     if (variant == HDRNET_VARIANT_TEX_WS) {
       if (gs.mode != 0 || tplan.seg_px > tplan.threads * 4) return HDRNET_E_UNSUPPORTED;
       return launch_ws(a, GuideFromInput{}, stream);
+    }
+    if (variant == HDRNET_VARIANT_TEX_ASYNC) {
+      // float32 guide-from-input form only
+      if (gs.mode != 0 || px || tplan.threads != kAsyncThreads - 32 ||
+          tplan.seg_px > tplan.threads * 4 || tplan.stages < 2)
+        return HDRNET_E_UNSUPPORTED;
+      // lean (per-quad) x indexing needs x cells at least 4 pixels wide
+      bool lean = static_cast<long long>(W) >= 4LL * gw;
+      if (const char* e = std::getenv("HDRNET_ASYNC_LEAN")) lean = lean && std::atoi(e) != 0;
+      int chunks = kTexChunksDefault;
+      if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);  // tuning knob
+      if (lean) {
+        switch (chunks) {
+          case 3: return launch_async<3, true>(a, stream);
+          case 5: return launch_async<5, true>(a, stream);
+          case 6: return launch_async<6, true>(a, stream);
+          default: return launch_async<kTexChunksDefault, true>(a, stream);
+        }
+      }
+      switch (chunks) {
+        case 5: return launch_async<5, false>(a, stream);
+        default: return launch_async<kTexChunksDefault, false>(a, stream);
+      }
     }
     if (variant == HDRNET_VARIANT_TEX_IN) {
       // float32 guide-from-input form only; pixel tensors addressable as 1-D float4 textures

@@ -72,6 +72,11 @@ extern "C" {
 #define HDRNET_VARIANT_TEX_IN 6  /* the texture-assisted kernel with the pixel INPUT fetched     */
                                  /* through the texture pipe as well (no input staging in    */
                                  /* shared memory); same requirements as HDRNET_VARIANT_TEX  */
+#define HDRNET_VARIANT_TEX_ASYNC 7 /* the texture-assisted kernel with an ISSUER warp: 15 math   */
+                                 /* warps that never wait for each other (mbarrier arrive    */
+                                 /* instead of block barriers) + one warp that issues every  */
+                                 /* bulk copy; per-quad index arithmetic.  Same requirements */
+                                 /* as HDRNET_VARIANT_TEX                                     */
 
 HDRNET_API int hdrnet_b200_abi_version(void);
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 VARIANTS = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "tma": _lib.VARIANT_TMA,
             "zsort": _lib.VARIANT_ZSORT, "tex": _lib.VARIANT_TEX, "tex_ws": _lib.VARIANT_TEX_WS,
-            "tex_in": _lib.VARIANT_TEX_IN}
+            "tex_in": _lib.VARIANT_TEX_IN, "tex_async": _lib.VARIANT_TEX_ASYNC}
 
 
 def cuda(a):
@@ -93,10 +93,11 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("variant", ["auto", "generic", "tma", "zsort", "tex", "tex_ws", "tex_in"])
+@pytest.mark.parametrize("variant", ["auto", "generic", "tma", "zsort", "tex", "tex_ws", "tex_in",
+                                     "tex_async"])
 def test_slice_apply_matches_oracle(shape, variant):
     B, H, W, gh, gw, gd = shape
-    if variant in ("tma", "zsort", "tex", "tex_ws", "tex_in") and W % 4 != 0:
+    if variant in ("tma", "zsort", "tex", "tex_ws", "tex_in", "tex_async") and W % 4 != 0:
         pytest.skip("TMA kernels need W % 4 == 0")
     grid, guide, inp = rand_case(1234, B, H, W, gh, gw, gd, signed=True)
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
@@ -185,6 +186,7 @@ def test_zsort_is_bitwise_equal_to_row_kernel():
     assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex"))   # texture-assisted form too
     assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex_ws"))  # and its warp-specialised form
     assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex_in"))  # and the texture-fed form
+    assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex_async"))  # issuer-warp form, per-quad indices
     # smooth (image-like) guide: long runs of equal depth cells, heavily unbalanced buckets
     yy, xx = np.mgrid[0:64, 0:3840]
     guide2 = np.stack([(0.5 + 0.5 * np.sin(xx / 700.0 + yy / 30.0)).astype(np.float32)] * 2)
@@ -193,6 +195,33 @@ def test_zsort_is_bitwise_equal_to_row_kernel():
     const = np.full_like(guide, 0.3)       # every pixel in ONE depth bucket
     assert np.array_equal(run_apply(grid, const, inp, True, "tma"),
                           run_apply(grid, const, inp, True, "zsort"))
+
+
+@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_LEAN="0"), dict(HDRNET_TEX_CHUNKS="5"),
+                                 dict(HDRNET_TEX_CHUNKS="3"), dict(HDRNET_TEX_CHUNKS="6"),
+                                 dict(HDRNET_ASYNC_LEAN="0", HDRNET_TEX_CHUNKS="5")],
+                         ids=lambda e: ",".join(f"{k[7:].lower()}={v}" for k, v in e.items()))
+def test_issuer_warp_kernel_knobs_are_bitwise_equal(env, monkeypatch):
+    """The issuer-warp form with per-pixel instead of per-quad index arithmetic, and with 3 / 5 / 6
+    of a pixel's 12 corner chunks on the texture pipe: identical bits; also on narrow x cells
+    (W < 4 gw: the kernel must fall back to per-pixel indices by itself), many rows per CTA, a
+    ragged last segment and out-of-range guides."""
+    cases = [rand_case(5, 2, 64, 3840, 16, 16, 8, signed=True),
+             rand_case(6, 1, 700, 1028, 5, 7, 3, signed=True),
+             rand_case(7, 3, 9, 128, 8, 64, 4, signed=True)]
+    cases[1][1][0, :, ::5] = 1.75
+    cases[1][1][0, :, 1::5] = -0.6
+    for grid, guide, inp in cases:
+        for k in ("HDRNET_ASYNC_LEAN", "HDRNET_TEX_CHUNKS"):
+            monkeypatch.delenv(k, raising=False)
+        want = run_apply(grid, guide, inp, True, "tex")
+        assert np.array_equal(want, run_apply(grid, guide, inp, True, "tex_async"))
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        if "HDRNET_TEX_CHUNKS" in env:   # the block-synchronous form honours the same knob
+            want_k = run_apply(grid, guide, inp, True, "tex")
+            assert np.array_equal(want, want_k)
+        assert np.array_equal(want, run_apply(grid, guide, inp, True, "tex_async"))
 
 
 def test_empty_batch_is_a_no_op():
@@ -251,7 +280,7 @@ def test_4k_frame_against_full_oracle():
     """One 3840x2160 frame, grid 16x16x8 (config 3's per-image shape), full oracle compare."""
     grid, guide, inp = rand_case(1234, 1, 2160, 3840, 16, 16, 8)
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
-    for v in ("tma", "generic", "zsort", "tex", "tex_ws", "tex_in"):
+    for v in ("tma", "generic", "zsort", "tex", "tex_ws", "tex_in", "tex_async"):
         got = run_apply(grid, guide, inp, True, v)
         assert_parity(got, expected, what=f"4K [{v}]")
     gidx = hdrnet_ops.slice_indices(cuda(guide), (16, 16, 8)).cpu().numpy()

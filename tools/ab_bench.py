@@ -10,12 +10,18 @@ grid = torch.rand(B, 16, 16, 8, 12, device="cuda", generator=gen)
 guide = torch.rand(B, 2160, 3840, device="cuda", generator=gen)
 inp = torch.rand(B, 2160, 3840, 3, device="cuda", generator=gen)
 out = torch.empty_like(inp)
-CONFIGS = {
+ALL_CONFIGS = {
     "auto": (dict(), _lib.VARIANT_AUTO),
     "tex t512 c4": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
     "tex t512 c5": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="5"), _lib.VARIANT_TEX),
     "tex t512 c3": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX),
     "tex t256 c4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
+    "async lean c4": (dict(HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX_ASYNC),
+    "async lean c5": (dict(HDRNET_TEX_CHUNKS="5"), _lib.VARIANT_TEX_ASYNC),
+    "async lean c3": (dict(HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX_ASYNC),
+    "async lean c6": (dict(HDRNET_TEX_CHUNKS="6"), _lib.VARIANT_TEX_ASYNC),
+    "async px   c4": (dict(HDRNET_TEX_CHUNKS="4", HDRNET_ASYNC_LEAN="0"), _lib.VARIANT_TEX_ASYNC),
+    "async px   c5": (dict(HDRNET_TEX_CHUNKS="5", HDRNET_ASYNC_LEAN="0"), _lib.VARIANT_TEX_ASYNC),
     "ws  t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TEX_WS),
     "ws  t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TEX_WS),
     "tex t320x3 c4": (dict(HDRNET_TMA_THREADS="320", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
@@ -26,7 +32,11 @@ CONFIGS = {
     "tma t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TMA),
     "tma t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TMA),
 }
-KEYS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC")
+# python tools/ab_bench.py [substring ...]: only the configurations whose name contains one
+sel = sys.argv[1:]
+CONFIGS = {k: v for k, v in ALL_CONFIGS.items() if not sel or any(t in k for t in sel)}
+KEYS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC",
+        "HDRNET_ASYNC_LEAN")
 def burst(env, variant, iters=40):
     for k in KEYS: os.environ.pop(k, None)
     os.environ.update(env)
