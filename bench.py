@@ -40,6 +40,17 @@ WORKLOAD = (f"4K ({W4K}x{H4K}) batch={B_PER_GPU} per GPU, fused slice-apply, "
             f"grid {GH}x{GW}x{GD}x{GC}, has_offset, f32")
 
 
+KERNEL_TEXT = {
+    7: "tex_async (AUTO with workspace): yblend_rows_kernel pre-pass + "
+       "slice_apply_rows_async_kernel<5 texture chunks, per-quad indices, 512 threads = 15 math warps + "
+       "issuer warp>, both inside every timed step",
+    4: "tex (AUTO with workspace): yblend_rows_kernel pre-pass + "
+       "slice_apply_rows_tma_kernel<GuideFromInput,4,2,512,f32,f32>, both inside every timed step",
+    2: "tma: slice_apply_rows_tma_kernel (all-LSU form)",
+    1: "generic: one thread per pixel",
+}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -319,9 +330,7 @@ def run_b200_arm(args):
             "config": {"workload": WORKLOAD, "frames_per_gpu": B, "global_frames": B * world,
                        "parallelism": f"batch-shard x{world}, no data-path collective",
                        "l2": "1.86 GB touched per step >> 126 MB L2: no flush between iterations",
-                       "kernel": {"variant": "tex (AUTO with workspace): yblend_rows_kernel pre-pass + "
-                                             "slice_apply_rows_tma_kernel<GuideFromInput,4,2,512,f32,f32>, both inside "
-                                             "every timed step",
+                       "kernel": {"variant": KERNEL_TEXT.get(variant.value, f"variant {variant.value}"),
                                   "ctas": ctas.value, "threads": threads.value,
                                   "dyn_smem_bytes": smem.value, "workspace_bytes": ws_bytes}},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

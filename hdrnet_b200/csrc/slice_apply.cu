@@ -264,6 +264,11 @@ constexpr int kTmaThreadsDefault = 256;  // all-LSU form; 512 = 64-register form
 constexpr int kTexThreadsDefault = 512;  // texture-assisted form: measured 7 % faster at 512
 constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the texture-assisted kernel
 constexpr int kAsyncThreads = 512;        // issuer-warp form: 15 math warps + the issuer
+constexpr int kAsyncThreadsDefault = 512; // HDRNET_ASYNC_THREADS / HDRNET_ASYNC_OCC
+constexpr int kAsyncOccDefault = 2;
+constexpr int kAsyncTexChunksDefault = 5; // its tuning defaults (HDRNET_TEX_CHUNKS / _ASYNC_STORE / _SLAB)
+constexpr int kAsyncStoreDefault = 0;
+constexpr int kAsyncSlabDefault = 0;
 constexpr int kMaxStages = 8;
 constexpr int kGc = 12;
 
@@ -879,15 +884,107 @@ slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn g
 // are one of three precomputed values; the depth cell uses F2I.FLOOR + I2FP (one XU-pipe op)
 // instead of FRND + F2I (two).  t_i, the fractions and every weight are computed by the same
 // rounded operations as spatial_axis / range_axis: results are bitwise those of the other forms.
-template <int kTexChunks>
+//
+// Two more switches, both aimed at the shared-memory data pipe that bounds this form (ncu: 90 % of
+// its peak; 1.57 wavefronts per pixel = 1.0 gather + 0.1 x-cell straddles + 0.22 tile reads /
+// writes by the threads + 0.23 reads / writes of the same tiles by the TMA engine):
+//   kStore == 1: results leave the registers by 3 x STG.128 (streaming) instead of 3 x STS.128 +
+//     a bulk store -- the output tile never crosses shared memory (-0.09 wavefronts per pixel).
+//   kSlab == 1: the ISSUER WARP blends each image row's two grid rows (L2-resident, 786 KB for
+//     the whole batch) into the shared-memory slab, two rows ahead of the math warps, so the
+//     pre-pass only has to materialise what the texture pipe fetches: the trailing part(s) of
+//     every cell (16 of its 48 bytes for four texture chunks, 32 beyond) -- a third of the
+//     pre-pass traffic, and the row kernel no longer reads slab rows back from HBM.
+
+// Which of a pixel's 12 corner chunks -- corner c = 0..3 (v00, v01, v10, v11), part p = 0..2 --
+// travel through the texture pipe.  kSlab == 0: the last kTexChunks of the ids 3 c + p (the
+// workspace holds whole slab rows).  kSlab == 1: part 2 of every corner, then part 1 of corners
+// 3, 2, ... for the chunks beyond four (the workspace holds parts 3 - P .. 2 of every cell).
+template <int kTexChunks, int kSlab>
+__host__ __device__ constexpr bool chunk_on_tex(int c, int p) {
+  if (kSlab == 0) return c * 3 + p >= 12 - kTexChunks;
+  return p == 2 || (p == 1 && c >= 8 - kTexChunks);
+}
+__host__ __device__ constexpr int tex_parts(int tex_chunks) { return tex_chunks > 4 ? 2 : 1; }
+
+template <int kTexChunks, int kSlab, int kC, int kP>
+__device__ __forceinline__ ulonglong2 fetch_chunk(const unsigned char* __restrict__ slab_b,
+                                                  cudaTextureObject_t tex, int off_b, int tex_idx) {
+  if constexpr (chunk_on_tex<kTexChunks, kSlab>(kC, kP)) {
+    // tex_idx: texel of the cell's part 0 (kSlab 0) / of its first stored part (kSlab 1)
+    constexpr int kFirst = (kSlab == 0) ? 0 : 3 - tex_parts(kTexChunks);
+    const float4 v = tex1Dfetch<float4>(tex, tex_idx + (kP - kFirst));
+    ulonglong2 r;
+    r.x = pack2(v.x, v.y);
+    r.y = pack2(v.z, v.w);
+    return r;
+  } else {
+    return *reinterpret_cast<const ulonglong2*>(slab_b + off_b + 16 * kP);
+  }
+}
+
+// blend_apply with byte offsets and per-corner texel indices (unused ones are dead code).
+template <int kTexChunks, int kSlab>
+__device__ __forceinline__ void blend_apply_q(const unsigned char* __restrict__ slab_b,
+                                              cudaTextureObject_t tex, const int (&off)[4],
+                                              const int (&tix)[4], const float (&w)[4], float r,
+                                              float g, float b, float& out_r, float& out_g,
+                                              float& out_b) {
+  const unsigned long long W00 = pack2(w[0], w[0]), W01 = pack2(w[1], w[1]);
+  const unsigned long long W10 = pack2(w[2], w[2]), W11 = pack2(w[3], w[3]);
+  const ulonglong2 a0 = fetch_chunk<kTexChunks, kSlab, 0, 0>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 a1 = fetch_chunk<kTexChunks, kSlab, 0, 1>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 a2 = fetch_chunk<kTexChunks, kSlab, 0, 2>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 b0 = fetch_chunk<kTexChunks, kSlab, 1, 0>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 b1 = fetch_chunk<kTexChunks, kSlab, 1, 1>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 b2 = fetch_chunk<kTexChunks, kSlab, 1, 2>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 c0 = fetch_chunk<kTexChunks, kSlab, 2, 0>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 c1 = fetch_chunk<kTexChunks, kSlab, 2, 1>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 c2 = fetch_chunk<kTexChunks, kSlab, 2, 2>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 d0 = fetch_chunk<kTexChunks, kSlab, 3, 0>(slab_b, tex, off[3], tix[3]);
+  const ulonglong2 d1 = fetch_chunk<kTexChunks, kSlab, 3, 1>(slab_b, tex, off[3], tix[3]);
+  const ulonglong2 d2 = fetch_chunk<kTexChunks, kSlab, 3, 2>(slab_b, tex, off[3], tix[3]);
+  unsigned long long acc[6];  // same order of operations as blend_apply: identical bits
+  acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
+  acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
+  acc[2] = fma2(W11, d1.x, fma2(W10, c1.x, fma2(W01, b1.x, mul2(W00, a1.x))));
+  acc[3] = fma2(W11, d1.y, fma2(W10, c1.y, fma2(W01, b1.y, mul2(W00, a1.y))));
+  acc[4] = fma2(W11, d2.x, fma2(W10, c2.x, fma2(W01, b2.x, mul2(W00, a2.x))));
+  acc[5] = fma2(W11, d2.y, fma2(W10, c2.y, fma2(W01, b2.y, mul2(W00, a2.y))));
+  float a0f, a1f, a2f, a3f;
+  unpack2(acc[0], a0f, a1f);
+  unpack2(acc[1], a2f, a3f);
+  out_r = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[2], a0f, a1f);
+  unpack2(acc[3], a2f, a3f);
+  out_g = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[4], a0f, a1f);
+  unpack2(acc[5], a2f, a3f);
+  out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+}
+
+__device__ __forceinline__ void stg128_stream(float* p, float x, float y, float z, float w) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ldg128_stream(const float4* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// tex_base: kSlab 0 -- texel of the row's first cell (row * gw * gd * 3); kSlab 1 -- the row's first
+// CELL in the part workspace (row * gw * gd).  out_row: this image row in `out` (kStore 1 only).
+template <int kTexChunks, int kStore, int kSlab>
 __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const unsigned char* tile,
                                                   unsigned char* out_tile,
                                                   const unsigned char* guide_tile,
-                                                  const unsigned char* slab_b, int tex_row, int x0,
-                                                  int q) {
+                                                  const unsigned char* slab_b, int tex_base,
+                                                  float* out_row, int x0, int q) {
   const SliceGeom& g = args.g;
   const float gd_f = static_cast<float>(g.gd);
-  const int xsb = g.gd * (kGc * 4);  // bytes between x cells of the slab row
   float pr[4], pg[4], pb[4];
   load_quad<kPxF32>(tile, q, pr, pg, pb);
   const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
@@ -902,17 +999,19 @@ __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const uns
     tx[i] = __fsub_rn(__fmul_rn(__fadd_rn(xf, static_cast<float>(i) + 0.5f), g.scale_x), 0.5f);
   const int ix0 = __float2int_rd(tx[0]);
   const float fl0 = static_cast<float>(ix0), fl1 = fl0 + 1.0f;
-  const int c0 = clampi(ix0, 0, g.gw - 1) * xsb;
-  const int c1 = clampi(ix0 + 1, 0, g.gw - 1) * xsb;
-  const int c2 = clampi(ix0 + 2, 0, g.gw - 1) * xsb;
+  // the three x cells a quad can touch, as slab cell indices (x-major, gd depth cells each)
+  const int c0 = clampi(ix0, 0, g.gw - 1) * g.gd;
+  const int c1 = clampi(ix0 + 1, 0, g.gw - 1) * g.gd;
+  const int c2 = clampi(ix0 + 2, 0, g.gw - 1) * g.gd;
+  const int b0 = c0 * 48, b1 = c1 * 48, b2 = c2 * 48;   // and as byte offsets
 
   float o_r[4], o_g[4], o_b[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const bool step = (i > 0) && (tx[i] >= fl1);     // this pixel sits in the next x cell
     const float fx = tx[i] - (step ? fl1 : fl0);
-    const int xo0 = step ? c1 : c0;
-    const int xo1 = step ? c2 : c1;
+    const int xo0 = step ? b1 : b0;
+    const int xo1 = step ? b2 : b1;
     // depth axis (range_axis with one conversion)
     const float tz = __fsub_rn(__fmul_rn(gv[i], gd_f), 0.5f);
     const int iz = __float2int_rd(tz);
@@ -922,19 +1021,39 @@ __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const uns
     float wz0, wz1;
     smoothed_weights(fz, wz0, wz1);
     const float wx1 = fx, wx0 = 1.0f - fx;
-    blend_apply<kTexChunks, true>(reinterpret_cast<const float*>(slab_b), args.slab_tex, tex_row,
-                                  zc0 * 48 + xo0, zc1 * 48 + xo0, zc0 * 48 + xo1, zc1 * 48 + xo1,
-                                  wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i], pg[i], pb[i],
-                                  o_r[i], o_g[i], o_b[i]);
+    const int off[4] = {zc0 * 48 + xo0, zc1 * 48 + xo0, zc0 * 48 + xo1, zc1 * 48 + xo1};
+    int tix[4];
+    if constexpr (kSlab == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tix[c] = tex_base + (off[c] >> 4);
+    } else {
+      constexpr int P = tex_parts(kTexChunks);
+      const int xc0 = tex_base + (step ? c1 : c0), xc1 = tex_base + (step ? c2 : c1);
+      tix[0] = (xc0 + zc0) * P; tix[1] = (xc0 + zc1) * P;
+      tix[2] = (xc1 + zc0) * P; tix[3] = (xc1 + zc1) * P;
+    }
+    const float w[4] = {wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1};
+    blend_apply_q<kTexChunks, kSlab>(slab_b, args.slab_tex, off, tix, w, pr[i], pg[i], pb[i],
+                                     o_r[i], o_g[i], o_b[i]);
   }
-  store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
-  fence_proxy_async_smem();
+  if constexpr (kStore == 0) {
+    store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
+    fence_proxy_async_smem();
+  } else {
+    float* op = out_row + static_cast<size_t>(x0 + 4 * q) * 3;
+    stg128_stream(op, o_r[0], o_g[0], o_b[0], o_r[1]);
+    stg128_stream(op + 4, o_g[1], o_b[1], o_r[2], o_g[2]);
+    stg128_stream(op + 8, o_b[2], o_r[3], o_g[3], o_b[3]);
+  }
 }
 
-template <int kTexChunks, bool kLean, int kThreads = 512>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = 512,
+          int kMinBlocks = 2>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 slice_apply_rows_async_kernel(const TmaArgs args) {
-  static_assert(kTexChunks > 0, "the issuer-warp kernel reads slab rows from the workspace");
+  static_assert(kTexChunks > 0, "the issuer-warp kernel serves part of the gather by texture");
+  static_assert(kLean || (kStore == 0 && kSlab == 0), "the switches exist in the lean form only");
+  static_assert(kSlab == 0 || (kTexChunks >= 4 && kTexChunks <= 8), "part workspace: 4..8 chunks");
   constexpr int kMathWarps = kThreads / 32 - 1;
   extern __shared__ __align__(128) unsigned char smem[];
   const SliceGeom& g = args.g;
@@ -942,7 +1061,7 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]  TMA landed
-  uint64_t* done = full + kMaxStages;                    // [kMaxStages]  every math warp has written
+  uint64_t* done = full + kMaxStages;                    // [kMaxStages]  every math warp is through
   uint64_t* slab_full = done + kMaxStages;               // [2]
   unsigned char* raw0 = smem + pl.off_raw;               // two slab rows
   unsigned char* stage_base = smem + pl.off_stage;
@@ -962,20 +1081,57 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
 
   const int NS = pl.stages;
   const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+  auto arrive = [&](uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  };
 
   if (warp == kMathWarps) {
-    // ------------------------------- issuer -------------------------------------------------
-    if (lane != 0) return;
-    auto load_slab = [&](long long row) {
+    // ------------------------------- issuer warp --------------------------------------------
+    // Lane 0 issues every bulk copy; the whole warp blends slab rows when kSlab == 1.
+    if (kSlab == 0 && lane != 0) return;
+    auto make_slab = [&](long long row) {
       const int rb = static_cast<int>(row - r_begin) & 1;
-      mbar_expect_tx(&slab_full[rb], slab_bytes);
-      tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
-                  args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes, &slab_full[rb]);
+      if constexpr (kSlab == 0) {
+        if (lane == 0) {
+          mbar_expect_tx(&slab_full[rb], slab_bytes);
+          tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
+                      args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes,
+                      &slab_full[rb]);
+        }
+      } else {
+        // yslab[r] = (1 - fy) G[b][gy0] + fy G[b][gy1], exactly yblend_rows_kernel's arithmetic
+        const int b = static_cast<int>(row / g.rows);
+        const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
+        const Axis ay = spatial_axis(y, g.scale_y);
+        const float wy1 = ay.f, wy0 = 1.0f - ay.f;
+        const float* gb = args.grid + static_cast<size_t>(b) * g.gh * pl.row_floats;
+        const float4* a4 = reinterpret_cast<const float4*>(
+            gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * pl.row_floats);
+        const float4* b4 = reinterpret_cast<const float4*>(
+            gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * pl.row_floats);
+        float4* s4 = reinterpret_cast<float4*>(raw0 + static_cast<size_t>(rb) * slab_bytes);
+        const int n4 = pl.row_floats / 4;
+        // six cells' loads in flight per lane and batch (L2 latency, not bandwidth, is the cost)
+        for (int e0 = lane; e0 < n4; e0 += 32 * 6) {
+          float4 va[6], vb[6];
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {
+            const int e = min(e0 + 32 * u, n4 - 1);
+            va[u] = ldg128_stream(a4 + e);
+            vb[u] = ldg128_stream(b4 + e);
+          }
+#pragma unroll
+          for (int u = 0; u < 6; ++u)
+            if (e0 + 32 * u < n4) s4[e0 + 32 * u] = lerp4(wy0, va[u], wy1, vb[u]);
+        }
+        __syncwarp();
+        if (lane == 0) arrive(&slab_full[rb]);
+      }
     };
-    // load cursor: runs NS - 1 items ahead of the store cursor
+    // load cursor: runs NS - 1 items ahead of the math warps
     long long l_row = r_begin;
     int l_x0 = 0, l_s = 0;
-    auto issue_next_load = [&]() {
+    auto issue_next_load = [&]() {  // lane 0
       if (l_row >= r_end) return;
       const int npx = min(pl.seg_px, g.W - l_x0);
       unsigned char* st = stage_base + static_cast<size_t>(l_s) * pl.stage_bytes;
@@ -987,57 +1143,72 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
       l_x0 += pl.seg_px;
       if (l_x0 >= g.W) { l_x0 = 0; ++l_row; }
     };
-    load_slab(r_begin);
-    if (r_begin + 1 < r_end) load_slab(r_begin + 1);
-    for (int i = 0; i < NS - 1; ++i) issue_next_load();
+    // kStore 0: the stage refilled after item i is item i-1's (its bulk store must have drained);
+    // kStore 1: item i's own stage -- one more item of prefetch from the same ring.
+    if (lane == 0)
+      for (int i = 0; i < NS - (kStore == 0 ? 1 : 0); ++i) issue_next_load();
+    make_slab(r_begin);
+    if (r_begin + 1 < r_end) make_slab(r_begin + 1);
 
+    // Lane 0 alone runs the per-item protocol; the other lanes park at the row's __syncwarp (a
+    // blocked WARPSYNC costs nothing, whereas 31 lanes spinning in a try_wait loop on the same
+    // mbarrier delay lane 0's serial section: measured +10 % kernel time).
     int s = 0;
     uint32_t ph = 0;
     for (long long row = r_begin; row < r_end; ++row) {
-      for (int x0 = 0; x0 < g.W; x0 += pl.seg_px) {
-        const int npx = min(pl.seg_px, g.W - x0);
-        unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
-        mbar_wait(&done[s], ph);  // every math warp has written (and proxy-fenced) its results
-        const size_t pix = static_cast<size_t>(row) * g.W + x0;
-        tma_store_1d(args.out + pix * 12, st, static_cast<uint32_t>(npx) * 12u);
-        tma_store_commit();
-        if (l_row < r_end) {
-          tma_store_wait_read<1>();  // the previous item's store has drained the stage refilled now
-          issue_next_load();
+      if (lane == 0) {
+        for (int x0 = 0; x0 < g.W; x0 += pl.seg_px) {
+          mbar_wait(&done[s], ph);  // every math warp is through with this stage
+          if constexpr (kStore == 0) {  // results were written in place (and proxy-fenced)
+            const int npx = min(pl.seg_px, g.W - x0);
+            unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+            const size_t pix = static_cast<size_t>(row) * g.W + x0;
+            tma_store_1d(args.out + pix * 12, st, static_cast<uint32_t>(npx) * 12u);
+            tma_store_commit();
+            if (l_row < r_end) {
+              tma_store_wait_read<1>();  // the previous item's store has drained the stage refilled now
+              issue_next_load();
+            }
+          } else {
+            issue_next_load();          // refills THIS stage: nothing reads it any more
+          }
+          if (++s == NS) { s = 0; ph ^= 1u; }
         }
-        if (++s == NS) { s = 0; ph ^= 1u; }
       }
+      __syncwarp();
       // the row's slab buffer is free: every math warp arrived after its last read of it
-      if (row + 2 < r_end) load_slab(row + 2);
+      if (row + 2 < r_end) make_slab(row + 2);
     }
-    tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
     return;
   }
 
   // --------------------------------- math warps ---------------------------------------------
   const int q = warp * 32 + lane;  // this thread's quad inside a segment
+  const int cells = g.gw * g.gd;
   int s = 0;
   uint32_t ph = 0;
   for (long long row = r_begin; row < r_end; ++row) {
     const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
     mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
     const unsigned char* slab_b = raw0 + static_cast<size_t>(rb) * slab_bytes;
-    const int tex_row = static_cast<int>(row) * (pl.row_floats / 4);
+    const int tex_base = static_cast<int>(row) * (kSlab == 0 ? cells * 3 : cells);
+    float* out_row = reinterpret_cast<float*>(args.out) + static_cast<size_t>(row) * g.W * 3;
     for (int x0 = 0; x0 < g.W; x0 += pl.seg_px) {
       const int npx = min(pl.seg_px, g.W - x0);
       unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
       mbar_wait(&full[s], ph);
       if (q * 4 < npx) {
         if constexpr (kLean)
-          process_quad_lean<kTexChunks>(args, st, st, st + pl.off_guide, slab_b, tex_row, x0, q);
+          process_quad_lean<kTexChunks, kStore, kSlab>(args, st, st, st + pl.off_guide, slab_b,
+                                                       tex_base, out_row, x0, q);
         else
           process_quad<GuideFromInput, kTexChunks>(args, GuideFromInput{}, st, st, st + pl.off_guide,
-                                                   reinterpret_cast<const float*>(slab_b), tex_row,
+                                                   reinterpret_cast<const float*>(slab_b), tex_base,
                                                    row, x0, q);
       }
       __syncwarp();
-      if (lane == 0)
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&done[s])) : "memory");
+      if (lane == 0) arrive(&done[s]);
       if (++s == NS) { s = 0; ph ^= 1u; }
     }
   }
@@ -1240,22 +1411,58 @@ static bool make_slice_plan(const SliceGeom& g, int max_smem, int sms, SlicePlan
   return true;
 }
 
-// Pre-pass of the texture-assisted form: yslab[r] = (1 - fy) * G[b][gy0] + fy * G[b][gy1] for
+// Pre-pass of the texture-assisted forms: yslab[r] = (1 - fy) * G[b][gy0] + fy * G[b][gy1] for
 // every buffer row r = (b, y) -- the same y pre-blend the row kernel does in shared memory,
-// materialised once (gw*gd*48 B per image row: +11 % HBM traffic at 4K / 16x16x8).
-__global__ void __launch_bounds__(128)
-yblend_rows_kernel(const float* __restrict__ grid, float* __restrict__ yslab, SliceGeom g,
+// materialised once.  kParts == 0: whole slab rows (gw*gd*48 B per image row: +11 % HBM traffic at
+// 4K / 16x16x8); kParts == P > 0: only the trailing P 16-byte parts of every cell, [row][cell][P]
+// (what the issuer-warp form with kSlab == 1 fetches through the texture pipe).
+// One CTA owns kYblendRows consecutive rows and a thread one output float4 column of them: the two
+// grid rows it blends change every H / gh image rows, so they live in registers and the kernel
+// is a stream of coalesced stores (the first version -- one CTA per row, two dependent L2 loads
+// per thread -- took 22 us for 106 MB, latency-bound).
+constexpr int kYblendRows = 16;
+template <int kParts>
+__global__ void __launch_bounds__(256)
+yblend_rows_kernel(const float* __restrict__ grid, float4* __restrict__ ws, SliceGeom g,
                    int row_floats) {
-  const long long row = blockIdx.x;
-  const int b = static_cast<int>(row / g.rows);
-  const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
-  const Axis ay = spatial_axis(y, g.scale_y);
-  const float wy1 = ay.f, wy0 = 1.0f - ay.f;
-  const float* gb = grid + static_cast<size_t>(b) * g.gh * row_floats;
-  const float4* a4 = reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * row_floats);
-  const float4* b4 = reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * row_floats);
-  float4* o4 = reinterpret_cast<float4*>(yslab + static_cast<size_t>(row) * row_floats);
-  for (int e = threadIdx.x; e < row_floats / 4; e += blockDim.x) o4[e] = lerp4(wy0, __ldg(a4 + e), wy1, __ldg(b4 + e));
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const long long r0 = static_cast<long long>(blockIdx.x) * kYblendRows;
+  const long long r1 = min(r0 + kYblendRows, total_rows);
+  const int cells = row_floats / kGc;
+  const int n_out = (kParts == 0) ? row_floats / 4 : cells * kParts;   // float4 per output row
+  for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
+    int src = e;                                                       // float4 index in a grid row
+    if constexpr (kParts > 0) {
+      const int cell = e / kParts;
+      src = cell * 3 + (3 - kParts) + (e - cell * kParts);
+    }
+    int cur_b = -1, cur_i0 = INT_MIN;
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+    int b = static_cast<int>(r0 / g.rows);                                   // one division per CTA column
+    int yl = static_cast<int>(r0 - static_cast<long long>(b) * g.rows);      // row inside the image's band
+    for (long long row = r0; row < r1; ++row, ++yl) {
+      if (yl == g.rows) { yl = 0; ++b; }
+      const Axis ay = spatial_axis(g.y_off + yl, g.scale_y);
+      if (b != cur_b || ay.i0 != cur_i0) {
+        const float* gb = grid + static_cast<size_t>(b) * g.gh * row_floats;
+        va = __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * row_floats) + src);
+        vb = __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * row_floats) + src);
+        cur_b = b;
+        cur_i0 = ay.i0;
+      }
+      ws[static_cast<size_t>(row) * n_out + e] = lerp4(1.0f - ay.f, va, ay.f, vb);
+    }
+  }
+}
+
+static void launch_yblend(const float* grid, float* ws, const SliceGeom& g, int row_floats, int parts,
+                          cudaStream_t stream) {
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const unsigned blocks = static_cast<unsigned>((total_rows + kYblendRows - 1) / kYblendRows);
+  float4* ws4 = reinterpret_cast<float4*>(ws);
+  if (parts == 1) yblend_rows_kernel<1><<<blocks, 256, 0, stream>>>(grid, ws4, g, row_floats);
+  else if (parts == 2) yblend_rows_kernel<2><<<blocks, 256, 0, stream>>>(grid, ws4, g, row_floats);
+  else yblend_rows_kernel<0><<<blocks, 256, 0, stream>>>(grid, ws4, g, row_floats);
 }
 
 // =========================================================================================
@@ -1283,7 +1490,7 @@ static int device_max_smem_optin() {
 // separate slab region (lets 32x32x16 grids keep two CTAs per SM).
 static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out,
                           bool tex_mode = false, int threads = kTmaThreads, int in_fmt = kPxF32,
-                          int out_fmt = kPxF32) {
+                          int out_fmt = kPxF32, int occ_override = 0) {
   // Bulk copies move 16-byte units: a row and every segment must start on one.  float32 pixels
   // need W % 4 == 0, uint16 W % 8 == 0, uint8 W % 16 == 0 (12 / 6 / 3 bytes per pixel).
   const int in_bpp = 3 * px_bytes_per_channel(in_fmt), out_bpp = 3 * px_bytes_per_channel(out_fmt);
@@ -1309,12 +1516,19 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
   // residency.
   int want_occ = (threads == 320) ? 3 : 2;  // 320 threads: three 10-warp CTAs per SM, 64 registers
   if (const char* e = std::getenv("HDRNET_TMA_OCC")) want_occ = std::atoi(e);
+  if (occ_override > 0) want_occ = occ_override;
   const int per_cta_3 = (max_smem + 1024) / 3 - 1024;
   const int per_cta_2 = (max_smem + 1024) / 2 - 1024;  // ~113 KB when 227 KB opt-in
   int stages = 0, resident = 0;
   if (want_occ == 3) {
     for (int ns = 3; ns >= 2; --ns)
       if (p.off_stage + ns * p.stage_bytes <= per_cta_3) { stages = ns; resident = 3; break; }
+  }
+  if (occ_override >= 3) {  // issuer-warp form with small CTAs: deepest ring that keeps the residency
+    stages = 0;
+    const int per_cta_n = (max_smem + 1024) / occ_override - 1024;
+    for (int ns = 4; ns >= 2; --ns)
+      if (p.off_stage + ns * p.stage_bytes <= per_cta_n) { stages = ns; resident = occ_override; break; }
   }
   int max_ns = 4;
   if (const char* e = std::getenv("HDRNET_TMA_STAGES")) max_ns = std::min(std::max(std::atoi(e), 2), kMaxStages);
@@ -1424,13 +1638,14 @@ static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
   return launch_ws_n<GuideFn, 8>(a, fn, stream);
 }
 
-template <int kTexChunks, bool kLean>
+template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = kAsyncThreads,
+          int kMinBlocks = 2>
 static int launch_async(const TmaArgs& a, cudaStream_t stream) {
-  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kAsyncThreads>;
+  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kStore, kSlab, kThreads, kMinBlocks>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<a.p.ctas, kAsyncThreads, a.p.smem_bytes, stream>>>(a);
+  kern<<<a.p.ctas, kThreads, a.p.smem_bytes, stream>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1550,9 +1765,17 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   const size_t tex_need = tma_shape ? static_cast<size_t>(B) * rows * plan.row_floats * sizeof(float) : 0;
   const bool tex_ok = tma_shape && gs.workspace && gs.workspace_bytes >= tex_need &&
                       aligned16(gs.workspace) && tex_need / 16 <= (1u << 27);
-  // AUTO prefers it once the image is large enough to amortise the pre-pass launch.
-  if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21))
+  // AUTO prefers it once the image is large enough to amortise the pre-pass launch: the
+  // issuer-warp form for the op-API shape it exists for (float32 pixels, guide as an input; it
+  // needs a plan whose segments fit its 15 math warps), else the block-synchronous form.
+  if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21)) {
     variant = HDRNET_VARIANT_TEX;
+    TmaPlan ap;
+    if (gs.mode == 0 && !px &&
+        make_tma_plan(g, device_max_smem_optin(), sms, &ap, /*tex_mode=*/true, kAsyncThreads - 32,
+                      kPxF32, kPxF32, 2) && ap.stages >= 2)
+      variant = HDRNET_VARIANT_TEX_ASYNC;
+  }
   if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_WS ||
       variant == HDRNET_VARIANT_TEX_IN || variant == HDRNET_VARIANT_TEX_ASYNC) {
     const size_t need = tex_need;
@@ -1565,9 +1788,33 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     // warp-specialised form: the 512-thread CTA is 15 math warps (480 pixel quads) + the producer
     if (variant == HDRNET_VARIANT_TEX_WS && tex_threads == 512) tex_threads = 480;
     // issuer-warp form: the plan covers the math warps only (segments of <= 4 * 480 pixels)
-    if (variant == HDRNET_VARIANT_TEX_ASYNC) tex_threads = kAsyncThreads - 32;
+    // CTA shape of the issuer-warp form: threads (math warps + the issuer) x CTAs per SM.
+    //   512 x 2: 15 math warps, 64 registers      352 x 2: 10 math warps, 88 registers
+    //   224 x 3:  6 math warps, 96 registers      224 x 4:  6 math warps, 72 registers
+    int async_threads = kAsyncThreadsDefault, async_occ = kAsyncOccDefault;
+    if (const char* e = std::getenv("HDRNET_ASYNC_THREADS")) {
+      const int t = std::atoi(e);
+      if (t == 512 || t == 352 || t == 224) { async_threads = t; async_occ = (t == 224) ? 3 : 2; }
+    }
+    if (const char* e = std::getenv("HDRNET_ASYNC_OCC")) {
+      const int o = std::atoi(e);
+      if (async_threads == 224 && (o == 3 || o == 4)) async_occ = o;
+    }
+    // the other knobs of that form (per-quad indices, texture chunks, direct stores, in-kernel
+    // slab rows); the small CTA shapes exist for the plain lean form with 4 / 5 / 6 chunks only
+    bool async_lean = static_cast<long long>(W) >= 4LL * gw;   // x cells at least 4 pixels wide
+    if (const char* e = std::getenv("HDRNET_ASYNC_LEAN")) async_lean = async_lean && std::atoi(e) != 0;
+    int async_chunks = kAsyncTexChunksDefault, async_store = kAsyncStoreDefault, async_slab = kAsyncSlabDefault;
+    if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) async_chunks = std::atoi(e);
+    if (const char* e = std::getenv("HDRNET_ASYNC_STORE")) async_store = std::atoi(e) != 0;
+    if (const char* e = std::getenv("HDRNET_ASYNC_SLAB")) async_slab = std::atoi(e) != 0;
+    if (async_chunks < 3 || async_chunks > 6) async_chunks = kAsyncTexChunksDefault;
+    if (async_chunks == 3) async_slab = 0;
+    if (!async_lean) { async_store = 0; async_slab = 0; if (async_chunks != 4) async_chunks = 5; }
+    if (!async_lean || async_store || async_slab || async_chunks == 3) { async_threads = 512; async_occ = 2; }
+    if (variant == HDRNET_VARIANT_TEX_ASYNC) tex_threads = async_threads - 32;
     if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true, tex_threads,
-                       gs.in_fmt, gs.out_fmt))
+                       gs.in_fmt, gs.out_fmt, variant == HDRNET_VARIANT_TEX_ASYNC ? async_occ : 0))
       tplan = plan;
     TmaArgs a;
     a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr;
@@ -1575,34 +1822,51 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     a.g = g; a.p = tplan; a.yslab = gs.workspace;
     rc = get_slab_texture(gs.workspace, need, &a.slab_tex);
     if (rc != 0) return rc;
-    yblend_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows), 128, 0, stream>>>(
-        grid, gs.workspace, g, plan.row_floats);
+    // issuer-warp form, float32 guide-from-input only: its own (smaller) pre-pass when kSlab == 1
+    if (variant == HDRNET_VARIANT_TEX_ASYNC) {
+      if (gs.mode != 0 || px || tplan.threads != async_threads - 32 ||
+          tplan.seg_px > tplan.threads * 4 || tplan.stages < 2)
+        return HDRNET_E_UNSUPPORTED;
+      const bool lean = async_lean;
+      const int chunks = async_chunks, store = async_store, slab = async_slab;
+      launch_yblend(grid, gs.workspace, g, plan.row_floats, slab ? (chunks == 4 ? 1 : 2) : 0, stream);
+      if (async_threads != 512 && lean && !store && !slab) {
+#define HDRNET_ASYNC_SHAPE(K)                                                                  \
+        if (chunks == K) {                                                                       \
+          if (async_threads == 352) return launch_async<K, true, 0, 0, 352, 2>(a, stream);       \
+          if (async_occ == 3) return launch_async<K, true, 0, 0, 224, 3>(a, stream);            \
+          return launch_async<K, true, 0, 0, 224, 4>(a, stream);                                 \
+        }
+        HDRNET_ASYNC_SHAPE(4)
+        HDRNET_ASYNC_SHAPE(5)
+        HDRNET_ASYNC_SHAPE(6)
+#undef HDRNET_ASYNC_SHAPE
+        return HDRNET_E_UNSUPPORTED;
+      }
+      if (!lean) {
+        switch (chunks) {
+          case 5: return launch_async<5, false>(a, stream);
+          default: return launch_async<kTexChunksDefault, false>(a, stream);
+        }
+      }
+#define HDRNET_ASYNC_CASE(K)                                                              \
+      if (chunks == K) {                                                                    \
+        if (store && slab) return launch_async<K, true, 1, 1>(a, stream);                   \
+        if (store) return launch_async<K, true, 1, 0>(a, stream);                           \
+        if (slab) return launch_async<K, true, 0, 1>(a, stream);                            \
+        return launch_async<K, true, 0, 0>(a, stream);                                      \
+      }
+      HDRNET_ASYNC_CASE(4)
+      HDRNET_ASYNC_CASE(5)
+      HDRNET_ASYNC_CASE(6)
+#undef HDRNET_ASYNC_CASE
+      if (chunks == 3) return launch_async<3, true, 0, 0>(a, stream);
+      return HDRNET_E_UNSUPPORTED;
+    }
+    launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);
     if (variant == HDRNET_VARIANT_TEX_WS) {
       if (gs.mode != 0 || tplan.seg_px > tplan.threads * 4) return HDRNET_E_UNSUPPORTED;
       return launch_ws(a, GuideFromInput{}, stream);
-    }
-    if (variant == HDRNET_VARIANT_TEX_ASYNC) {
-      // float32 guide-from-input form only
-      if (gs.mode != 0 || px || tplan.threads != kAsyncThreads - 32 ||
-          tplan.seg_px > tplan.threads * 4 || tplan.stages < 2)
-        return HDRNET_E_UNSUPPORTED;
-      // lean (per-quad) x indexing needs x cells at least 4 pixels wide
-      bool lean = static_cast<long long>(W) >= 4LL * gw;
-      if (const char* e = std::getenv("HDRNET_ASYNC_LEAN")) lean = lean && std::atoi(e) != 0;
-      int chunks = kTexChunksDefault;
-      if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);  // tuning knob
-      if (lean) {
-        switch (chunks) {
-          case 3: return launch_async<3, true>(a, stream);
-          case 5: return launch_async<5, true>(a, stream);
-          case 6: return launch_async<6, true>(a, stream);
-          default: return launch_async<kTexChunksDefault, true>(a, stream);
-        }
-      }
-      switch (chunks) {
-        case 5: return launch_async<5, false>(a, stream);
-        default: return launch_async<kTexChunksDefault, false>(a, stream);
-      }
     }
     if (variant == HDRNET_VARIANT_TEX_IN) {
       // float32 guide-from-input form only; pixel tensors addressable as 1-D float4 textures
@@ -1956,7 +2220,15 @@ int hdrnet_slice_apply_plan_ws(int B, int H, int W, int gh, int gw, int gd, int 
   const bool tma = (n_in == 3 && n_out == 3 && has_offset) && W >= 128 &&
                    make_tma_plan(g, device_max_smem_optin(), sms, &plan, tex,
                                  tex ? kTexThreadsDefault : kTmaThreadsDefault);
-  if (variant) *variant = tma ? (tex ? HDRNET_VARIANT_TEX : HDRNET_VARIANT_TMA) : HDRNET_VARIANT_GENERIC;
+  // what AUTO runs with a workspace: the issuer-warp form when its plan exists (see
+  // launch_slice_apply_impl); `threads` is the launch size (math warps + the issuer warp)
+  TmaPlan ap;
+  const bool async_form = tma && tex &&
+                          make_tma_plan(g, device_max_smem_optin(), sms, &ap, true, kAsyncThreads - 32,
+                                        kPxF32, kPxF32, 2) && ap.stages >= 2;
+  if (async_form) { plan = ap; plan.threads = kAsyncThreads; }
+  if (variant) *variant = tma ? (tex ? (async_form ? HDRNET_VARIANT_TEX_ASYNC : HDRNET_VARIANT_TEX) : HDRNET_VARIANT_TMA)
+                              : HDRNET_VARIANT_GENERIC;
   if (ctas) *ctas = tma ? plan.ctas : generic_grid(npix, sms);
   if (threads) *threads = tma ? plan.threads : 256;
   if (smem_bytes) *smem_bytes = tma ? plan.smem_bytes : 0;

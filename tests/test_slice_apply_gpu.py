@@ -197,13 +197,21 @@ def test_zsort_is_bitwise_equal_to_row_kernel():
                           run_apply(grid, const, inp, True, "zsort"))
 
 
-@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_LEAN="0"), dict(HDRNET_TEX_CHUNKS="5"),
+@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_LEAN="0"), dict(HDRNET_TEX_CHUNKS="4"),
                                  dict(HDRNET_TEX_CHUNKS="3"), dict(HDRNET_TEX_CHUNKS="6"),
-                                 dict(HDRNET_ASYNC_LEAN="0", HDRNET_TEX_CHUNKS="5")],
+                                 dict(HDRNET_ASYNC_LEAN="0", HDRNET_TEX_CHUNKS="4"),
+                                 dict(HDRNET_ASYNC_STORE="1"), dict(HDRNET_ASYNC_SLAB="1"),
+                                 dict(HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1"),
+                                 dict(HDRNET_ASYNC_STORE="0", HDRNET_ASYNC_SLAB="0"),
+                                 dict(HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1", HDRNET_TEX_CHUNKS="4"),
+                                 dict(HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1", HDRNET_TEX_CHUNKS="6"),
+                                 dict(HDRNET_ASYNC_SLAB="1", HDRNET_TEX_CHUNKS="4")],
                          ids=lambda e: ",".join(f"{k[7:].lower()}={v}" for k, v in e.items()))
 def test_issuer_warp_kernel_knobs_are_bitwise_equal(env, monkeypatch):
     """The issuer-warp form with per-pixel instead of per-quad index arithmetic, and with 3 / 5 / 6
-    of a pixel's 12 corner chunks on the texture pipe: identical bits; also on narrow x cells
+    of a pixel's 12 corner chunks on the texture pipe, with results stored straight from the
+    registers (ASYNC_STORE) and with the slab rows blended by the issuer warp (ASYNC_SLAB: the
+    pre-pass then writes only the texture-fetched parts): identical bits; also on narrow x cells
     (W < 4 gw: the kernel must fall back to per-pixel indices by itself), many rows per CTA, a
     ragged last segment and out-of-range guides."""
     cases = [rand_case(5, 2, 64, 3840, 16, 16, 8, signed=True),
@@ -212,7 +220,7 @@ def test_issuer_warp_kernel_knobs_are_bitwise_equal(env, monkeypatch):
     cases[1][1][0, :, ::5] = 1.75
     cases[1][1][0, :, 1::5] = -0.6
     for grid, guide, inp in cases:
-        for k in ("HDRNET_ASYNC_LEAN", "HDRNET_TEX_CHUNKS"):
+        for k in ("HDRNET_ASYNC_LEAN", "HDRNET_TEX_CHUNKS", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB"):
             monkeypatch.delenv(k, raising=False)
         want = run_apply(grid, guide, inp, True, "tex")
         assert np.array_equal(want, run_apply(grid, guide, inp, True, "tex_async"))

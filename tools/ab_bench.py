@@ -16,12 +16,18 @@ ALL_CONFIGS = {
     "tex t512 c5": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="5"), _lib.VARIANT_TEX),
     "tex t512 c3": (dict(HDRNET_TMA_THREADS="512", HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX),
     "tex t256 c4": (dict(HDRNET_TMA_THREADS="256", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
-    "async lean c4": (dict(HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX_ASYNC),
-    "async lean c5": (dict(HDRNET_TEX_CHUNKS="5"), _lib.VARIANT_TEX_ASYNC),
-    "async lean c3": (dict(HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX_ASYNC),
-    "async lean c6": (dict(HDRNET_TEX_CHUNKS="6"), _lib.VARIANT_TEX_ASYNC),
-    "async px   c4": (dict(HDRNET_TEX_CHUNKS="4", HDRNET_ASYNC_LEAN="0"), _lib.VARIANT_TEX_ASYNC),
-    "async px   c5": (dict(HDRNET_TEX_CHUNKS="5", HDRNET_ASYNC_LEAN="0"), _lib.VARIANT_TEX_ASYNC),
+    "async c4": (dict(HDRNET_TEX_CHUNKS="4", HDRNET_ASYNC_STORE="0", HDRNET_ASYNC_SLAB="0"), _lib.VARIANT_TEX_ASYNC),
+    "async c5": (dict(HDRNET_TEX_CHUNKS="5", HDRNET_ASYNC_STORE="0", HDRNET_ASYNC_SLAB="0"), _lib.VARIANT_TEX_ASYNC),
+    "async c4 stg": (dict(HDRNET_TEX_CHUNKS="4", HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="0"), _lib.VARIANT_TEX_ASYNC),
+    "async c5 stg": (dict(HDRNET_TEX_CHUNKS="5", HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="0"), _lib.VARIANT_TEX_ASYNC),
+    "async c6 stg": (dict(HDRNET_TEX_CHUNKS="6", HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="0"), _lib.VARIANT_TEX_ASYNC),
+    "async c4 slab": (dict(HDRNET_TEX_CHUNKS="4", HDRNET_ASYNC_STORE="0", HDRNET_ASYNC_SLAB="1"), _lib.VARIANT_TEX_ASYNC),
+    "async c5 slab": (dict(HDRNET_TEX_CHUNKS="5", HDRNET_ASYNC_STORE="0", HDRNET_ASYNC_SLAB="1"), _lib.VARIANT_TEX_ASYNC),
+    "async c4 stg slab": (dict(HDRNET_TEX_CHUNKS="4", HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1"), _lib.VARIANT_TEX_ASYNC),
+    "async c5 stg slab": (dict(HDRNET_TEX_CHUNKS="5", HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1"), _lib.VARIANT_TEX_ASYNC),
+    "async c6 stg slab": (dict(HDRNET_TEX_CHUNKS="6", HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1"), _lib.VARIANT_TEX_ASYNC),
+    "async c3": (dict(HDRNET_TEX_CHUNKS="3"), _lib.VARIANT_TEX_ASYNC),
+    "async px c5": (dict(HDRNET_TEX_CHUNKS="5", HDRNET_ASYNC_LEAN="0"), _lib.VARIANT_TEX_ASYNC),
     "ws  t256": (dict(HDRNET_TMA_THREADS="256"), _lib.VARIANT_TEX_WS),
     "ws  t512": (dict(HDRNET_TMA_THREADS="512"), _lib.VARIANT_TEX_WS),
     "tex t320x3 c4": (dict(HDRNET_TMA_THREADS="320", HDRNET_TEX_CHUNKS="4"), _lib.VARIANT_TEX),
@@ -36,7 +42,7 @@ ALL_CONFIGS = {
 sel = sys.argv[1:]
 CONFIGS = {k: v for k, v in ALL_CONFIGS.items() if not sel or any(t in k for t in sel)}
 KEYS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC",
-        "HDRNET_ASYNC_LEAN")
+        "HDRNET_ASYNC_LEAN", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB")
 def burst(env, variant, iters=40):
     for k in KEYS: os.environ.pop(k, None)
     os.environ.update(env)
@@ -55,7 +61,7 @@ for r in range(7):
 lines = []
 for k, v in res.items():
     med = statistics.median(v)
-    lines.append(f"{k:15s} median {med:.4f} ms  min {min(v):.4f}  max {max(v):.4f}  frac {8*2160*3840*28/med/1e6/6577.4:.4f}")
+    lines.append(f"{k:18s} median {med:.4f} ms  min {min(v):.4f}  max {max(v):.4f}  frac {8*2160*3840*28/med/1e6/6577.4:.4f}")
 print("\n".join(lines))
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/ab_bench.txt", "w") as f:

@@ -1,48 +1,80 @@
-"""Same-box A/B of two builds of libhdrnet_b200.so at the headline shape (box-to-box spread is
-+-4 %, larger than most kernel changes): python tools/ab_lib.py old.so new.so [variant]
-Both libraries are driven directly through the C-ABI (hdrnet_slice_apply_f32_ws), interleaved
-bursts, median reported."""
-import ctypes, statistics, sys, torch
+"""Same-box A/B of builds / knob settings of libhdrnet_b200.so at the headline shape (box-to-box
+spread is +-4 %, larger than most kernel changes).
+    python tools/ab_lib.py SPEC [SPEC ...]      SPEC = path.so[:variant[:KEY=VAL,KEY=VAL...]]
+Every configuration is driven directly through the C-ABI (hdrnet_slice_apply_f32_ws) in
+interleaved bursts; all burst times and the SM clock sampled after each burst are printed, the
+median is reported.  Outputs of all configurations must be bitwise equal."""
+import ctypes, os, statistics, sys, torch
+try:
+    import pynvml
+    pynvml.nvmlInit()
+    _h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    sm_clock = lambda: pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM)
+except Exception:
+    sm_clock = lambda: 0
 
-paths = sys.argv[1:3]
-variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 B, H, W, GH, GW, GD = 8, 2160, 3840, 16, 16, 8
 gen = torch.Generator(device="cuda").manual_seed(1234)
 grid = torch.rand(B, GH, GW, GD, 12, device="cuda", generator=gen)
 guide = torch.rand(B, H, W, device="cuda", generator=gen)
 inp = torch.rand(B, H, W, 3, device="cuda", generator=gen)
-outs = [torch.empty_like(inp) for _ in paths]
-libs = []
-for p in paths:
-    lib = ctypes.CDLL(p)
-    lib.hdrnet_slice_apply_workspace_bytes.restype = ctypes.c_size_t
-    lib.hdrnet_slice_apply_workspace_bytes.argtypes = [ctypes.c_int] * 4
-    lib.hdrnet_slice_apply_f32_ws.restype = ctypes.c_int
-    lib.hdrnet_slice_apply_f32_ws.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 10 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-    n = lib.hdrnet_slice_apply_workspace_bytes(B, H, GW, GD)
-    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
-    libs.append((lib, ws, n))
+KNOBS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC",
+         "HDRNET_ASYNC_LEAN", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB", "HDRNET_ASYNC_THREADS")
+libs, cfgs = {}, []
+for spec in sys.argv[1:]:
+    parts = spec.split(":")
+    path = parts[0]
+    variant = int(parts[1]) if len(parts) > 1 and parts[1] else 0
+    env = dict(kv.split("=") for kv in parts[2].split(",")) if len(parts) > 2 and parts[2] else {}
+    if path not in libs:
+        lib = ctypes.CDLL(os.path.abspath(path))
+        lib.hdrnet_slice_apply_workspace_bytes.restype = ctypes.c_size_t
+        lib.hdrnet_slice_apply_workspace_bytes.argtypes = [ctypes.c_int] * 4
+        lib.hdrnet_slice_apply_f32_ws.restype = ctypes.c_int
+        lib.hdrnet_slice_apply_f32_ws.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 10 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        libs[path] = lib
+    cfgs.append((spec, libs[path], variant, env))
+n_ws = next(iter(libs.values())).hdrnet_slice_apply_workspace_bytes(B, H, GW, GD)
+ws = torch.empty(n_ws, dtype=torch.uint8, device="cuda")
+out = torch.empty_like(inp)
+ref = None
 stream = torch.cuda.current_stream().cuda_stream
 
-def run(i):
-    lib, ws, n = libs[i]
-    rc = lib.hdrnet_slice_apply_f32_ws(grid.data_ptr(), guide.data_ptr(), inp.data_ptr(), outs[i].data_ptr(),
-                                       B, H, W, GH, GW, GD, 3, 3, 1, variant, ws.data_ptr(), n, stream)
-    assert rc == 0, rc
+def run(cfg):
+    _, lib, variant, _ = cfg
+    rc = lib.hdrnet_slice_apply_f32_ws(grid.data_ptr(), guide.data_ptr(), inp.data_ptr(), out.data_ptr(),
+                                       B, H, W, GH, GW, GD, 3, 3, 1, variant, ws.data_ptr(), n_ws, stream)
+    assert rc == 0, (cfg[0], rc)
 
-def burst(i, iters=40):
-    for _ in range(3): run(i)
+def burst(cfg, iters=40):
+    for k in KNOBS: os.environ.pop(k, None)
+    os.environ.update(cfg[3])
+    for _ in range(3): run(cfg)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(iters): run(i)
+    for _ in range(iters): run(cfg)
     b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    return a.elapsed_time(b) / iters, sm_clock()
 
-res = [[] for _ in paths]
-for r in range(9):
-    for i in range(len(paths)): res[i].append(burst(i))
-for i, p in enumerate(paths):
-    med = statistics.median(res[i])
-    print(f"{p:48s} median {med:.4f} ms  min {min(res[i]):.4f}  frac {B*H*W*28/med/1e6/6577.4:.4f}")
-print("max |A - B| =", float((outs[0] - outs[1]).abs().max()))
+equal = True
+for cfg in cfgs:   # correctness first: every configuration produces the same bits
+    for k in KNOBS: os.environ.pop(k, None)
+    os.environ.update(cfg[3])
+    out.zero_(); run(cfg); torch.cuda.synchronize()
+    if ref is None: ref = out.clone()
+    elif not torch.equal(ref, out): equal = False; print("MISMATCH:", cfg[0], float((ref - out).abs().max()))
+res = {c[0]: [] for c in cfgs}
+rounds = int(os.environ.get("AB_ROUNDS", "9"))
+for r in range(rounds):
+    for cfg in cfgs: res[cfg[0]].append(burst(cfg))
+lines = []
+for spec, v in res.items():
+    t = [x[0] for x in v]
+    med = statistics.median(t)
+    lines.append(f"{spec:70s} median {med:.4f} ms  min {min(t):.4f}  max {max(t):.4f}  frac {B*H*W*28/med/1e6/6577.4:.4f}")
+    lines.append("    bursts " + " ".join(f"{x[0]:.4f}@{x[1]}" for x in v))
+lines.append(f"all outputs bitwise equal: {equal}")
+print("\n".join(lines))
+os.makedirs("gpurun_out", exist_ok=True)
+open("gpurun_out/ab_lib.txt", "w").write("# tools/ab_lib.py " + " ".join(sys.argv[1:]) + "\n" + "\n".join(lines) + "\n")

@@ -1,13 +1,19 @@
 #!/bin/bash
-# One gpurun call for the issuer-warp kernel: its parity tests, the interleaved A/B, one full ncu capture.
+# One gpurun call: parity of the CTA shapes, same-box A/B of knobs, launch-level timing of pre-pass + main kernel.
 set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.csv 2>&1
-timeout 600 python -m pytest tests/test_slice_apply_gpu.py -q --timeout 120 -p no:cacheprovider \
-    -k "async or bitwise or 4k_frame or oracle" -x > gpurun_out/pytest_async.log 2>&1
-echo "pytest exit $?" | tee -a gpurun_out/pytest_async.log
-tail -8 gpurun_out/pytest_async.log
-timeout 300 python tools/ab_bench.py "tex t512" async > gpurun_out/ab_stdout.txt 2>&1; echo "ab exit $?"; cat gpurun_out/ab_stdout.txt | tail -12
-HDRNET_TEX_CHUNKS=4 timeout 300 ncu --set full --clock-control none --import-source on -k regex:slice_apply_rows_async -s 2 -c 1 \
-    -f -o gpurun_out/prof_async python tools/prof_variant.py 7 > gpurun_out/ncu_async.log 2>&1
-echo "ncu exit $?"
+L=hdrnet_b200/lib/libhdrnet_b200.so; V1=tools/abtmp/lib_v1.so
+for cfg in "352 2" "224 3" "224 4"; do set -- $cfg
+  HDRNET_ASYNC_THREADS=$1 HDRNET_ASYNC_OCC=$2 timeout 300 python -m pytest tests/test_slice_apply_gpu.py -q --timeout 120 -p no:cacheprovider \
+    -k "tex_async or bitwise" -x 2>&1 | tail -2
+done > gpurun_out/pytest_shapes.log 2>&1; cat gpurun_out/pytest_shapes.log
+AB_ROUNDS=5 timeout 400 python tools/ab_lib.py $L:4:HDRNET_TEX_CHUNKS=4 $V1:7:HDRNET_TEX_CHUNKS=5 \
+  $L:7:HDRNET_TEX_CHUNKS=5 $L:7:HDRNET_TEX_CHUNKS=5,HDRNET_ASYNC_LEAN=0 \
+  $L:7:HDRNET_TEX_CHUNKS=4,HDRNET_ASYNC_THREADS=352 $L:7:HDRNET_TEX_CHUNKS=5,HDRNET_ASYNC_THREADS=352 $L:7:HDRNET_TEX_CHUNKS=6,HDRNET_ASYNC_THREADS=352 \
+  $L:7:HDRNET_TEX_CHUNKS=4,HDRNET_ASYNC_THREADS=224 $L:7:HDRNET_TEX_CHUNKS=5,HDRNET_ASYNC_THREADS=224 $L:7:HDRNET_TEX_CHUNKS=6,HDRNET_ASYNC_THREADS=224 \
+  $L:7:HDRNET_TEX_CHUNKS=4,HDRNET_ASYNC_THREADS=224,HDRNET_ASYNC_OCC=4 $L:7:HDRNET_TEX_CHUNKS=5,HDRNET_ASYNC_THREADS=224,HDRNET_ASYNC_OCC=4 $L:7:HDRNET_TEX_CHUNKS=6,HDRNET_ASYNC_THREADS=224,HDRNET_ASYNC_OCC=4 \
+  > gpurun_out/ab_lib_stdout.txt 2>&1; echo "ab exit $?"; grep -v bursts gpurun_out/ab_lib_stdout.txt | tail -16
+for cfg in "512 2 5" "352 2 5" "224 3 5" "224 4 5"; do set -- $cfg
+HDRNET_ASYNC_THREADS=$1 HDRNET_ASYNC_OCC=$2 HDRNET_TEX_CHUNKS=$3 timeout 200 ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.avg,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,sm__cycles_elapsed.avg.per_second --clock-control none -k regex:"slice_apply_rows_async|yblend" -s 4 -c 2 --csv \
+    --log-file gpurun_out/launch_$1_$2_$3.csv python tools/prof_variant.py 7 > /dev/null 2>&1; echo "ncu $cfg exit $?"
+done

@@ -14,7 +14,10 @@ if [ "${1:-}" != "quick" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:slice_apply_rows_tma -s 3 -c 2 \
-      -f -o gpurun_out/prof_tma python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:slice_apply_rows_async -s 3 -c 2 \
+      -f -o gpurun_out/prof_main python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"
+fi
+if [ "${1:-}" = "configs" ] || [ "${2:-}" = "configs" ]; then
+  timeout 300 python tools/bench_configs.py > gpurun_out/bench_configs.jsonl 2> gpurun_out/bench_configs.err; echo "bench_configs exit $?"; tail -12 gpurun_out/bench_configs.jsonl
 fi
