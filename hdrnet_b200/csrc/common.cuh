@@ -122,6 +122,15 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
   return d;
 }
 
+// ---- programmatic dependent launch (sm_90+); both are no-ops in a grid launched without the
+// programmatic-stream-serialization attribute
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void grid_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- mbarrier / TMA bulk-copy PTX wrappers (cp.async.bulk -> SASS UBLKCP) ---------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

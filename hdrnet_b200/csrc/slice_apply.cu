@@ -266,6 +266,7 @@ constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the texture-as
 constexpr int kAsyncThreads = 512;        // issuer-warp form: 15 math warps + the issuer
 constexpr int kAsyncThreadsDefault = 512; // HDRNET_ASYNC_THREADS / HDRNET_ASYNC_OCC
 constexpr int kAsyncOccDefault = 2;
+constexpr bool kAsyncPdlDefault = false;  // HDRNET_ASYNC_PDL=1: measured +14 % step time (profiles/r01_async_ab_pdl.txt)
 constexpr int kAsyncTexChunksDefault = 5; // its tuning defaults (HDRNET_TEX_CHUNKS / _ASYNC_STORE / _SLAB)
 constexpr int kAsyncStoreDefault = 0;
 constexpr int kAsyncSlabDefault = 0;
@@ -1066,10 +1067,23 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
   unsigned char* raw0 = smem + pl.off_raw;               // two slab rows
   unsigned char* stage_base = smem + pl.off_stage;
 
-  const long long total_rows = static_cast<long long>(g.B) * g.rows;
-  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
-  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
-  if (r_end <= r_begin) return;
+  // Work split in ITEMS (row segments), not rows: 17280 rows over 296 CTAs leave some CTAs 59 rows
+  // and others 58 (1.1 % of the kernel is the tail); in half-row items the imbalance is 0.2 %.
+  // A CTA covers items [i_begin, i_end): rows r_begin .. r_end-1, the first row from pixel
+  // x_first, the last row up to pixel x_last (a row split between two CTAs has its slab row
+  // loaded by both).
+  const long long total_items = static_cast<long long>(g.B) * g.rows * pl.nseg;
+  const long long i_begin = total_items * blockIdx.x / gridDim.x;
+  const long long i_end = total_items * (blockIdx.x + 1) / gridDim.x;
+  // Programmatic dependent launch (no-ops when launched without the attribute): let the next
+  // kernel in the stream be scheduled as this grid's CTAs retire.
+  grid_launch_dependents();
+  if (i_end <= i_begin) return;
+  const long long r_begin = i_begin / pl.nseg, r_end = (i_end - 1) / pl.nseg + 1;
+  const int x_first = static_cast<int>(i_begin - r_begin * pl.nseg) * pl.seg_px;
+  const int x_last = min(g.W, (static_cast<int>((i_end - 1) - (r_end - 1) * pl.nseg) + 1) * pl.seg_px);
+  auto row_x0 = [&](long long row) { return row == r_begin ? x_first : 0; };
+  auto row_x1 = [&](long long row) { return row == r_end - 1 ? x_last : g.W; };
 
   if (tid == 0) {
     for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kMathWarps); }
@@ -1130,7 +1144,7 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
     };
     // load cursor: runs NS - 1 items ahead of the math warps
     long long l_row = r_begin;
-    int l_x0 = 0, l_s = 0;
+    int l_x0 = x_first, l_s = 0;
     auto issue_next_load = [&]() {  // lane 0
       if (l_row >= r_end) return;
       const int npx = min(pl.seg_px, g.W - l_x0);
@@ -1141,12 +1155,15 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
       tma_load_1d(st + pl.off_guide, args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[l_s]);
       if (++l_s == NS) l_s = 0;
       l_x0 += pl.seg_px;
-      if (l_x0 >= g.W) { l_x0 = 0; ++l_row; }
+      if (l_x0 >= row_x1(l_row)) { l_x0 = 0; ++l_row; }
     };
     // kStore 0: the stage refilled after item i is item i-1's (its bulk store must have drained);
     // kStore 1: item i's own stage -- one more item of prefetch from the same ring.
+    // The pixel tensors are the caller's inputs (complete before the pre-pass started): their
+    // loads may precede the dependency wait; the workspace written by the pre-pass may not.
     if (lane == 0)
       for (int i = 0; i < NS - (kStore == 0 ? 1 : 0); ++i) issue_next_load();
+    grid_dependency_wait();
     make_slab(r_begin);
     if (r_begin + 1 < r_end) make_slab(r_begin + 1);
 
@@ -1157,7 +1174,8 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
     uint32_t ph = 0;
     for (long long row = r_begin; row < r_end; ++row) {
       if (lane == 0) {
-        for (int x0 = 0; x0 < g.W; x0 += pl.seg_px) {
+        const int x_end = row_x1(row);
+        for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
           mbar_wait(&done[s], ph);  // every math warp is through with this stage
           if constexpr (kStore == 0) {  // results were written in place (and proxy-fenced)
             const int npx = min(pl.seg_px, g.W - x0);
@@ -1194,7 +1212,8 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
     const unsigned char* slab_b = raw0 + static_cast<size_t>(rb) * slab_bytes;
     const int tex_base = static_cast<int>(row) * (kSlab == 0 ? cells * 3 : cells);
     float* out_row = reinterpret_cast<float*>(args.out) + static_cast<size_t>(row) * g.W * 3;
-    for (int x0 = 0; x0 < g.W; x0 += pl.seg_px) {
+    const int x_end = row_x1(row);
+    for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
       const int npx = min(pl.seg_px, g.W - x0);
       unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
       mbar_wait(&full[s], ph);
@@ -1425,6 +1444,12 @@ template <int kParts>
 __global__ void __launch_bounds__(256)
 yblend_rows_kernel(const float* __restrict__ grid, float4* __restrict__ ws, SliceGeom g,
                    int row_floats) {
+  // Programmatic dependent launch: everything before this grid in the stream (the previous
+  // call's row kernel may still be reading this workspace) must be complete before the first
+  // write; the row kernel that follows may be scheduled as these CTAs retire.  Both are no-ops
+  // for a plain launch.
+  grid_dependency_wait();
+  grid_launch_dependents();
   const long long total_rows = static_cast<long long>(g.B) * g.rows;
   const long long r0 = static_cast<long long>(blockIdx.x) * kYblendRows;
   const long long r1 = min(r0 + kYblendRows, total_rows);
@@ -1455,14 +1480,33 @@ yblend_rows_kernel(const float* __restrict__ grid, float4* __restrict__ ws, Slic
   }
 }
 
+// Launch with (pdl) or without the programmatic-stream-serialization attribute.  With it the
+// kernel may be SCHEDULED before its predecessor in the stream has drained; every kernel launched
+// this way executes griddepcontrol.wait before its first dependent memory access.
+template <class... KArgs, class... Args>
+static cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                    cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static void launch_yblend(const float* grid, float* ws, const SliceGeom& g, int row_floats, int parts,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool pdl = false) {
   const long long total_rows = static_cast<long long>(g.B) * g.rows;
   const unsigned blocks = static_cast<unsigned>((total_rows + kYblendRows - 1) / kYblendRows);
   float4* ws4 = reinterpret_cast<float4*>(ws);
-  if (parts == 1) yblend_rows_kernel<1><<<blocks, 256, 0, stream>>>(grid, ws4, g, row_floats);
-  else if (parts == 2) yblend_rows_kernel<2><<<blocks, 256, 0, stream>>>(grid, ws4, g, row_floats);
-  else yblend_rows_kernel<0><<<blocks, 256, 0, stream>>>(grid, ws4, g, row_floats);
+  if (parts == 1) launch_maybe_pdl(yblend_rows_kernel<1>, blocks, 256, 0, stream, pdl, grid, ws4, g, row_floats);
+  else if (parts == 2) launch_maybe_pdl(yblend_rows_kernel<2>, blocks, 256, 0, stream, pdl, grid, ws4, g, row_floats);
+  else launch_maybe_pdl(yblend_rows_kernel<0>, blocks, 256, 0, stream, pdl, grid, ws4, g, row_floats);
 }
 
 // =========================================================================================
@@ -1640,12 +1684,14 @@ static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
 
 template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = kAsyncThreads,
           int kMinBlocks = 2>
-static int launch_async(const TmaArgs& a, cudaStream_t stream) {
+static int launch_async(const TmaArgs& a, cudaStream_t stream, bool pdl) {
   auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kStore, kSlab, kThreads, kMinBlocks>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<a.p.ctas, kThreads, a.p.smem_bytes, stream>>>(a);
+  e = launch_maybe_pdl(kern, static_cast<unsigned>(a.p.ctas), kThreads,
+                       static_cast<size_t>(a.p.smem_bytes), stream, pdl, a);
+  if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1829,13 +1875,15 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
         return HDRNET_E_UNSUPPORTED;
       const bool lean = async_lean;
       const int chunks = async_chunks, store = async_store, slab = async_slab;
-      launch_yblend(grid, gs.workspace, g, plan.row_floats, slab ? (chunks == 4 ? 1 : 2) : 0, stream);
+      bool pdl = kAsyncPdlDefault;   // programmatic dependent launch of pre-pass and row kernel
+      if (const char* e = std::getenv("HDRNET_ASYNC_PDL")) pdl = std::atoi(e) != 0;
+      launch_yblend(grid, gs.workspace, g, plan.row_floats, slab ? (chunks == 4 ? 1 : 2) : 0, stream, pdl);
       if (async_threads != 512 && lean && !store && !slab) {
 #define HDRNET_ASYNC_SHAPE(K)                                                                  \
         if (chunks == K) {                                                                       \
-          if (async_threads == 352) return launch_async<K, true, 0, 0, 352, 2>(a, stream);       \
-          if (async_occ == 3) return launch_async<K, true, 0, 0, 224, 3>(a, stream);            \
-          return launch_async<K, true, 0, 0, 224, 4>(a, stream);                                 \
+          if (async_threads == 352) return launch_async<K, true, 0, 0, 352, 2>(a, stream, pdl);       \
+          if (async_occ == 3) return launch_async<K, true, 0, 0, 224, 3>(a, stream, pdl);            \
+          return launch_async<K, true, 0, 0, 224, 4>(a, stream, pdl);                                 \
         }
         HDRNET_ASYNC_SHAPE(4)
         HDRNET_ASYNC_SHAPE(5)
@@ -1845,22 +1893,22 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       }
       if (!lean) {
         switch (chunks) {
-          case 5: return launch_async<5, false>(a, stream);
-          default: return launch_async<kTexChunksDefault, false>(a, stream);
+          case 5: return launch_async<5, false>(a, stream, pdl);
+          default: return launch_async<kTexChunksDefault, false>(a, stream, pdl);
         }
       }
 #define HDRNET_ASYNC_CASE(K)                                                              \
       if (chunks == K) {                                                                    \
-        if (store && slab) return launch_async<K, true, 1, 1>(a, stream);                   \
-        if (store) return launch_async<K, true, 1, 0>(a, stream);                           \
-        if (slab) return launch_async<K, true, 0, 1>(a, stream);                            \
-        return launch_async<K, true, 0, 0>(a, stream);                                      \
+        if (store && slab) return launch_async<K, true, 1, 1>(a, stream, pdl);                   \
+        if (store) return launch_async<K, true, 1, 0>(a, stream, pdl);                           \
+        if (slab) return launch_async<K, true, 0, 1>(a, stream, pdl);                            \
+        return launch_async<K, true, 0, 0>(a, stream, pdl);                                      \
       }
       HDRNET_ASYNC_CASE(4)
       HDRNET_ASYNC_CASE(5)
       HDRNET_ASYNC_CASE(6)
 #undef HDRNET_ASYNC_CASE
-      if (chunks == 3) return launch_async<3, true, 0, 0>(a, stream);
+      if (chunks == 3) return launch_async<3, true, 0, 0>(a, stream, pdl);
       return HDRNET_E_UNSUPPORTED;
     }
     launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);

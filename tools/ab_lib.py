@@ -19,7 +19,8 @@ grid = torch.rand(B, GH, GW, GD, 12, device="cuda", generator=gen)
 guide = torch.rand(B, H, W, device="cuda", generator=gen)
 inp = torch.rand(B, H, W, 3, device="cuda", generator=gen)
 KNOBS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC",
-         "HDRNET_ASYNC_LEAN", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB", "HDRNET_ASYNC_THREADS")
+         "HDRNET_ASYNC_LEAN", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB", "HDRNET_ASYNC_THREADS", "HDRNET_ASYNC_OCC",
+         "HDRNET_ASYNC_PDL")
 libs, cfgs = {}, []
 for spec in sys.argv[1:]:
     parts = spec.split(":")
