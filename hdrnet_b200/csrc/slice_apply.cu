@@ -266,6 +266,10 @@ constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the texture-as
 constexpr int kAsyncThreads = 512;        // issuer-warp form: 15 math warps + the issuer
 constexpr int kAsyncThreadsDefault = 512; // HDRNET_ASYNC_THREADS / HDRNET_ASYNC_OCC
 constexpr int kAsyncOccDefault = 2;
+// AUTO takes the issuer-warp form only with a ring of >= 3 stages at two CTAs per SM: with the two
+// stages that 32x32 grids leave (24 / 48 KB of slab rows) it measured SLOWER than the
+// block-synchronous form (32x32x8: 46.9 % vs 53.2 % of HBM peak; 32x32x16: 31.1 % vs 37.5 %).
+constexpr int kAsyncAutoMinStages = 3;
 constexpr bool kAsyncPdlDefault = false;  // HDRNET_ASYNC_PDL=1: measured +14 % step time (profiles/r01_async_ab_pdl.txt)
 constexpr int kAsyncTexChunksDefault = 5; // its tuning defaults (HDRNET_TEX_CHUNKS / _ASYNC_STORE / _SLAB)
 constexpr int kAsyncStoreDefault = 0;
@@ -1819,7 +1823,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     TmaPlan ap;
     if (gs.mode == 0 && !px &&
         make_tma_plan(g, device_max_smem_optin(), sms, &ap, /*tex_mode=*/true, kAsyncThreads - 32,
-                      kPxF32, kPxF32, 2) && ap.stages >= 2)
+                      kPxF32, kPxF32, 2) && ap.resident == 2 && ap.stages >= kAsyncAutoMinStages)
       variant = HDRNET_VARIANT_TEX_ASYNC;
   }
   if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_WS ||
@@ -2273,7 +2277,8 @@ int hdrnet_slice_apply_plan_ws(int B, int H, int W, int gh, int gw, int gd, int 
   TmaPlan ap;
   const bool async_form = tma && tex &&
                           make_tma_plan(g, device_max_smem_optin(), sms, &ap, true, kAsyncThreads - 32,
-                                        kPxF32, kPxF32, 2) && ap.stages >= 2;
+                                        kPxF32, kPxF32, 2) && ap.resident == 2 &&
+                          ap.stages >= kAsyncAutoMinStages;
   if (async_form) { plan = ap; plan.threads = kAsyncThreads; }
   if (variant) *variant = tma ? (tex ? (async_form ? HDRNET_VARIANT_TEX_ASYNC : HDRNET_VARIANT_TEX) : HDRNET_VARIANT_TMA)
                               : HDRNET_VARIANT_GENERIC;

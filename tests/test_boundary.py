@@ -129,3 +129,37 @@ def test_layers_apply_matches_reference_semantics():
     assert torch.allclose(out, ref, atol=1e-6)
     with pytest.raises(ValueError):
         layers.apply(sliced, im[:, :4], has_affine_term=True)
+
+
+def _plan(lib, B, H, W, gh, gw, gd, with_ws, n_in=3, n_out=3, has_offset=1):
+    import ctypes
+    v, c, t, sm = (ctypes.c_int() for _ in range(4))
+    rc = lib.hdrnet_slice_apply_plan_ws(B, H, W, gh, gw, gd, n_in, n_out, has_offset, with_ws,
+                                        ctypes.byref(v), ctypes.byref(c), ctypes.byref(t), ctypes.byref(sm))
+    assert rc == 0
+    return v.value, c.value, t.value, sm.value
+
+
+def test_kernel_selection_plan(built_lib):
+    """Host-side kernel selection (no launch; without a device the planner assumes a B200: 148 SMs,
+    227 KB of opt-in shared memory): which form AUTO runs for BASELINE.json's shapes."""
+    from hdrnet_b200 import _lib
+    lib = built_lib
+    # config 3 (headline): issuer-warp texture-assisted form, 2 CTAs x 148 SMs, 15 math warps + issuer
+    assert _plan(lib, 8, 2160, 3840, 16, 16, 8, 1) == (_lib.VARIANT_TEX_ASYNC, 296, 512, 104704)
+    # no workspace lent: the all-LSU TMA row kernel
+    v, c, t, _ = _plan(lib, 8, 2160, 3840, 16, 16, 8, 0)
+    assert (v, c, t) == (_lib.VARIANT_TMA, 296, 256)
+    # config 4 (12 MP, 8 frames per GPU): three 1344-pixel segments per row, 4-stage ring
+    v, c, t, sm = _plan(lib, 8, 3024, 4032, 16, 16, 8, 1)
+    assert (v, c, t) == (_lib.VARIANT_TEX_ASYNC, 296, 512) and sm <= 115712
+    # config 5's 32x32 grids leave a 2-stage ring: the block-synchronous texture form
+    assert _plan(lib, 8, 2160, 3840, 32, 32, 8, 1)[0] == _lib.VARIANT_TEX
+    assert _plan(lib, 8, 2160, 3840, 32, 32, 16, 1)[0] == _lib.VARIANT_TEX
+    assert _plan(lib, 8, 2160, 3840, 8, 8, 4, 1)[0] == _lib.VARIANT_TEX_ASYNC
+    # config 2 (one 1080p frame, < 2 Mi px): no pre-pass, TMA row kernel
+    assert _plan(lib, 1, 1080, 1920, 16, 16, 8, 1)[0] == _lib.VARIANT_TMA
+    # shapes the row kernels cannot take: odd width, other channel counts, tiny images
+    assert _plan(lib, 8, 2160, 3841, 16, 16, 8, 1)[0] == _lib.VARIANT_GENERIC
+    assert _plan(lib, 8, 2160, 3840, 16, 16, 8, 1, n_out=4)[0] == _lib.VARIANT_GENERIC
+    assert _plan(lib, 1, 16, 64, 4, 4, 4, 1)[0] == _lib.VARIANT_GENERIC
