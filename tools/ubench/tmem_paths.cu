@@ -3,7 +3,13 @@
 // with A written to TENSOR MEMORY by the threads (tcgen05.st), B in shared memory, D read back with
 // tcgen05.ld.  Questions: (1) is the A-in-TMEM operand layout lane=row / column=k?  (2) what do
 // tcgen05.ld, tcgen05.st and the tiny MMA cost per SM when 4..16 warps drive them?
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I hdrnet_b200/csrc -o tools/ubench/bin/tmem_paths tools/ubench/tmem_paths.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I hdrnet_b200/csrc -I include -o tools/ubench/bin/tmem_paths tools/ubench/tmem_paths.cu
+// CAUTION (found in round 1): the first version of the rate loops indexed the register array with a
+// runtime value (r[it & 31]); nvcc then keeps the array in LOCAL memory and every iteration
+// spills / reloads it through the LSU -- its "tcgen05.ld = 51 B/clk/SM" was spill traffic, not
+// tensor memory (profiles/r01_tmem_paths.txt).  With static indices LDTM.x16 sustains ~900 B/clk/SM
+// (profiles/r01_tmem_paths_v2.txt, section 3).  Check `cuobjdump -sass | grep -c STL` = 0 in a loop
+// before believing its number.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -139,11 +145,11 @@ __global__ void __launch_bounds__(1024) rate_kernel(int iters, long long* cycles
     for (int it = 0; it < iters; ++it) {
       tmem_ld32(tb + lane_base + col0 + (it & 1) * 32, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc += __uint_as_float(r[it & 31]);
+      acc += __uint_as_float(r[0]) + __uint_as_float(r[17]) + __uint_as_float(r[31]);
     }
   } else if (MODE == 1) {
     for (int it = 0; it < iters; ++it) {
-      r[it & 15] += it;
+      r[0] += it; r[9] ^= it;
       tmem_st16(tb + lane_base + col0 + (it & 3) * 16, r);
       if ((it & 3) == 3) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(1024) rate_kernel(int iters, long long* cycles
     // every warpgroup: st 16 columns of A, (thread 0 of the warpgroup) 3 MMAs, everyone ld 32 columns.
     // No cross-thread ordering is enforced here: this measures pipe throughput, not a correct pipeline.
     for (int it = 0; it < iters; ++it) {
-      r[it & 15] += it;
+      r[0] += it; r[9] ^= it;
       tmem_st16(tb + lane_base + col0 + 32, r);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       if ((tid & 127) == 0) {
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(1024) rate_kernel(int iters, long long* cycles
       }
       tmem_ld32(tb + lane_base + col0, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc += __uint_as_float(r[it & 31]);
+      acc += __uint_as_float(r[0]) + __uint_as_float(r[17]) + __uint_as_float(r[31]);
     }
     if (tid == 0) { mma_commit(&bar); mbar_wait(&bar, 0); }
   }
@@ -178,6 +184,111 @@ __global__ void __launch_bounds__(1024) rate_kernel(int iters, long long* cycles
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) tmem_free(tb, 512);
+}
+
+// ---- 3. is tensor memory a THIRD on-chip path next to the LSU? ----------------------------------
+// The fused slice-apply kernel is bound by the shared-memory data pipe (LSU, 128 B/clk/SM) with
+// the texture pipe (64 B/clk/SM) as the only helper so far.  Candidate: read the staged INPUT
+// tile (16 B/px) through tensor memory -- tcgen05.cp copies it shared -> TMEM, tcgen05.ld brings it
+// to registers.  Questions: does tcgen05.ld overlap with LDS.128 (mode 1 vs 0 + 2), what does
+// tcgen05.cp cost (mode 3), and does it take shared-memory bandwidth away from LDS (mode 4)?
+//   mode 0: 4 x LDS.128 per thread and iteration (64 B)         mode 2: both, same iteration
+//   mode 1: tcgen05.ld 32x32b.x16 per thread and iteration (64 B)
+//   mode 3: thread 0 issues tcgen05.cp 128x128b (2 KB each), 8 per iteration, nobody else works
+//   mode 4: mode 0 in warps 1.., mode 3 in warp 0
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_cp_128x128b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) path_kernel(int iters, long long* cycles, float* sink) {
+  extern __shared__ __align__(128) unsigned char dsm[];   // 32 KB of "tile" data
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tbase_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tbase_s, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int e = tid; e < 8192; e += blockDim.x) reinterpret_cast<float*>(dsm)[e] = static_cast<float>(e & 255);
+  fence_proxy_async_smem();
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tb = tbase_s;
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t col0 = static_cast<uint32_t>((warp >> 2) * 64) & 511u;
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = 0;
+  float acc = 0.f;
+  const bool cp_warp = (MODE == 3) || (MODE == 4 && warp == 0);
+  const bool lds_warp = (MODE == 0) || (MODE == 2) || (MODE == 4 && warp != 0);
+  const bool ld_warp = (MODE == 1) || (MODE == 2);
+  const uint32_t smem_base = smem_u32(dsm);
+  __syncthreads();
+  const long long t0 = clock64();
+  if (cp_warp) {
+    if (tid == 0) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)   // 128 rows x 16 B, core matrices 128 B apart, into 4 columns each
+          tmem_cp_128x128b(tb + 256 + ((it & 1) * 8 + u) * 4, kmajor_desc(smem_base + u * 2048, 128, 128));
+      }
+      mma_commit(&bar);
+      mbar_wait(&bar, 0);
+    }
+  }
+  if (lds_warp || ld_warp) {
+    for (int it = 0; it < iters; ++it) {
+      if (lds_warp) {
+        // 48-byte lane stride, as the kernel's RGB reads: conflict-free quarter-warps
+        const uint32_t a = smem_base + ((static_cast<uint32_t>(tid) * 48u + static_cast<uint32_t>(it) * 16u) & 32767u & ~15u);
+        float4 v0 = lds128(reinterpret_cast<const void*>(__cvta_shared_to_generic(a)));
+        float4 v1 = lds128(reinterpret_cast<const void*>(__cvta_shared_to_generic((a + 4096u) & 32767u)));
+        float4 v2 = lds128(reinterpret_cast<const void*>(__cvta_shared_to_generic((a + 8192u) & 32767u)));
+        float4 v3 = lds128(reinterpret_cast<const void*>(__cvta_shared_to_generic((a + 12288u) & 32767u)));
+        acc += v0.x + v1.y + v2.z + v3.w;
+      }
+      if (ld_warp) {
+        tmem_ld16(tb + lane_base + col0 + (it & 3) * 16, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        acc += __uint_as_float(r[0]) + __uint_as_float(r[7]) + __uint_as_float(r[15]);
+      }
+    }
+  }
+  const long long t1 = clock64();
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;                       // cp rate (modes 3, 4) / loop time
+  if (tid == blockDim.x - 1) cycles[148 + blockIdx.x] = t1 - t0;    // a worker warp's loop time
+  sink[blockIdx.x * blockDim.x + tid] = acc;
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) tmem_free(tb, 512);
+}
+
+template <int MODE>
+static void run_path(const char* name, int threads, long long* d_cyc, float* d_sink) {
+  const int iters = 1024;
+  CK(cudaFuncSetAttribute(path_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+  for (int rep = 0; rep < 2; ++rep) {
+    path_kernel<MODE><<<148, threads, 32768>>>(iters, d_cyc, d_sink);
+    CK(cudaDeviceSynchronize());
+  }
+  long long c[296];
+  CK(cudaMemcpy(c, d_cyc, sizeof(c), cudaMemcpyDeviceToHost));
+  double a0 = 0, a1 = 0;
+  for (int i = 0; i < 148; ++i) { a0 += c[i]; a1 += c[148 + i]; }
+  a0 /= 148.0 * iters; a1 /= 148.0 * iters;
+  printf("%-44s threads %4d: thread 0 %8.1f clk/iter, last thread %8.1f clk/iter", name, threads, a0, a1);
+  if (MODE <= 2) printf("  -> %6.1f B/clk/SM per 64 B stream", 64.0 * threads / a1);
+  if (MODE == 3) printf("  -> %6.1f B/clk/SM (8 x 2 KB per iteration)", 16384.0 / a0);
+  if (MODE == 4) printf("  -> cp %6.1f B/clk/SM, LDS %6.1f B/clk/SM", 16384.0 / a0, 64.0 * (threads - 32) / a1);
+  printf("\n");
 }
 
 template <int MODE>
@@ -209,7 +320,7 @@ int main() {
   }
   float *dA, *dB, *dD; long long* d_cyc; float* d_sink;
   CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
-  CK(cudaMalloc(&d_cyc, 148 * 8)); CK(cudaMalloc(&d_sink, 148 * 1024 * 4));
+  CK(cudaMalloc(&d_cyc, 296 * 8)); CK(cudaMalloc(&d_sink, 148 * 1024 * 4));
   CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
   semantics_kernel<<<1, 128>>>(dA, dB, dD);
@@ -226,5 +337,13 @@ int main() {
   for (int threads : {128, 256, 512, 1024}) run_rate<1>("tcgen05.st 32x32b.x16 (2 KB/warp)", threads, 2048.0, d_cyc, d_sink);
   run_rate<2>("tcgen05.mma M128 N32 K8 tf32, A TMEM", 128, 0, d_cyc, d_sink);
   for (int threads : {128, 256, 512, 1024}) run_rate<3>("tile loop: st16 + 3 MMA + ld32", threads, 0, d_cyc, d_sink);
+  // ---- third path? ----
+  for (int threads : {512, 1024}) {
+    run_path<0>("4 x LDS.128 (64 B/thread)", threads, d_cyc, d_sink);
+    run_path<1>("tcgen05.ld x16 (64 B/thread)", threads, d_cyc, d_sink);
+    run_path<2>("4 x LDS.128 + tcgen05.ld x16 together", threads, d_cyc, d_sink);
+  }
+  run_path<3>("tcgen05.cp 128x128b smem -> TMEM alone", 128, d_cyc, d_sink);
+  run_path<4>("tcgen05.cp (warp 0) + 4 x LDS.128 (others)", 512, d_cyc, d_sink);
   return 0;
 }
