@@ -77,6 +77,10 @@ extern "C" {
                                  /* instead of block barriers) + one warp that issues every  */
                                  /* bulk copy; per-quad index arithmetic.  Same requirements */
                                  /* as HDRNET_VARIANT_TEX                                     */
+#define HDRNET_VARIANT_TC 8      /* EXPERIMENTAL, never picked by AUTO: depth interpolation on  */
+                                 /* the tensor cores (tcgen05.mma kind::tf32, 3xTF32, weights   */
+                                 /* and accumulator in tensor memory); gd == 8, gw >= 3,        */
+                                 /* W >= 128 gw, needs the workspace like HDRNET_VARIANT_TEX    */
 
 HDRNET_API int hdrnet_b200_abi_version(void);
 

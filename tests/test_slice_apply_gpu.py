@@ -3,6 +3,8 @@ the oracle on the same seeded inputs, against the committed golden fixtures from
 reference's JAX file, and -- at BASELINE.json's full 4K size -- against the full oracle on
 one frame plus size-independent properties.  Tolerance: 1e-5 relative (tests/util.py);
 cell indices bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -15,7 +17,12 @@ pytestmark = pytest.mark.gpu
 
 VARIANTS = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "tma": _lib.VARIANT_TMA,
             "zsort": _lib.VARIANT_ZSORT, "tex": _lib.VARIANT_TEX, "tex_ws": _lib.VARIANT_TEX_WS,
-            "tex_in": _lib.VARIANT_TEX_IN, "tex_async": _lib.VARIANT_TEX_ASYNC}
+            "tex_in": _lib.VARIANT_TEX_IN, "tex_async": _lib.VARIANT_TEX_ASYNC, "tc": _lib.VARIANT_TC}
+
+# Variants that have never run on a GPU (written after the round's GPU budget was spent): their
+# tests only run on request, so that a first-run bug cannot take the suite down.
+experimental = pytest.mark.skipif(os.environ.get("HDRNET_TEST_EXPERIMENTAL") != "1",
+                                  reason="set HDRNET_TEST_EXPERIMENTAL=1 to run the untested variants")
 
 
 def cuda(a):
@@ -328,3 +335,46 @@ def test_4k_batch8_properties():
     outp = hdrnet_ops.bilateral_slice_apply(grid[perm].contiguous(), guide[perm].contiguous(),
                                             inp[perm].contiguous(), True)
     assert torch.equal(outp, out[perm])
+
+
+# ---- experimental: depth interpolation on the tensor cores (csrc/slice_apply_tc.cu) -----------
+TC_SHAPES = [
+    (1, 6, 512, 4, 4, 8),        # one 512-pixel segment, four tiles, cells exactly one tile wide
+    (2, 9, 1156, 5, 7, 8),       # ragged last tile (1156 = 9 * 128 + 4), three-cell window at both borders
+    (1, 40, 3840, 16, 16, 8),    # the headline row shape: three 1280-pixel segments, ten tiles each
+    (3, 70, 1920, 8, 3, 8),      # gw = 3: the window never moves; more rows than fit one wave of CTAs
+]
+
+
+@experimental
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_tensor_core_form_matches_oracle(shape):
+    B, H, W, gh, gw, gd = shape
+    grid, guide, inp = rand_case(99, B, H, W, gh, gw, gd, signed=True)
+    guide[0, 0, :6] = [0.0, 1.0, -0.3, 1.7, 0.0625, 0.9375]
+    expected = checker().bilateral_slice_apply(grid, guide, inp, True)
+    assert_parity(run_apply(grid, guide, inp, True, "tc"), expected, what=f"{shape} [tc]")
+
+
+@experimental
+def test_tensor_core_form_4k_batch_against_row_kernel():
+    """8 x 4K: against the issuer-warp form (different summation order: 1e-5, not bitwise), twice
+    (the second launch reuses every barrier phase and TMEM column of a fresh CTA set)."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    grid = torch.randn(8, 16, 16, 8, 12, device="cuda", generator=gen)
+    guide = torch.rand(8, 2160, 3840, device="cuda", generator=gen)
+    inp = torch.randn(8, 2160, 3840, 3, device="cuda", generator=gen)
+    ref = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=_lib.VARIANT_TEX_ASYNC)
+    scale = ref.abs().max().item()
+    for _ in range(2):
+        out = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=_lib.VARIANT_TC)
+        assert (out - ref).abs().max().item() / scale <= RTOL
+
+
+@experimental
+def test_tensor_core_form_rejects_shapes_it_cannot_take():
+    for shape in [(1, 8, 512, 4, 4, 4), (1, 8, 512, 4, 2, 8), (1, 8, 256, 4, 4, 8)]:   # gd != 8, gw < 3, narrow cells
+        B, H, W, gh, gw, gd = shape
+        grid, guide, inp = rand_case(3, B, H, W, gh, gw, gd)
+        with pytest.raises(ValueError):
+            run_apply(grid, guide, inp, True, "tc")
