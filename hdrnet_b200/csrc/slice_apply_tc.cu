@@ -1,9 +1,12 @@
 // slice_apply_tc.cu -- EXPERIMENTAL (HDRNET_VARIANT_TC): fused BilateralSliceApply with the depth
 // interpolation on the 5th-generation tensor cores.  Written at the end of round 1 from the
 // corrected tensor-memory measurement (tools/ubench/tmem_paths.cu section 3: tcgen05.ld sustains
-// ~900 B/clk/SM, seven times the shared-memory crossbar that bounds every other form); compiled
-// and SASS-checked, NOT yet run on a GPU -- its tests are gated behind HDRNET_TEST_EXPERIMENTAL=1
-// and AUTO never selects it.
+// ~900 B/clk/SM, seven times the shared-memory crossbar that bounds every other form).  One GPU
+// run so far (tools/cabi_check.cu, 1 x 16 x 3840, grid 16x16x8: 6.8e-7 from the generic kernel, two
+// launches; profiles/r01_tc_first_run.txt); no timing at scale; its pytest cases are gated behind
+// HDRNET_TEST_EXPERIMENTAL=1 and AUTO never selects it.  Known cost of this first version: ~430 SASS
+// instructions per pixel (A-row construction ~60, three-cell selection ~50, per-tile barrier /
+// fence / wait overhead paid per pixel because a thread owns one pixel per tile).
 //
 // Replaces the per-pixel gather of hdrnet/ops/bilateral_slice_apply.cu.cc:36-126 by a tiny matrix
 // product per 128-pixel tile (gd == 8):
