@@ -1614,6 +1614,8 @@ static int generic_grid(long long npix, int sms) {
 // tensor-core form (slice_apply_tc.cu), experimental
 int launch_slice_apply_tc(const float* guide, const float* input, float* out, const float* yslab,
                           const SliceGeom& g, int max_smem, int sms, cudaStream_t stream);
+int launch_slice_apply_tcg(const float* guide, const float* input, float* out, const float* yslab,
+                           const SliceGeom& g, int max_smem, int sms, cudaStream_t stream);
 
 // z-bucketed variant (slice_apply_zsort.cu)
 struct ZsPlan {
@@ -1829,6 +1831,13 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
         make_tma_plan(g, device_max_smem_optin(), sms, &ap, /*tex_mode=*/true, kAsyncThreads - 32,
                       kPxF32, kPxF32, 2) && ap.resident == 2 && ap.stages >= kAsyncAutoMinStages)
       variant = HDRNET_VARIANT_TEX_ASYNC;
+  }
+  if (variant == HDRNET_VARIANT_TC_GATHER) {   // experimental, never run: tensor-core gather form
+    if (!tex_ok || gs.mode != 0 || px) return HDRNET_E_UNSUPPORTED;
+    if (gd != 8 || gw < 3 || static_cast<long long>(W) < 128LL * gw) return HDRNET_E_UNSUPPORTED;
+    launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);
+    return launch_slice_apply_tcg(gs.guide, input, out, gs.workspace, g, device_max_smem_optin(), sms,
+                                  stream);
   }
   if (variant == HDRNET_VARIANT_TC) {   // experimental tensor-core form: slab rows from the pre-pass
     if (!tex_ok || gs.mode != 0 || px) return HDRNET_E_UNSUPPORTED;

@@ -226,7 +226,7 @@ def bilateral_slice_apply(grid: torch.Tensor, guide: torch.Tensor, input: torch.
             # pick the texture-assisted kernel for large images (>= 2 Mi px, W % 4 == 0).
             ws_ptr, ws_bytes = 0, 0
             explicit_tex = int(variant) in (_lib.VARIANT_TEX, _lib.VARIANT_TEX_WS, _lib.VARIANT_TEX_IN,
-                                            _lib.VARIANT_TEX_ASYNC, _lib.VARIANT_TC)
+                                            _lib.VARIANT_TEX_ASYNC, _lib.VARIANT_TC, _lib.VARIANT_TC_GATHER)
             if (int(variant) == _lib.VARIANT_AUTO or explicit_tex) and n_in == 3 and n_out == 3 \
                     and has_offset and W % 4 == 0 and (explicit_tex or B * H * W >= (1 << 21)):
                 ws = _workspace(dev, lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))

@@ -81,6 +81,9 @@ extern "C" {
                                  /* the tensor cores (tcgen05.mma kind::tf32, 3xTF32, weights   */
                                  /* and accumulator in tensor memory); gd == 8, gw >= 3,        */
                                  /* W >= 128 gw, needs the workspace like HDRNET_VARIANT_TEX    */
+#define HDRNET_VARIANT_TC_GATHER 9 /* EXPERIMENTAL, never run: the tensor core as an exact gather */
+                                 /* engine (one-hot A, both depth rows per x cell in B, 2 MMAs  */
+                                 /* M128 N96 K8), trilinear blend in registers; same limits     */
 
 HDRNET_API int hdrnet_b200_abi_version(void);
 

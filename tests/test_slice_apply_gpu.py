@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 VARIANTS = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "tma": _lib.VARIANT_TMA,
             "zsort": _lib.VARIANT_ZSORT, "tex": _lib.VARIANT_TEX, "tex_ws": _lib.VARIANT_TEX_WS,
-            "tex_in": _lib.VARIANT_TEX_IN, "tex_async": _lib.VARIANT_TEX_ASYNC, "tc": _lib.VARIANT_TC}
+            "tex_in": _lib.VARIANT_TEX_IN, "tex_async": _lib.VARIANT_TEX_ASYNC, "tc": _lib.VARIANT_TC, "tc_gather": _lib.VARIANT_TC_GATHER}
 
 # Variants that have never run on a GPU (written after the round's GPU budget was spent): their
 # tests only run on request, so that a first-run bug cannot take the suite down.
@@ -347,13 +347,14 @@ TC_SHAPES = [
 
 
 @experimental
+@pytest.mark.parametrize("variant", ["tc", "tc_gather"])
 @pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_tensor_core_form_matches_oracle(shape):
+def test_tensor_core_form_matches_oracle(shape, variant):
     B, H, W, gh, gw, gd = shape
     grid, guide, inp = rand_case(99, B, H, W, gh, gw, gd, signed=True)
     guide[0, 0, :6] = [0.0, 1.0, -0.3, 1.7, 0.0625, 0.9375]
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
-    assert_parity(run_apply(grid, guide, inp, True, "tc"), expected, what=f"{shape} [tc]")
+    assert_parity(run_apply(grid, guide, inp, True, variant), expected, what=f"{shape} [{variant}]")
 
 
 @experimental
@@ -366,9 +367,9 @@ def test_tensor_core_form_4k_batch_against_row_kernel():
     inp = torch.randn(8, 2160, 3840, 3, device="cuda", generator=gen)
     ref = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=_lib.VARIANT_TEX_ASYNC)
     scale = ref.abs().max().item()
-    for _ in range(2):
-        out = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=_lib.VARIANT_TC)
-        assert (out - ref).abs().max().item() / scale <= RTOL
+    for variant in (_lib.VARIANT_TC, _lib.VARIANT_TC, _lib.VARIANT_TC_GATHER, _lib.VARIANT_TC_GATHER):
+        out = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=variant)
+        assert (out - ref).abs().max().item() / scale <= RTOL, variant
 
 
 @experimental
