@@ -34,8 +34,7 @@
 #include <cstdlib>
 #include <mutex>
 
-#include "common.cuh"
-#include "guide.cuh"
+#include "slice_rows.cuh"
 
 namespace hdrnet_b200 {
 
@@ -131,92 +130,9 @@ slice_indices_kernel(const float* __restrict__ guide, int32_t* __restrict__ idx,
   }
 }
 
-// =========================================================================================
-// Pixel storage formats of the model-path forms (row f-3): the full-resolution image may stay
-// in the integer format it was decoded to, and the result may leave as the uint8 the reference
-// writes (hdrnet/bin/run.py:145-169 img_as_float; :95 uint8(255 * clip(out, 0, 1))).
-// =========================================================================================
-constexpr int kPxF32 = HDRNET_PX_F32, kPxU8 = HDRNET_PX_U8, kPxU16 = HDRNET_PX_U16;
-
-__host__ __device__ constexpr int px_bytes_per_channel(int fmt) {
-  return fmt == kPxU8 ? 1 : (fmt == kPxU16 ? 2 : 4);
-}
-
-// skimage.img_as_float: v / 255 (uint8) or v / 65535 (uint16), evaluated in float64 and handed
-// to a float32 placeholder.  q0 = v * (1/D) with one Newton correction reproduces that float32
-// for EVERY code value (exhaustive check: tests/test_px_gpu.py) at 3 FMA-pipe instructions.
-template <int kFmt>
-__device__ __forceinline__ float px_to_float(unsigned v) {
-  constexpr float D = (kFmt == kPxU8) ? 255.0f : 65535.0f;
-  constexpr float R = 1.0f / D;
-  const float f = static_cast<float>(v);
-  const float q0 = f * R;
-  return fmaf(fmaf(-q0, D, f), R, q0);
-}
-
-// tf.cast(255.0 * tf.clip_by_value(x, 0, 1), tf.uint8): truncating conversion.
-__device__ __forceinline__ unsigned float_to_u8(float x) {
-  return __float2uint_rz(255.0f * fminf(fmaxf(x, 0.0f), 1.0f));
-}
-
-// One thread's 4 consecutive pixels, from / to a staged tile (shared memory) or global memory.
-template <int kFmt>
-__device__ __forceinline__ void load_quad(const unsigned char* tile, int q, float (&pr)[4],
-                                          float (&pg)[4], float (&pb)[4]) {
-  if constexpr (kFmt == kPxF32) {
-    const float4* rgb4 = reinterpret_cast<const float4*>(tile) + 3 * q;
-    const float4 c0 = rgb4[0], c1 = rgb4[1], c2 = rgb4[2];
-    pr[0] = c0.x; pg[0] = c0.y; pb[0] = c0.z; pr[1] = c0.w;
-    pg[1] = c1.x; pb[1] = c1.y; pr[2] = c1.z; pg[2] = c1.w;
-    pb[2] = c2.x; pr[3] = c2.y; pg[3] = c2.z; pb[3] = c2.w;
-  } else if constexpr (kFmt == kPxU8) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(tile) + 3 * q;  // 12 bytes
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    pr[0] = px_to_float<kPxU8>(w0 & 0xffu);         pg[0] = px_to_float<kPxU8>((w0 >> 8) & 0xffu);
-    pb[0] = px_to_float<kPxU8>((w0 >> 16) & 0xffu); pr[1] = px_to_float<kPxU8>(w0 >> 24);
-    pg[1] = px_to_float<kPxU8>(w1 & 0xffu);         pb[1] = px_to_float<kPxU8>((w1 >> 8) & 0xffu);
-    pr[2] = px_to_float<kPxU8>((w1 >> 16) & 0xffu); pg[2] = px_to_float<kPxU8>(w1 >> 24);
-    pb[2] = px_to_float<kPxU8>(w2 & 0xffu);         pr[3] = px_to_float<kPxU8>((w2 >> 8) & 0xffu);
-    pg[3] = px_to_float<kPxU8>((w2 >> 16) & 0xffu); pb[3] = px_to_float<kPxU8>(w2 >> 24);
-  } else {
-    const uint2* w = reinterpret_cast<const uint2*>(tile) + 3 * q;        // 24 bytes
-    const uint2 w0 = w[0], w1 = w[1], w2 = w[2];
-    pr[0] = px_to_float<kPxU16>(w0.x & 0xffffu); pg[0] = px_to_float<kPxU16>(w0.x >> 16);
-    pb[0] = px_to_float<kPxU16>(w0.y & 0xffffu); pr[1] = px_to_float<kPxU16>(w0.y >> 16);
-    pg[1] = px_to_float<kPxU16>(w1.x & 0xffffu); pb[1] = px_to_float<kPxU16>(w1.x >> 16);
-    pr[2] = px_to_float<kPxU16>(w1.y & 0xffffu); pg[2] = px_to_float<kPxU16>(w1.y >> 16);
-    pb[2] = px_to_float<kPxU16>(w2.x & 0xffffu); pr[3] = px_to_float<kPxU16>(w2.x >> 16);
-    pg[3] = px_to_float<kPxU16>(w2.y & 0xffffu); pb[3] = px_to_float<kPxU16>(w2.y >> 16);
-  }
-}
-
-template <int kFmt>
-__device__ __forceinline__ void store_quad(unsigned char* tile, int q, const float (&o_r)[4],
-                                           const float (&o_g)[4], const float (&o_b)[4]) {
-  if constexpr (kFmt == kPxF32) {
-    float4* rgb4 = reinterpret_cast<float4*>(tile) + 3 * q;
-    rgb4[0] = make_float4(o_r[0], o_g[0], o_b[0], o_r[1]);
-    rgb4[1] = make_float4(o_g[1], o_b[1], o_r[2], o_g[2]);
-    rgb4[2] = make_float4(o_b[2], o_r[3], o_g[3], o_b[3]);
-  } else {
-    static_assert(kFmt == kPxU8, "results leave as float32 or uint8");
-    uint32_t* w = reinterpret_cast<uint32_t*>(tile) + 3 * q;
-    w[0] = float_to_u8(o_r[0]) | (float_to_u8(o_g[0]) << 8) | (float_to_u8(o_b[0]) << 16) | (float_to_u8(o_r[1]) << 24);
-    w[1] = float_to_u8(o_g[1]) | (float_to_u8(o_b[1]) << 8) | (float_to_u8(o_r[2]) << 16) | (float_to_u8(o_g[2]) << 24);
-    w[2] = float_to_u8(o_b[2]) | (float_to_u8(o_r[3]) << 8) | (float_to_u8(o_g[3]) << 16) | (float_to_u8(o_b[3]) << 24);
-  }
-}
-
 // Any-shape fallback of the model-path forms with integer pixel I/O: one thread per pixel, guide
 // computed in registers, 8-corner gather as slice_generic_kernel<true> (same summation order, so
 // its float32 result equals guide kernel + generic kernel bit for bit).
-template <int kFmt>
-__device__ __forceinline__ float load_channel(const unsigned char* base, long long idx) {
-  if constexpr (kFmt == kPxF32) return __ldg(reinterpret_cast<const float*>(base) + idx);
-  else if constexpr (kFmt == kPxU8) return px_to_float<kPxU8>(__ldg(base + idx));
-  else return px_to_float<kPxU16>(__ldg(reinterpret_cast<const unsigned short*>(base) + idx));
-}
-
 template <class GuideFn, int kIn, int kOut>
 __global__ void __launch_bounds__(256)
 slice_apply_px_generic_kernel(const float* __restrict__ grid, const unsigned char* __restrict__ input,
@@ -253,199 +169,6 @@ slice_apply_px_generic_kernel(const float* __restrict__ grid, const unsigned cha
       out[3 * p + 2] = static_cast<unsigned char>(float_to_u8(o[2]));
     }
   }
-}
-
-// =========================================================================================
-// Persistent TMA row kernel: n_in = 3, n_out = 3, has_offset (gc = 12), W % 4 == 0.
-// =========================================================================================
-
-constexpr int kTmaThreads = 256;
-constexpr int kTmaThreadsDefault = 256;  // all-LSU form; 512 = 64-register form (HDRNET_TMA_THREADS)
-constexpr int kTexThreadsDefault = 512;  // texture-assisted form: measured 7 % faster at 512
-constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the texture-assisted kernel
-constexpr int kAsyncThreads = 512;        // issuer-warp form: 15 math warps + the issuer
-constexpr int kAsyncThreadsDefault = 512; // HDRNET_ASYNC_THREADS / HDRNET_ASYNC_OCC
-constexpr int kAsyncOccDefault = 2;
-// AUTO takes the issuer-warp form only with a ring of >= 3 stages at two CTAs per SM: with the two
-// stages that 32x32 grids leave (24 / 48 KB of slab rows) it measured SLOWER than the
-// block-synchronous form (32x32x8: 46.9 % vs 53.2 % of HBM peak; 32x32x16: 31.1 % vs 37.5 %).
-constexpr int kAsyncAutoMinStages = 3;
-constexpr bool kAsyncPdlDefault = false;  // HDRNET_ASYNC_PDL=1: measured +14 % step time (profiles/r01_async_ab_pdl.txt)
-constexpr int kAsyncTexChunksDefault = 5; // its tuning defaults (HDRNET_TEX_CHUNKS / _ASYNC_STORE / _SLAB)
-constexpr int kAsyncStoreDefault = 0;
-constexpr int kAsyncSlabDefault = 0;
-constexpr int kMaxStages = 8;
-constexpr int kGc = 12;
-
-static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-struct TmaPlan {
-  int ctas;
-  int threads;     // threads per CTA (256, or 512 = the 64-register / 32-warps-per-SM form)
-  int resident;    // CTAs per SM the plan was sized for (1, 2 or 3)
-  int stages;
-  int nseg;        // segments per row
-  int seg_px;      // pixels per segment (multiple of 4, <= 4 * kTmaThreads)
-  int row_floats;  // gw * gd * 12
-  int smem_bytes;
-  // byte offsets into dynamic shared memory
-  int off_raw, off_slab, off_stage, stage_bytes;
-  // pixel formats: bytes per pixel of the staged input / output tiles, and where the guide and
-  // output tiles sit inside a stage (off_out == 0: the result overwrites the input tile)
-  int in_bpp, out_bpp, off_guide, off_out;
-};
-
-struct TmaArgs {
-  const float* grid;
-  const float* guide;   // guide input (GuideFromInput), else unused
-  float* guide_out;     // optional guide dump for the fused forms, else nullptr
-  const unsigned char* input;   // [B * rows][W][3] in the kernel's input pixel format
-  unsigned char* out;           // [B * rows][W][3] in the kernel's output pixel format
-  cudaTextureObject_t in_tex;    // texture-fed form: float4 views of `input` and `guide`
-  cudaTextureObject_t guide_tex;
-  cudaTextureObject_t slab_tex;  // kTexChunks > 0: float4 view of the y-pre-blended slab rows
-  const float* yslab;            // kTexChunks > 0: [B * rows][gw * gd * 12] slab rows (workspace)
-  SliceGeom g;
-  TmaPlan p;
-};
-
-__device__ __forceinline__ float4 lerp4(float w0, float4 a, float w1, float4 b) {
-  return make_float4(fmaf(w1, b.x, w0 * a.x), fmaf(w1, b.y, w0 * a.y), fmaf(w1, b.z, w0 * a.z),
-                     fmaf(w1, b.w, w0 * a.w));
-}
-
-// One 16-byte chunk (4 coefficients) of a corner vector: from the shared-memory slab through
-// the LSU, or -- for the last kTexChunks of the 12 chunks a pixel needs -- from the same slab
-// row in global memory through the TEXTURE pipe, the one on-chip gather path that does not
-// share the LSU crossbar (tools/ubench/gather_paths.cu: LDS.128 + tex float4 overlap fully).
-// kBytes: `off` is a BYTE offset into the slab row (the lean index path) instead of a float one.
-template <int kTexChunks, int kChunkId, bool kBytes = false>
-__device__ __forceinline__ ulonglong2 corner_chunk(const float* __restrict__ slab,
-                                                   cudaTextureObject_t tex, int tex_row, int off) {
-  if constexpr (kChunkId >= 12 - kTexChunks) {
-    const float4 v = tex1Dfetch<float4>(tex, tex_row + (off >> (kBytes ? 4 : 2)) + (kChunkId % 3));
-    ulonglong2 r;
-    r.x = pack2(v.x, v.y);
-    r.y = pack2(v.z, v.w);
-    return r;
-  } else if constexpr (kBytes) {
-    return reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(slab) + off)[kChunkId % 3];
-  } else {
-    return reinterpret_cast<const ulonglong2*>(slab + off)[kChunkId % 3];
-  }
-}
-
-// Blend the four (x, z) corners of the y-pre-blended slab for one pixel and apply the
-// 3x4 affine transform to (r, g, b, 1).
-template <int kTexChunks, bool kBytes = false>
-__device__ __forceinline__ void blend_apply(const float* __restrict__ slab,
-                                            cudaTextureObject_t tex, int tex_row, int o00,
-                                            int o01, int o10, int o11, float w00, float w01,
-                                            float w10, float w11, float r, float g, float b,
-                                            float& out_r, float& out_g, float& out_b) {
-  const unsigned long long W00 = pack2(w00, w00), W01 = pack2(w01, w01);
-  const unsigned long long W10 = pack2(w10, w10), W11 = pack2(w11, w11);
-  // chunk ids: v00 -> 0..2, v01 -> 3..5, v10 -> 6..8, v11 -> 9..11
-  const ulonglong2 a0 = corner_chunk<kTexChunks, 0, kBytes>(slab, tex, tex_row, o00);
-  const ulonglong2 a1 = corner_chunk<kTexChunks, 1, kBytes>(slab, tex, tex_row, o00);
-  const ulonglong2 a2 = corner_chunk<kTexChunks, 2, kBytes>(slab, tex, tex_row, o00);
-  const ulonglong2 b0 = corner_chunk<kTexChunks, 3, kBytes>(slab, tex, tex_row, o01);
-  const ulonglong2 b1 = corner_chunk<kTexChunks, 4, kBytes>(slab, tex, tex_row, o01);
-  const ulonglong2 b2 = corner_chunk<kTexChunks, 5, kBytes>(slab, tex, tex_row, o01);
-  const ulonglong2 c0 = corner_chunk<kTexChunks, 6, kBytes>(slab, tex, tex_row, o10);
-  const ulonglong2 c1 = corner_chunk<kTexChunks, 7, kBytes>(slab, tex, tex_row, o10);
-  const ulonglong2 c2 = corner_chunk<kTexChunks, 8, kBytes>(slab, tex, tex_row, o10);
-  const ulonglong2 d0 = corner_chunk<kTexChunks, 9, kBytes>(slab, tex, tex_row, o11);
-  const ulonglong2 d1 = corner_chunk<kTexChunks, 10, kBytes>(slab, tex, tex_row, o11);
-  const ulonglong2 d2 = corner_chunk<kTexChunks, 11, kBytes>(slab, tex, tex_row, o11);
-  unsigned long long acc[6];
-  acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
-  acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
-  acc[2] = fma2(W11, d1.x, fma2(W10, c1.x, fma2(W01, b1.x, mul2(W00, a1.x))));
-  acc[3] = fma2(W11, d1.y, fma2(W10, c1.y, fma2(W01, b1.y, mul2(W00, a1.y))));
-  acc[4] = fma2(W11, d2.x, fma2(W10, c2.x, fma2(W01, b2.x, mul2(W00, a2.x))));
-  acc[5] = fma2(W11, d2.y, fma2(W10, c2.y, fma2(W01, b2.y, mul2(W00, a2.y))));
-  float a0f, a1f, a2f, a3f;
-  unpack2(acc[0], a0f, a1f);
-  unpack2(acc[1], a2f, a3f);
-  out_r = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-  unpack2(acc[2], a0f, a1f);
-  unpack2(acc[3], a2f, a3f);
-  out_g = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-  unpack2(acc[4], a0f, a1f);
-  unpack2(acc[5], a2f, a3f);
-  out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-}
-
-// Guide sources.  kFromInput: the op-API form, guide is an input tensor staged by TMA
-// (28 B/px).  The fused forms compute the guide from the pixel's RGB in registers
-// (24 B/px; the guide map never touches HBM) -- the model path of HDRNetCurves /
-// HDRNetPointwiseNNGuide (hdrnet/models.py:43-59).
-struct GuideFromInput {
-  static constexpr bool kFromInput = true;
-  __device__ __forceinline__ float operator()(float, float, float) const { return 0.0f; }
-};
-struct GuideCurves {
-  static constexpr bool kFromInput = false;
-  CurvesGuideParams p;
-  __device__ __forceinline__ float operator()(float r, float g, float b) const {
-    return curves_guide(p, r, g, b);
-  }
-};
-template <int kFeats>
-struct GuideNN {
-  static constexpr bool kFromInput = false;
-  NNGuideParams p;
-  __device__ __forceinline__ float operator()(float r, float g, float b) const {
-    return nn_guide<kFeats>(p, r, g, b);
-  }
-};
-
-
-// One thread's 4 consecutive pixels (quad `q` of a staged segment): guide (staged, or computed
-// from RGB), bit-exact cell indices, 4-corner blend + affine apply, result written IN PLACE over
-// the RGB tile.  Shared by the block-synchronous and the warp-specialised row kernels.
-template <class GuideFn, int kTexChunks, int kIn = kPxF32, int kOut = kPxF32>
-__device__ __forceinline__ void process_quad(const TmaArgs& args, const GuideFn& guide_fn,
-                                             const unsigned char* in_tile, unsigned char* out_tile,
-                                             const unsigned char* guide_tile, const float* slab,
-                                             int tex_row, long long row, int x0, int q) {
-  constexpr bool kGuideIn = GuideFn::kFromInput;
-  const SliceGeom& g = args.g;
-  const float gd_f = static_cast<float>(g.gd);
-  const int x_stride = g.gd * kGc;
-  float pr[4], pg[4], pb[4];
-  load_quad<kIn>(in_tile, q, pr, pg, pb);
-  float gv[4];
-  if (kGuideIn) {
-    const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
-    gv[0] = gq.x; gv[1] = gq.y; gv[2] = gq.z; gv[3] = gq.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) gv[i] = guide_fn(pr[i], pg[i], pb[i]);
-    if (args.guide_out != nullptr) {  // optional dump (hdrnet/bin/run.py --debug)
-      const size_t pix = static_cast<size_t>(row) * g.W + x0 + 4 * q;
-      *reinterpret_cast<float4*>(args.guide_out + pix) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-    }
-  }
-  float o_r[4], o_g[4], o_b[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const Axis ax = spatial_axis(x0 + 4 * q + i, g.scale_x);
-    const Axis az = range_axis(gv[i], gd_f);
-    const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride;
-    const int xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
-    const int zo0 = clampi(az.i0, 0, g.gd - 1) * kGc;
-    const int zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * kGc;
-    float wz0, wz1;
-    smoothed_weights(az.f, wz0, wz1);
-    const float wx1 = ax.f, wx0 = 1.0f - ax.f;
-    blend_apply<kTexChunks>(slab, args.slab_tex, tex_row, xo0 + zo0, xo0 + zo1, xo1 + zo0,
-                            xo1 + zo1, wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i], pg[i],
-                            pb[i], o_r[i], o_g[i], o_b[i]);
-  }
-  store_quad<kOut>(out_tile, q, o_r, o_g, o_b);
-  fence_proxy_async_smem();
 }
 
 template <class GuideFn, int kTexChunks, int kMinBlocks = 2, int kThreads = kTmaThreads,
@@ -595,647 +318,6 @@ slice_apply_rows_tma_kernel(const TmaArgs args, const __grid_constant__ GuideFn 
 }
 
 
-
-// =========================================================================================
-// Texture-fed form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_IN).
-// =========================================================================================
-// The block-synchronous kernel spends 0.25 of its 1.56 shared-memory wavefronts per pixel on
-// staging the INPUT: the TMA engine writes 16 B/px into the ring and the threads read them back
-// with LDS.128, while the texture pipe idles at 56 %.  Here a thread fetches its 4 pixels (3 RGB
-// texels + 1 guide texel, float4 views of the caller's tensors) through the texture pipe
-// straight into registers -- issued one item ahead, right before the block barrier, when no
-// other value is live -- and shared memory only carries the slab rows and the OUTPUT tiles
-// (3 x STS.128 per thread, one bulk store per segment).  Thread 0 asks the L2 for the segments two
-// items ahead (cp.async.bulk.prefetch.L2) so that the texture fetches are L2 hits.
-// Wavefronts per pixel: 1.29 (LSU) against 1.25 texture-pipe clocks -- the two pipes balanced.
-constexpr int kTexInStages = 3;
-
-template <int kTexChunks, int kThreads, int kMinBlocks = 2>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
-slice_apply_rows_texin_kernel(const TmaArgs args) {
-  static_assert(kTexChunks > 0, "slab rows come from the pre-pass workspace");
-  extern __shared__ __align__(128) unsigned char smem[];
-  const SliceGeom& g = args.g;
-  const TmaPlan& pl = args.p;
-  const int tid = threadIdx.x;
-
-  uint64_t* gridbar = reinterpret_cast<uint64_t*>(smem);  // [2] slab row landed
-  float* raw0 = reinterpret_cast<float*>(smem + pl.off_raw);
-  unsigned char* stage_base = smem + pl.off_stage;
-
-  const long long total_rows = static_cast<long long>(g.B) * g.rows;
-  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
-  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
-  const int nitems = static_cast<int>(r_end - r_begin) * pl.nseg;
-  if (nitems <= 0) return;
-
-  if (tid == 0) {
-    mbar_init(&gridbar[0], 1);
-    mbar_init(&gridbar[1], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  auto item_span = [&](int item, long long& row, int& x0, int& npx) {
-    const int rr = item / pl.nseg;
-    const int seg = item - rr * pl.nseg;
-    row = r_begin + rr;
-    x0 = seg * pl.seg_px;
-    npx = min(pl.seg_px, g.W - x0);
-  };
-  auto prefetch_l2 = [&](int item) {  // thread 0 only
-    long long row; int x0, npx;
-    item_span(item, row, x0, npx);
-    const size_t pix = static_cast<size_t>(row) * g.W + x0;
-    l2_prefetch_bulk(args.input + pix * 12, static_cast<uint32_t>(npx) * 12u);
-    l2_prefetch_bulk(args.guide + pix, static_cast<uint32_t>(npx) * 4u);
-  };
-  // This thread's quad of item `item`: three RGB texels and one guide texel into registers.
-  float4 c0, c1, c2, gq;
-  auto fetch = [&](int item) {
-    long long row; int x0, npx;
-    item_span(item, row, x0, npx);
-    if (tid * 4 < npx) {
-      const int quad = static_cast<int>((row * g.W + x0) >> 2) + tid;   // pixel quad index
-      c0 = tex1Dfetch<float4>(args.in_tex, 3 * quad);
-      c1 = tex1Dfetch<float4>(args.in_tex, 3 * quad + 1);
-      c2 = tex1Dfetch<float4>(args.in_tex, 3 * quad + 2);
-      gq = tex1Dfetch<float4>(args.guide_tex, quad);
-    }
-  };
-
-  if (tid == 0) {
-    const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
-    mbar_expect_tx(&gridbar[0], bytes);
-    tma_load_1d(raw0, args.yslab + static_cast<size_t>(r_begin) * pl.row_floats, bytes, &gridbar[0]);
-    prefetch_l2(0);
-    if (nitems > 1) prefetch_l2(1);
-    if (nitems > 2) prefetch_l2(2);
-  }
-  fetch(0);
-
-  const float gd_f = static_cast<float>(g.gd);
-  const int x_stride = g.gd * kGc;
-  const float* slab = raw0;
-  int tex_row = 0;
-
-  for (int item = 0; item < nitems; ++item) {
-    long long row; int x0, npx;
-    item_span(item, row, x0, npx);
-    if (x0 == 0) {  // new image row: its slab row (double-buffered one row ahead)
-      const int rowk = item / pl.nseg;
-      const int cur = rowk & 1;
-      slab = raw0 + cur * pl.row_floats;
-      mbar_wait(&gridbar[cur], static_cast<uint32_t>(rowk >> 1) & 1u);
-      if (tid == 0 && row + 1 < r_end) {
-        const uint32_t bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
-        mbar_expect_tx(&gridbar[cur ^ 1], bytes);
-        tma_load_1d(raw0 + (cur ^ 1) * pl.row_floats,
-                    args.yslab + static_cast<size_t>(row + 1) * pl.row_floats, bytes, &gridbar[cur ^ 1]);
-      }
-      tex_row = static_cast<int>(row) * (pl.row_floats / 4);
-    }
-    unsigned char* otile = stage_base + static_cast<size_t>(item % kTexInStages) * pl.stage_bytes;
-
-    if (tid * 4 < npx) {
-      const float pr[4] = {c0.x, c0.w, c1.z, c2.y};
-      const float pg[4] = {c0.y, c1.x, c1.w, c2.z};
-      const float pb[4] = {c0.z, c1.y, c2.x, c2.w};
-      const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
-      float o_r[4], o_g[4], o_b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const Axis ax = spatial_axis(x0 + 4 * tid + i, g.scale_x);
-        const Axis az = range_axis(gv[i], gd_f);
-        const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride;
-        const int xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
-        const int zo0 = clampi(az.i0, 0, g.gd - 1) * kGc;
-        const int zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * kGc;
-        float wz0, wz1;
-        smoothed_weights(az.f, wz0, wz1);
-        const float wx1 = ax.f, wx0 = 1.0f - ax.f;
-        blend_apply<kTexChunks>(slab, args.slab_tex, tex_row, xo0 + zo0, xo0 + zo1, xo1 + zo0,
-                                xo1 + zo1, wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1, pr[i], pg[i],
-                                pb[i], o_r[i], o_g[i], o_b[i]);
-      }
-      store_quad<kPxF32>(otile, tid, o_r, o_g, o_b);
-      fence_proxy_async_smem();
-    }
-    // Next item's pixels: issued here, when nothing else is live; they land during the barrier.
-    if (item + 1 < nitems) fetch(item + 1);
-    // Thread 0: the output stage the NEXT item writes must have been drained by its last store.
-    if (tid == 0) tma_store_wait_read<kTexInStages - 2>();
-    __syncthreads();
-
-    if (tid == 0) {
-      const size_t pix = static_cast<size_t>(row) * g.W + x0;
-      tma_store_1d(args.out + pix * 12, otile, static_cast<uint32_t>(npx) * 12u);
-      tma_store_commit();
-      if (item + 3 < nitems) prefetch_l2(item + 3);
-    }
-  }
-  if (tid == 0) tma_store_wait_all<0>();
-}
-
-// =========================================================================================
-// Warp-specialised form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_WS).
-// =========================================================================================
-// ncu stall sampling of the block-synchronous kernel: ~20 % of samples sit in synchronisation
-// (the per-item __syncthreads before the bulk store, and all 256 threads spinning on the TMA
-// barrier).  Here nothing is block-synchronous after start-up:
-//   * warp 8 (one lane) is the PRODUCER: it issues every TMA load -- per item the RGB + guide
-//     segment into the stage ring, per image row the y-pre-blended slab row (from the pre-pass
-//     workspace) into one of two slab buffers -- gated by stage_free[] / slab_free[] mbarriers;
-//   * warps 0..7 are CONSUMERS and never wait for each other: a warp waits for its stage
-//     (full[]) and slab (slab_full[]), processes its own 128 pixels in place, issues ITS OWN
-//     bulk store (lane 0), and one item later -- once cp.async.bulk.wait_group.read says the
-//     store has drained the tile -- arrives on stage_free[]; after a row's last item it arrives
-//     on slab_free[].  stage_free / slab_free count kWsConsumerWarps arrivals per phase.
-constexpr int kTexChunksWs = 4;
-
-template <class GuideFn, int kTexChunks, int kWsConsumerWarps>
-__global__ void __launch_bounds__((kWsConsumerWarps + 1) * 32, 2)
-slice_apply_rows_ws_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
-  static_assert(kTexChunks > 0, "the warp-specialised kernel reads slab rows from the workspace");
-  constexpr bool kGuideIn = GuideFn::kFromInput;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const SliceGeom& g = args.g;
-  const TmaPlan& pl = args.p;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]  TMA landed
-  uint64_t* stage_free = full + kMaxStages;              // [kMaxStages]  all consumers done + stored
-  uint64_t* slab_full = stage_free + kMaxStages;         // [2]
-  uint64_t* slab_free = slab_full + 2;                   // [2]
-  float* raw0 = reinterpret_cast<float*>(smem + pl.off_raw);
-  unsigned char* stage_base = smem + pl.off_stage;
-
-  const long long total_rows = static_cast<long long>(g.B) * g.rows;
-  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
-  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
-  const int nitems = static_cast<int>(r_end - r_begin) * pl.nseg;
-  if (nitems <= 0) return;
-
-  if (tid == 0) {
-    for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&stage_free[s], kWsConsumerWarps); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&slab_full[b], 1); mbar_init(&slab_free[b], kWsConsumerWarps); }
-    fence_mbar_init();
-  }
-  __syncthreads();  // the only block-wide barrier
-
-  const int NS = pl.stages;
-  const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
-  auto stage_rgb = [&](int s) { return stage_base + static_cast<size_t>(s) * pl.stage_bytes; };
-  auto stage_guide = [&](int s) { return stage_rgb(s) + pl.off_guide; };
-  auto item_span = [&](int item, long long& row, int& x0, int& npx) {
-    const int rr = item / pl.nseg;
-    const int seg = item - rr * pl.nseg;
-    row = r_begin + rr;
-    x0 = seg * pl.seg_px;
-    npx = min(pl.seg_px, g.W - x0);
-  };
-  auto arrive = [&](uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-  };
-
-  if (warp == kWsConsumerWarps) {
-    // ------------------------------- producer ---------------------------------------------
-    if (lane != 0) return;
-    for (int item = 0; item < nitems; ++item) {
-      long long row; int x0, npx;
-      item_span(item, row, x0, npx);
-      const int s = item % NS;
-      const int use = item / NS;
-      if (x0 == 0) {  // first item of an image row: its slab row, two buffers deep
-        const int rowk = item / pl.nseg, rb = rowk & 1, v = rowk >> 1;
-        if (v >= 1) mbar_wait(&slab_free[rb], static_cast<uint32_t>(v - 1) & 1u);
-        mbar_expect_tx(&slab_full[rb], slab_bytes);
-        tma_load_1d(raw0 + rb * pl.row_floats, args.yslab + static_cast<size_t>(row) * pl.row_floats,
-                    slab_bytes, &slab_full[rb]);
-      }
-      if (use >= 1) mbar_wait(&stage_free[s], static_cast<uint32_t>(use - 1) & 1u);
-      const size_t pix = static_cast<size_t>(row) * g.W + x0;
-      mbar_expect_tx(&full[s], static_cast<uint32_t>(npx) * (kGuideIn ? 16u : 12u));
-      tma_load_1d(stage_rgb(s), args.input + pix * 12, static_cast<uint32_t>(npx) * 12u, &full[s]);
-      if (kGuideIn)
-        tma_load_1d(stage_guide(s), args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[s]);
-    }
-    return;
-  }
-
-  // --------------------------------- consumers ----------------------------------------------
-  const int px0w = warp * 128;   // this warp's pixels inside a segment
-  const float* slab = raw0;
-  int tex_row = 0;
-  for (int item = 0; item < nitems; ++item) {
-    long long row; int x0, npx;
-    item_span(item, row, x0, npx);
-    const int s = item % NS;
-    const int rowk = item / pl.nseg, rb = rowk & 1;
-    mbar_wait(&full[s], static_cast<uint32_t>(item / NS) & 1u);
-    if (x0 == 0) {
-      mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
-      slab = raw0 + rb * pl.row_floats;
-      tex_row = static_cast<int>(row) * (pl.row_floats / 4);
-    }
-    const int q = (px0w >> 2) + lane;
-    if (q * 4 < npx)
-      process_quad<GuideFn, kTexChunks>(args, guide_fn, stage_rgb(s), stage_rgb(s), stage_guide(s),
-                                        slab, tex_row, row, x0, q);
-    __syncwarp();
-    if (lane == 0) {
-      const int nw = min(128, npx - px0w);
-      if (nw > 0) {
-        const size_t pix = static_cast<size_t>(row) * g.W + x0 + px0w;
-        tma_store_1d(args.out + pix * 12, stage_rgb(s) + static_cast<size_t>(px0w) * 12,
-                     static_cast<uint32_t>(nw) * 12u);
-      }
-      tma_store_commit();            // one (possibly empty) group per item keeps the counting simple
-      if (item >= 1) {
-        tma_store_wait_read<1>();    // this warp's store of item-1 has drained its tile
-        arrive(&stage_free[(item - 1) % NS]);
-      }
-      if (x0 + pl.seg_px >= g.W) arrive(&slab_free[rb]);  // row finished: slab no longer read here
-    }
-  }
-  if (lane == 0) tma_store_wait_all<0>();
-}
-
-// =========================================================================================
-// Issuer-warp form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_ASYNC).
-// =========================================================================================
-// What the block-synchronous kernel loses (ncu, profiles/r01_final_ncu_full_summary.txt): 1.8
-// barrier stalls per issue and ~116 warp instructions per item outside the pixel body.  After
-// every segment's __syncthreads thread 0 runs a SERIAL section (bulk store, wait for the previous
-// store, an integer division for the next item, expect_tx, two bulk loads) while its own warp's
-// pixels wait -- so warp 0 reaches the next barrier late by that section and the other fifteen
-// warps wait for it, every item.  The first warp-specialised form (above) moved the loads to a
-// producer warp but left a serial store / wait / arrive section in lane 0 of EVERY math warp.
-//
-// Here the serial work has a warp of its own and nothing else is synchronous:
-//   * warps 0..N-2 are MATH warps.  Per item a warp waits for the stage's TMA barrier (full[s]),
-//     processes its 128 pixels in place, and one lane ARRIVES on done[s] -- an mbarrier arrive
-//     does not block, the warp goes straight on to the next stage.  No __syncthreads, no bulk
-//     copies, no divisions (row / segment are nested loop counters) in a math warp.
-//   * warp N-1 (one lane) is the ISSUER: it waits on done[s], issues the segment's ONE bulk store,
-//     refills the stage freed one item earlier, and after a row's last segment prefetches the slab
-//     row two rows ahead into the buffer that row just released.
-// 512 threads = 15 math warps (480 quads = one 1920-pixel segment, half a 4K row) + the issuer:
-// the 16th warp of the block-synchronous 512-thread form was idle at this width anyway.
-//
-// kLean: index arithmetic per QUAD instead of per pixel where the x cells are at least 4 pixels
-// wide (W >= 4 gw).  floor(t_i) of the quad's pixels is floor(t_0) or floor(t_0) + 1 (t grows by
-// scale_x <= 1/4 per pixel), so one float->int conversion serves four pixels and the cell offsets
-// are one of three precomputed values; the depth cell uses F2I.FLOOR + I2FP (one XU-pipe op)
-// instead of FRND + F2I (two).  t_i, the fractions and every weight are computed by the same
-// rounded operations as spatial_axis / range_axis: results are bitwise those of the other forms.
-//
-// Two more switches, both aimed at the shared-memory data pipe that bounds this form (ncu: 90 % of
-// its peak; 1.57 wavefronts per pixel = 1.0 gather + 0.1 x-cell straddles + 0.22 tile reads /
-// writes by the threads + 0.23 reads / writes of the same tiles by the TMA engine):
-//   kStore == 1: results leave the registers by 3 x STG.128 (streaming) instead of 3 x STS.128 +
-//     a bulk store -- the output tile never crosses shared memory (-0.09 wavefronts per pixel).
-//   kSlab == 1: the ISSUER WARP blends each image row's two grid rows (L2-resident, 786 KB for
-//     the whole batch) into the shared-memory slab, two rows ahead of the math warps, so the
-//     pre-pass only has to materialise what the texture pipe fetches: the trailing part(s) of
-//     every cell (16 of its 48 bytes for four texture chunks, 32 beyond) -- a third of the
-//     pre-pass traffic, and the row kernel no longer reads slab rows back from HBM.
-
-// Which of a pixel's 12 corner chunks -- corner c = 0..3 (v00, v01, v10, v11), part p = 0..2 --
-// travel through the texture pipe.  kSlab == 0: the last kTexChunks of the ids 3 c + p (the
-// workspace holds whole slab rows).  kSlab == 1: part 2 of every corner, then part 1 of corners
-// 3, 2, ... for the chunks beyond four (the workspace holds parts 3 - P .. 2 of every cell).
-template <int kTexChunks, int kSlab>
-__host__ __device__ constexpr bool chunk_on_tex(int c, int p) {
-  if (kSlab == 0) return c * 3 + p >= 12 - kTexChunks;
-  return p == 2 || (p == 1 && c >= 8 - kTexChunks);
-}
-__host__ __device__ constexpr int tex_parts(int tex_chunks) { return tex_chunks > 4 ? 2 : 1; }
-
-template <int kTexChunks, int kSlab, int kC, int kP>
-__device__ __forceinline__ ulonglong2 fetch_chunk(const unsigned char* __restrict__ slab_b,
-                                                  cudaTextureObject_t tex, int off_b, int tex_idx) {
-  if constexpr (chunk_on_tex<kTexChunks, kSlab>(kC, kP)) {
-    // tex_idx: texel of the cell's part 0 (kSlab 0) / of its first stored part (kSlab 1)
-    constexpr int kFirst = (kSlab == 0) ? 0 : 3 - tex_parts(kTexChunks);
-    const float4 v = tex1Dfetch<float4>(tex, tex_idx + (kP - kFirst));
-    ulonglong2 r;
-    r.x = pack2(v.x, v.y);
-    r.y = pack2(v.z, v.w);
-    return r;
-  } else {
-    return *reinterpret_cast<const ulonglong2*>(slab_b + off_b + 16 * kP);
-  }
-}
-
-// blend_apply with byte offsets and per-corner texel indices (unused ones are dead code).
-template <int kTexChunks, int kSlab>
-__device__ __forceinline__ void blend_apply_q(const unsigned char* __restrict__ slab_b,
-                                              cudaTextureObject_t tex, const int (&off)[4],
-                                              const int (&tix)[4], const float (&w)[4], float r,
-                                              float g, float b, float& out_r, float& out_g,
-                                              float& out_b) {
-  const unsigned long long W00 = pack2(w[0], w[0]), W01 = pack2(w[1], w[1]);
-  const unsigned long long W10 = pack2(w[2], w[2]), W11 = pack2(w[3], w[3]);
-  const ulonglong2 a0 = fetch_chunk<kTexChunks, kSlab, 0, 0>(slab_b, tex, off[0], tix[0]);
-  const ulonglong2 a1 = fetch_chunk<kTexChunks, kSlab, 0, 1>(slab_b, tex, off[0], tix[0]);
-  const ulonglong2 a2 = fetch_chunk<kTexChunks, kSlab, 0, 2>(slab_b, tex, off[0], tix[0]);
-  const ulonglong2 b0 = fetch_chunk<kTexChunks, kSlab, 1, 0>(slab_b, tex, off[1], tix[1]);
-  const ulonglong2 b1 = fetch_chunk<kTexChunks, kSlab, 1, 1>(slab_b, tex, off[1], tix[1]);
-  const ulonglong2 b2 = fetch_chunk<kTexChunks, kSlab, 1, 2>(slab_b, tex, off[1], tix[1]);
-  const ulonglong2 c0 = fetch_chunk<kTexChunks, kSlab, 2, 0>(slab_b, tex, off[2], tix[2]);
-  const ulonglong2 c1 = fetch_chunk<kTexChunks, kSlab, 2, 1>(slab_b, tex, off[2], tix[2]);
-  const ulonglong2 c2 = fetch_chunk<kTexChunks, kSlab, 2, 2>(slab_b, tex, off[2], tix[2]);
-  const ulonglong2 d0 = fetch_chunk<kTexChunks, kSlab, 3, 0>(slab_b, tex, off[3], tix[3]);
-  const ulonglong2 d1 = fetch_chunk<kTexChunks, kSlab, 3, 1>(slab_b, tex, off[3], tix[3]);
-  const ulonglong2 d2 = fetch_chunk<kTexChunks, kSlab, 3, 2>(slab_b, tex, off[3], tix[3]);
-  unsigned long long acc[6];  // same order of operations as blend_apply: identical bits
-  acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
-  acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
-  acc[2] = fma2(W11, d1.x, fma2(W10, c1.x, fma2(W01, b1.x, mul2(W00, a1.x))));
-  acc[3] = fma2(W11, d1.y, fma2(W10, c1.y, fma2(W01, b1.y, mul2(W00, a1.y))));
-  acc[4] = fma2(W11, d2.x, fma2(W10, c2.x, fma2(W01, b2.x, mul2(W00, a2.x))));
-  acc[5] = fma2(W11, d2.y, fma2(W10, c2.y, fma2(W01, b2.y, mul2(W00, a2.y))));
-  float a0f, a1f, a2f, a3f;
-  unpack2(acc[0], a0f, a1f);
-  unpack2(acc[1], a2f, a3f);
-  out_r = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-  unpack2(acc[2], a0f, a1f);
-  unpack2(acc[3], a2f, a3f);
-  out_g = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-  unpack2(acc[4], a0f, a1f);
-  unpack2(acc[5], a2f, a3f);
-  out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-}
-
-__device__ __forceinline__ void stg128_stream(float* p, float x, float y, float z, float w) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w)
-               : "memory");
-}
-__device__ __forceinline__ float4 ldg128_stream(const float4* p) {
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-
-// tex_base: kSlab 0 -- texel of the row's first cell (row * gw * gd * 3); kSlab 1 -- the row's first
-// CELL in the part workspace (row * gw * gd).  out_row: this image row in `out` (kStore 1 only).
-template <int kTexChunks, int kStore, int kSlab>
-__device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const unsigned char* tile,
-                                                  unsigned char* out_tile,
-                                                  const unsigned char* guide_tile,
-                                                  const unsigned char* slab_b, int tex_base,
-                                                  float* out_row, int x0, int q) {
-  const SliceGeom& g = args.g;
-  const float gd_f = static_cast<float>(g.gd);
-  float pr[4], pg[4], pb[4];
-  load_quad<kPxF32>(tile, q, pr, pg, pb);
-  const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
-  const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
-
-  // x axis, once per quad: t_i = (x_i + 0.5f) * scale - 0.5f with the reference's roundings
-  // (float(X + i) + 0.5f == float(X) + (i + 0.5f): both exact below 2^22).
-  const float xf = static_cast<float>(x0 + 4 * q);
-  float tx[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    tx[i] = __fsub_rn(__fmul_rn(__fadd_rn(xf, static_cast<float>(i) + 0.5f), g.scale_x), 0.5f);
-  const int ix0 = __float2int_rd(tx[0]);
-  const float fl0 = static_cast<float>(ix0), fl1 = fl0 + 1.0f;
-  // the three x cells a quad can touch, as slab cell indices (x-major, gd depth cells each)
-  const int c0 = clampi(ix0, 0, g.gw - 1) * g.gd;
-  const int c1 = clampi(ix0 + 1, 0, g.gw - 1) * g.gd;
-  const int c2 = clampi(ix0 + 2, 0, g.gw - 1) * g.gd;
-  const int b0 = c0 * 48, b1 = c1 * 48, b2 = c2 * 48;   // and as byte offsets
-
-  float o_r[4], o_g[4], o_b[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool step = (i > 0) && (tx[i] >= fl1);     // this pixel sits in the next x cell
-    const float fx = tx[i] - (step ? fl1 : fl0);
-    const int xo0 = step ? b1 : b0;
-    const int xo1 = step ? b2 : b1;
-    // depth axis (range_axis with one conversion)
-    const float tz = __fsub_rn(__fmul_rn(gv[i], gd_f), 0.5f);
-    const int iz = __float2int_rd(tz);
-    const float fz = tz - static_cast<float>(iz);
-    const int zc0 = clampi(iz, 0, g.gd - 1);
-    const int zc1 = clampi(iz + 1, 0, g.gd - 1);
-    float wz0, wz1;
-    smoothed_weights(fz, wz0, wz1);
-    const float wx1 = fx, wx0 = 1.0f - fx;
-    const int off[4] = {zc0 * 48 + xo0, zc1 * 48 + xo0, zc0 * 48 + xo1, zc1 * 48 + xo1};
-    int tix[4];
-    if constexpr (kSlab == 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tix[c] = tex_base + (off[c] >> 4);
-    } else {
-      constexpr int P = tex_parts(kTexChunks);
-      const int xc0 = tex_base + (step ? c1 : c0), xc1 = tex_base + (step ? c2 : c1);
-      tix[0] = (xc0 + zc0) * P; tix[1] = (xc0 + zc1) * P;
-      tix[2] = (xc1 + zc0) * P; tix[3] = (xc1 + zc1) * P;
-    }
-    const float w[4] = {wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1};
-    blend_apply_q<kTexChunks, kSlab>(slab_b, args.slab_tex, off, tix, w, pr[i], pg[i], pb[i],
-                                     o_r[i], o_g[i], o_b[i]);
-  }
-  if constexpr (kStore == 0) {
-    store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
-    fence_proxy_async_smem();
-  } else {
-    float* op = out_row + static_cast<size_t>(x0 + 4 * q) * 3;
-    stg128_stream(op, o_r[0], o_g[0], o_b[0], o_r[1]);
-    stg128_stream(op + 4, o_g[1], o_b[1], o_r[2], o_g[2]);
-    stg128_stream(op + 8, o_b[2], o_r[3], o_g[3], o_b[3]);
-  }
-}
-
-template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = 512,
-          int kMinBlocks = 2>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
-slice_apply_rows_async_kernel(const TmaArgs args) {
-  static_assert(kTexChunks > 0, "the issuer-warp kernel serves part of the gather by texture");
-  static_assert(kLean || (kStore == 0 && kSlab == 0), "the switches exist in the lean form only");
-  static_assert(kSlab == 0 || (kTexChunks >= 4 && kTexChunks <= 8), "part workspace: 4..8 chunks");
-  constexpr int kMathWarps = kThreads / 32 - 1;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const SliceGeom& g = args.g;
-  const TmaPlan& pl = args.p;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]  TMA landed
-  uint64_t* done = full + kMaxStages;                    // [kMaxStages]  every math warp is through
-  uint64_t* slab_full = done + kMaxStages;               // [2]
-  unsigned char* raw0 = smem + pl.off_raw;               // two slab rows
-  unsigned char* stage_base = smem + pl.off_stage;
-
-  // Work split in ITEMS (row segments), not rows: 17280 rows over 296 CTAs leave some CTAs 59 rows
-  // and others 58 (1.1 % of the kernel is the tail); in half-row items the imbalance is 0.2 %.
-  // A CTA covers items [i_begin, i_end): rows r_begin .. r_end-1, the first row from pixel
-  // x_first, the last row up to pixel x_last (a row split between two CTAs has its slab row
-  // loaded by both).
-  const long long total_items = static_cast<long long>(g.B) * g.rows * pl.nseg;
-  const long long i_begin = total_items * blockIdx.x / gridDim.x;
-  const long long i_end = total_items * (blockIdx.x + 1) / gridDim.x;
-  // Programmatic dependent launch (no-ops when launched without the attribute): let the next
-  // kernel in the stream be scheduled as this grid's CTAs retire.
-  grid_launch_dependents();
-  if (i_end <= i_begin) return;
-  const long long r_begin = i_begin / pl.nseg, r_end = (i_end - 1) / pl.nseg + 1;
-  const int x_first = static_cast<int>(i_begin - r_begin * pl.nseg) * pl.seg_px;
-  const int x_last = min(g.W, (static_cast<int>((i_end - 1) - (r_end - 1) * pl.nseg) + 1) * pl.seg_px);
-  auto row_x0 = [&](long long row) { return row == r_begin ? x_first : 0; };
-  auto row_x1 = [&](long long row) { return row == r_end - 1 ? x_last : g.W; };
-
-  if (tid == 0) {
-    for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kMathWarps); }
-    mbar_init(&slab_full[0], 1);
-    mbar_init(&slab_full[1], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();  // the only block-wide barrier
-
-  const int NS = pl.stages;
-  const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
-  auto arrive = [&](uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-  };
-
-  if (warp == kMathWarps) {
-    // ------------------------------- issuer warp --------------------------------------------
-    // Lane 0 issues every bulk copy; the whole warp blends slab rows when kSlab == 1.
-    if (kSlab == 0 && lane != 0) return;
-    auto make_slab = [&](long long row) {
-      const int rb = static_cast<int>(row - r_begin) & 1;
-      if constexpr (kSlab == 0) {
-        if (lane == 0) {
-          mbar_expect_tx(&slab_full[rb], slab_bytes);
-          tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
-                      args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes,
-                      &slab_full[rb]);
-        }
-      } else {
-        // yslab[r] = (1 - fy) G[b][gy0] + fy G[b][gy1], exactly yblend_rows_kernel's arithmetic
-        const int b = static_cast<int>(row / g.rows);
-        const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
-        const Axis ay = spatial_axis(y, g.scale_y);
-        const float wy1 = ay.f, wy0 = 1.0f - ay.f;
-        const float* gb = args.grid + static_cast<size_t>(b) * g.gh * pl.row_floats;
-        const float4* a4 = reinterpret_cast<const float4*>(
-            gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * pl.row_floats);
-        const float4* b4 = reinterpret_cast<const float4*>(
-            gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * pl.row_floats);
-        float4* s4 = reinterpret_cast<float4*>(raw0 + static_cast<size_t>(rb) * slab_bytes);
-        const int n4 = pl.row_floats / 4;
-        // six cells' loads in flight per lane and batch (L2 latency, not bandwidth, is the cost)
-        for (int e0 = lane; e0 < n4; e0 += 32 * 6) {
-          float4 va[6], vb[6];
-#pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            const int e = min(e0 + 32 * u, n4 - 1);
-            va[u] = ldg128_stream(a4 + e);
-            vb[u] = ldg128_stream(b4 + e);
-          }
-#pragma unroll
-          for (int u = 0; u < 6; ++u)
-            if (e0 + 32 * u < n4) s4[e0 + 32 * u] = lerp4(wy0, va[u], wy1, vb[u]);
-        }
-        __syncwarp();
-        if (lane == 0) arrive(&slab_full[rb]);
-      }
-    };
-    // load cursor: runs NS - 1 items ahead of the math warps
-    long long l_row = r_begin;
-    int l_x0 = x_first, l_s = 0;
-    auto issue_next_load = [&]() {  // lane 0
-      if (l_row >= r_end) return;
-      const int npx = min(pl.seg_px, g.W - l_x0);
-      unsigned char* st = stage_base + static_cast<size_t>(l_s) * pl.stage_bytes;
-      const size_t pix = static_cast<size_t>(l_row) * g.W + l_x0;
-      mbar_expect_tx(&full[l_s], static_cast<uint32_t>(npx) * 16u);
-      tma_load_1d(st, args.input + pix * 12, static_cast<uint32_t>(npx) * 12u, &full[l_s]);
-      tma_load_1d(st + pl.off_guide, args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[l_s]);
-      if (++l_s == NS) l_s = 0;
-      l_x0 += pl.seg_px;
-      if (l_x0 >= row_x1(l_row)) { l_x0 = 0; ++l_row; }
-    };
-    // kStore 0: the stage refilled after item i is item i-1's (its bulk store must have drained);
-    // kStore 1: item i's own stage -- one more item of prefetch from the same ring.
-    // The pixel tensors are the caller's inputs (complete before the pre-pass started): their
-    // loads may precede the dependency wait; the workspace written by the pre-pass may not.
-    if (lane == 0)
-      for (int i = 0; i < NS - (kStore == 0 ? 1 : 0); ++i) issue_next_load();
-    grid_dependency_wait();
-    make_slab(r_begin);
-    if (r_begin + 1 < r_end) make_slab(r_begin + 1);
-
-    // Lane 0 alone runs the per-item protocol; the other lanes park at the row's __syncwarp (a
-    // blocked WARPSYNC costs nothing, whereas 31 lanes spinning in a try_wait loop on the same
-    // mbarrier delay lane 0's serial section: measured +10 % kernel time).
-    int s = 0;
-    uint32_t ph = 0;
-    for (long long row = r_begin; row < r_end; ++row) {
-      if (lane == 0) {
-        const int x_end = row_x1(row);
-        for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
-          mbar_wait(&done[s], ph);  // every math warp is through with this stage
-          if constexpr (kStore == 0) {  // results were written in place (and proxy-fenced)
-            const int npx = min(pl.seg_px, g.W - x0);
-            unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
-            const size_t pix = static_cast<size_t>(row) * g.W + x0;
-            tma_store_1d(args.out + pix * 12, st, static_cast<uint32_t>(npx) * 12u);
-            tma_store_commit();
-            if (l_row < r_end) {
-              tma_store_wait_read<1>();  // the previous item's store has drained the stage refilled now
-              issue_next_load();
-            }
-          } else {
-            issue_next_load();          // refills THIS stage: nothing reads it any more
-          }
-          if (++s == NS) { s = 0; ph ^= 1u; }
-        }
-      }
-      __syncwarp();
-      // the row's slab buffer is free: every math warp arrived after its last read of it
-      if (row + 2 < r_end) make_slab(row + 2);
-    }
-    if (lane == 0) tma_store_wait_all<0>();
-    return;
-  }
-
-  // --------------------------------- math warps ---------------------------------------------
-  const int q = warp * 32 + lane;  // this thread's quad inside a segment
-  const int cells = g.gw * g.gd;
-  int s = 0;
-  uint32_t ph = 0;
-  for (long long row = r_begin; row < r_end; ++row) {
-    const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
-    mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
-    const unsigned char* slab_b = raw0 + static_cast<size_t>(rb) * slab_bytes;
-    const int tex_base = static_cast<int>(row) * (kSlab == 0 ? cells * 3 : cells);
-    float* out_row = reinterpret_cast<float*>(args.out) + static_cast<size_t>(row) * g.W * 3;
-    const int x_end = row_x1(row);
-    for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
-      const int npx = min(pl.seg_px, g.W - x0);
-      unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
-      mbar_wait(&full[s], ph);
-      if (q * 4 < npx) {
-        if constexpr (kLean)
-          process_quad_lean<kTexChunks, kStore, kSlab>(args, st, st, st + pl.off_guide, slab_b,
-                                                       tex_base, out_row, x0, q);
-        else
-          process_quad<GuideFromInput, kTexChunks>(args, GuideFromInput{}, st, st, st + pl.off_guide,
-                                                   reinterpret_cast<const float*>(slab_b), tex_base,
-                                                   row, x0, q);
-      }
-      __syncwarp();
-      if (lane == 0) arrive(&done[s]);
-      if (++s == NS) { s = 0; ph ^= 1u; }
-    }
-  }
-}
 
 // =========================================================================================
 // Un-fused slice, persistent TMA row kernel (gc = 12, W % 4 == 0): out[b,y,x,0..11].
@@ -1484,25 +566,6 @@ yblend_rows_kernel(const float* __restrict__ grid, float4* __restrict__ ws, Slic
   }
 }
 
-// Launch with (pdl) or without the programmatic-stream-serialization attribute.  With it the
-// kernel may be SCHEDULED before its predecessor in the stream has drained; every kernel launched
-// this way executes griddepcontrol.wait before its first dependent memory access.
-template <class... KArgs, class... Args>
-static cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem,
-                                    cudaStream_t stream, bool pdl, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-
 static void launch_yblend(const float* grid, float* ws, const SliceGeom& g, int row_floats, int parts,
                           cudaStream_t stream, bool pdl = false) {
   const long long total_rows = static_cast<long long>(g.B) * g.rows;
@@ -1664,47 +727,6 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream, 
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
-template <int kTexChunks, int kThreads, int kMinBlocks = 2>
-static int launch_texin(const TmaArgs& a, cudaStream_t stream) {
-  auto kern = slice_apply_rows_texin_kernel<kTexChunks, kThreads, kMinBlocks>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       a.p.smem_bytes);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<a.p.ctas, kThreads, a.p.smem_bytes, stream>>>(a);
-  return static_cast<int>(cudaGetLastError());
-}
-
-template <class GuideFn, int kConsumerWarps>
-static int launch_ws_n(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  auto kern = slice_apply_rows_ws_kernel<GuideFn, kTexChunksWs, kConsumerWarps>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       a.p.smem_bytes);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<a.p.ctas, (kConsumerWarps + 1) * 32, a.p.smem_bytes, stream>>>(a, fn);
-  return static_cast<int>(cudaGetLastError());
-}
-
-template <class GuideFn>
-static int launch_ws(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
-  // consumer warps = planned threads / 32 (8 for the 256-thread plan, 15 for the 480-quad one)
-  // 15 consumer warps + the producer warp = 512 threads: 64 registers at two CTAs per SM
-  if (a.p.threads == 480) return launch_ws_n<GuideFn, 15>(a, fn, stream);
-  return launch_ws_n<GuideFn, 8>(a, fn, stream);
-}
-
-template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = kAsyncThreads,
-          int kMinBlocks = 2>
-static int launch_async(const TmaArgs& a, cudaStream_t stream, bool pdl) {
-  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kStore, kSlab, kThreads, kMinBlocks>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       a.p.smem_bytes);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  e = launch_maybe_pdl(kern, static_cast<unsigned>(a.p.ctas), kThreads,
-                       static_cast<size_t>(a.p.smem_bytes), stream, pdl, a);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  return static_cast<int>(cudaGetLastError());
-}
-
 // Texture objects over caller workspaces, cached by (pointer, bytes): creating one is a
 // host-side driver call that should not sit inside a timed loop.
 struct TexCacheEntry { const void* ptr; size_t bytes; int dev; cudaTextureObject_t tex; };
@@ -1749,7 +771,6 @@ struct GuideSpec {
   int out_fmt = kPxF32;
 };
 
-constexpr int kTexChunksDefault = 4;
 
 template <class GuideFn>
 static int launch_px_generic(const float* grid, const void* input, void* out, float* guide_out,
@@ -1902,43 +923,12 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       bool pdl = kAsyncPdlDefault;   // programmatic dependent launch of pre-pass and row kernel
       if (const char* e = std::getenv("HDRNET_ASYNC_PDL")) pdl = std::atoi(e) != 0;
       launch_yblend(grid, gs.workspace, g, plan.row_floats, slab ? (chunks == 4 ? 1 : 2) : 0, stream, pdl);
-      if (async_threads != 512 && lean && !store && !slab) {
-#define HDRNET_ASYNC_SHAPE(K)                                                                  \
-        if (chunks == K) {                                                                       \
-          if (async_threads == 352) return launch_async<K, true, 0, 0, 352, 2>(a, stream, pdl);       \
-          if (async_occ == 3) return launch_async<K, true, 0, 0, 224, 3>(a, stream, pdl);            \
-          return launch_async<K, true, 0, 0, 224, 4>(a, stream, pdl);                                 \
-        }
-        HDRNET_ASYNC_SHAPE(4)
-        HDRNET_ASYNC_SHAPE(5)
-        HDRNET_ASYNC_SHAPE(6)
-#undef HDRNET_ASYNC_SHAPE
-        return HDRNET_E_UNSUPPORTED;
-      }
-      if (!lean) {
-        switch (chunks) {
-          case 5: return launch_async<5, false>(a, stream, pdl);
-          default: return launch_async<kTexChunksDefault, false>(a, stream, pdl);
-        }
-      }
-#define HDRNET_ASYNC_CASE(K)                                                              \
-      if (chunks == K) {                                                                    \
-        if (store && slab) return launch_async<K, true, 1, 1>(a, stream, pdl);                   \
-        if (store) return launch_async<K, true, 1, 0>(a, stream, pdl);                           \
-        if (slab) return launch_async<K, true, 0, 1>(a, stream, pdl);                            \
-        return launch_async<K, true, 0, 0>(a, stream, pdl);                                      \
-      }
-      HDRNET_ASYNC_CASE(4)
-      HDRNET_ASYNC_CASE(5)
-      HDRNET_ASYNC_CASE(6)
-#undef HDRNET_ASYNC_CASE
-      if (chunks == 3) return launch_async<3, true, 0, 0>(a, stream, pdl);
-      return HDRNET_E_UNSUPPORTED;
+      return launch_async_form(a, chunks, lean, store, slab, async_threads, async_occ, pdl, stream);
     }
     launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);
     if (variant == HDRNET_VARIANT_TEX_WS) {
       if (gs.mode != 0 || tplan.seg_px > tplan.threads * 4) return HDRNET_E_UNSUPPORTED;
-      return launch_ws(a, GuideFromInput{}, stream);
+      return launch_ws_form(a, stream);
     }
     if (variant == HDRNET_VARIANT_TEX_IN) {
       // float32 guide-from-input form only; pixel tensors addressable as 1-D float4 textures
@@ -1964,16 +954,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       if (rc != 0) return rc;
       int chunks = kTexChunksDefault;
       if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);
-      if (a.p.threads == 512) {
-        switch (chunks) {
-          case 3: return launch_texin<3, 512>(a, stream);
-          case 5: return launch_texin<5, 512>(a, stream);
-          default: return launch_texin<kTexChunksDefault, 512>(a, stream);
-        }
-      }
-      if (a.p.resident == 4) return launch_texin<kTexChunksDefault, kTmaThreads, 4>(a, stream);
-      if (a.p.resident == 3) return launch_texin<kTexChunksDefault, kTmaThreads, 3>(a, stream);
-      return launch_texin<kTexChunksDefault, kTmaThreads>(a, stream);
+      return launch_texin_form(a, chunks, stream);
     }
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
                         return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt); }

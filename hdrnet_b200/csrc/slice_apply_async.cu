@@ -1,0 +1,440 @@
+// slice_apply_async.cu -- the issuer-warp form of the texture-assisted row kernel
+// (HDRNET_VARIANT_TEX_ASYNC; what AUTO runs for large images when a workspace is lent).
+// Shared device code: slice_rows.cuh.  Host dispatch: launch_slice_apply_impl in slice_apply.cu.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+
+#include "slice_rows.cuh"
+
+namespace hdrnet_b200 {
+
+// =========================================================================================
+// Issuer-warp form of the texture-assisted row kernel (HDRNET_VARIANT_TEX_ASYNC).
+// =========================================================================================
+// What the block-synchronous kernel loses (ncu, profiles/r01_final_ncu_full_summary.txt): 1.8
+// barrier stalls per issue and ~116 warp instructions per item outside the pixel body.  After
+// every segment's __syncthreads thread 0 runs a SERIAL section (bulk store, wait for the previous
+// store, an integer division for the next item, expect_tx, two bulk loads) while its own warp's
+// pixels wait -- so warp 0 reaches the next barrier late by that section and the other fifteen
+// warps wait for it, every item.  The first warp-specialised form (above) moved the loads to a
+// producer warp but left a serial store / wait / arrive section in lane 0 of EVERY math warp.
+//
+// Here the serial work has a warp of its own and nothing else is synchronous:
+//   * warps 0..N-2 are MATH warps.  Per item a warp waits for the stage's TMA barrier (full[s]),
+//     processes its 128 pixels in place, and one lane ARRIVES on done[s] -- an mbarrier arrive
+//     does not block, the warp goes straight on to the next stage.  No __syncthreads, no bulk
+//     copies, no divisions (row / segment are nested loop counters) in a math warp.
+//   * warp N-1 (one lane) is the ISSUER: it waits on done[s], issues the segment's ONE bulk store,
+//     refills the stage freed one item earlier, and after a row's last segment prefetches the slab
+//     row two rows ahead into the buffer that row just released.
+// 512 threads = 15 math warps (480 quads = one 1920-pixel segment, half a 4K row) + the issuer:
+// the 16th warp of the block-synchronous 512-thread form was idle at this width anyway.
+//
+// kLean: index arithmetic per QUAD instead of per pixel where the x cells are at least 4 pixels
+// wide (W >= 4 gw).  floor(t_i) of the quad's pixels is floor(t_0) or floor(t_0) + 1 (t grows by
+// scale_x <= 1/4 per pixel), so one float->int conversion serves four pixels and the cell offsets
+// are one of three precomputed values; the depth cell uses F2I.FLOOR + I2FP (one XU-pipe op)
+// instead of FRND + F2I (two).  t_i, the fractions and every weight are computed by the same
+// rounded operations as spatial_axis / range_axis: results are bitwise those of the other forms.
+//
+// Two more switches, both aimed at the shared-memory data pipe that bounds this form (ncu: 90 % of
+// its peak; 1.57 wavefronts per pixel = 1.0 gather + 0.1 x-cell straddles + 0.22 tile reads /
+// writes by the threads + 0.23 reads / writes of the same tiles by the TMA engine):
+//   kStore == 1: results leave the registers by 3 x STG.128 (streaming) instead of 3 x STS.128 +
+//     a bulk store -- the output tile never crosses shared memory (-0.09 wavefronts per pixel).
+//   kSlab == 1: the ISSUER WARP blends each image row's two grid rows (L2-resident, 786 KB for
+//     the whole batch) into the shared-memory slab, two rows ahead of the math warps, so the
+//     pre-pass only has to materialise what the texture pipe fetches: the trailing part(s) of
+//     every cell (16 of its 48 bytes for four texture chunks, 32 beyond) -- a third of the
+//     pre-pass traffic, and the row kernel no longer reads slab rows back from HBM.
+
+// Which of a pixel's 12 corner chunks -- corner c = 0..3 (v00, v01, v10, v11), part p = 0..2 --
+// travel through the texture pipe.  kSlab == 0: the last kTexChunks of the ids 3 c + p (the
+// workspace holds whole slab rows).  kSlab == 1: part 2 of every corner, then part 1 of corners
+// 3, 2, ... for the chunks beyond four (the workspace holds parts 3 - P .. 2 of every cell).
+template <int kTexChunks, int kSlab>
+__host__ __device__ constexpr bool chunk_on_tex(int c, int p) {
+  if (kSlab == 0) return c * 3 + p >= 12 - kTexChunks;
+  return p == 2 || (p == 1 && c >= 8 - kTexChunks);
+}
+__host__ __device__ constexpr int tex_parts(int tex_chunks) { return tex_chunks > 4 ? 2 : 1; }
+
+template <int kTexChunks, int kSlab, int kC, int kP>
+__device__ __forceinline__ ulonglong2 fetch_chunk(const unsigned char* __restrict__ slab_b,
+                                                  cudaTextureObject_t tex, int off_b, int tex_idx) {
+  if constexpr (chunk_on_tex<kTexChunks, kSlab>(kC, kP)) {
+    // tex_idx: texel of the cell's part 0 (kSlab 0) / of its first stored part (kSlab 1)
+    constexpr int kFirst = (kSlab == 0) ? 0 : 3 - tex_parts(kTexChunks);
+    const float4 v = tex1Dfetch<float4>(tex, tex_idx + (kP - kFirst));
+    ulonglong2 r;
+    r.x = pack2(v.x, v.y);
+    r.y = pack2(v.z, v.w);
+    return r;
+  } else {
+    return *reinterpret_cast<const ulonglong2*>(slab_b + off_b + 16 * kP);
+  }
+}
+
+// blend_apply with byte offsets and per-corner texel indices (unused ones are dead code).
+template <int kTexChunks, int kSlab>
+__device__ __forceinline__ void blend_apply_q(const unsigned char* __restrict__ slab_b,
+                                              cudaTextureObject_t tex, const int (&off)[4],
+                                              const int (&tix)[4], const float (&w)[4], float r,
+                                              float g, float b, float& out_r, float& out_g,
+                                              float& out_b) {
+  const unsigned long long W00 = pack2(w[0], w[0]), W01 = pack2(w[1], w[1]);
+  const unsigned long long W10 = pack2(w[2], w[2]), W11 = pack2(w[3], w[3]);
+  const ulonglong2 a0 = fetch_chunk<kTexChunks, kSlab, 0, 0>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 a1 = fetch_chunk<kTexChunks, kSlab, 0, 1>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 a2 = fetch_chunk<kTexChunks, kSlab, 0, 2>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 b0 = fetch_chunk<kTexChunks, kSlab, 1, 0>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 b1 = fetch_chunk<kTexChunks, kSlab, 1, 1>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 b2 = fetch_chunk<kTexChunks, kSlab, 1, 2>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 c0 = fetch_chunk<kTexChunks, kSlab, 2, 0>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 c1 = fetch_chunk<kTexChunks, kSlab, 2, 1>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 c2 = fetch_chunk<kTexChunks, kSlab, 2, 2>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 d0 = fetch_chunk<kTexChunks, kSlab, 3, 0>(slab_b, tex, off[3], tix[3]);
+  const ulonglong2 d1 = fetch_chunk<kTexChunks, kSlab, 3, 1>(slab_b, tex, off[3], tix[3]);
+  const ulonglong2 d2 = fetch_chunk<kTexChunks, kSlab, 3, 2>(slab_b, tex, off[3], tix[3]);
+  unsigned long long acc[6];  // same order of operations as blend_apply: identical bits
+  acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
+  acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
+  acc[2] = fma2(W11, d1.x, fma2(W10, c1.x, fma2(W01, b1.x, mul2(W00, a1.x))));
+  acc[3] = fma2(W11, d1.y, fma2(W10, c1.y, fma2(W01, b1.y, mul2(W00, a1.y))));
+  acc[4] = fma2(W11, d2.x, fma2(W10, c2.x, fma2(W01, b2.x, mul2(W00, a2.x))));
+  acc[5] = fma2(W11, d2.y, fma2(W10, c2.y, fma2(W01, b2.y, mul2(W00, a2.y))));
+  float a0f, a1f, a2f, a3f;
+  unpack2(acc[0], a0f, a1f);
+  unpack2(acc[1], a2f, a3f);
+  out_r = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[2], a0f, a1f);
+  unpack2(acc[3], a2f, a3f);
+  out_g = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[4], a0f, a1f);
+  unpack2(acc[5], a2f, a3f);
+  out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+}
+
+__device__ __forceinline__ void stg128_stream(float* p, float x, float y, float z, float w) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ldg128_stream(const float4* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// tex_base: kSlab 0 -- texel of the row's first cell (row * gw * gd * 3); kSlab 1 -- the row's first
+// CELL in the part workspace (row * gw * gd).  out_row: this image row in `out` (kStore 1 only).
+template <int kTexChunks, int kStore, int kSlab>
+__device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const unsigned char* tile,
+                                                  unsigned char* out_tile,
+                                                  const unsigned char* guide_tile,
+                                                  const unsigned char* slab_b, int tex_base,
+                                                  float* out_row, int x0, int q) {
+  const SliceGeom& g = args.g;
+  const float gd_f = static_cast<float>(g.gd);
+  float pr[4], pg[4], pb[4];
+  load_quad<kPxF32>(tile, q, pr, pg, pb);
+  const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
+  const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+
+  // x axis, once per quad: t_i = (x_i + 0.5f) * scale - 0.5f with the reference's roundings
+  // (float(X + i) + 0.5f == float(X) + (i + 0.5f): both exact below 2^22).
+  const float xf = static_cast<float>(x0 + 4 * q);
+  float tx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    tx[i] = __fsub_rn(__fmul_rn(__fadd_rn(xf, static_cast<float>(i) + 0.5f), g.scale_x), 0.5f);
+  const int ix0 = __float2int_rd(tx[0]);
+  const float fl0 = static_cast<float>(ix0), fl1 = fl0 + 1.0f;
+  // the three x cells a quad can touch, as slab cell indices (x-major, gd depth cells each)
+  const int c0 = clampi(ix0, 0, g.gw - 1) * g.gd;
+  const int c1 = clampi(ix0 + 1, 0, g.gw - 1) * g.gd;
+  const int c2 = clampi(ix0 + 2, 0, g.gw - 1) * g.gd;
+  const int b0 = c0 * 48, b1 = c1 * 48, b2 = c2 * 48;   // and as byte offsets
+
+  float o_r[4], o_g[4], o_b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool step = (i > 0) && (tx[i] >= fl1);     // this pixel sits in the next x cell
+    const float fx = tx[i] - (step ? fl1 : fl0);
+    const int xo0 = step ? b1 : b0;
+    const int xo1 = step ? b2 : b1;
+    // depth axis (range_axis with one conversion)
+    const float tz = __fsub_rn(__fmul_rn(gv[i], gd_f), 0.5f);
+    const int iz = __float2int_rd(tz);
+    const float fz = tz - static_cast<float>(iz);
+    const int zc0 = clampi(iz, 0, g.gd - 1);
+    const int zc1 = clampi(iz + 1, 0, g.gd - 1);
+    float wz0, wz1;
+    smoothed_weights(fz, wz0, wz1);
+    const float wx1 = fx, wx0 = 1.0f - fx;
+    const int off[4] = {zc0 * 48 + xo0, zc1 * 48 + xo0, zc0 * 48 + xo1, zc1 * 48 + xo1};
+    int tix[4];
+    if constexpr (kSlab == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tix[c] = tex_base + (off[c] >> 4);
+    } else {
+      constexpr int P = tex_parts(kTexChunks);
+      const int xc0 = tex_base + (step ? c1 : c0), xc1 = tex_base + (step ? c2 : c1);
+      tix[0] = (xc0 + zc0) * P; tix[1] = (xc0 + zc1) * P;
+      tix[2] = (xc1 + zc0) * P; tix[3] = (xc1 + zc1) * P;
+    }
+    const float w[4] = {wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1};
+    blend_apply_q<kTexChunks, kSlab>(slab_b, args.slab_tex, off, tix, w, pr[i], pg[i], pb[i],
+                                     o_r[i], o_g[i], o_b[i]);
+  }
+  if constexpr (kStore == 0) {
+    store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
+    fence_proxy_async_smem();
+  } else {
+    float* op = out_row + static_cast<size_t>(x0 + 4 * q) * 3;
+    stg128_stream(op, o_r[0], o_g[0], o_b[0], o_r[1]);
+    stg128_stream(op + 4, o_g[1], o_b[1], o_r[2], o_g[2]);
+    stg128_stream(op + 8, o_b[2], o_r[3], o_g[3], o_b[3]);
+  }
+}
+
+template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = 512,
+          int kMinBlocks = 2>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+slice_apply_rows_async_kernel(const TmaArgs args) {
+  static_assert(kTexChunks > 0, "the issuer-warp kernel serves part of the gather by texture");
+  static_assert(kLean || (kStore == 0 && kSlab == 0), "the switches exist in the lean form only");
+  static_assert(kSlab == 0 || (kTexChunks >= 4 && kTexChunks <= 8), "part workspace: 4..8 chunks");
+  constexpr int kMathWarps = kThreads / 32 - 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SliceGeom& g = args.g;
+  const TmaPlan& pl = args.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]  TMA landed
+  uint64_t* done = full + kMaxStages;                    // [kMaxStages]  every math warp is through
+  uint64_t* slab_full = done + kMaxStages;               // [2]
+  unsigned char* raw0 = smem + pl.off_raw;               // two slab rows
+  unsigned char* stage_base = smem + pl.off_stage;
+
+  // Work split in ITEMS (row segments), not rows: 17280 rows over 296 CTAs leave some CTAs 59 rows
+  // and others 58 (1.1 % of the kernel is the tail); in half-row items the imbalance is 0.2 %.
+  // A CTA covers items [i_begin, i_end): rows r_begin .. r_end-1, the first row from pixel
+  // x_first, the last row up to pixel x_last (a row split between two CTAs has its slab row
+  // loaded by both).
+  const long long total_items = static_cast<long long>(g.B) * g.rows * pl.nseg;
+  const long long i_begin = total_items * blockIdx.x / gridDim.x;
+  const long long i_end = total_items * (blockIdx.x + 1) / gridDim.x;
+  // Programmatic dependent launch (no-ops when launched without the attribute): let the next
+  // kernel in the stream be scheduled as this grid's CTAs retire.
+  grid_launch_dependents();
+  if (i_end <= i_begin) return;
+  const long long r_begin = i_begin / pl.nseg, r_end = (i_end - 1) / pl.nseg + 1;
+  const int x_first = static_cast<int>(i_begin - r_begin * pl.nseg) * pl.seg_px;
+  const int x_last = min(g.W, (static_cast<int>((i_end - 1) - (r_end - 1) * pl.nseg) + 1) * pl.seg_px);
+  auto row_x0 = [&](long long row) { return row == r_begin ? x_first : 0; };
+  auto row_x1 = [&](long long row) { return row == r_end - 1 ? x_last : g.W; };
+
+  if (tid == 0) {
+    for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kMathWarps); }
+    mbar_init(&slab_full[0], 1);
+    mbar_init(&slab_full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();  // the only block-wide barrier
+
+  const int NS = pl.stages;
+  const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+  auto arrive = [&](uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  };
+
+  if (warp == kMathWarps) {
+    // ------------------------------- issuer warp --------------------------------------------
+    // Lane 0 issues every bulk copy; the whole warp blends slab rows when kSlab == 1.
+    if (kSlab == 0 && lane != 0) return;
+    auto make_slab = [&](long long row) {
+      const int rb = static_cast<int>(row - r_begin) & 1;
+      if constexpr (kSlab == 0) {
+        if (lane == 0) {
+          mbar_expect_tx(&slab_full[rb], slab_bytes);
+          tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
+                      args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes,
+                      &slab_full[rb]);
+        }
+      } else {
+        // yslab[r] = (1 - fy) G[b][gy0] + fy G[b][gy1], exactly yblend_rows_kernel's arithmetic
+        const int b = static_cast<int>(row / g.rows);
+        const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
+        const Axis ay = spatial_axis(y, g.scale_y);
+        const float wy1 = ay.f, wy0 = 1.0f - ay.f;
+        const float* gb = args.grid + static_cast<size_t>(b) * g.gh * pl.row_floats;
+        const float4* a4 = reinterpret_cast<const float4*>(
+            gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * pl.row_floats);
+        const float4* b4 = reinterpret_cast<const float4*>(
+            gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * pl.row_floats);
+        float4* s4 = reinterpret_cast<float4*>(raw0 + static_cast<size_t>(rb) * slab_bytes);
+        const int n4 = pl.row_floats / 4;
+        // six cells' loads in flight per lane and batch (L2 latency, not bandwidth, is the cost)
+        for (int e0 = lane; e0 < n4; e0 += 32 * 6) {
+          float4 va[6], vb[6];
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {
+            const int e = min(e0 + 32 * u, n4 - 1);
+            va[u] = ldg128_stream(a4 + e);
+            vb[u] = ldg128_stream(b4 + e);
+          }
+#pragma unroll
+          for (int u = 0; u < 6; ++u)
+            if (e0 + 32 * u < n4) s4[e0 + 32 * u] = lerp4(wy0, va[u], wy1, vb[u]);
+        }
+        __syncwarp();
+        if (lane == 0) arrive(&slab_full[rb]);
+      }
+    };
+    // load cursor: runs NS - 1 items ahead of the math warps
+    long long l_row = r_begin;
+    int l_x0 = x_first, l_s = 0;
+    auto issue_next_load = [&]() {  // lane 0
+      if (l_row >= r_end) return;
+      const int npx = min(pl.seg_px, g.W - l_x0);
+      unsigned char* st = stage_base + static_cast<size_t>(l_s) * pl.stage_bytes;
+      const size_t pix = static_cast<size_t>(l_row) * g.W + l_x0;
+      mbar_expect_tx(&full[l_s], static_cast<uint32_t>(npx) * 16u);
+      tma_load_1d(st, args.input + pix * 12, static_cast<uint32_t>(npx) * 12u, &full[l_s]);
+      tma_load_1d(st + pl.off_guide, args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[l_s]);
+      if (++l_s == NS) l_s = 0;
+      l_x0 += pl.seg_px;
+      if (l_x0 >= row_x1(l_row)) { l_x0 = 0; ++l_row; }
+    };
+    // kStore 0: the stage refilled after item i is item i-1's (its bulk store must have drained);
+    // kStore 1: item i's own stage -- one more item of prefetch from the same ring.
+    // The pixel tensors are the caller's inputs (complete before the pre-pass started): their
+    // loads may precede the dependency wait; the workspace written by the pre-pass may not.
+    if (lane == 0)
+      for (int i = 0; i < NS - (kStore == 0 ? 1 : 0); ++i) issue_next_load();
+    grid_dependency_wait();
+    make_slab(r_begin);
+    if (r_begin + 1 < r_end) make_slab(r_begin + 1);
+
+    // Lane 0 alone runs the per-item protocol; the other lanes park at the row's __syncwarp (a
+    // blocked WARPSYNC costs nothing, whereas 31 lanes spinning in a try_wait loop on the same
+    // mbarrier delay lane 0's serial section: measured +10 % kernel time).
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long row = r_begin; row < r_end; ++row) {
+      if (lane == 0) {
+        const int x_end = row_x1(row);
+        for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
+          mbar_wait(&done[s], ph);  // every math warp is through with this stage
+          if constexpr (kStore == 0) {  // results were written in place (and proxy-fenced)
+            const int npx = min(pl.seg_px, g.W - x0);
+            unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+            const size_t pix = static_cast<size_t>(row) * g.W + x0;
+            tma_store_1d(args.out + pix * 12, st, static_cast<uint32_t>(npx) * 12u);
+            tma_store_commit();
+            if (l_row < r_end) {
+              tma_store_wait_read<1>();  // the previous item's store has drained the stage refilled now
+              issue_next_load();
+            }
+          } else {
+            issue_next_load();          // refills THIS stage: nothing reads it any more
+          }
+          if (++s == NS) { s = 0; ph ^= 1u; }
+        }
+      }
+      __syncwarp();
+      // the row's slab buffer is free: every math warp arrived after its last read of it
+      if (row + 2 < r_end) make_slab(row + 2);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+    return;
+  }
+
+  // --------------------------------- math warps ---------------------------------------------
+  const int q = warp * 32 + lane;  // this thread's quad inside a segment
+  const int cells = g.gw * g.gd;
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long row = r_begin; row < r_end; ++row) {
+    const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
+    mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
+    const unsigned char* slab_b = raw0 + static_cast<size_t>(rb) * slab_bytes;
+    const int tex_base = static_cast<int>(row) * (kSlab == 0 ? cells * 3 : cells);
+    float* out_row = reinterpret_cast<float*>(args.out) + static_cast<size_t>(row) * g.W * 3;
+    const int x_end = row_x1(row);
+    for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
+      const int npx = min(pl.seg_px, g.W - x0);
+      unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+      mbar_wait(&full[s], ph);
+      if (q * 4 < npx) {
+        if constexpr (kLean)
+          process_quad_lean<kTexChunks, kStore, kSlab>(args, st, st, st + pl.off_guide, slab_b,
+                                                       tex_base, out_row, x0, q);
+        else
+          process_quad<GuideFromInput, kTexChunks>(args, GuideFromInput{}, st, st, st + pl.off_guide,
+                                                   reinterpret_cast<const float*>(slab_b), tex_base,
+                                                   row, x0, q);
+      }
+      __syncwarp();
+      if (lane == 0) arrive(&done[s]);
+      if (++s == NS) { s = 0; ph ^= 1u; }
+    }
+  }
+}
+
+template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = kAsyncThreads,
+          int kMinBlocks = 2>
+static int launch_async(const TmaArgs& a, cudaStream_t stream, bool pdl) {
+  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kStore, kSlab, kThreads, kMinBlocks>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       a.p.smem_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = launch_maybe_pdl(kern, static_cast<unsigned>(a.p.ctas), kThreads,
+                       static_cast<size_t>(a.p.smem_bytes), stream, pdl, a);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Knobs -> instantiation (launch_slice_apply_impl has validated them).
+int launch_async_form(const TmaArgs& a, int chunks, bool lean, int store, int slab, int async_threads,
+                      int async_occ, bool pdl, cudaStream_t stream) {
+      if (async_threads != 512 && lean && !store && !slab) {
+#define HDRNET_ASYNC_SHAPE(K)                                                                  \
+        if (chunks == K) {                                                                       \
+          if (async_threads == 352) return launch_async<K, true, 0, 0, 352, 2>(a, stream, pdl);       \
+          if (async_occ == 3) return launch_async<K, true, 0, 0, 224, 3>(a, stream, pdl);            \
+          return launch_async<K, true, 0, 0, 224, 4>(a, stream, pdl);                                 \
+        }
+        HDRNET_ASYNC_SHAPE(4)
+        HDRNET_ASYNC_SHAPE(5)
+        HDRNET_ASYNC_SHAPE(6)
+#undef HDRNET_ASYNC_SHAPE
+        return HDRNET_E_UNSUPPORTED;
+      }
+      if (!lean) {
+        switch (chunks) {
+          case 5: return launch_async<5, false>(a, stream, pdl);
+          default: return launch_async<kTexChunksDefault, false>(a, stream, pdl);
+        }
+      }
+#define HDRNET_ASYNC_CASE(K)                                                              \
+      if (chunks == K) {                                                                    \
+        if (store && slab) return launch_async<K, true, 1, 1>(a, stream, pdl);                   \
+        if (store) return launch_async<K, true, 1, 0>(a, stream, pdl);                           \
+        if (slab) return launch_async<K, true, 0, 1>(a, stream, pdl);                            \
+        return launch_async<K, true, 0, 0>(a, stream, pdl);                                      \
+      }
+      HDRNET_ASYNC_CASE(4)
+      HDRNET_ASYNC_CASE(5)
+      HDRNET_ASYNC_CASE(6)
+#undef HDRNET_ASYNC_CASE
+      if (chunks == 3) return launch_async<3, true, 0, 0>(a, stream, pdl);
+      return HDRNET_E_UNSUPPORTED;
+}
+
+}  // namespace hdrnet_b200
