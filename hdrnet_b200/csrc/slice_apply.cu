@@ -26,6 +26,13 @@
 //     only on-chip gather path that does not share the LSU crossbar.
 //   * template parameter GuideFn fuses the curves / pointwise-NN guide (model path, 24 B/px).
 // slice_rows_tma_kernel is the un-fused bilateral_slice on the same plan (write-bound).
+//
+// Files: slice_rows.cuh (device code shared by the row kernels: tile accessors, 4-corner blend,
+// guide sources, plan / argument structs), this file (generic kernels, the block-synchronous row
+// kernel, the un-fused slice kernel, the y pre-pass, planning, kernel selection, C-ABI),
+// slice_apply_async.cu (issuer-warp form: what AUTO runs for large images with a workspace),
+// slice_apply_variants.cu + slice_apply_zsort.cu (opt-in forms that measured slower),
+// slice_apply_tc.cu (experimental tensor-core forms).
 #include <cuda_runtime.h>
 
 #include <algorithm>
