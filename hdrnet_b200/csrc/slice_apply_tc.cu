@@ -636,9 +636,17 @@ slice_apply_rows_tcg_kernel(const TcArgs args) {
             tc_ld16(c0 + 48, d11);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const float w00 = wx0 * wz0, w01 = wx0 * wz1, w10 = wx1 * wz0, w11 = wx1 * wz1;
+            // packed fp32x2 (FFMA2), the row kernels' order of operations
+            const unsigned long long W00 = pack2(w00, w00), W01 = pack2(w01, w01);
+            const unsigned long long W10 = pack2(w10, w10), W11 = pack2(w11, w11);
 #pragma unroll
-            for (int c = 0; c < 12; ++c)
-              v[c] = fmaf(w11, d11[c], fmaf(w10, d10[c], fmaf(w01, d01[c], w00 * d00[c])));
+            for (int c = 0; c < 12; c += 2) {
+              const unsigned long long acc =
+                  fma2(W11, pack2(d11[c], d11[c + 1]),
+                       fma2(W10, pack2(d10[c], d10[c + 1]),
+                            fma2(W01, pack2(d01[c], d01[c + 1]), mul2(W00, pack2(d00[c], d00[c + 1])))));
+              unpack2(acc, v[c], v[c + 1]);
+            }
           } else {
             // the tile's three cells, weighted: a cell that is not one of the pixel's two gets 0
             float wc[3];
