@@ -930,7 +930,9 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       bool pdl = kAsyncPdlDefault;   // programmatic dependent launch of pre-pass and row kernel
       if (const char* e = std::getenv("HDRNET_ASYNC_PDL")) pdl = std::atoi(e) != 0;
       launch_yblend(grid, gs.workspace, g, plan.row_floats, slab ? (chunks == 4 ? 1 : 2) : 0, stream, pdl);
-      return launch_async_form(a, chunks, lean, store, slab, async_threads, async_occ, pdl, stream);
+      bool pipe = false;             // HDRNET_ASYNC_PIPE=1: texture fetches one pixel ahead (not yet run)
+      if (const char* e = std::getenv("HDRNET_ASYNC_PIPE")) pipe = std::atoi(e) != 0;
+      return launch_async_form(a, chunks, lean, store, slab, async_threads, async_occ, pdl, pipe, stream);
     }
     launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);
     if (variant == HDRNET_VARIANT_TEX_WS) {

@@ -202,10 +202,138 @@ __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const uns
   }
 }
 
+// kPipe (HDRNET_ASYNC_PIPE=1, opt-in, NOT YET RUN ON A GPU): the same quad with the texture fetches
+// software-pipelined one pixel ahead.  The final capture of the default form shows a quarter of
+// all warp-state samples on the FFMA2 that consume a pixel's texture results, issued ~25
+// instructions after the TLD burst; here pixel i+1's indices, weights and TLDs are issued before
+// pixel i's shared-memory chunks and FMAs.  Two pixels' texture data in flight cost 2 x 4 x
+// kTexChunks registers: meant for the 352-thread / 88-register shape.  Same operations in the same
+// order per pixel: identical bits.
+template <int kTexChunks>
+struct PixFront {
+  int off[4];                 // byte offsets of the four corners in the slab row
+  float w[4];                 // corner weights
+  float4 t[kTexChunks];       // texture-fetched chunks: ids 12 - kTexChunks .. 11 (id = 3 corner + part)
+};
+
+template <int kTexChunks>
+__device__ __forceinline__ void pix_front(const TmaArgs& args, int tex_base, float gv, float tx_i,
+                                          bool first, float fl0, float fl1, int b0, int b1, int b2,
+                                          float gd_f, float& fx_out, PixFront<kTexChunks>& f) {
+  const SliceGeom& g = args.g;
+  const bool step = !first && (tx_i >= fl1);
+  const float fx = tx_i - (step ? fl1 : fl0);
+  const int xo0 = step ? b1 : b0;
+  const int xo1 = step ? b2 : b1;
+  const float tz = __fsub_rn(__fmul_rn(gv, gd_f), 0.5f);
+  const int iz = __float2int_rd(tz);
+  const float fz = tz - static_cast<float>(iz);
+  const int zc0 = clampi(iz, 0, g.gd - 1);
+  const int zc1 = clampi(iz + 1, 0, g.gd - 1);
+  float wz0, wz1;
+  smoothed_weights(fz, wz0, wz1);
+  const float wx1 = fx, wx0 = 1.0f - fx;
+  f.off[0] = zc0 * 48 + xo0; f.off[1] = zc1 * 48 + xo0;
+  f.off[2] = zc0 * 48 + xo1; f.off[3] = zc1 * 48 + xo1;
+  f.w[0] = wx0 * wz0; f.w[1] = wx0 * wz1; f.w[2] = wx1 * wz0; f.w[3] = wx1 * wz1;
+  fx_out = fx;
+#pragma unroll
+  for (int id = 12 - kTexChunks; id < 12; ++id) {
+    const int c = id / 3, p = id - 3 * c;
+    f.t[id - (12 - kTexChunks)] = tex1Dfetch<float4>(args.slab_tex, tex_base + (f.off[c] >> 4) + p);
+  }
+}
+
+template <int kTexChunks, int kC, int kP>
+__device__ __forceinline__ ulonglong2 pipe_chunk(const unsigned char* __restrict__ slab_b,
+                                                 const PixFront<kTexChunks>& f) {
+  constexpr int id = 3 * kC + kP;
+  if constexpr (id >= 12 - kTexChunks) {
+    const float4 v = f.t[id - (12 - kTexChunks)];
+    ulonglong2 r;
+    r.x = pack2(v.x, v.y);
+    r.y = pack2(v.z, v.w);
+    return r;
+  } else {
+    return *reinterpret_cast<const ulonglong2*>(slab_b + f.off[kC] + 16 * kP);
+  }
+}
+
+template <int kTexChunks>
+__device__ __forceinline__ void pix_back(const unsigned char* __restrict__ slab_b,
+                                         const PixFront<kTexChunks>& f, float r, float g, float b,
+                                         float& out_r, float& out_g, float& out_b) {
+  const unsigned long long W00 = pack2(f.w[0], f.w[0]), W01 = pack2(f.w[1], f.w[1]);
+  const unsigned long long W10 = pack2(f.w[2], f.w[2]), W11 = pack2(f.w[3], f.w[3]);
+  const ulonglong2 a0 = pipe_chunk<kTexChunks, 0, 0>(slab_b, f), a1 = pipe_chunk<kTexChunks, 0, 1>(slab_b, f);
+  const ulonglong2 a2 = pipe_chunk<kTexChunks, 0, 2>(slab_b, f), b0 = pipe_chunk<kTexChunks, 1, 0>(slab_b, f);
+  const ulonglong2 b1 = pipe_chunk<kTexChunks, 1, 1>(slab_b, f), b2 = pipe_chunk<kTexChunks, 1, 2>(slab_b, f);
+  const ulonglong2 c0 = pipe_chunk<kTexChunks, 2, 0>(slab_b, f), c1 = pipe_chunk<kTexChunks, 2, 1>(slab_b, f);
+  const ulonglong2 c2 = pipe_chunk<kTexChunks, 2, 2>(slab_b, f), d0 = pipe_chunk<kTexChunks, 3, 0>(slab_b, f);
+  const ulonglong2 d1 = pipe_chunk<kTexChunks, 3, 1>(slab_b, f), d2 = pipe_chunk<kTexChunks, 3, 2>(slab_b, f);
+  unsigned long long acc[6];  // blend_apply's order of operations
+  acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
+  acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
+  acc[2] = fma2(W11, d1.x, fma2(W10, c1.x, fma2(W01, b1.x, mul2(W00, a1.x))));
+  acc[3] = fma2(W11, d1.y, fma2(W10, c1.y, fma2(W01, b1.y, mul2(W00, a1.y))));
+  acc[4] = fma2(W11, d2.x, fma2(W10, c2.x, fma2(W01, b2.x, mul2(W00, a2.x))));
+  acc[5] = fma2(W11, d2.y, fma2(W10, c2.y, fma2(W01, b2.y, mul2(W00, a2.y))));
+  float a0f, a1f, a2f, a3f;
+  unpack2(acc[0], a0f, a1f);
+  unpack2(acc[1], a2f, a3f);
+  out_r = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[2], a0f, a1f);
+  unpack2(acc[3], a2f, a3f);
+  out_g = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+  unpack2(acc[4], a0f, a1f);
+  unpack2(acc[5], a2f, a3f);
+  out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
+}
+
+template <int kTexChunks>
+__device__ __forceinline__ void process_quad_lean_pipe(const TmaArgs& args, const unsigned char* tile,
+                                                       unsigned char* out_tile,
+                                                       const unsigned char* guide_tile,
+                                                       const unsigned char* slab_b, int tex_base,
+                                                       int x0, int q) {
+  const SliceGeom& g = args.g;
+  const float gd_f = static_cast<float>(g.gd);
+  float pr[4], pg[4], pb[4];
+  load_quad<kPxF32>(tile, q, pr, pg, pb);
+  const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
+  const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+  const float xf = static_cast<float>(x0 + 4 * q);
+  float tx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    tx[i] = __fsub_rn(__fmul_rn(__fadd_rn(xf, static_cast<float>(i) + 0.5f), g.scale_x), 0.5f);
+  const int ix0 = __float2int_rd(tx[0]);
+  const float fl0 = static_cast<float>(ix0), fl1 = fl0 + 1.0f;
+  const int b0 = clampi(ix0, 0, g.gw - 1) * g.gd * 48;
+  const int b1 = clampi(ix0 + 1, 0, g.gw - 1) * g.gd * 48;
+  const int b2 = clampi(ix0 + 2, 0, g.gw - 1) * g.gd * 48;
+
+  PixFront<kTexChunks> f[2];
+  float fx_unused;
+  pix_front<kTexChunks>(args, tex_base, gv[0], tx[0], true, fl0, fl1, b0, b1, b2, gd_f, fx_unused, f[0]);
+  float o_r[4], o_g[4], o_b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i + 1 < 4)   // next pixel's indices, weights and texture fetches first ...
+      pix_front<kTexChunks>(args, tex_base, gv[i + 1], tx[i + 1], false, fl0, fl1, b0, b1, b2, gd_f,
+                            fx_unused, f[(i + 1) & 1]);
+    // ... then this pixel's shared-memory chunks and arithmetic
+    pix_back<kTexChunks>(slab_b, f[i & 1], pr[i], pg[i], pb[i], o_r[i], o_g[i], o_b[i]);
+  }
+  store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
+  fence_proxy_async_smem();
+}
+
 template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = 512,
-          int kMinBlocks = 2>
+          int kMinBlocks = 2, bool kPipe = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 slice_apply_rows_async_kernel(const TmaArgs args) {
+  static_assert(!kPipe || (kLean && kStore == 0 && kSlab == 0), "pipelined quad: plain lean form only");
   static_assert(kTexChunks > 0, "the issuer-warp kernel serves part of the gather by texture");
   static_assert(kLean || (kStore == 0 && kSlab == 0), "the switches exist in the lean form only");
   static_assert(kSlab == 0 || (kTexChunks >= 4 && kTexChunks <= 8), "part workspace: 4..8 chunks");
@@ -372,7 +500,9 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
       unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
       mbar_wait(&full[s], ph);
       if (q * 4 < npx) {
-        if constexpr (kLean)
+        if constexpr (kPipe)
+          process_quad_lean_pipe<kTexChunks>(args, st, st, st + pl.off_guide, slab_b, tex_base, x0, q);
+        else if constexpr (kLean)
           process_quad_lean<kTexChunks, kStore, kSlab>(args, st, st, st + pl.off_guide, slab_b,
                                                        tex_base, out_row, x0, q);
         else
@@ -388,9 +518,9 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
 }
 
 template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = kAsyncThreads,
-          int kMinBlocks = 2>
+          int kMinBlocks = 2, bool kPipe = false>
 static int launch_async(const TmaArgs& a, cudaStream_t stream, bool pdl) {
-  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kStore, kSlab, kThreads, kMinBlocks>;
+  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kStore, kSlab, kThreads, kMinBlocks, kPipe>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -402,7 +532,19 @@ static int launch_async(const TmaArgs& a, cudaStream_t stream, bool pdl) {
 
 // Knobs -> instantiation (launch_slice_apply_impl has validated them).
 int launch_async_form(const TmaArgs& a, int chunks, bool lean, int store, int slab, int async_threads,
-                      int async_occ, bool pdl, cudaStream_t stream) {
+                      int async_occ, bool pdl, bool pipe, cudaStream_t stream) {
+  if (pipe) {   // opt-in: texture fetches one pixel ahead (plain lean form, 4 / 5 chunks, 512 x 2 or 352 x 2)
+    if (!lean || store || slab || (chunks != 4 && chunks != 5)) return HDRNET_E_UNSUPPORTED;
+    if (async_threads == 512) {
+      if (chunks == 4) return launch_async<4, true, 0, 0, 512, 2, true>(a, stream, pdl);
+      return launch_async<5, true, 0, 0, 512, 2, true>(a, stream, pdl);
+    }
+    if (async_threads == 352) {
+      if (chunks == 4) return launch_async<4, true, 0, 0, 352, 2, true>(a, stream, pdl);
+      return launch_async<5, true, 0, 0, 352, 2, true>(a, stream, pdl);
+    }
+    return HDRNET_E_UNSUPPORTED;
+  }
       if (async_threads != 512 && lean && !store && !slab) {
 #define HDRNET_ASYNC_SHAPE(K)                                                                  \
         if (chunks == K) {                                                                       \

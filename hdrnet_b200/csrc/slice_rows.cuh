@@ -314,7 +314,7 @@ static cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), unsigned grid, unsig
 // Entry points of the other translation units (non-template: the knobs select the instantiation).
 //   slice_apply_async.cu
 int launch_async_form(const TmaArgs& a, int chunks, bool lean, int store, int slab, int threads, int occ,
-                      bool pdl, cudaStream_t stream);
+                      bool pdl, bool pipe, cudaStream_t stream);
 //   slice_apply_variants.cu
 int launch_texin_form(const TmaArgs& a, int chunks, cudaStream_t stream);
 int launch_ws_form(const TmaArgs& a, cudaStream_t stream);

@@ -379,3 +379,24 @@ def test_tensor_core_form_rejects_shapes_it_cannot_take():
         grid, guide, inp = rand_case(3, B, H, W, gh, gw, gd)
         with pytest.raises(ValueError):
             run_apply(grid, guide, inp, True, "tc")
+
+
+@experimental
+@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_PIPE="1"), dict(HDRNET_ASYNC_PIPE="1", HDRNET_TEX_CHUNKS="4"),
+                                 dict(HDRNET_ASYNC_PIPE="1", HDRNET_ASYNC_THREADS="352"),
+                                 dict(HDRNET_ASYNC_PIPE="1", HDRNET_ASYNC_THREADS="352", HDRNET_TEX_CHUNKS="4")],
+                         ids=lambda e: ",".join(f"{k[7:].lower()}={v}" for k, v in e.items()))
+def test_issuer_warp_kernel_pipelined_texture_fetches_are_bitwise_equal(env, monkeypatch):
+    """HDRNET_ASYNC_PIPE=1 (texture fetches issued one pixel ahead; written after the round's GPU
+    budget was spent): same operations in the same order per pixel, so identical bits."""
+    cases = [rand_case(5, 2, 64, 3840, 16, 16, 8, signed=True),
+             rand_case(6, 1, 700, 1028, 5, 7, 3, signed=True)]
+    cases[1][1][0, :, ::5] = 1.75
+    cases[1][1][0, :, 1::5] = -0.6
+    for grid, guide, inp in cases:
+        for k in ("HDRNET_ASYNC_PIPE", "HDRNET_ASYNC_THREADS", "HDRNET_TEX_CHUNKS"):
+            monkeypatch.delenv(k, raising=False)
+        want = run_apply(grid, guide, inp, True, "tex")
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        assert np.array_equal(want, run_apply(grid, guide, inp, True, "tex_async"))

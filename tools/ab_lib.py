@@ -20,7 +20,7 @@ guide = torch.rand(B, H, W, device="cuda", generator=gen)
 inp = torch.rand(B, H, W, 3, device="cuda", generator=gen)
 KNOBS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC",
          "HDRNET_ASYNC_LEAN", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB", "HDRNET_ASYNC_THREADS", "HDRNET_ASYNC_OCC",
-         "HDRNET_ASYNC_PDL")
+         "HDRNET_ASYNC_PDL", "HDRNET_ASYNC_PIPE")
 libs, cfgs = {}, []
 for spec in sys.argv[1:]:
     parts = spec.split(":")

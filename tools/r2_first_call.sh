@@ -24,3 +24,11 @@ for v in 8 9; do
   timeout 200 ncu --set full --clock-control none --import-source on -k regex:"slice_apply_rows_tc" -s 2 -c 1 \
       -f -o gpurun_out/r2_prof_tc$v python tools/prof_variant.py $v > gpurun_out/r2_ncu_tc$v.log 2>&1; echo "ncu $v exit $?"
 done
+# 5. same-box A/B of the issuer-warp form's opt-in knobs that have not been measured yet:
+#    texture fetches one pixel ahead (HDRNET_ASYNC_PIPE), in the 64- and the 80-register shape
+L=hdrnet_b200/lib/libhdrnet_b200.so
+HDRNET_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_slice_apply_gpu.py -q --timeout 120 -p no:cacheprovider \
+    -k "pipelined" 2>&1 | tail -5
+AB_ROUNDS=5 timeout 300 python tools/ab_lib.py $L:7 $L:7:HDRNET_ASYNC_PIPE=1 $L:7:HDRNET_ASYNC_THREADS=352 \
+  $L:7:HDRNET_ASYNC_THREADS=352,HDRNET_ASYNC_PIPE=1 $L:7:HDRNET_TEX_CHUNKS=4,HDRNET_ASYNC_THREADS=352,HDRNET_ASYNC_PIPE=1 \
+  $L:7:HDRNET_TEX_CHUNKS=6,HDRNET_ASYNC_THREADS=352 > gpurun_out/r2_ab_pipe.txt 2>&1; grep -v bursts gpurun_out/r2_ab_pipe.txt | tail -8
