@@ -965,6 +965,20 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
       if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);
       return launch_texin_form(a, chunks, stream);
     }
+    // opt-in (HDRNET_FUSED_ASYNC=1, not yet run): the fused-guide forms under the issuer-warp control flow
+    if (gs.mode != 0 && variant == HDRNET_VARIANT_TEX) {
+      bool fused_async = false;
+      if (const char* e = std::getenv("HDRNET_FUSED_ASYNC")) fused_async = std::atoi(e) != 0;
+      TmaPlan fplan;
+      if (fused_async &&
+          make_tma_plan(g, device_max_smem_optin(), sms, &fplan, /*tex_mode=*/true, kFusedAsyncMathThreads,
+                        gs.in_fmt, gs.out_fmt, 2) &&
+          fplan.resident == 2 && fplan.stages >= 3) {
+        a.p = fplan;
+        a.guide_out = gs.guide_out;
+        return launch_async_fused(a, gs.mode, gs.curves, gs.nn, gs.in_fmt, gs.out_fmt, stream);
+      }
+    }
     if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
                         return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt); }
     if (gs.mode == 2) {

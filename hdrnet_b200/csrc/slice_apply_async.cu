@@ -530,6 +530,162 @@ static int launch_async(const TmaArgs& a, cudaStream_t stream, bool pdl) {
   return static_cast<int>(cudaGetLastError());
 }
 
+// =========================================================================================
+// Issuer-warp control flow for the FUSED-GUIDE (model path) forms -- opt-in, HDRNET_FUSED_ASYNC=1,
+// NOT YET RUN ON A GPU.
+// =========================================================================================
+// HDRNetCurves / HDRNetPointwiseNNGuide compute the guide from the pixel's RGB in registers
+// (24 B/px, models.py:43-59) and may read / write integer pixels; they still run the
+// block-synchronous kernel (slice_apply.cu).  This is that kernel's per-pixel code (process_quad:
+// identical bits) under the issuer-warp control flow above: math warps that only wait for their
+// stage and ARRIVE on done[s], one warp that issues every bulk copy.  8 math warps + the issuer
+// (288 threads, 112 registers at two CTAs per SM: the fused forms are issue-bound and want their
+// registers), texture chunks as the block-synchronous fused form (4).
+constexpr int kFusedAsyncThreads = 288;
+
+template <class GuideFn, int kTexChunks, int kIn, int kOut>
+__global__ void __launch_bounds__(kFusedAsyncThreads, 2)
+slice_apply_rows_async_fused_kernel(const TmaArgs args, const __grid_constant__ GuideFn guide_fn) {
+  static_assert(!GuideFn::kFromInput, "fused-guide forms only");
+  constexpr int kMathWarps = kFusedAsyncThreads / 32 - 1;
+  constexpr uint32_t kInBpp = 3u * px_bytes_per_channel(kIn), kOutBpp = 3u * px_bytes_per_channel(kOut);
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SliceGeom& g = args.g;
+  const TmaPlan& pl = args.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* done = full + kMaxStages;
+  uint64_t* slab_full = done + kMaxStages;
+  unsigned char* raw0 = smem + pl.off_raw;
+  unsigned char* stage_base = smem + pl.off_stage;
+
+  const long long total_items = static_cast<long long>(g.B) * g.rows * pl.nseg;
+  const long long i_begin = total_items * blockIdx.x / gridDim.x;
+  const long long i_end = total_items * (blockIdx.x + 1) / gridDim.x;
+  if (i_end <= i_begin) return;
+  const long long r_begin = i_begin / pl.nseg, r_end = (i_end - 1) / pl.nseg + 1;
+  const int x_first = static_cast<int>(i_begin - r_begin * pl.nseg) * pl.seg_px;
+  const int x_last = min(g.W, (static_cast<int>((i_end - 1) - (r_end - 1) * pl.nseg) + 1) * pl.seg_px);
+  auto row_x0 = [&](long long row) { return row == r_begin ? x_first : 0; };
+  auto row_x1 = [&](long long row) { return row == r_end - 1 ? x_last : g.W; };
+
+  if (tid == 0) {
+    for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kMathWarps); }
+    mbar_init(&slab_full[0], 1);
+    mbar_init(&slab_full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int NS = pl.stages;
+  const uint32_t slab_bytes = static_cast<uint32_t>(pl.row_floats) * 4u;
+  // same pixel size in and out: the result overwrites the input tile (plan.off_out == 0)
+  auto stage_out = [&](unsigned char* st) { return st + (kInBpp == kOutBpp ? 0 : pl.off_out); };
+
+  if (warp == kMathWarps) {
+    // ------------------------------- issuer (lane 0) ----------------------------------------
+    if (lane != 0) return;
+    auto load_slab = [&](long long row) {
+      const int rb = static_cast<int>(row - r_begin) & 1;
+      mbar_expect_tx(&slab_full[rb], slab_bytes);
+      tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
+                  args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes, &slab_full[rb]);
+    };
+    long long l_row = r_begin;
+    int l_x0 = x_first, l_s = 0;
+    auto issue_next_load = [&]() {
+      if (l_row >= r_end) return;
+      const int npx = min(pl.seg_px, g.W - l_x0);
+      unsigned char* st = stage_base + static_cast<size_t>(l_s) * pl.stage_bytes;
+      const size_t pix = static_cast<size_t>(l_row) * g.W + l_x0;
+      mbar_expect_tx(&full[l_s], static_cast<uint32_t>(npx) * kInBpp);
+      tma_load_1d(st, args.input + pix * kInBpp, static_cast<uint32_t>(npx) * kInBpp, &full[l_s]);
+      if (++l_s == NS) l_s = 0;
+      l_x0 += pl.seg_px;
+      if (l_x0 >= row_x1(l_row)) { l_x0 = 0; ++l_row; }
+    };
+    for (int i = 0; i < NS - 1; ++i) issue_next_load();
+    load_slab(r_begin);
+    if (r_begin + 1 < r_end) load_slab(r_begin + 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long row = r_begin; row < r_end; ++row) {
+      const int x_end = row_x1(row);
+      for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
+        mbar_wait(&done[s], ph);
+        const int npx = min(pl.seg_px, g.W - x0);
+        unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+        const size_t pix = static_cast<size_t>(row) * g.W + x0;
+        tma_store_1d(args.out + pix * kOutBpp, stage_out(st), static_cast<uint32_t>(npx) * kOutBpp);
+        tma_store_commit();
+        if (l_row < r_end) {
+          tma_store_wait_read<1>();
+          issue_next_load();
+        }
+        if (++s == NS) { s = 0; ph ^= 1u; }
+      }
+      if (row + 2 < r_end) load_slab(row + 2);
+    }
+    tma_store_wait_all<0>();
+    return;
+  }
+
+  // --------------------------------- math warps ---------------------------------------------
+  const int q = warp * 32 + lane;
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long row = r_begin; row < r_end; ++row) {
+    const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
+    mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
+    const float* slab = reinterpret_cast<const float*>(raw0 + static_cast<size_t>(rb) * slab_bytes);
+    const int tex_row = static_cast<int>(row) * (pl.row_floats / 4);
+    const int x_end = row_x1(row);
+    for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
+      const int npx = min(pl.seg_px, g.W - x0);
+      unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+      mbar_wait(&full[s], ph);
+      if (q * 4 < npx)
+        process_quad<GuideFn, kTexChunks, kIn, kOut>(args, guide_fn, st, stage_out(st), st + pl.off_guide,
+                                                     slab, tex_row, row, x0, q);
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&done[s])) : "memory");
+      if (++s == NS) { s = 0; ph ^= 1u; }
+    }
+  }
+}
+
+template <class GuideFn, int kIn, int kOut>
+static int launch_async_fused_fmt(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
+  auto kern = slice_apply_rows_async_fused_kernel<GuideFn, kTexChunksDefault, kIn, kOut>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.p.smem_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  kern<<<a.p.ctas, kFusedAsyncThreads, a.p.smem_bytes, stream>>>(a, fn);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <class GuideFn>
+static int launch_async_fused_guide(const TmaArgs& a, const GuideFn& fn, int in_fmt, int out_fmt,
+                                    cudaStream_t stream) {
+  if (in_fmt == kPxF32 && out_fmt == kPxF32) return launch_async_fused_fmt<GuideFn, kPxF32, kPxF32>(a, fn, stream);
+  if (in_fmt == kPxU8 && out_fmt == kPxU8) return launch_async_fused_fmt<GuideFn, kPxU8, kPxU8>(a, fn, stream);
+  if (in_fmt == kPxU16 && out_fmt == kPxU8) return launch_async_fused_fmt<GuideFn, kPxU16, kPxU8>(a, fn, stream);
+  return HDRNET_E_UNSUPPORTED;
+}
+
+// mode 1 = curves guide, 2 = pointwise-NN guide (plan: (kFusedAsyncThreads - 32) quads per segment)
+int launch_async_fused(const TmaArgs& a, int mode, const CurvesGuideParams* curves, const NNGuideParams* nn,
+                       int in_fmt, int out_fmt, cudaStream_t stream) {
+  if (mode == 1) { GuideCurves fn; fn.p = *curves; return launch_async_fused_guide(a, fn, in_fmt, out_fmt, stream); }
+  if (mode == 2) {
+    if (nn->feats <= 16) { GuideNN<16> fn; fn.p = *nn; return launch_async_fused_guide(a, fn, in_fmt, out_fmt, stream); }
+    GuideNN<kMaxGuideFeats> fn; fn.p = *nn;
+    return launch_async_fused_guide(a, fn, in_fmt, out_fmt, stream);
+  }
+  return HDRNET_E_UNSUPPORTED;
+}
+
 // Knobs -> instantiation (launch_slice_apply_impl has validated them).
 int launch_async_form(const TmaArgs& a, int chunks, bool lean, int store, int slab, int async_threads,
                       int async_occ, bool pdl, bool pipe, cudaStream_t stream) {

@@ -315,6 +315,9 @@ static cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), unsigned grid, unsig
 //   slice_apply_async.cu
 int launch_async_form(const TmaArgs& a, int chunks, bool lean, int store, int slab, int threads, int occ,
                       bool pdl, bool pipe, cudaStream_t stream);
+int launch_async_fused(const TmaArgs& a, int mode, const CurvesGuideParams* curves, const NNGuideParams* nn,
+                       int in_fmt, int out_fmt, cudaStream_t stream);
+constexpr int kFusedAsyncMathThreads = 256;   // 8 math warps (+ the issuer warp) of the fused-guide issuer-warp form
 //   slice_apply_variants.cu
 int launch_texin_form(const TmaArgs& a, int chunks, cudaStream_t stream);
 int launch_ws_form(const TmaArgs& a, cudaStream_t stream);

@@ -10,6 +10,8 @@ What is checked, and to what bar:
     code value (and < 0.1 % of samples) when the float path runs a different family;
   * the whole image path against the oracle model: within one code value.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -166,3 +168,34 @@ def test_unsupported_formats_are_refused():
     assert lib.hdrnet_lowres_nearest_f32(z.data_ptr(), 9, z.data_ptr(), 1, 1, 1, 1, 1, 0) == -5
     with pytest.raises(TypeError):
         models.lowres_from_image(torch.zeros(1, 4, 4, 3, dtype=torch.int32, device="cuda"), 2)
+
+
+# ---- experimental (never run on a GPU): fused-guide forms under the issuer-warp control flow -----
+experimental = pytest.mark.skipif(os.environ.get("HDRNET_TEST_EXPERIMENTAL") != "1",
+                                  reason="set HDRNET_TEST_EXPERIMENTAL=1 to run the untested variants")
+
+
+@experimental
+@pytest.mark.parametrize("kind", ["curves", "nn"])
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8, np.uint16])
+def test_fused_guide_issuer_warp_form_is_bitwise_equal(kind, dtype, monkeypatch):
+    """HDRNET_FUSED_ASYNC=1 runs the same per-pixel code (process_quad) under the issuer-warp control
+    flow: the output of the model's full-resolution stage must not change by a bit."""
+    cls = models.HDRNetCurves if kind == "curves" else models.HDRNetPointwiseNNGuide
+    p = params_for(kind)
+    rng = np.random.RandomState(5)
+    B, H, W = 2, 300, 3840           # >= 2 Mi pixels: the texture-assisted fused kernel
+    if dtype == np.float32:
+        im = rng.rand(B, H, W, 3).astype(np.float32)
+        low = cuda(rng.rand(B, p["net_input_size"], p["net_input_size"], 3).astype(np.float32))
+        out_dtype = torch.float32
+    else:
+        im = rand_image(rng, B, H, W, dtype)
+        low = models.lowres_from_image(cuda(im), p["net_input_size"])
+        out_dtype = torch.uint8
+    coeffs = cls._coefficients(low, p)
+    monkeypatch.delenv("HDRNET_FUSED_ASYNC", raising=False)
+    want = cls._fullres(coeffs, cuda(im), p, out_dtype).cpu().numpy()
+    monkeypatch.setenv("HDRNET_FUSED_ASYNC", "1")
+    got = cls._fullres(coeffs, cuda(im), p, out_dtype).cpu().numpy()
+    assert np.array_equal(got, want)
