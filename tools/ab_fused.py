@@ -1,5 +1,6 @@
 """Interleaved A/B of the CTA shapes of the fused-guide (model path) row kernel at 4K x 8:
 256 threads x 2 CTAs/SM (default), 256 x 3 (HDRNET_TMA_OCC=3), 512 x 2 (HDRNET_TMA_THREADS=512),
+and the issuer-warp control flow (HDRNET_FUSED_ASYNC=1, 8 math warps + issuer),
 for the curves / pointwise-NN guides and float32 / uint8 pixels."""
 import os, sys, statistics, torch
 sys.path.insert(0, ".")
@@ -8,8 +9,9 @@ B, H, W = 8, 2160, 3840
 gen = torch.Generator(device="cuda").manual_seed(1)
 im8 = torch.randint(0, 256, (B, H, W, 3), device="cuda", generator=gen, dtype=torch.uint8)
 imf = models.image_to_float(im8)
-ENVS = {"256x2": {}, "256x3": {"HDRNET_TMA_OCC": "3"}, "512x2": {"HDRNET_TMA_THREADS": "512"}}
-KEYS = ("HDRNET_TMA_OCC", "HDRNET_TMA_THREADS")
+ENVS = {"256x2": {}, "256x3": {"HDRNET_TMA_OCC": "3"}, "512x2": {"HDRNET_TMA_THREADS": "512"},
+        "issuer-warp 288x2": {"HDRNET_FUSED_ASYNC": "1"}}
+KEYS = ("HDRNET_TMA_OCC", "HDRNET_TMA_THREADS", "HDRNET_FUSED_ASYNC")
 cases = {}
 for kind, name in (("curves", "HDRNetCurves"), ("nn", "HDRNetPointwiseNNGuide")):
     p = dict(models.DEFAULT_PARAMS, model_name=name)

@@ -32,3 +32,7 @@ HDRNET_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_slice_apply_g
 AB_ROUNDS=5 timeout 300 python tools/ab_lib.py $L:7 $L:7:HDRNET_ASYNC_PIPE=1 $L:7:HDRNET_ASYNC_THREADS=352 \
   $L:7:HDRNET_ASYNC_THREADS=352,HDRNET_ASYNC_PIPE=1 $L:7:HDRNET_TEX_CHUNKS=4,HDRNET_ASYNC_THREADS=352,HDRNET_ASYNC_PIPE=1 \
   $L:7:HDRNET_TEX_CHUNKS=6,HDRNET_ASYNC_THREADS=352 > gpurun_out/r2_ab_pipe.txt 2>&1; grep -v bursts gpurun_out/r2_ab_pipe.txt | tail -8
+# 6. fused-guide (model path) forms under the issuer-warp control flow (HDRNET_FUSED_ASYNC=1, never run)
+HDRNET_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_px_gpu.py -q --timeout 120 -p no:cacheprovider \
+    -k "issuer_warp" 2>&1 | tail -5
+timeout 200 python tools/ab_fused.py > gpurun_out/r2_ab_fused.txt 2>&1; tail -20 gpurun_out/r2_ab_fused.txt
