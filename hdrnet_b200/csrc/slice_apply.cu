@@ -687,6 +687,10 @@ int launch_slice_apply_tc(const float* guide, const float* input, float* out, co
 int launch_slice_apply_tcg(const float* guide, const float* input, float* out, const float* yslab,
                            const SliceGeom& g, int max_smem, int sms, cudaStream_t stream);
 
+// tensor-core gather form (slice_apply_mma.cu): no workspace, no pre-pass
+int launch_slice_apply_mma(const float* grid, const float* guide, const float* input, float* out,
+                           const SliceGeom& g, int nsplit, int max_smem, int sms, cudaStream_t stream);
+
 // z-bucketed variant (slice_apply_zsort.cu)
 struct ZsPlan {
   int ctas, stages, nseg, seg_px, row_floats, smem_bytes;
@@ -859,6 +863,12 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
         make_tma_plan(g, device_max_smem_optin(), sms, &ap, /*tex_mode=*/true, kAsyncThreads - 32,
                       kPxF32, kPxF32, 2) && ap.resident == 2 && ap.stages >= kAsyncAutoMinStages)
       variant = HDRNET_VARIANT_TEX_ASYNC;
+  }
+  if (variant == HDRNET_VARIANT_MMA || variant == HDRNET_VARIANT_MMA3) {
+    if (gs.mode != 0 || px || n_in != 3 || n_out != 3 || !has_offset) return HDRNET_E_UNSUPPORTED;
+    if (!aligned16(grid) || !aligned16(input) || !aligned16(out) || !aligned16(gs.guide)) return HDRNET_E_UNSUPPORTED;
+    return launch_slice_apply_mma(grid, gs.guide, input, out, g, variant == HDRNET_VARIANT_MMA3 ? 3 : 2,
+                                  device_max_smem_optin(), sms, stream);
   }
   if (variant == HDRNET_VARIANT_TC_GATHER) {   // experimental, never run: tensor-core gather form
     if (!tex_ok || gs.mode != 0 || px) return HDRNET_E_UNSUPPORTED;

@@ -85,6 +85,11 @@ extern "C" {
                                  /* engine (one-hot A, both depth rows per x cell in B, 2 MMAs  */
                                  /* M128 N96 K8), trilinear blend in registers; same limits     */
 
+#define HDRNET_VARIANT_MMA 10     /* tensor-core gather form: tiles aligned to x cells, exact   */
+                                 /* one-hot A in tensor memory, B' built in the kernel (no       */
+                                 /* workspace, no pre-pass); 2-way TF32 split of the slab        */
+#define HDRNET_VARIANT_MMA3 11    /* the same with a 3-way split (exact copy of the slab values) */
+
 HDRNET_API int hdrnet_b200_abi_version(void);
 
 /* Human-readable text for a return code of this library (static storage). */
