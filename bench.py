@@ -42,8 +42,8 @@ WORKLOAD = (f"4K ({W4K}x{H4K}) batch={B_PER_GPU} per GPU, fused slice-apply, "
 
 KERNEL_TEXT = {
     7: "tex_async (AUTO with workspace): yblend_rows_kernel pre-pass + "
-       "slice_apply_rows_async_kernel<5 texture chunks, per-quad indices, 512 threads = 15 math warps + "
-       "issuer warp>, both inside every timed step",
+       "slice_apply_rows_async_kernel<5 texture chunks, per-quad indices, math warps + issuer warp> "
+       "(threads: see `threads`), both inside every timed step",
     4: "tex (AUTO with workspace): yblend_rows_kernel pre-pass + "
        "slice_apply_rows_tma_kernel<GuideFromInput,4,2,512,f32,f32>, both inside every timed step",
     2: "tma: slice_apply_rows_tma_kernel (all-LSU form)",
@@ -215,6 +215,118 @@ def run_reference_arm(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------
+# Extra records of the GPU arm (BASELINE.json configs 2, 4, 5, the model path, a sustained run).
+# The headline `value` above them is untouched; these ride along in the same JSON line.
+# ------------------------------------------------------------------------------------------
+def _time_ms(torch, stream, fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(iters):
+        fn()
+    b.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def _op_case(torch, lib, _lib, dev, stream, B, H, W, gh, gw, gd, iters, peak):
+    """Device-resident op-API call (guide as an input, f32) through the C-ABI with a lent workspace."""
+    gen = torch.Generator(device=dev).manual_seed(7)
+    grid = torch.rand(B, gh, gw, gd, GC, device=dev, generator=gen)
+    guide = torch.rand(B, H, W, device=dev, generator=gen)
+    inp = torch.rand(B, H, W, N_IN, device=dev, generator=gen)
+    out = torch.empty(B, H, W, N_OUT, device=dev)
+    nws = int(lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))
+    ws = torch.empty(max(nws, 16) // 4, dtype=torch.float32, device=dev)
+
+    def step():
+        rc = lib.hdrnet_slice_apply_f32_ws(grid.data_ptr(), guide.data_ptr(), inp.data_ptr(), out.data_ptr(),
+                                           B, H, W, gh, gw, gd, N_IN, N_OUT, 1, _lib.VARIANT_AUTO,
+                                           ws.data_ptr(), nws, stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError(_lib.error_string(rc))
+    ms = _time_ms(torch, stream, step, iters)
+    v = ctypes.c_int()
+    lib.hdrnet_slice_apply_plan_ws(B, H, W, gh, gw, gd, N_IN, N_OUT, 1, 1, ctypes.byref(v), None, None, None)
+    nbytes = B * H * W * BYTES_PER_PX + grid.numel() * 4
+    return {"ms": round(ms, 5), "mp_s": round(B * H * W / ms / 1e3, 1), "gb_s": round(nbytes / ms / 1e6, 1),
+            "frac": round(nbytes / ms / 1e6 / peak, 4), "variant": v.value}
+
+
+def extra_records(torch, dist, lib, _lib, dev, stream, world, rank, peak, args):
+    """Everything is timed with CUDA events on the launch stream; multi-rank numbers take the max
+    over ranks.  Synthetic inputs, seeded synthetic weights (no pretrained model in the tree)."""
+    from hdrnet_b200 import models
+    ex = {}
+
+    def agg(ms):   # slowest rank
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- model path at the headline shape: guide computed in the slice-apply kernel (24 B/px) ----
+    gen = torch.Generator(device=dev).manual_seed(11 + rank)
+    im_f = torch.rand(B_PER_GPU, H4K, W4K, 3, device=dev, generator=gen)
+    model = {}
+    for name in ("HDRNetCurves", "HDRNetPointwiseNNGuide"):
+        p = dict(models.DEFAULT_PARAMS, model_name=name)
+        p["weights"] = models.init_weights(p, seed=0, model_name=name)
+        cls = getattr(models, name)
+        low = models.lowres_from_image(im_f, 256)
+        coeffs = cls._coefficients(low, p)
+        ms_full = agg(_time_ms(torch, stream, lambda: cls._fullres(coeffs, im_f, p, torch.float32), 20))
+        ms_cnn = agg(_time_ms(torch, stream, lambda: cls._coefficients(low, p), 10))
+        nbytes = B_PER_GPU * H4K * W4K * 24
+        model[name] = {"ms_guide_plus_slice_apply": round(ms_full, 5), "ms_coefficient_cnn_batch8": round(ms_cnn, 5),
+                       "bytes_per_px": 24, "gb_s": round(nbytes / ms_full / 1e6, 1),
+                       "frac": round(nbytes / ms_full / 1e6 / peak, 4),
+                       "mp_s_all_gpus": round(world * B_PER_GPU * H4K * W4K / (ms_full + ms_cnn) / 1e3, 1)}
+    ex["model_4k_x8"] = model
+    del im_f
+
+    # ---- config 4: HDR+ 16-bit linear 12 MP, 8 frames per GPU (64 over 8), uint16 in -> uint8 out ----
+    H12, W12 = 3024, 4032
+    im16 = torch.randint(0, 32768, (B_PER_GPU, H12, W12, 3), device=dev, generator=gen, dtype=torch.int32).to(torch.uint16)
+    p = dict(models.DEFAULT_PARAMS, model_name="HDRNetCurves")
+    p["weights"] = models.init_weights(p, seed=0, model_name="HDRNetCurves")
+    cls = models.HDRNetCurves
+    low = models.lowres_from_image(im16, 256)
+    coeffs = cls._coefficients(low, p)
+    ms_k = agg(_time_ms(torch, stream, lambda: cls._fullres(coeffs, im16, p, torch.uint8), 10))
+    ms_all = agg(_time_ms(torch, stream, lambda: cls.inference_image(im16, p), 5))
+    px = B_PER_GPU * H12 * W12
+    ex["C4_12mp_u16_x8_per_gpu"] = {
+        "frames_all_gpus": B_PER_GPU * world, "ms_fullres_kernel": round(ms_k, 5),
+        "ms_inference_image": round(ms_all, 5), "bytes_per_px": 9,
+        "gb_s": round(px * 9 / ms_k / 1e6, 1), "frac": round(px * 9 / ms_k / 1e6 / peak, 4),
+        "mp_s_all_gpus": round(world * px / ms_all / 1e3, 1),
+        "path": "models.HDRNetCurves.inference_image: lowres_nearest_kernel + coefficient CNN + fused-guide "
+                "slice-apply reading uint16, writing uint8 (hdrnet/bin/run.py:145-169, :95)"}
+    del im16
+
+    if rank == 0:   # single-GPU records
+        # ---- config 2: one 1080p frame (op and model) ----
+        ex["C2_1080p_x1_op"] = _op_case(torch, lib, _lib, dev, stream, 1, 1080, 1920, GH, GW, GD, 200, peak)
+        im = torch.rand(1, 1080, 1920, 3, device=dev, generator=gen)
+        low1 = models.lowres_from_image(im, 256)
+        ms_m = _time_ms(torch, stream, lambda: cls.inference(low1, im, p), 50)
+        ms_c = _time_ms(torch, stream, lambda: cls._coefficients(low1, p), 50)
+        ex["C2_1080p_x1_model"] = {"ms_inference": round(ms_m, 5), "ms_coefficient_cnn": round(ms_c, 5),
+                                   "mp_s": round(1080 * 1920 / ms_m / 1e3, 1),
+                                   "weights": "seeded synthetic (local_laplacian_sample is not in the tree)"}
+        # ---- config 5: grid sweep at 4K x 8 ----
+        sweep = {}
+        for gh, gw, gd in ((8, 8, 4), (16, 16, 4), (16, 16, 8), (32, 32, 8), (32, 32, 16)):
+            sweep[f"{gh}x{gw}x{gd}"] = _op_case(torch, lib, _lib, dev, stream, B_PER_GPU, H4K, W4K, gh, gw, gd, 30, peak)
+        ex["C5_grid_sweep_4k_x8"] = sweep
+    return ex
+
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
@@ -231,6 +343,10 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device; hdrnet_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # Bind this rank to the CPUs (and so the memory) of its GPU's NUMA node BEFORE any pinned
+    # allocation: the end-to-end leg moves 1.9 GB per step and rank through host memory.
+    from hdrnet_b200 import parallel
+    numa_cpus = parallel.bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if args.gpus != world and rank == 0:
@@ -309,12 +425,63 @@ def run_b200_arm(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e_ok = bool(torch.equal(h_out, out.cpu()))
+    e2e_h2d = int((h_grid.numel() + h_guide.numel() + h_inp.numel()) * 4)
+    e2e_d2h = int(h_out.numel() * 4)
+    del h_grid, h_guide, h_inp, h_out
+
+    # ---- end to end, integer image path: what hdrnet/bin/run.py moves per frame -- decoded uint8
+    # pixels in, uint8 prediction out (3 + 3 B/px over PCIe), whole model (CNN + guide + slice-apply)
+    from hdrnet_b200 import models
+    mp = dict(models.DEFAULT_PARAMS, model_name="HDRNetCurves")
+    mp["weights"] = models.init_weights(mp, seed=0, model_name="HDRNetCurves")
+    h_im8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8).pin_memory()
+    h_out8 = torch.empty(B, H, W, 3, dtype=torch.uint8).pin_memory()
+
+    def e2e_u8_step():
+        d_im = h_im8.to(dev, non_blocking=True)
+        h_out8.copy_(models.HDRNetCurves.inference_image(d_im, mp), non_blocking=True)
+    e2e_u8_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_u8_step()
+    torch.cuda.synchronize()
+    e2e8_s = time.perf_counter() - t0
+    te = torch.tensor([e2e8_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e8_s = float(te.item())
+    del h_im8, h_out8
+
+    # ---- sustained: the same step for >= 2 s (the boxes power-cap under sustained load) ----
+    sus_steps = max(args.steps, int(2200.0 / max(own_launch_ms, 1e-3)))
+    sus = ClockSampler(local_rank)
+    sus.start()
+    torch.cuda.synchronize()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sus.window[0] = time.perf_counter()
+    s0.record(stream)
+    for _ in range(sus_steps):
+        step()
+    s1.record(stream)
+    torch.cuda.synchronize()
+    sus.window[1] = time.perf_counter()
+    sus.stop_flag.set()
+    sus.join(timeout=2)
+    ts = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    sus_ms = float(ts.item()) / sus_steps
+
+    peak, peak_src = measured_peaks()
+    extra = {} if args.no_extra else extra_records(torch, dist, lib, _lib, dev, stream, world, rank, peak, args)
 
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
         achieved = algo_bytes / (own_launch_ms * 1e-3) / 1e9
         variant, ctas, threads, smem = (ctypes.c_int() for _ in range(4))
         lib.hdrnet_slice_apply_plan_ws(B, H, W, GH, GW, GD, N_IN, N_OUT, 1, 1, ctypes.byref(variant),
@@ -341,14 +508,24 @@ def run_b200_arm(args):
                          "note": "duration = whole step (pre-pass + main kernel); the main kernel "
                                  "alone is ~5 % shorter (profiles/)"},
             "e2e": {"value": round(world * npix * e2e_steps / e2e_s / 1e6, 1), "unit": UNIT,
-                    "h2d_bytes_per_step": int((h_grid.numel() + h_guide.numel() + h_inp.numel()) * 4),
-                    "d2h_bytes_per_step": int(h_out.numel() * 4), "steps": e2e_steps,
+                    "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h, "steps": e2e_steps,
                     "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3),
                     "path": "hdrnet_ops.bilateral_slice_apply on pinned CPU tensors -> "
                             "hdrnet_slice_apply_host_f32 (row-band H2D/kernel/D2H pipeline)",
-                    "matches_device_result": e2e_ok},
+                    "matches_device_result": e2e_ok,
+                    "u8_image_path": {
+                        "value": round(world * npix * e2e_steps / e2e8_s / 1e6, 1), "unit": UNIT,
+                        "h2d_bytes_per_step": int(npix * 3), "d2h_bytes_per_step": int(npix * 3),
+                        "ms_per_step": round(e2e8_s / e2e_steps * 1e3, 3),
+                        "path": "pinned uint8 frames -> models.HDRNetCurves.inference_image (lowres gather + "
+                                "coefficient CNN + fused-guide slice-apply, uint8 in / out) -> pinned uint8"},
+                    "numa_cpus_bound": len(numa_cpus)},
             "gpu_launches": 2 * args.steps * world,
             "clocks": sampler.summary(),
+            "sustained": {"steps": sus_steps, "ms_per_step": round(sus_ms, 5),
+                          "value": round(world * npix / sus_ms / 1e3, 1), "unit": UNIT,
+                          "frac": round(algo_bytes / sus_ms / 1e6 / peak, 4), "clocks": sus.summary()},
+            "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
@@ -366,6 +543,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra records (configs 2, 4, 5, model path)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -20,10 +20,7 @@ HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "include", "hdrnet_b200
 OK = 0
 E_NULL_POINTER, E_BAD_SHAPE, E_BAD_CHANNELS, E_TOO_LARGE, E_UNSUPPORTED, E_BAD_CONTEXT = (
     -1, -2, -3, -4, -5, -6)
-VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_ZSORT, VARIANT_TEX, VARIANT_TEX_WS, VARIANT_TEX_IN = 0, 1, 2, 3, 4, 5, 6
-VARIANT_TEX_ASYNC = 7
-VARIANT_TC = 8
-VARIANT_TC_GATHER = 9
+VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_TEX, VARIANT_TEX_ASYNC = 0, 1, 2, 4, 7
 
 _c_int = ctypes.c_int
 _vp = ctypes.c_void_p

@@ -30,9 +30,9 @@
 // Files: slice_rows.cuh (device code shared by the row kernels: tile accessors, 4-corner blend,
 // guide sources, plan / argument structs), this file (generic kernels, the block-synchronous row
 // kernel, the un-fused slice kernel, the y pre-pass, planning, kernel selection, C-ABI),
-// slice_apply_async.cu (issuer-warp form: what AUTO runs for large images with a workspace),
-// slice_apply_variants.cu + slice_apply_zsort.cu (opt-in forms that measured slower),
-// slice_apply_tc.cu (experimental tensor-core forms).
+// slice_apply_async.cu (issuer-warp form: what AUTO runs for large images with a workspace).
+// Forms that measured slower (z-bucketed, texture-fed input, producer-warp, three tensor-core
+// gather forms) live in tools/experiments/ with their profiles; they are not part of the library.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -40,6 +40,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "slice_rows.cuh"
 
@@ -525,35 +526,20 @@ static bool make_slice_plan(const SliceGeom& g, int max_smem, int sms, SlicePlan
 
 // Pre-pass of the texture-assisted forms: yslab[r] = (1 - fy) * G[b][gy0] + fy * G[b][gy1] for
 // every buffer row r = (b, y) -- the same y pre-blend the row kernel does in shared memory,
-// materialised once.  kParts == 0: whole slab rows (gw*gd*48 B per image row: +11 % HBM traffic at
-// 4K / 16x16x8); kParts == P > 0: only the trailing P 16-byte parts of every cell, [row][cell][P]
-// (what the issuer-warp form with kSlab == 1 fetches through the texture pipe).
+// materialised once (gw*gd*48 B per image row: +11 % HBM traffic at 4K / 16x16x8).
 // One CTA owns kYblendRows consecutive rows and a thread one output float4 column of them: the two
 // grid rows it blends change every H / gh image rows, so they live in registers and the kernel
 // is a stream of coalesced stores (the first version -- one CTA per row, two dependent L2 loads
 // per thread -- took 22 us for 106 MB, latency-bound).
 constexpr int kYblendRows = 16;
-template <int kParts>
 __global__ void __launch_bounds__(256)
 yblend_rows_kernel(const float* __restrict__ grid, float4* __restrict__ ws, SliceGeom g,
                    int row_floats) {
-  // Programmatic dependent launch: everything before this grid in the stream (the previous
-  // call's row kernel may still be reading this workspace) must be complete before the first
-  // write; the row kernel that follows may be scheduled as these CTAs retire.  Both are no-ops
-  // for a plain launch.
-  grid_dependency_wait();
-  grid_launch_dependents();
   const long long total_rows = static_cast<long long>(g.B) * g.rows;
   const long long r0 = static_cast<long long>(blockIdx.x) * kYblendRows;
   const long long r1 = min(r0 + kYblendRows, total_rows);
-  const int cells = row_floats / kGc;
-  const int n_out = (kParts == 0) ? row_floats / 4 : cells * kParts;   // float4 per output row
+  const int n_out = row_floats / 4;   // float4 per output row
   for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
-    int src = e;                                                       // float4 index in a grid row
-    if constexpr (kParts > 0) {
-      const int cell = e / kParts;
-      src = cell * 3 + (3 - kParts) + (e - cell * kParts);
-    }
     int cur_b = -1, cur_i0 = INT_MIN;
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
     int b = static_cast<int>(r0 / g.rows);                                   // one division per CTA column
@@ -563,8 +549,8 @@ yblend_rows_kernel(const float* __restrict__ grid, float4* __restrict__ ws, Slic
       const Axis ay = spatial_axis(g.y_off + yl, g.scale_y);
       if (b != cur_b || ay.i0 != cur_i0) {
         const float* gb = grid + static_cast<size_t>(b) * g.gh * row_floats;
-        va = __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * row_floats) + src);
-        vb = __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * row_floats) + src);
+        va = __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * row_floats) + e);
+        vb = __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * row_floats) + e);
         cur_b = b;
         cur_i0 = ay.i0;
       }
@@ -573,14 +559,11 @@ yblend_rows_kernel(const float* __restrict__ grid, float4* __restrict__ ws, Slic
   }
 }
 
-static void launch_yblend(const float* grid, float* ws, const SliceGeom& g, int row_floats, int parts,
-                          cudaStream_t stream, bool pdl = false) {
+static int launch_yblend(const float* grid, float* ws, const SliceGeom& g, int row_floats, cudaStream_t stream) {
   const long long total_rows = static_cast<long long>(g.B) * g.rows;
   const unsigned blocks = static_cast<unsigned>((total_rows + kYblendRows - 1) / kYblendRows);
-  float4* ws4 = reinterpret_cast<float4*>(ws);
-  if (parts == 1) launch_maybe_pdl(yblend_rows_kernel<1>, blocks, 256, 0, stream, pdl, grid, ws4, g, row_floats);
-  else if (parts == 2) launch_maybe_pdl(yblend_rows_kernel<2>, blocks, 256, 0, stream, pdl, grid, ws4, g, row_floats);
-  else launch_maybe_pdl(yblend_rows_kernel<0>, blocks, 256, 0, stream, pdl, grid, ws4, g, row_floats);
+  yblend_rows_kernel<<<blocks, 256, 0, stream>>>(grid, reinterpret_cast<float4*>(ws), g, row_floats);
+  return static_cast<int>(cudaGetLastError());
 }
 
 // =========================================================================================
@@ -629,12 +612,8 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
   p.off_raw = 256;  // barriers: up to 2 * kMaxStages + 4 (warp-specialised form) = 160 bytes
   p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
   p.off_stage = p.off_slab + (tex_mode ? 0 : round_up(p.row_floats * 4, 128));
-  // Residency: HDRNET_TMA_OCC=3 asks for three CTAs per SM (3-stage ring, 85 registers) when
-  // the shared memory allows; default two CTAs with 4 stages; shrink the ring before giving up
-  // residency.
-  int want_occ = (threads == 320) ? 3 : 2;  // 320 threads: three 10-warp CTAs per SM, 64 registers
-  if (const char* e = std::getenv("HDRNET_TMA_OCC")) want_occ = std::atoi(e);
-  if (occ_override > 0) want_occ = occ_override;
+  // Residency: two CTAs per SM with a 4-stage ring; shrink the ring before giving up residency.
+  const int want_occ = occ_override > 0 ? occ_override : 2;
   const int per_cta_3 = (max_smem + 1024) / 3 - 1024;
   const int per_cta_2 = (max_smem + 1024) / 2 - 1024;  // ~113 KB when 227 KB opt-in
   int stages = 0, resident = 0;
@@ -648,8 +627,7 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
     for (int ns = 4; ns >= 2; --ns)
       if (p.off_stage + ns * p.stage_bytes <= per_cta_n) { stages = ns; resident = occ_override; break; }
   }
-  int max_ns = 4;
-  if (const char* e = std::getenv("HDRNET_TMA_STAGES")) max_ns = std::min(std::max(std::atoi(e), 2), kMaxStages);
+  const int max_ns = 4;
   if (stages == 0) {
     for (int ns = max_ns; ns >= 2; --ns)
       if (p.off_stage + ns * p.stage_bytes <= per_cta_2) { stages = ns; resident = 2; break; }
@@ -681,26 +659,6 @@ static int generic_grid(long long npix, int sms) {
   return static_cast<int>(std::min<long long>(blocks, static_cast<long long>(sms) * 16));
 }
 
-// tensor-core form (slice_apply_tc.cu), experimental
-int launch_slice_apply_tc(const float* guide, const float* input, float* out, const float* yslab,
-                          const SliceGeom& g, int max_smem, int sms, cudaStream_t stream);
-int launch_slice_apply_tcg(const float* guide, const float* input, float* out, const float* yslab,
-                           const SliceGeom& g, int max_smem, int sms, cudaStream_t stream);
-
-// tensor-core gather form (slice_apply_mma.cu): no workspace, no pre-pass
-int launch_slice_apply_mma(const float* grid, const float* guide, const float* input, float* out,
-                           const SliceGeom& g, int nsplit, int max_smem, int sms, cudaStream_t stream);
-
-// z-bucketed variant (slice_apply_zsort.cu)
-struct ZsPlan {
-  int ctas, stages, nseg, seg_px, row_floats, smem_bytes;
-  int pieces;
-  int off_raw, off_slab, off_rec, off_cnt, off_stage, stage_bytes;
-};
-bool make_zsort_plan(const SliceGeom& g, int max_smem, int sms, ZsPlan* out);
-int launch_zsort(const float* grid, const float* guide, const float* input, float* out,
-                 const SliceGeom& g, const ZsPlan& plan, cudaStream_t stream);
-
 template <class GuideFn, int kTexChunks = 0, int kMinBlocks = 2, int kThreads = kTmaThreads,
           int kIn = kPxF32, int kOut = kPxF32>
 static int launch_tma_occ(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream) {
@@ -716,15 +674,8 @@ template <class GuideFn, int kTexChunks = 0>
 static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream, int in_fmt = kPxF32,
                       int out_fmt = kPxF32) {
   if constexpr (GuideFn::kFromInput) {
-    // plan.resident == 3 (HDRNET_TMA_OCC=3, tuning knob): three CTAs per SM, registers capped at
-    // 85 per thread; plan.threads == 512: 64 registers per thread (no spills), 32 warps per SM.
-    if (a.p.resident == 3 && a.p.threads == kTmaThreads)
-      return launch_tma_occ<GuideFn, kTexChunks, 3>(a, fn, stream);
+    // plan.threads == 512: 64 registers per thread (no spills), 32 warps per SM
     if (a.p.threads == 512) return launch_tma_occ<GuideFn, kTexChunks, 2, 512>(a, fn, stream);
-    if (a.p.threads == 320) {
-      if (a.p.resident != 3) return HDRNET_E_UNSUPPORTED;
-      return launch_tma_occ<GuideFn, kTexChunks, 3, 320>(a, fn, stream);
-    }
   } else {
     // The fused-guide forms are issue-bound and need their registers: 256 threads x 2 CTAs.
     // Measured at 4K x 8 (tools/ab_fused.py): curves 0.69 ms against 0.71 (256 x 3) and 0.80
@@ -738,19 +689,44 @@ static int launch_tma(const TmaArgs& a, const GuideFn& fn, cudaStream_t stream, 
   return launch_tma_occ<GuideFn, kTexChunks, 2>(a, fn, stream);
 }
 
-// Texture objects over caller workspaces, cached by (pointer, bytes): creating one is a
-// host-side driver call that should not sit inside a timed loop.
-struct TexCacheEntry { const void* ptr; size_t bytes; int dev; cudaTextureObject_t tex; };
+// Texture objects over caller workspaces.  Creating one is a host-side driver call that should
+// not sit inside a timed loop, so they are cached, keyed by (device, pointer, lent bytes) -- the
+// whole workspace, not the part a call uses, so one entry serves every shape.  An entry remembers
+// an event recorded after the last launch that uses it; an evicted texture is destroyed only once
+// that event has completed (else it waits in a graveyard that later calls drain): a texture object
+// is never destroyed under a kernel that may still fetch through it.  This cache (and the tuning
+// record below) is the library's only process-wide state.
+struct TexCacheEntry { const void* ptr; size_t bytes; int dev; cudaTextureObject_t tex; cudaEvent_t last_use; };
+constexpr int kTexCacheEntries = 16;
 static std::mutex g_tex_mutex;
-static TexCacheEntry g_tex_cache[8];
+static TexCacheEntry g_tex_cache[kTexCacheEntries];
 static int g_tex_next = 0;
+static std::vector<TexCacheEntry> g_tex_graveyard;
 
-static int get_slab_texture(const float* ws, size_t bytes, cudaTextureObject_t* out) {
+static void drain_tex_graveyard_locked() {
+  for (size_t i = 0; i < g_tex_graveyard.size();) {
+    TexCacheEntry& e = g_tex_graveyard[i];
+    if (cudaEventQuery(e.last_use) == cudaSuccess) {
+      cudaDestroyTextureObject(e.tex);
+      cudaEventDestroy(e.last_use);
+      g_tex_graveyard[i] = g_tex_graveyard.back();
+      g_tex_graveyard.pop_back();
+    } else {
+      ++i;
+    }
+  }
+  (void)cudaGetLastError();   // cudaErrorNotReady of a pending event is not an error of this call
+}
+
+// The texture over [ws, ws + bytes); `*use` must be recorded on the launch stream after the last
+// kernel of this call that fetches through it (mark_texture_used).
+static int get_slab_texture(const float* ws, size_t bytes, cudaTextureObject_t* out, cudaEvent_t* use) {
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(g_tex_mutex);
+  if (!g_tex_graveyard.empty()) drain_tex_graveyard_locked();
   for (auto& e : g_tex_cache)
-    if (e.ptr == ws && e.bytes == bytes && e.dev == dev && e.tex) { *out = e.tex; return 0; }
+    if (e.tex && e.ptr == ws && e.bytes == bytes && e.dev == dev) { *out = e.tex; *use = e.last_use; return 0; }
   cudaResourceDesc rd = {};
   rd.resType = cudaResourceTypeLinear;
   rd.res.linear.devPtr = const_cast<float*>(ws);
@@ -761,11 +737,15 @@ static int get_slab_texture(const float* ws, size_t bytes, cudaTextureObject_t* 
   cudaTextureObject_t tex = 0;
   cudaError_t err = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
   if (err != cudaSuccess) return static_cast<int>(err);
+  cudaEvent_t ev = nullptr;
+  err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (err != cudaSuccess) { cudaDestroyTextureObject(tex); return static_cast<int>(err); }
   TexCacheEntry& slot = g_tex_cache[g_tex_next];
-  g_tex_next = (g_tex_next + 1) % 8;
-  if (slot.tex) cudaDestroyTextureObject(slot.tex);
-  slot = TexCacheEntry{ws, bytes, dev, tex};
+  g_tex_next = (g_tex_next + 1) % kTexCacheEntries;
+  if (slot.tex) { g_tex_graveyard.push_back(slot); drain_tex_graveyard_locked(); }
+  slot = TexCacheEntry{ws, bytes, dev, tex, ev};
   *out = tex;
+  *use = ev;
   return 0;
 }
 
@@ -805,6 +785,24 @@ static int launch_px_generic(const float* grid, const void* input, void* out, fl
   return HDRNET_E_UNSUPPORTED;
 }
 
+// Tuning record: read ONCE per process (first call) from the environment, for same-box A/B runs
+// (tools/ab_lib.py loads one copy of the library per setting).  Nothing reads the environment on
+// the launch path.
+//   HDRNET_ASYNC_THREADS = 512 | 352   CTA shape of the issuer-warp kernel (15 / 10 math warps)
+//   HDRNET_TEX_CHUNKS    = 4 | 5       corner chunks per pixel served by the texture pipe there
+//   HDRNET_FUSED_ASYNC   = 0 | 1       force the block-synchronous / issuer-warp fused-guide form
+struct Tuning { int async_threads, async_chunks, fused_async; };
+static const Tuning& tuning() {
+  static const Tuning t = [] {
+    Tuning v{kAsyncThreadsDefault, kAsyncTexChunksDefault, -1};
+    if (const char* e = std::getenv("HDRNET_ASYNC_THREADS")) { const int x = std::atoi(e); if (x == 512 || x == 352) v.async_threads = x; }
+    if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) { const int x = std::atoi(e); if (x == 4 || x == 5) v.async_chunks = x; }
+    if (const char* e = std::getenv("HDRNET_FUSED_ASYNC")) v.fused_async = std::atoi(e) != 0 ? 1 : 0;
+    return v;
+  }();
+  return t;
+}
+
 static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const void* input_v,
                                    void* out_v, int B, int H, int W, int rows, int y_off, int gh,
                                    int gw, int gd, int n_in, int n_out, int has_offset,
@@ -816,7 +814,6 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     if (gs.mode == 0 || n_in != 3 || n_out != 3 || !has_offset) return HDRNET_E_UNSUPPORTED;
     if (gs.in_fmt < kPxF32 || gs.in_fmt > kPxU16 || (gs.out_fmt != kPxF32 && gs.out_fmt != kPxU8))
       return HDRNET_E_UNSUPPORTED;
-    if (variant == HDRNET_VARIANT_ZSORT || variant == HDRNET_VARIANT_TEX_WS) return HDRNET_E_UNSUPPORTED;
   }
   int rc = validate_common(B, H, W, gh, gw, gd);
   if (rc != HDRNET_OK) return rc;
@@ -827,212 +824,104 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   const int J = n_in + (has_offset ? 1 : 0);
   const long long grid_floats = static_cast<long long>(gh) * gw * gd * n_out * J;
   if (grid_floats > INT_MAX || static_cast<long long>(rows) * B > INT_MAX / 4) return HDRNET_E_TOO_LARGE;
+  if (variant != HDRNET_VARIANT_AUTO && variant != HDRNET_VARIANT_GENERIC && variant != HDRNET_VARIANT_TMA &&
+      variant != HDRNET_VARIANT_TEX && variant != HDRNET_VARIANT_TEX_ASYNC)
+    return HDRNET_E_UNSUPPORTED;
 
   const SliceGeom g = make_geom(B, H, W, rows, y_off, gh, gw, gd);
   const int sms = device_sm_count();
-  int tma_threads = kTmaThreadsDefault;
-  if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tma_threads = (std::atoi(e) == 512) ? 512 : (std::atoi(e) == 320 ? 320 : 256);
-  if (gs.mode != 0) tma_threads = kFusedThreadsDefault;
+  const int max_smem = device_max_smem_optin();
+  const Tuning& tune = tuning();
 
+  // The persistent row kernels take the 3 -> 3 affine op with offset on 16-byte aligned, bulk-copy
+  // sized rows; everything else runs the generic kernel.
   TmaPlan plan;
-  const bool tma_shape = (n_in == 3 && n_out == 3 && has_offset) &&
-                         make_tma_plan(g, device_max_smem_optin(), sms, &plan, false, tma_threads,
-                                       gs.in_fmt, gs.out_fmt) &&
-                         // the row kernel has (u8 | u16) -> u8 and f32 -> f32 pixel forms
+  const bool row_shape = (n_in == 3 && n_out == 3 && has_offset) &&
+                         make_tma_plan(g, max_smem, sms, &plan, false,
+                                       gs.mode != 0 ? kFusedThreadsDefault : kTmaThreadsDefault, gs.in_fmt,
+                                       gs.out_fmt) &&
+                         // (u8 | u16) -> u8 and f32 -> f32 pixel forms
                          (!px || (gs.in_fmt != kPxF32 && gs.out_fmt == kPxU8)) &&
                          aligned16(grid) && aligned16(input) && aligned16(out) &&
                          (gs.mode != 0 || aligned16(gs.guide)) &&
                          (gs.guide_out == nullptr || aligned16(gs.guide_out));
-  if (variant == HDRNET_VARIANT_ZSORT) {
-    ZsPlan zp;
-    if (!tma_shape || gs.mode != 0 || !make_zsort_plan(g, device_max_smem_optin(), sms, &zp))
-      return HDRNET_E_UNSUPPORTED;
-    return launch_zsort(grid, gs.guide, input, out, g, zp, stream);
-  }
-  // Texture-assisted form: possible when the caller lent a workspace for the slab rows.
-  const size_t tex_need = tma_shape ? static_cast<size_t>(B) * rows * plan.row_floats * sizeof(float) : 0;
-  const bool tex_ok = tma_shape && gs.workspace && gs.workspace_bytes >= tex_need &&
-                      aligned16(gs.workspace) && tex_need / 16 <= (1u << 27);
-  // AUTO prefers it once the image is large enough to amortise the pre-pass launch: the
-  // issuer-warp form for the op-API shape it exists for (float32 pixels, guide as an input; it
-  // needs a plan whose segments fit its 15 math warps), else the block-synchronous form.
-  if (variant == HDRNET_VARIANT_AUTO && tex_ok && W >= 128 && npix >= (1LL << 21)) {
-    variant = HDRNET_VARIANT_TEX;
-    TmaPlan ap;
-    if (gs.mode == 0 && !px &&
-        make_tma_plan(g, device_max_smem_optin(), sms, &ap, /*tex_mode=*/true, kAsyncThreads - 32,
-                      kPxF32, kPxF32, 2) && ap.resident == 2 && ap.stages >= kAsyncAutoMinStages)
-      variant = HDRNET_VARIANT_TEX_ASYNC;
-  }
-  if (variant == HDRNET_VARIANT_MMA || variant == HDRNET_VARIANT_MMA3) {
-    if (gs.mode != 0 || px || n_in != 3 || n_out != 3 || !has_offset) return HDRNET_E_UNSUPPORTED;
-    if (!aligned16(grid) || !aligned16(input) || !aligned16(out) || !aligned16(gs.guide)) return HDRNET_E_UNSUPPORTED;
-    return launch_slice_apply_mma(grid, gs.guide, input, out, g, variant == HDRNET_VARIANT_MMA3 ? 3 : 2,
-                                  device_max_smem_optin(), sms, stream);
-  }
-  if (variant == HDRNET_VARIANT_TC_GATHER) {   // experimental, never run: tensor-core gather form
-    if (!tex_ok || gs.mode != 0 || px) return HDRNET_E_UNSUPPORTED;
-    if (gd != 8 || gw < 3 || static_cast<long long>(W) < 128LL * gw) return HDRNET_E_UNSUPPORTED;
-    launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);
-    return launch_slice_apply_tcg(gs.guide, input, out, gs.workspace, g, device_max_smem_optin(), sms,
-                                  stream);
-  }
-  if (variant == HDRNET_VARIANT_TC) {   // experimental tensor-core form: slab rows from the pre-pass
-    if (!tex_ok || gs.mode != 0 || px) return HDRNET_E_UNSUPPORTED;
-    if (gd != 8 || gw < 3 || static_cast<long long>(W) < 128LL * gw) return HDRNET_E_UNSUPPORTED;
-    launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);
-    return launch_slice_apply_tc(gs.guide, input, out, gs.workspace, g, device_max_smem_optin(), sms,
-                                 stream);
-  }
-  if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_WS ||
-      variant == HDRNET_VARIANT_TEX_IN || variant == HDRNET_VARIANT_TEX_ASYNC) {
-    const size_t need = tex_need;
-    if (!tex_ok) return HDRNET_E_UNSUPPORTED;
-    TmaPlan tplan;
-    // the texture forms default to the 512-thread / 64-register plan (32 warps per SM)
-    int tex_threads = kTexThreadsDefault;
-    if (const char* e = std::getenv("HDRNET_TMA_THREADS")) tex_threads = (std::atoi(e) == 512) ? 512 : (std::atoi(e) == 320 ? 320 : 256);
-    if (gs.mode != 0) tex_threads = kFusedThreadsDefault;
-    // warp-specialised form: the 512-thread CTA is 15 math warps (480 pixel quads) + the producer
-    if (variant == HDRNET_VARIANT_TEX_WS && tex_threads == 512) tex_threads = 480;
-    // issuer-warp form: the plan covers the math warps only (segments of <= 4 * 480 pixels)
-    // CTA shape of the issuer-warp form: threads (math warps + the issuer) x CTAs per SM.
-    //   512 x 2: 15 math warps, 64 registers      352 x 2: 10 math warps, 88 registers
-    //   224 x 3:  6 math warps, 96 registers      224 x 4:  6 math warps, 72 registers
-    int async_threads = kAsyncThreadsDefault, async_occ = kAsyncOccDefault;
-    if (const char* e = std::getenv("HDRNET_ASYNC_THREADS")) {
-      const int t = std::atoi(e);
-      if (t == 512 || t == 352 || t == 224) { async_threads = t; async_occ = (t == 224) ? 3 : 2; }
-    }
-    if (const char* e = std::getenv("HDRNET_ASYNC_OCC")) {
-      const int o = std::atoi(e);
-      if (async_threads == 224 && (o == 3 || o == 4)) async_occ = o;
-    }
-    // the other knobs of that form (per-quad indices, texture chunks, direct stores, in-kernel
-    // slab rows); the small CTA shapes exist for the plain lean form with 4 / 5 / 6 chunks only
-    bool async_lean = static_cast<long long>(W) >= 4LL * gw;   // x cells at least 4 pixels wide
-    if (const char* e = std::getenv("HDRNET_ASYNC_LEAN")) async_lean = async_lean && std::atoi(e) != 0;
-    int async_chunks = kAsyncTexChunksDefault, async_store = kAsyncStoreDefault, async_slab = kAsyncSlabDefault;
-    if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) async_chunks = std::atoi(e);
-    if (const char* e = std::getenv("HDRNET_ASYNC_STORE")) async_store = std::atoi(e) != 0;
-    if (const char* e = std::getenv("HDRNET_ASYNC_SLAB")) async_slab = std::atoi(e) != 0;
-    if (async_chunks < 3 || async_chunks > 6) async_chunks = kAsyncTexChunksDefault;
-    if (async_chunks == 3) async_slab = 0;
-    if (!async_lean) { async_store = 0; async_slab = 0; if (async_chunks != 4) async_chunks = 5; }
-    if (!async_lean || async_store || async_slab || async_chunks == 3) { async_threads = 512; async_occ = 2; }
-    if (variant == HDRNET_VARIANT_TEX_ASYNC) tex_threads = async_threads - 32;
-    if (!make_tma_plan(g, device_max_smem_optin(), sms, &tplan, /*tex_mode=*/true, tex_threads,
-                       gs.in_fmt, gs.out_fmt, variant == HDRNET_VARIANT_TEX_ASYNC ? async_occ : 0))
-      tplan = plan;
-    TmaArgs a;
-    a.grid = grid; a.guide = gs.guide; a.guide_out = nullptr;
-    a.input = static_cast<const unsigned char*>(input_v); a.out = static_cast<unsigned char*>(out_v);
-    a.g = g; a.p = tplan; a.yslab = gs.workspace;
-    rc = get_slab_texture(gs.workspace, need, &a.slab_tex);
-    if (rc != 0) return rc;
-    // issuer-warp form, float32 guide-from-input only: its own (smaller) pre-pass when kSlab == 1
-    if (variant == HDRNET_VARIANT_TEX_ASYNC) {
-      if (gs.mode != 0 || px || tplan.threads != async_threads - 32 ||
-          tplan.seg_px > tplan.threads * 4 || tplan.stages < 2)
-        return HDRNET_E_UNSUPPORTED;
-      const bool lean = async_lean;
-      const int chunks = async_chunks, store = async_store, slab = async_slab;
-      bool pdl = kAsyncPdlDefault;   // programmatic dependent launch of pre-pass and row kernel
-      if (const char* e = std::getenv("HDRNET_ASYNC_PDL")) pdl = std::atoi(e) != 0;
-      launch_yblend(grid, gs.workspace, g, plan.row_floats, slab ? (chunks == 4 ? 1 : 2) : 0, stream, pdl);
-      bool pipe = false;             // HDRNET_ASYNC_PIPE=1: texture fetches one pixel ahead (not yet run)
-      if (const char* e = std::getenv("HDRNET_ASYNC_PIPE")) pipe = std::atoi(e) != 0;
-      return launch_async_form(a, chunks, lean, store, slab, async_threads, async_occ, pdl, pipe, stream);
-    }
-    launch_yblend(grid, gs.workspace, g, plan.row_floats, 0, stream);
-    if (variant == HDRNET_VARIANT_TEX_WS) {
-      if (gs.mode != 0 || tplan.seg_px > tplan.threads * 4) return HDRNET_E_UNSUPPORTED;
-      return launch_ws_form(a, stream);
-    }
-    if (variant == HDRNET_VARIANT_TEX_IN) {
-      // float32 guide-from-input form only; pixel tensors addressable as 1-D float4 textures
-      const size_t in_bytes = static_cast<size_t>(npix) * 12, guide_bytes = static_cast<size_t>(npix) * 4;
-      if (gs.mode != 0 || px || in_bytes / 16 > (1u << 27)) return HDRNET_E_UNSUPPORTED;
-      // shared memory: two slab rows + kTexInStages output tiles (no input ring)
-      a.p.stage_bytes = round_up(a.p.seg_px * 12, 128);
-      a.p.stages = kTexInStages;
-      a.p.smem_bytes = a.p.off_stage + kTexInStages * a.p.stage_bytes;
-      if (a.p.smem_bytes > (device_max_smem_optin() + 1024) / 2 - 1024) return HDRNET_E_UNSUPPORTED;
-      // no input ring: the 256-thread form fits three or four CTAs per SM (HDRNET_TEXIN_OCC)
-      int occ = 2;
-      if (const char* e = std::getenv("HDRNET_TEXIN_OCC")) occ = std::atoi(e);
-      if (a.p.threads == kTmaThreads && (occ == 3 || occ == 4) &&
-          a.p.smem_bytes <= (device_max_smem_optin() + 1024) / occ - 1024) {
-        const long long total_rows = static_cast<long long>(B) * rows;
-        a.p.ctas = static_cast<int>(std::min<long long>(total_rows, static_cast<long long>(sms) * occ));
-        a.p.resident = occ;
-      }
-      rc = get_slab_texture(input, in_bytes, &a.in_tex);
-      if (rc != 0) return rc;
-      rc = get_slab_texture(gs.guide, guide_bytes, &a.guide_tex);
-      if (rc != 0) return rc;
-      int chunks = kTexChunksDefault;
-      if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);
-      return launch_texin_form(a, chunks, stream);
-    }
-    // opt-in (HDRNET_FUSED_ASYNC=1, not yet run): the fused-guide forms under the issuer-warp control flow
-    if (gs.mode != 0 && variant == HDRNET_VARIANT_TEX) {
-      bool fused_async = false;
-      if (const char* e = std::getenv("HDRNET_FUSED_ASYNC")) fused_async = std::atoi(e) != 0;
-      TmaPlan fplan;
-      if (fused_async &&
-          make_tma_plan(g, device_max_smem_optin(), sms, &fplan, /*tex_mode=*/true, kFusedAsyncMathThreads,
-                        gs.in_fmt, gs.out_fmt, 2) &&
-          fplan.resident == 2 && fplan.stages >= 3) {
-        a.p = fplan;
-        a.guide_out = gs.guide_out;
-        return launch_async_fused(a, gs.mode, gs.curves, gs.nn, gs.in_fmt, gs.out_fmt, stream);
-      }
-    }
-    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves; a.guide_out = gs.guide_out;
-                        return launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt); }
-    if (gs.mode == 2) {
-      a.guide_out = gs.guide_out;
-      if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn;
-                                return launch_tma<GuideNN<16>, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt); }
-      GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
-      return launch_tma<GuideNN<kMaxGuideFeats>, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt);
-    }
-    int chunks = kTexChunksDefault;
-    if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) chunks = std::atoi(e);  // tuning knob
-    switch (chunks) {
-      case 2: return launch_tma<GuideFromInput, 2>(a, GuideFromInput{}, stream);
-      case 3: return launch_tma<GuideFromInput, 3>(a, GuideFromInput{}, stream);
-      case 5: return launch_tma<GuideFromInput, 5>(a, GuideFromInput{}, stream);
-      case 6: return launch_tma<GuideFromInput, 6>(a, GuideFromInput{}, stream);
-      default: return launch_tma<GuideFromInput, kTexChunksDefault>(a, GuideFromInput{}, stream);
-    }
-  }
-  bool use_tma;
-  if (variant == HDRNET_VARIANT_TMA) {
-    if (!tma_shape) return HDRNET_E_UNSUPPORTED;
-    use_tma = true;
-  } else if (variant == HDRNET_VARIANT_GENERIC) {
-    use_tma = false;
-  } else if (variant == HDRNET_VARIANT_AUTO) {
-    use_tma = tma_shape && W >= 128;
-  } else {
-    return HDRNET_E_UNSUPPORTED;
-  }
-  // Integer pixel I/O on shapes the row kernel cannot take: the per-pixel fused kernel.
-  if (!use_tma && px) {
-    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves;
-                        return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream); }
-    if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn;
-                              return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream); }
-    GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
-    return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream);
-  }
-  // The float32 fused-guide forms exist only in the TMA kernel; other shapes run the standalone
-  // guide kernel first (the caller does that: see hdrnet_slice_apply_{curves,nn}_f32).
-  if (!use_tma && gs.mode != 0) return HDRNET_E_UNSUPPORTED;
+  // Texture-assisted forms: possible when the caller lent a workspace for the slab rows.
+  const size_t tex_need = row_shape ? static_cast<size_t>(B) * rows * plan.row_floats * sizeof(float) : 0;
+  const bool tex_ok = row_shape && gs.workspace && gs.workspace_bytes >= tex_need &&
+                      aligned16(gs.workspace) && gs.workspace_bytes / 16 <= (1u << 27);
+  // Issuer-warp form: float32 pixels, guide as an input, a ring of >= 3 stages at two CTAs per SM.
+  TmaPlan aplan;
+  const bool async_ok = tex_ok && gs.mode == 0 && !px &&
+                        make_tma_plan(g, max_smem, sms, &aplan, /*tex_mode=*/true, tune.async_threads - 32,
+                                      kPxF32, kPxF32, 2) &&
+                        aplan.resident == 2 && aplan.seg_px <= aplan.threads * 4;
+  // ... and its fused-guide forms (8 math warps + the issuer).  Measured at 4K x 8
+  // (profiles/r02_ab_fused_issuer_warp.txt): curves 0.628 ms against 0.700 block-synchronous (u8:
+  // 0.668 / 0.729); pointwise NN 0.628 / 0.625 (u8: 0.694 / 0.654) -- AUTO takes it for the
+  // curves guide only.
+  TmaPlan fplan;
+  const bool fused_async_ok = tex_ok && gs.mode != 0 &&
+                              make_tma_plan(g, max_smem, sms, &fplan, /*tex_mode=*/true, kFusedAsyncMathThreads,
+                                            gs.in_fmt, gs.out_fmt, 2) &&
+                              fplan.resident == 2 && fplan.stages >= 3;
 
-  if (use_tma) {
+  if (variant == HDRNET_VARIANT_AUTO) {
+    // the texture-assisted forms pay a pre-pass launch: large images only
+    if (tex_ok && W >= 128 && npix >= (1LL << 21))
+      variant = (async_ok && aplan.stages >= kAsyncAutoMinStages) ? HDRNET_VARIANT_TEX_ASYNC : HDRNET_VARIANT_TEX;
+    else
+      variant = (row_shape && W >= 128) ? HDRNET_VARIANT_TMA : HDRNET_VARIANT_GENERIC;
+  }
+
+  if (variant == HDRNET_VARIANT_TEX || variant == HDRNET_VARIANT_TEX_ASYNC) {
+    if (!tex_ok) return HDRNET_E_UNSUPPORTED;
+    if (variant == HDRNET_VARIANT_TEX_ASYNC && !async_ok) return HDRNET_E_UNSUPPORTED;
+    TmaArgs a;
+    a.grid = grid; a.guide = gs.guide; a.guide_out = gs.guide_out;
+    a.input = static_cast<const unsigned char*>(input_v); a.out = static_cast<unsigned char*>(out_v);
+    a.g = g; a.yslab = gs.workspace;
+    cudaEvent_t tex_use = nullptr;
+    rc = get_slab_texture(gs.workspace, gs.workspace_bytes, &a.slab_tex, &tex_use);
+    if (rc != 0) return rc;
+    rc = launch_yblend(grid, gs.workspace, g, plan.row_floats, stream);
+    if (rc != 0) return rc;
+    if (variant == HDRNET_VARIANT_TEX_ASYNC) {
+      a.p = aplan;
+      a.guide_out = nullptr;
+      const bool lean = static_cast<long long>(W) >= 4LL * gw;   // x cells at least 4 pixels wide
+      rc = launch_async_form(a, tune.async_chunks, lean, tune.async_threads, stream);
+    } else {
+      bool fused_async = gs.mode == 1;
+      if (tune.fused_async >= 0) fused_async = tune.fused_async != 0;
+      // the block-synchronous texture form: 512 threads for the op-API shape, 256 for fused guides
+      TmaPlan tplan;
+      if (!make_tma_plan(g, max_smem, sms, &tplan, /*tex_mode=*/true,
+                         gs.mode != 0 ? kFusedThreadsDefault : kTexThreadsDefault, gs.in_fmt, gs.out_fmt))
+        tplan = plan;
+      a.p = tplan;
+      if (gs.mode != 0 && fused_async && fused_async_ok) {
+        a.p = fplan;
+        rc = launch_async_fused(a, gs.mode, gs.curves, gs.nn, gs.in_fmt, gs.out_fmt, stream);
+      } else if (gs.mode == 1) {
+        GuideCurves fn; fn.p = *gs.curves;
+        rc = launch_tma<GuideCurves, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt);
+      } else if (gs.mode == 2 && gs.nn->feats <= 16) {
+        GuideNN<16> fn; fn.p = *gs.nn;
+        rc = launch_tma<GuideNN<16>, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt);
+      } else if (gs.mode == 2) {
+        GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
+        rc = launch_tma<GuideNN<kMaxGuideFeats>, kTexChunksDefault>(a, fn, stream, gs.in_fmt, gs.out_fmt);
+      } else {
+        rc = launch_tma<GuideFromInput, kTexChunksDefault>(a, GuideFromInput{}, stream);
+      }
+    }
+    // the texture must outlive every kernel that fetches through it (get_slab_texture)
+    if (rc == 0 && cudaEventRecord(tex_use, stream) != cudaSuccess) rc = static_cast<int>(cudaGetLastError());
+    return rc;
+  }
+
+  if (variant == HDRNET_VARIANT_TMA) {
+    if (!row_shape) return HDRNET_E_UNSUPPORTED;
     TmaArgs a;
     a.grid = grid; a.guide = gs.guide; a.guide_out = gs.guide_out;
     a.input = static_cast<const unsigned char*>(input_v); a.out = static_cast<unsigned char*>(out_v);
@@ -1043,6 +932,19 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
     return launch_tma(a, fn, stream, gs.in_fmt, gs.out_fmt);
   }
+
+  // HDRNET_VARIANT_GENERIC: one thread per pixel.
+  if (px) {   // integer pixel I/O on shapes the row kernel cannot take: the per-pixel fused kernel
+    if (gs.mode == 1) { GuideCurves fn; fn.p = *gs.curves;
+                        return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream); }
+    if (gs.nn->feats <= 16) { GuideNN<16> fn; fn.p = *gs.nn;
+                              return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream); }
+    GuideNN<kMaxGuideFeats> fn; fn.p = *gs.nn;
+    return launch_px_generic(grid, input_v, out_v, gs.guide_out, g, npix, sms, gs.in_fmt, gs.out_fmt, fn, stream);
+  }
+  // The float32 fused-guide forms exist only in the row kernels; other shapes run the standalone
+  // guide kernel first (the caller does that: see hdrnet_slice_apply_{curves,nn}_f32).
+  if (gs.mode != 0) return HDRNET_E_UNSUPPORTED;
   slice_generic_kernel<true><<<generic_grid(npix, sms), 256, 0, stream>>>(
       grid, gs.guide, input, out, g, n_in, n_out, J, npix);
   return static_cast<int>(cudaGetLastError());
@@ -1310,10 +1212,10 @@ int hdrnet_slice_apply_plan_ws(int B, int H, int W, int gh, int gw, int gd, int 
   // launch_slice_apply_impl); `threads` is the launch size (math warps + the issuer warp)
   TmaPlan ap;
   const bool async_form = tma && tex &&
-                          make_tma_plan(g, device_max_smem_optin(), sms, &ap, true, kAsyncThreads - 32,
+                          make_tma_plan(g, device_max_smem_optin(), sms, &ap, true, tuning().async_threads - 32,
                                         kPxF32, kPxF32, 2) && ap.resident == 2 &&
-                          ap.stages >= kAsyncAutoMinStages;
-  if (async_form) { plan = ap; plan.threads = kAsyncThreads; }
+                          ap.seg_px <= ap.threads * 4 && ap.stages >= kAsyncAutoMinStages;
+  if (async_form) { plan = ap; plan.threads = tuning().async_threads; }
   if (variant) *variant = tma ? (tex ? (async_form ? HDRNET_VARIANT_TEX_ASYNC : HDRNET_VARIANT_TEX) : HDRNET_VARIANT_TMA)
                               : HDRNET_VARIANT_GENERIC;
   if (ctas) *ctas = tma ? plan.ctas : generic_grid(npix, sms);

@@ -40,35 +40,20 @@ namespace hdrnet_b200 {
 // instead of FRND + F2I (two).  t_i, the fractions and every weight are computed by the same
 // rounded operations as spatial_axis / range_axis: results are bitwise those of the other forms.
 //
-// Two more switches, both aimed at the shared-memory data pipe that bounds this form (ncu: 90 % of
-// its peak; 1.57 wavefronts per pixel = 1.0 gather + 0.1 x-cell straddles + 0.22 tile reads /
-// writes by the threads + 0.23 reads / writes of the same tiles by the TMA engine):
-//   kStore == 1: results leave the registers by 3 x STG.128 (streaming) instead of 3 x STS.128 +
-//     a bulk store -- the output tile never crosses shared memory (-0.09 wavefronts per pixel).
-//   kSlab == 1: the ISSUER WARP blends each image row's two grid rows (L2-resident, 786 KB for
-//     the whole batch) into the shared-memory slab, two rows ahead of the math warps, so the
-//     pre-pass only has to materialise what the texture pipe fetches: the trailing part(s) of
-//     every cell (16 of its 48 bytes for four texture chunks, 32 beyond) -- a third of the
-//     pre-pass traffic, and the row kernel no longer reads slab rows back from HBM.
+// Tried on this form and removed (results in DESIGN.md section 3): results stored by STG.128 from
+// registers (+10 %), slab rows blended by the issuer warp from L2 (2x slower), texture fetches
+// software-pipelined one pixel ahead (no gain), programmatic dependent launch of the pre-pass (+14 %).
 
 // Which of a pixel's 12 corner chunks -- corner c = 0..3 (v00, v01, v10, v11), part p = 0..2 --
-// travel through the texture pipe.  kSlab == 0: the last kTexChunks of the ids 3 c + p (the
-// workspace holds whole slab rows).  kSlab == 1: part 2 of every corner, then part 1 of corners
-// 3, 2, ... for the chunks beyond four (the workspace holds parts 3 - P .. 2 of every cell).
-template <int kTexChunks, int kSlab>
-__host__ __device__ constexpr bool chunk_on_tex(int c, int p) {
-  if (kSlab == 0) return c * 3 + p >= 12 - kTexChunks;
-  return p == 2 || (p == 1 && c >= 8 - kTexChunks);
-}
-__host__ __device__ constexpr int tex_parts(int tex_chunks) { return tex_chunks > 4 ? 2 : 1; }
+// travel through the texture pipe: the last kTexChunks of the ids 3 c + p.
+template <int kTexChunks>
+__host__ __device__ constexpr bool chunk_on_tex(int c, int p) { return c * 3 + p >= 12 - kTexChunks; }
 
-template <int kTexChunks, int kSlab, int kC, int kP>
+template <int kTexChunks, int kC, int kP>
 __device__ __forceinline__ ulonglong2 fetch_chunk(const unsigned char* __restrict__ slab_b,
                                                   cudaTextureObject_t tex, int off_b, int tex_idx) {
-  if constexpr (chunk_on_tex<kTexChunks, kSlab>(kC, kP)) {
-    // tex_idx: texel of the cell's part 0 (kSlab 0) / of its first stored part (kSlab 1)
-    constexpr int kFirst = (kSlab == 0) ? 0 : 3 - tex_parts(kTexChunks);
-    const float4 v = tex1Dfetch<float4>(tex, tex_idx + (kP - kFirst));
+  if constexpr (chunk_on_tex<kTexChunks>(kC, kP)) {
+    const float4 v = tex1Dfetch<float4>(tex, tex_idx + kP);   // tex_idx: texel of the cell's part 0
     ulonglong2 r;
     r.x = pack2(v.x, v.y);
     r.y = pack2(v.z, v.w);
@@ -79,7 +64,7 @@ __device__ __forceinline__ ulonglong2 fetch_chunk(const unsigned char* __restric
 }
 
 // blend_apply with byte offsets and per-corner texel indices (unused ones are dead code).
-template <int kTexChunks, int kSlab>
+template <int kTexChunks>
 __device__ __forceinline__ void blend_apply_q(const unsigned char* __restrict__ slab_b,
                                               cudaTextureObject_t tex, const int (&off)[4],
                                               const int (&tix)[4], const float (&w)[4], float r,
@@ -87,18 +72,18 @@ __device__ __forceinline__ void blend_apply_q(const unsigned char* __restrict__ 
                                               float& out_b) {
   const unsigned long long W00 = pack2(w[0], w[0]), W01 = pack2(w[1], w[1]);
   const unsigned long long W10 = pack2(w[2], w[2]), W11 = pack2(w[3], w[3]);
-  const ulonglong2 a0 = fetch_chunk<kTexChunks, kSlab, 0, 0>(slab_b, tex, off[0], tix[0]);
-  const ulonglong2 a1 = fetch_chunk<kTexChunks, kSlab, 0, 1>(slab_b, tex, off[0], tix[0]);
-  const ulonglong2 a2 = fetch_chunk<kTexChunks, kSlab, 0, 2>(slab_b, tex, off[0], tix[0]);
-  const ulonglong2 b0 = fetch_chunk<kTexChunks, kSlab, 1, 0>(slab_b, tex, off[1], tix[1]);
-  const ulonglong2 b1 = fetch_chunk<kTexChunks, kSlab, 1, 1>(slab_b, tex, off[1], tix[1]);
-  const ulonglong2 b2 = fetch_chunk<kTexChunks, kSlab, 1, 2>(slab_b, tex, off[1], tix[1]);
-  const ulonglong2 c0 = fetch_chunk<kTexChunks, kSlab, 2, 0>(slab_b, tex, off[2], tix[2]);
-  const ulonglong2 c1 = fetch_chunk<kTexChunks, kSlab, 2, 1>(slab_b, tex, off[2], tix[2]);
-  const ulonglong2 c2 = fetch_chunk<kTexChunks, kSlab, 2, 2>(slab_b, tex, off[2], tix[2]);
-  const ulonglong2 d0 = fetch_chunk<kTexChunks, kSlab, 3, 0>(slab_b, tex, off[3], tix[3]);
-  const ulonglong2 d1 = fetch_chunk<kTexChunks, kSlab, 3, 1>(slab_b, tex, off[3], tix[3]);
-  const ulonglong2 d2 = fetch_chunk<kTexChunks, kSlab, 3, 2>(slab_b, tex, off[3], tix[3]);
+  const ulonglong2 a0 = fetch_chunk<kTexChunks, 0, 0>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 a1 = fetch_chunk<kTexChunks, 0, 1>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 a2 = fetch_chunk<kTexChunks, 0, 2>(slab_b, tex, off[0], tix[0]);
+  const ulonglong2 b0 = fetch_chunk<kTexChunks, 1, 0>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 b1 = fetch_chunk<kTexChunks, 1, 1>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 b2 = fetch_chunk<kTexChunks, 1, 2>(slab_b, tex, off[1], tix[1]);
+  const ulonglong2 c0 = fetch_chunk<kTexChunks, 2, 0>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 c1 = fetch_chunk<kTexChunks, 2, 1>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 c2 = fetch_chunk<kTexChunks, 2, 2>(slab_b, tex, off[2], tix[2]);
+  const ulonglong2 d0 = fetch_chunk<kTexChunks, 3, 0>(slab_b, tex, off[3], tix[3]);
+  const ulonglong2 d1 = fetch_chunk<kTexChunks, 3, 1>(slab_b, tex, off[3], tix[3]);
+  const ulonglong2 d2 = fetch_chunk<kTexChunks, 3, 2>(slab_b, tex, off[3], tix[3]);
   unsigned long long acc[6];  // same order of operations as blend_apply: identical bits
   acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
   acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
@@ -118,26 +103,12 @@ __device__ __forceinline__ void blend_apply_q(const unsigned char* __restrict__ 
   out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
 }
 
-__device__ __forceinline__ void stg128_stream(float* p, float x, float y, float z, float w) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w)
-               : "memory");
-}
-__device__ __forceinline__ float4 ldg128_stream(const float4* p) {
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-
-// tex_base: kSlab 0 -- texel of the row's first cell (row * gw * gd * 3); kSlab 1 -- the row's first
-// CELL in the part workspace (row * gw * gd).  out_row: this image row in `out` (kStore 1 only).
-template <int kTexChunks, int kStore, int kSlab>
+// tex_base: texel of the row's first cell in the slab workspace (row * gw * gd * 3).
+template <int kTexChunks>
 __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const unsigned char* tile,
                                                   unsigned char* out_tile,
                                                   const unsigned char* guide_tile,
-                                                  const unsigned char* slab_b, int tex_base,
-                                                  float* out_row, int x0, int q) {
+                                                  const unsigned char* slab_b, int tex_base, int x0, int q) {
   const SliceGeom& g = args.g;
   const float gd_f = static_cast<float>(g.gd);
   float pr[4], pg[4], pb[4];
@@ -154,11 +125,10 @@ __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const uns
     tx[i] = __fsub_rn(__fmul_rn(__fadd_rn(xf, static_cast<float>(i) + 0.5f), g.scale_x), 0.5f);
   const int ix0 = __float2int_rd(tx[0]);
   const float fl0 = static_cast<float>(ix0), fl1 = fl0 + 1.0f;
-  // the three x cells a quad can touch, as slab cell indices (x-major, gd depth cells each)
-  const int c0 = clampi(ix0, 0, g.gw - 1) * g.gd;
-  const int c1 = clampi(ix0 + 1, 0, g.gw - 1) * g.gd;
-  const int c2 = clampi(ix0 + 2, 0, g.gw - 1) * g.gd;
-  const int b0 = c0 * 48, b1 = c1 * 48, b2 = c2 * 48;   // and as byte offsets
+  // the three x cells a quad can touch, as byte offsets into the slab row (x-major, gd depth cells each)
+  const int b0 = clampi(ix0, 0, g.gw - 1) * g.gd * 48;
+  const int b1 = clampi(ix0 + 1, 0, g.gw - 1) * g.gd * 48;
+  const int b2 = clampi(ix0 + 2, 0, g.gw - 1) * g.gd * 48;
 
   float o_r[4], o_g[4], o_b[4];
 #pragma unroll
@@ -178,165 +148,19 @@ __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const uns
     const float wx1 = fx, wx0 = 1.0f - fx;
     const int off[4] = {zc0 * 48 + xo0, zc1 * 48 + xo0, zc0 * 48 + xo1, zc1 * 48 + xo1};
     int tix[4];
-    if constexpr (kSlab == 0) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tix[c] = tex_base + (off[c] >> 4);
-    } else {
-      constexpr int P = tex_parts(kTexChunks);
-      const int xc0 = tex_base + (step ? c1 : c0), xc1 = tex_base + (step ? c2 : c1);
-      tix[0] = (xc0 + zc0) * P; tix[1] = (xc0 + zc1) * P;
-      tix[2] = (xc1 + zc0) * P; tix[3] = (xc1 + zc1) * P;
-    }
+    for (int c = 0; c < 4; ++c) tix[c] = tex_base + (off[c] >> 4);
     const float w[4] = {wx0 * wz0, wx0 * wz1, wx1 * wz0, wx1 * wz1};
-    blend_apply_q<kTexChunks, kSlab>(slab_b, args.slab_tex, off, tix, w, pr[i], pg[i], pb[i],
-                                     o_r[i], o_g[i], o_b[i]);
-  }
-  if constexpr (kStore == 0) {
-    store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
-    fence_proxy_async_smem();
-  } else {
-    float* op = out_row + static_cast<size_t>(x0 + 4 * q) * 3;
-    stg128_stream(op, o_r[0], o_g[0], o_b[0], o_r[1]);
-    stg128_stream(op + 4, o_g[1], o_b[1], o_r[2], o_g[2]);
-    stg128_stream(op + 8, o_b[2], o_r[3], o_g[3], o_b[3]);
-  }
-}
-
-// kPipe (HDRNET_ASYNC_PIPE=1, opt-in, NOT YET RUN ON A GPU): the same quad with the texture fetches
-// software-pipelined one pixel ahead.  The final capture of the default form shows a quarter of
-// all warp-state samples on the FFMA2 that consume a pixel's texture results, issued ~25
-// instructions after the TLD burst; here pixel i+1's indices, weights and TLDs are issued before
-// pixel i's shared-memory chunks and FMAs.  Two pixels' texture data in flight cost 2 x 4 x
-// kTexChunks registers: meant for the 352-thread / 88-register shape.  Same operations in the same
-// order per pixel: identical bits.
-template <int kTexChunks>
-struct PixFront {
-  int off[4];                 // byte offsets of the four corners in the slab row
-  float w[4];                 // corner weights
-  float4 t[kTexChunks];       // texture-fetched chunks: ids 12 - kTexChunks .. 11 (id = 3 corner + part)
-};
-
-template <int kTexChunks>
-__device__ __forceinline__ void pix_front(const TmaArgs& args, int tex_base, float gv, float tx_i,
-                                          bool first, float fl0, float fl1, int b0, int b1, int b2,
-                                          float gd_f, float& fx_out, PixFront<kTexChunks>& f) {
-  const SliceGeom& g = args.g;
-  const bool step = !first && (tx_i >= fl1);
-  const float fx = tx_i - (step ? fl1 : fl0);
-  const int xo0 = step ? b1 : b0;
-  const int xo1 = step ? b2 : b1;
-  const float tz = __fsub_rn(__fmul_rn(gv, gd_f), 0.5f);
-  const int iz = __float2int_rd(tz);
-  const float fz = tz - static_cast<float>(iz);
-  const int zc0 = clampi(iz, 0, g.gd - 1);
-  const int zc1 = clampi(iz + 1, 0, g.gd - 1);
-  float wz0, wz1;
-  smoothed_weights(fz, wz0, wz1);
-  const float wx1 = fx, wx0 = 1.0f - fx;
-  f.off[0] = zc0 * 48 + xo0; f.off[1] = zc1 * 48 + xo0;
-  f.off[2] = zc0 * 48 + xo1; f.off[3] = zc1 * 48 + xo1;
-  f.w[0] = wx0 * wz0; f.w[1] = wx0 * wz1; f.w[2] = wx1 * wz0; f.w[3] = wx1 * wz1;
-  fx_out = fx;
-#pragma unroll
-  for (int id = 12 - kTexChunks; id < 12; ++id) {
-    const int c = id / 3, p = id - 3 * c;
-    f.t[id - (12 - kTexChunks)] = tex1Dfetch<float4>(args.slab_tex, tex_base + (f.off[c] >> 4) + p);
-  }
-}
-
-template <int kTexChunks, int kC, int kP>
-__device__ __forceinline__ ulonglong2 pipe_chunk(const unsigned char* __restrict__ slab_b,
-                                                 const PixFront<kTexChunks>& f) {
-  constexpr int id = 3 * kC + kP;
-  if constexpr (id >= 12 - kTexChunks) {
-    const float4 v = f.t[id - (12 - kTexChunks)];
-    ulonglong2 r;
-    r.x = pack2(v.x, v.y);
-    r.y = pack2(v.z, v.w);
-    return r;
-  } else {
-    return *reinterpret_cast<const ulonglong2*>(slab_b + f.off[kC] + 16 * kP);
-  }
-}
-
-template <int kTexChunks>
-__device__ __forceinline__ void pix_back(const unsigned char* __restrict__ slab_b,
-                                         const PixFront<kTexChunks>& f, float r, float g, float b,
-                                         float& out_r, float& out_g, float& out_b) {
-  const unsigned long long W00 = pack2(f.w[0], f.w[0]), W01 = pack2(f.w[1], f.w[1]);
-  const unsigned long long W10 = pack2(f.w[2], f.w[2]), W11 = pack2(f.w[3], f.w[3]);
-  const ulonglong2 a0 = pipe_chunk<kTexChunks, 0, 0>(slab_b, f), a1 = pipe_chunk<kTexChunks, 0, 1>(slab_b, f);
-  const ulonglong2 a2 = pipe_chunk<kTexChunks, 0, 2>(slab_b, f), b0 = pipe_chunk<kTexChunks, 1, 0>(slab_b, f);
-  const ulonglong2 b1 = pipe_chunk<kTexChunks, 1, 1>(slab_b, f), b2 = pipe_chunk<kTexChunks, 1, 2>(slab_b, f);
-  const ulonglong2 c0 = pipe_chunk<kTexChunks, 2, 0>(slab_b, f), c1 = pipe_chunk<kTexChunks, 2, 1>(slab_b, f);
-  const ulonglong2 c2 = pipe_chunk<kTexChunks, 2, 2>(slab_b, f), d0 = pipe_chunk<kTexChunks, 3, 0>(slab_b, f);
-  const ulonglong2 d1 = pipe_chunk<kTexChunks, 3, 1>(slab_b, f), d2 = pipe_chunk<kTexChunks, 3, 2>(slab_b, f);
-  unsigned long long acc[6];  // blend_apply's order of operations
-  acc[0] = fma2(W11, d0.x, fma2(W10, c0.x, fma2(W01, b0.x, mul2(W00, a0.x))));
-  acc[1] = fma2(W11, d0.y, fma2(W10, c0.y, fma2(W01, b0.y, mul2(W00, a0.y))));
-  acc[2] = fma2(W11, d1.x, fma2(W10, c1.x, fma2(W01, b1.x, mul2(W00, a1.x))));
-  acc[3] = fma2(W11, d1.y, fma2(W10, c1.y, fma2(W01, b1.y, mul2(W00, a1.y))));
-  acc[4] = fma2(W11, d2.x, fma2(W10, c2.x, fma2(W01, b2.x, mul2(W00, a2.x))));
-  acc[5] = fma2(W11, d2.y, fma2(W10, c2.y, fma2(W01, b2.y, mul2(W00, a2.y))));
-  float a0f, a1f, a2f, a3f;
-  unpack2(acc[0], a0f, a1f);
-  unpack2(acc[1], a2f, a3f);
-  out_r = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-  unpack2(acc[2], a0f, a1f);
-  unpack2(acc[3], a2f, a3f);
-  out_g = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-  unpack2(acc[4], a0f, a1f);
-  unpack2(acc[5], a2f, a3f);
-  out_b = fmaf(a2f, b, fmaf(a1f, g, fmaf(a0f, r, a3f)));
-}
-
-template <int kTexChunks>
-__device__ __forceinline__ void process_quad_lean_pipe(const TmaArgs& args, const unsigned char* tile,
-                                                       unsigned char* out_tile,
-                                                       const unsigned char* guide_tile,
-                                                       const unsigned char* slab_b, int tex_base,
-                                                       int x0, int q) {
-  const SliceGeom& g = args.g;
-  const float gd_f = static_cast<float>(g.gd);
-  float pr[4], pg[4], pb[4];
-  load_quad<kPxF32>(tile, q, pr, pg, pb);
-  const float4 gq = lds128(reinterpret_cast<const float4*>(guide_tile) + q);
-  const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
-  const float xf = static_cast<float>(x0 + 4 * q);
-  float tx[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    tx[i] = __fsub_rn(__fmul_rn(__fadd_rn(xf, static_cast<float>(i) + 0.5f), g.scale_x), 0.5f);
-  const int ix0 = __float2int_rd(tx[0]);
-  const float fl0 = static_cast<float>(ix0), fl1 = fl0 + 1.0f;
-  const int b0 = clampi(ix0, 0, g.gw - 1) * g.gd * 48;
-  const int b1 = clampi(ix0 + 1, 0, g.gw - 1) * g.gd * 48;
-  const int b2 = clampi(ix0 + 2, 0, g.gw - 1) * g.gd * 48;
-
-  PixFront<kTexChunks> f[2];
-  float fx_unused;
-  pix_front<kTexChunks>(args, tex_base, gv[0], tx[0], true, fl0, fl1, b0, b1, b2, gd_f, fx_unused, f[0]);
-  float o_r[4], o_g[4], o_b[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (i + 1 < 4)   // next pixel's indices, weights and texture fetches first ...
-      pix_front<kTexChunks>(args, tex_base, gv[i + 1], tx[i + 1], false, fl0, fl1, b0, b1, b2, gd_f,
-                            fx_unused, f[(i + 1) & 1]);
-    // ... then this pixel's shared-memory chunks and arithmetic
-    pix_back<kTexChunks>(slab_b, f[i & 1], pr[i], pg[i], pb[i], o_r[i], o_g[i], o_b[i]);
+    blend_apply_q<kTexChunks>(slab_b, args.slab_tex, off, tix, w, pr[i], pg[i], pb[i], o_r[i], o_g[i], o_b[i]);
   }
   store_quad<kPxF32>(out_tile, q, o_r, o_g, o_b);
   fence_proxy_async_smem();
 }
 
-template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = 512,
-          int kMinBlocks = 2, bool kPipe = false>
+template <int kTexChunks, bool kLean, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 slice_apply_rows_async_kernel(const TmaArgs args) {
-  static_assert(!kPipe || (kLean && kStore == 0 && kSlab == 0), "pipelined quad: plain lean form only");
   static_assert(kTexChunks > 0, "the issuer-warp kernel serves part of the gather by texture");
-  static_assert(kLean || (kStore == 0 && kSlab == 0), "the switches exist in the lean form only");
-  static_assert(kSlab == 0 || (kTexChunks >= 4 && kTexChunks <= 8), "part workspace: 4..8 chunks");
   constexpr int kMathWarps = kThreads / 32 - 1;
   extern __shared__ __align__(128) unsigned char smem[];
   const SliceGeom& g = args.g;
@@ -357,9 +181,6 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
   const long long total_items = static_cast<long long>(g.B) * g.rows * pl.nseg;
   const long long i_begin = total_items * blockIdx.x / gridDim.x;
   const long long i_end = total_items * (blockIdx.x + 1) / gridDim.x;
-  // Programmatic dependent launch (no-ops when launched without the attribute): let the next
-  // kernel in the stream be scheduled as this grid's CTAs retire.
-  grid_launch_dependents();
   if (i_end <= i_begin) return;
   const long long r_begin = i_begin / pl.nseg, r_end = (i_end - 1) / pl.nseg + 1;
   const int x_first = static_cast<int>(i_begin - r_begin * pl.nseg) * pl.seg_px;
@@ -383,51 +204,18 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
 
   if (warp == kMathWarps) {
     // ------------------------------- issuer warp --------------------------------------------
-    // Lane 0 issues every bulk copy; the whole warp blends slab rows when kSlab == 1.
-    if (kSlab == 0 && lane != 0) return;
-    auto make_slab = [&](long long row) {
+    // Lane 0 issues every bulk copy.
+    if (lane != 0) return;
+    auto make_slab = [&](long long row) {   // the row's y-pre-blended slab, from the pre-pass workspace
       const int rb = static_cast<int>(row - r_begin) & 1;
-      if constexpr (kSlab == 0) {
-        if (lane == 0) {
-          mbar_expect_tx(&slab_full[rb], slab_bytes);
-          tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
-                      args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes,
-                      &slab_full[rb]);
-        }
-      } else {
-        // yslab[r] = (1 - fy) G[b][gy0] + fy G[b][gy1], exactly yblend_rows_kernel's arithmetic
-        const int b = static_cast<int>(row / g.rows);
-        const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
-        const Axis ay = spatial_axis(y, g.scale_y);
-        const float wy1 = ay.f, wy0 = 1.0f - ay.f;
-        const float* gb = args.grid + static_cast<size_t>(b) * g.gh * pl.row_floats;
-        const float4* a4 = reinterpret_cast<const float4*>(
-            gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * pl.row_floats);
-        const float4* b4 = reinterpret_cast<const float4*>(
-            gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * pl.row_floats);
-        float4* s4 = reinterpret_cast<float4*>(raw0 + static_cast<size_t>(rb) * slab_bytes);
-        const int n4 = pl.row_floats / 4;
-        // six cells' loads in flight per lane and batch (L2 latency, not bandwidth, is the cost)
-        for (int e0 = lane; e0 < n4; e0 += 32 * 6) {
-          float4 va[6], vb[6];
-#pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            const int e = min(e0 + 32 * u, n4 - 1);
-            va[u] = ldg128_stream(a4 + e);
-            vb[u] = ldg128_stream(b4 + e);
-          }
-#pragma unroll
-          for (int u = 0; u < 6; ++u)
-            if (e0 + 32 * u < n4) s4[e0 + 32 * u] = lerp4(wy0, va[u], wy1, vb[u]);
-        }
-        __syncwarp();
-        if (lane == 0) arrive(&slab_full[rb]);
-      }
+      mbar_expect_tx(&slab_full[rb], slab_bytes);
+      tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
+                  args.yslab + static_cast<size_t>(row) * pl.row_floats, slab_bytes, &slab_full[rb]);
     };
     // load cursor: runs NS - 1 items ahead of the math warps
     long long l_row = r_begin;
     int l_x0 = x_first, l_s = 0;
-    auto issue_next_load = [&]() {  // lane 0
+    auto issue_next_load = [&]() {
       if (l_row >= r_end) return;
       const int npx = min(pl.seg_px, g.W - l_x0);
       unsigned char* st = stage_base + static_cast<size_t>(l_s) * pl.stage_bytes;
@@ -439,47 +227,32 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
       l_x0 += pl.seg_px;
       if (l_x0 >= row_x1(l_row)) { l_x0 = 0; ++l_row; }
     };
-    // kStore 0: the stage refilled after item i is item i-1's (its bulk store must have drained);
-    // kStore 1: item i's own stage -- one more item of prefetch from the same ring.
-    // The pixel tensors are the caller's inputs (complete before the pre-pass started): their
-    // loads may precede the dependency wait; the workspace written by the pre-pass may not.
-    if (lane == 0)
-      for (int i = 0; i < NS - (kStore == 0 ? 1 : 0); ++i) issue_next_load();
-    grid_dependency_wait();
+    // the stage refilled after item i is item i-1's (its bulk store must have drained)
+    for (int i = 0; i < NS - 1; ++i) issue_next_load();
     make_slab(r_begin);
     if (r_begin + 1 < r_end) make_slab(r_begin + 1);
 
-    // Lane 0 alone runs the per-item protocol; the other lanes park at the row's __syncwarp (a
-    // blocked WARPSYNC costs nothing, whereas 31 lanes spinning in a try_wait loop on the same
-    // mbarrier delay lane 0's serial section: measured +10 % kernel time).
     int s = 0;
     uint32_t ph = 0;
     for (long long row = r_begin; row < r_end; ++row) {
-      if (lane == 0) {
-        const int x_end = row_x1(row);
-        for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
-          mbar_wait(&done[s], ph);  // every math warp is through with this stage
-          if constexpr (kStore == 0) {  // results were written in place (and proxy-fenced)
-            const int npx = min(pl.seg_px, g.W - x0);
-            unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
-            const size_t pix = static_cast<size_t>(row) * g.W + x0;
-            tma_store_1d(args.out + pix * 12, st, static_cast<uint32_t>(npx) * 12u);
-            tma_store_commit();
-            if (l_row < r_end) {
-              tma_store_wait_read<1>();  // the previous item's store has drained the stage refilled now
-              issue_next_load();
-            }
-          } else {
-            issue_next_load();          // refills THIS stage: nothing reads it any more
-          }
-          if (++s == NS) { s = 0; ph ^= 1u; }
+      const int x_end = row_x1(row);
+      for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
+        mbar_wait(&done[s], ph);  // every math warp is through with this stage (results written in place, proxy-fenced)
+        const int npx = min(pl.seg_px, g.W - x0);
+        unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
+        const size_t pix = static_cast<size_t>(row) * g.W + x0;
+        tma_store_1d(args.out + pix * 12, st, static_cast<uint32_t>(npx) * 12u);
+        tma_store_commit();
+        if (l_row < r_end) {
+          tma_store_wait_read<1>();  // the previous item's store has drained the stage refilled now
+          issue_next_load();
         }
+        if (++s == NS) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
       // the row's slab buffer is free: every math warp arrived after its last read of it
       if (row + 2 < r_end) make_slab(row + 2);
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    tma_store_wait_all<0>();
     return;
   }
 
@@ -492,19 +265,15 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
     const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
     mbar_wait(&slab_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u);
     const unsigned char* slab_b = raw0 + static_cast<size_t>(rb) * slab_bytes;
-    const int tex_base = static_cast<int>(row) * (kSlab == 0 ? cells * 3 : cells);
-    float* out_row = reinterpret_cast<float*>(args.out) + static_cast<size_t>(row) * g.W * 3;
+    const int tex_base = static_cast<int>(row) * cells * 3;
     const int x_end = row_x1(row);
     for (int x0 = row_x0(row); x0 < x_end; x0 += pl.seg_px) {
       const int npx = min(pl.seg_px, g.W - x0);
       unsigned char* st = stage_base + static_cast<size_t>(s) * pl.stage_bytes;
       mbar_wait(&full[s], ph);
       if (q * 4 < npx) {
-        if constexpr (kPipe)
-          process_quad_lean_pipe<kTexChunks>(args, st, st, st + pl.off_guide, slab_b, tex_base, x0, q);
-        else if constexpr (kLean)
-          process_quad_lean<kTexChunks, kStore, kSlab>(args, st, st, st + pl.off_guide, slab_b,
-                                                       tex_base, out_row, x0, q);
+        if constexpr (kLean)
+          process_quad_lean<kTexChunks>(args, st, st, st + pl.off_guide, slab_b, tex_base, x0, q);
         else
           process_quad<GuideFromInput, kTexChunks>(args, GuideFromInput{}, st, st, st + pl.off_guide,
                                                    reinterpret_cast<const float*>(slab_b), tex_base,
@@ -517,26 +286,21 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
   }
 }
 
-template <int kTexChunks, bool kLean, int kStore = 0, int kSlab = 0, int kThreads = kAsyncThreads,
-          int kMinBlocks = 2, bool kPipe = false>
-static int launch_async(const TmaArgs& a, cudaStream_t stream, bool pdl) {
-  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kStore, kSlab, kThreads, kMinBlocks, kPipe>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       a.p.smem_bytes);
+template <int kTexChunks, bool kLean, int kThreads>
+static int launch_async(const TmaArgs& a, cudaStream_t stream) {
+  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kThreads, 2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  e = launch_maybe_pdl(kern, static_cast<unsigned>(a.p.ctas), kThreads,
-                       static_cast<size_t>(a.p.smem_bytes), stream, pdl, a);
-  if (e != cudaSuccess) return static_cast<int>(e);
+  kern<<<a.p.ctas, kThreads, a.p.smem_bytes, stream>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
 // =========================================================================================
-// Issuer-warp control flow for the FUSED-GUIDE (model path) forms -- opt-in, HDRNET_FUSED_ASYNC=1,
-// NOT YET RUN ON A GPU.
+// Issuer-warp control flow for the FUSED-GUIDE (model path) forms.
 // =========================================================================================
 // HDRNetCurves / HDRNetPointwiseNNGuide compute the guide from the pixel's RGB in registers
-// (24 B/px, models.py:43-59) and may read / write integer pixels; they still run the
-// block-synchronous kernel (slice_apply.cu).  This is that kernel's per-pixel code (process_quad:
+// (24 B/px, models.py:43-59) and may read / write integer pixels.  This is the block-synchronous
+// kernel's per-pixel code (slice_apply.cu, process_quad:
 // identical bits) under the issuer-warp control flow above: math warps that only wait for their
 // stage and ARRIVE on done[s], one warp that issues every bulk copy.  8 math warps + the issuer
 // (288 threads, 112 registers at two CTAs per SM: the fused forms are issue-bound and want their
@@ -686,53 +450,17 @@ int launch_async_fused(const TmaArgs& a, int mode, const CurvesGuideParams* curv
   return HDRNET_E_UNSUPPORTED;
 }
 
-// Knobs -> instantiation (launch_slice_apply_impl has validated them).
-int launch_async_form(const TmaArgs& a, int chunks, bool lean, int store, int slab, int async_threads,
-                      int async_occ, bool pdl, bool pipe, cudaStream_t stream) {
-  if (pipe) {   // opt-in: texture fetches one pixel ahead (plain lean form, 4 / 5 chunks, 512 x 2 or 352 x 2)
-    if (!lean || store || slab || (chunks != 4 && chunks != 5)) return HDRNET_E_UNSUPPORTED;
-    if (async_threads == 512) {
-      if (chunks == 4) return launch_async<4, true, 0, 0, 512, 2, true>(a, stream, pdl);
-      return launch_async<5, true, 0, 0, 512, 2, true>(a, stream, pdl);
-    }
-    if (async_threads == 352) {
-      if (chunks == 4) return launch_async<4, true, 0, 0, 352, 2, true>(a, stream, pdl);
-      return launch_async<5, true, 0, 0, 352, 2, true>(a, stream, pdl);
-    }
-    return HDRNET_E_UNSUPPORTED;
+// chunks (4 | 5), per-quad index arithmetic or not, CTA shape (512 | 352 threads) -> instantiation
+int launch_async_form(const TmaArgs& a, int chunks, bool lean, int threads, cudaStream_t stream) {
+  if (threads == 352) {
+    if (lean) return chunks == 4 ? launch_async<4, true, 352>(a, stream) : launch_async<5, true, 352>(a, stream);
+    return chunks == 4 ? launch_async<4, false, 352>(a, stream) : launch_async<5, false, 352>(a, stream);
   }
-      if (async_threads != 512 && lean && !store && !slab) {
-#define HDRNET_ASYNC_SHAPE(K)                                                                  \
-        if (chunks == K) {                                                                       \
-          if (async_threads == 352) return launch_async<K, true, 0, 0, 352, 2>(a, stream, pdl);       \
-          if (async_occ == 3) return launch_async<K, true, 0, 0, 224, 3>(a, stream, pdl);            \
-          return launch_async<K, true, 0, 0, 224, 4>(a, stream, pdl);                                 \
-        }
-        HDRNET_ASYNC_SHAPE(4)
-        HDRNET_ASYNC_SHAPE(5)
-        HDRNET_ASYNC_SHAPE(6)
-#undef HDRNET_ASYNC_SHAPE
-        return HDRNET_E_UNSUPPORTED;
-      }
-      if (!lean) {
-        switch (chunks) {
-          case 5: return launch_async<5, false>(a, stream, pdl);
-          default: return launch_async<kTexChunksDefault, false>(a, stream, pdl);
-        }
-      }
-#define HDRNET_ASYNC_CASE(K)                                                              \
-      if (chunks == K) {                                                                    \
-        if (store && slab) return launch_async<K, true, 1, 1>(a, stream, pdl);                   \
-        if (store) return launch_async<K, true, 1, 0>(a, stream, pdl);                           \
-        if (slab) return launch_async<K, true, 0, 1>(a, stream, pdl);                            \
-        return launch_async<K, true, 0, 0>(a, stream, pdl);                                      \
-      }
-      HDRNET_ASYNC_CASE(4)
-      HDRNET_ASYNC_CASE(5)
-      HDRNET_ASYNC_CASE(6)
-#undef HDRNET_ASYNC_CASE
-      if (chunks == 3) return launch_async<3, true, 0, 0>(a, stream, pdl);
-      return HDRNET_E_UNSUPPORTED;
+  if (threads == 512) {
+    if (lean) return chunks == 4 ? launch_async<4, true, 512>(a, stream) : launch_async<5, true, 512>(a, stream);
+    return chunks == 4 ? launch_async<4, false, 512>(a, stream) : launch_async<5, false, 512>(a, stream);
+  }
+  return HDRNET_E_UNSUPPORTED;
 }
 
 }  // namespace hdrnet_b200

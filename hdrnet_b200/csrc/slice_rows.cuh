@@ -102,23 +102,18 @@ __device__ __forceinline__ float load_channel(const unsigned char* base, long lo
 // =========================================================================================
 
 constexpr int kTmaThreads = 256;
-constexpr int kTmaThreadsDefault = 256;  // all-LSU form; 512 = 64-register form (HDRNET_TMA_THREADS)
-constexpr int kTexThreadsDefault = 512;  // texture-assisted form: measured 7 % faster at 512
-constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the texture-assisted kernel
-constexpr int kAsyncThreads = 512;        // issuer-warp form: 15 math warps + the issuer
-constexpr int kAsyncThreadsDefault = 512; // HDRNET_ASYNC_THREADS / HDRNET_ASYNC_OCC
-constexpr int kAsyncOccDefault = 2;
+constexpr int kTmaThreadsDefault = 256;  // all-LSU form
+constexpr int kTexThreadsDefault = 512;  // block-synchronous texture-assisted form: measured 7 % faster at 512 (64 registers)
+constexpr int kFusedThreadsDefault = 256; // fused-guide forms of the block-synchronous kernel
+constexpr int kAsyncThreadsDefault = 352; // issuer-warp form: 10 math warps + the issuer, two CTAs per SM, 88 registers
+                                          // (same-box A/B, profiles/r02_ab_async_pipe.txt: 0.4451 ms against 0.4563 at 512)
 // AUTO takes the issuer-warp form only with a ring of >= 3 stages at two CTAs per SM: with the two
 // stages that 32x32 grids leave (24 / 48 KB of slab rows) it measured SLOWER than the
 // block-synchronous form (32x32x8: 46.9 % vs 53.2 % of HBM peak; 32x32x16: 31.1 % vs 37.5 %).
 constexpr int kAsyncAutoMinStages = 3;
-constexpr bool kAsyncPdlDefault = false;  // HDRNET_ASYNC_PDL=1: measured +14 % step time (profiles/r01_async_ab_pdl.txt)
-constexpr int kAsyncTexChunksDefault = 5; // its tuning defaults (HDRNET_TEX_CHUNKS / _ASYNC_STORE / _SLAB)
-constexpr int kAsyncStoreDefault = 0;
-constexpr int kAsyncSlabDefault = 0;
+constexpr int kAsyncTexChunksDefault = 5; // corner chunks per pixel through the texture pipe (HDRNET_TEX_CHUNKS)
 constexpr int kMaxStages = 8;
 constexpr int kTexChunksDefault = 4;   // texture chunks of the block-synchronous and opt-in forms
-constexpr int kTexInStages = 3;   // output tiles of the texture-fed input form (no input ring)
 constexpr int kGc = 12;
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -145,8 +140,6 @@ struct TmaArgs {
   float* guide_out;     // optional guide dump for the fused forms, else nullptr
   const unsigned char* input;   // [B * rows][W][3] in the kernel's input pixel format
   unsigned char* out;           // [B * rows][W][3] in the kernel's output pixel format
-  cudaTextureObject_t in_tex;    // texture-fed form: float4 views of `input` and `guide`
-  cudaTextureObject_t guide_tex;
   cudaTextureObject_t slab_tex;  // kTexChunks > 0: float4 view of the y-pre-blended slab rows
   const float* yslab;            // kTexChunks > 0: [B * rows][gw * gd * 12] slab rows (workspace)
   SliceGeom g;
@@ -292,34 +285,10 @@ __device__ __forceinline__ void process_quad(const TmaArgs& args, const GuideFn&
   fence_proxy_async_smem();
 }
 
-// Launch with (pdl) or without the programmatic-stream-serialization attribute.  With it the
-// kernel may be SCHEDULED before its predecessor in the stream has drained; every kernel launched
-// this way executes griddepcontrol.wait before its first dependent memory access.
-template <class... KArgs, class... Args>
-static cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem,
-                                    cudaStream_t stream, bool pdl, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-
-// Entry points of the other translation units (non-template: the knobs select the instantiation).
-//   slice_apply_async.cu
-int launch_async_form(const TmaArgs& a, int chunks, bool lean, int store, int slab, int threads, int occ,
-                      bool pdl, bool pipe, cudaStream_t stream);
+// Entry points of slice_apply_async.cu (non-template: the arguments select the instantiation).
+int launch_async_form(const TmaArgs& a, int chunks, bool lean, int threads, cudaStream_t stream);
 int launch_async_fused(const TmaArgs& a, int mode, const CurvesGuideParams* curves, const NNGuideParams* nn,
                        int in_fmt, int out_fmt, cudaStream_t stream);
 constexpr int kFusedAsyncMathThreads = 256;   // 8 math warps (+ the issuer warp) of the fused-guide issuer-warp form
-//   slice_apply_variants.cu
-int launch_texin_form(const TmaArgs& a, int chunks, cudaStream_t stream);
-int launch_ws_form(const TmaArgs& a, cudaStream_t stream);
 
 }  // namespace hdrnet_b200

@@ -55,6 +55,14 @@ def _same_device(*ts: torch.Tensor) -> torch.device:
     return dev
 
 
+_host_locks = {}  # device index -> lock serialising calls on that device's host context
+
+
+def _host_call_lock(device_index: int) -> threading.Lock:
+    with _ctx_lock:
+        return _host_locks.setdefault(device_index, threading.Lock())
+
+
 def _host_context(device_index: int):
     with _ctx_lock:
         ctx = _host_ctx.get(device_index)
@@ -67,15 +75,13 @@ def _host_context(device_index: int):
         return ctx
 
 
-_ws_cache = {}  # device -> float32 workspace tensor (grown on demand)
-
-
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    ws = _ws_cache.get(dev)
-    if ws is None or ws.numel() * 4 < nbytes:
-        ws = torch.empty((max(int(nbytes), 16) + 3) // 4, dtype=torch.float32, device=dev)
-        _ws_cache[dev] = ws
-    return ws
+    """Slab-row workspace of ONE call, from torch's caching allocator on the current stream (the
+    library never allocates).  Per call on purpose: a block cached across calls would be shared by
+    calls on different streams / threads, whose pre-passes overwrite each other's slab rows.  The
+    allocator hands a freed block back to the same stream only (stream-ordered reuse), so dropping
+    the tensor right after the launch is safe."""
+    return torch.empty((max(int(nbytes), 16) + 3) // 4, dtype=torch.float32, device=dev)
 
 
 def _check_slice_args(grid, guide, grid_msg):
@@ -225,8 +231,7 @@ def bilateral_slice_apply(grid: torch.Tensor, guide: torch.Tensor, input: torch.
             # A workspace from torch's caching allocator (the library never allocates) lets AUTO
             # pick the texture-assisted kernel for large images (>= 2 Mi px, W % 4 == 0).
             ws_ptr, ws_bytes = 0, 0
-            explicit_tex = int(variant) in (_lib.VARIANT_TEX, _lib.VARIANT_TEX_WS, _lib.VARIANT_TEX_IN,
-                                            _lib.VARIANT_TEX_ASYNC, _lib.VARIANT_TC, _lib.VARIANT_TC_GATHER)
+            explicit_tex = int(variant) in (_lib.VARIANT_TEX, _lib.VARIANT_TEX_ASYNC)
             if (int(variant) == _lib.VARIANT_AUTO or explicit_tex) and n_in == 3 and n_out == 3 \
                     and has_offset and W % 4 == 0 and (explicit_tex or B * H * W >= (1 << 21)):
                 ws = _workspace(dev, lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))
@@ -242,7 +247,9 @@ def bilateral_slice_apply(grid: torch.Tensor, guide: torch.Tensor, input: torch.
         out = torch.empty(shape, dtype=torch.float32, pin_memory=guide.is_pinned())
     device_index = torch.cuda.current_device()
     ctx = _host_context(device_index)
-    with torch.cuda.device(device_index):
+    # one call at a time per context: its staging buffers and streams are the context's own
+    # (ctypes releases the GIL, so threads could otherwise interleave inside the library)
+    with _host_call_lock(device_index), torch.cuda.device(device_index):
         rc = lib.hdrnet_slice_apply_host_f32(ctx, grid.data_ptr(), guide.data_ptr(),
                                              input.data_ptr(), out.data_ptr(), B, H, W, gh, gw,
                                              gd, n_in, n_out, int(has_offset))

@@ -24,6 +24,7 @@ Execution (all hand-written sm_100a kernels through the C-ABI, no torch math on 
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import math
 
@@ -144,7 +145,16 @@ def init_weights(params, seed: int = 0, model_name: str | None = None) -> dict:
 
 
 # ---- prepared (device-resident, BN-folded) weights ---------------------------------------------
-_prepared: dict = {}
+# Keyed by the identity of the weights dict: an entry keeps a reference to its dict (so the id
+# cannot be recycled while the entry lives), the cache holds the most recent kPreparedMax entries,
+# and a dict UPDATED IN PLACE must be announced with invalidate_prepared().
+_prepared: "collections.OrderedDict" = collections.OrderedDict()
+kPreparedMax = 8
+
+
+def invalidate_prepared() -> None:
+    """Drop every cached device copy of model weights (call after mutating a weights dict in place)."""
+    _prepared.clear()
 
 
 def _fold(wts, scope, use_bn, use_bias):
@@ -211,7 +221,12 @@ def _prepare(wts, params, device, nn_guide) -> _Prepared:
     prep = _prepared.get(key)
     if prep is None:
         prep = _Prepared(wts, params, device, nn_guide)
+        prep.source = wts                      # pins id(wts) for the lifetime of the entry
         _prepared[key] = prep
+        while len(_prepared) > kPreparedMax:
+            _prepared.popitem(last=False)
+    else:
+        _prepared.move_to_end(key)
     return prep
 
 

@@ -17,7 +17,43 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["init_distributed", "shard_batch", "shard_rows", "broadcast_weights",
-           "max_over_ranks", "finalize"]
+           "max_over_ranks", "finalize", "bind_to_gpu_numa", "gpu_cpu_affinity"]
+
+
+def gpu_cpu_affinity(device_index: int) -> list[int]:
+    """CPUs of the NUMA node / root complex GPU `device_index` hangs off (NVML's "ideal CPU
+    affinity", what `nvidia-smi topo -m` prints), restricted to the CPUs this process may run on.
+    Empty when NVML or the information is not available."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+    except Exception:
+        return []
+    try:
+        allowed = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        allowed = set(range(os.cpu_count() or 1))
+    return sorted(c for c in cpus if c in allowed)
+
+
+def bind_to_gpu_numa(device_index: int) -> list[int]:
+    """Pin this process (and the threads it starts later: the host path's copy threads, pinned
+    allocations' first touch) to the CPUs local to its GPU.  Call BEFORE allocating pinned host
+    memory: with eight ranks feeding 1.9 GB per step each, buffers that land on the other socket
+    cross the inter-socket link on every H2D / D2H copy (SCALE_r01: end-to-end efficiency 0.45 at
+    8 GPUs with device-timed 0.99).  Returns the CPU list it bound to ([] = left unbound)."""
+    cpus = gpu_cpu_affinity(device_index)
+    if not cpus:
+        return []
+    try:
+        os.sched_setaffinity(0, cpus)
+    except (AttributeError, OSError):
+        return []
+    return cpus
 
 
 def init_distributed(backend: str | None = None):

@@ -57,39 +57,17 @@ extern "C" {
 #define HDRNET_VARIANT_TMA 2     /* persistent TMA-staged row kernel (needs W % 4 == 0,    */
                                  /* 16-byte aligned buffers; n_in == 3, n_out == 3,        */
                                  /* has_offset for slice-apply)                            */
-#define HDRNET_VARIANT_ZSORT 3   /* z-bucketed TMA kernel: pixels of a row segment are     */
-                                 /* counting-sorted by (x cell, depth cell) so one load    */
-                                 /* of the corner vectors serves 4 pixels (same shape      */
-                                 /* limits as TMA, plus (gd + 1) * cells-per-segment <= 64)*/
 #define HDRNET_VARIANT_TEX 4     /* texture-assisted TMA kernel: a pre-pass writes the      */
                                  /* y-pre-blended slab rows to a caller workspace; the row  */
                                  /* kernel then fetches part of each pixel's corner data    */
                                  /* through the texture pipe, which does not share the      */
                                  /* shared-memory crossbar.  Needs hdrnet_slice_apply_f32_ws*/
-#define HDRNET_VARIANT_TEX_WS 5  /* the same, warp-specialised: a producer warp issues all  */
-                                 /* TMA loads, 8 math warps run without block barriers     */
-
-#define HDRNET_VARIANT_TEX_IN 6  /* the texture-assisted kernel with the pixel INPUT fetched     */
-                                 /* through the texture pipe as well (no input staging in    */
-                                 /* shared memory); same requirements as HDRNET_VARIANT_TEX  */
-#define HDRNET_VARIANT_TEX_ASYNC 7 /* the texture-assisted kernel with an ISSUER warp: 15 math   */
+#define HDRNET_VARIANT_TEX_ASYNC 7 /* the texture-assisted kernel with an ISSUER warp: math      */
                                  /* warps that never wait for each other (mbarrier arrive    */
                                  /* instead of block barriers) + one warp that issues every  */
                                  /* bulk copy; per-quad index arithmetic.  Same requirements */
-                                 /* as HDRNET_VARIANT_TEX                                     */
-#define HDRNET_VARIANT_TC 8      /* EXPERIMENTAL, never picked by AUTO: depth interpolation on  */
-                                 /* the tensor cores (tcgen05.mma kind::tf32, 3xTF32, weights   */
-                                 /* and accumulator in tensor memory); gd == 8, gw >= 3,        */
-                                 /* W >= 128 gw, needs the workspace like HDRNET_VARIANT_TEX    */
-#define HDRNET_VARIANT_TC_GATHER 9 /* EXPERIMENTAL, never run: the tensor core as an exact gather */
-                                 /* engine (one-hot A, both depth rows per x cell in B, 2 MMAs  */
-                                 /* M128 N96 K8), trilinear blend in registers; same limits     */
-
-#define HDRNET_VARIANT_MMA 10     /* tensor-core gather form: tiles aligned to x cells, exact   */
-                                 /* one-hot A in tensor memory, B' built in the kernel (no       */
-                                 /* workspace, no pre-pass); 2-way TF32 split of the slab        */
-#define HDRNET_VARIANT_MMA3 11    /* the same with a 3-way split (exact copy of the slab values) */
-
+                                 /* as HDRNET_VARIANT_TEX.  (Values 3, 5, 6, 8-11 named forms */
+                                 /* that measured slower; they live in tools/experiments/.)   */
 HDRNET_API int hdrnet_b200_abi_version(void);
 
 /* Human-readable text for a return code of this library (static storage). */

@@ -63,3 +63,18 @@ def test_weight_broadcast_and_timing_reduction_world2():
     assert s0["inference/coefficients/splat/conv1/weights"] == (3, 3, 3, 8)
     assert t0 == t1 == 11.0                       # max over ranks
     assert span0 == (0, 5) and span1 == (5, 9)    # batch shard covers all 9 images
+
+
+def test_numa_binding_is_safe_without_nvml_and_never_widens_the_mask():
+    """bind_to_gpu_numa must be a no-op when NVML / the GPU is absent (this container), and when it
+    does bind, the new mask is a subset of the CPUs the process was allowed before."""
+    import os
+    from hdrnet_b200 import parallel
+    before = os.sched_getaffinity(0)
+    try:
+        cpus = parallel.bind_to_gpu_numa(0)
+        after = os.sched_getaffinity(0)
+        assert set(cpus) <= before and after <= before
+        assert (not cpus and after == before) or (cpus and after == set(cpus))
+    finally:
+        os.sched_setaffinity(0, before)

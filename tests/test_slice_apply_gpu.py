@@ -16,13 +16,8 @@ from util import RTOL, assert_parity, load_golden, rand_case, rel_err
 pytestmark = pytest.mark.gpu
 
 VARIANTS = {"auto": _lib.VARIANT_AUTO, "generic": _lib.VARIANT_GENERIC, "tma": _lib.VARIANT_TMA,
-            "zsort": _lib.VARIANT_ZSORT, "tex": _lib.VARIANT_TEX, "tex_ws": _lib.VARIANT_TEX_WS,
-            "tex_in": _lib.VARIANT_TEX_IN, "tex_async": _lib.VARIANT_TEX_ASYNC, "tc": _lib.VARIANT_TC, "tc_gather": _lib.VARIANT_TC_GATHER}
-
-# Variants that have never run on a GPU (written after the round's GPU budget was spent): their
-# tests only run on request, so that a first-run bug cannot take the suite down.
-experimental = pytest.mark.skipif(os.environ.get("HDRNET_TEST_EXPERIMENTAL") != "1",
-                                  reason="set HDRNET_TEST_EXPERIMENTAL=1 to run the untested variants")
+            "tex": _lib.VARIANT_TEX, "tex_async": _lib.VARIANT_TEX_ASYNC}
+ROW_KERNELS = ("tma", "tex", "tex_async")
 
 
 def cuda(a):
@@ -100,21 +95,18 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("variant", ["auto", "generic", "tma", "zsort", "tex", "tex_ws", "tex_in",
-                                     "tex_async"])
+@pytest.mark.parametrize("variant", ["auto", "generic", "tma", "tex", "tex_async"])
 def test_slice_apply_matches_oracle(shape, variant):
     B, H, W, gh, gw, gd = shape
-    if variant in ("tma", "zsort", "tex", "tex_ws", "tex_in", "tex_async") and W % 4 != 0:
+    if variant in ROW_KERNELS and W % 4 != 0:
         pytest.skip("TMA kernels need W % 4 == 0")
     grid, guide, inp = rand_case(1234, B, H, W, gh, gw, gd, signed=True)
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
     try:
         got = run_apply(grid, guide, inp, True, variant)
     except ValueError as e:
-        if variant == "zsort" and "cannot run these shapes" in str(e):
-            pytest.skip("z-bucketed kernel does not take this grid / width")
-        if variant == "tex_in" and gw * gd * 48 >= 24 * 1024 and "cannot run these shapes" in str(e):
-            pytest.skip("texture-fed kernel: slab rows + output tiles exceed two CTAs' shared memory")
+        if variant == "tex_async" and gw * gd * 48 >= 24 * 1024 and "cannot run these shapes" in str(e):
+            pytest.skip("issuer-warp kernel: two slab rows + a 3-stage ring exceed two CTAs' shared memory")
         raise
     assert_parity(got, expected, what=f"{shape} [{variant}]")
 
@@ -181,62 +173,56 @@ def test_guide_outside_unit_range_clamps_like_reference():
     guide[0, :, 1::3] = 1.5
     guide[0, 0, :4] = [0.0, 1.0, 100.0, -100.0]
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
-    assert_parity(run_apply(grid, guide, inp, True, "zsort"), expected, what="zsort")
+    for v in ROW_KERNELS:
+        assert_parity(run_apply(grid, guide, inp, True, v), expected, what=v)
 
 
-def test_zsort_is_bitwise_equal_to_row_kernel():
-    """Same per-pixel arithmetic in a different order: results must be identical bits."""
+def test_row_kernels_are_bitwise_equal():
+    """Same per-pixel arithmetic whatever path a corner chunk travels (shared memory / texture) and
+    whatever the control flow (block-synchronous / issuer warp, per-pixel / per-quad indices):
+    results must be identical bits."""
     grid, guide, inp = rand_case(77, 2, 64, 3840, 16, 16, 8, signed=True)
     a = run_apply(grid, guide, inp, True, "tma")
-    b = run_apply(grid, guide, inp, True, "zsort")
-    assert np.array_equal(a, b)
-    assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex"))   # texture-assisted form too
-    assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex_ws"))  # and its warp-specialised form
-    assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex_in"))  # and the texture-fed form
-    assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex_async"))  # issuer-warp form, per-quad indices
-    # smooth (image-like) guide: long runs of equal depth cells, heavily unbalanced buckets
+    assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex"))
+    assert np.array_equal(a, run_apply(grid, guide, inp, True, "tex_async"))
+    # smooth (image-like) guide: long runs of equal depth cells; and a constant guide
     yy, xx = np.mgrid[0:64, 0:3840]
     guide2 = np.stack([(0.5 + 0.5 * np.sin(xx / 700.0 + yy / 30.0)).astype(np.float32)] * 2)
-    assert np.array_equal(run_apply(grid, guide2, inp, True, "tma"),
-                          run_apply(grid, guide2, inp, True, "zsort"))
-    const = np.full_like(guide, 0.3)       # every pixel in ONE depth bucket
-    assert np.array_equal(run_apply(grid, const, inp, True, "tma"),
-                          run_apply(grid, const, inp, True, "zsort"))
+    const = np.full_like(guide, 0.3)
+    for gu in (guide2, const):
+        a = run_apply(grid, gu, inp, True, "tma")
+        assert np.array_equal(a, run_apply(grid, gu, inp, True, "tex_async"))
 
 
-@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_LEAN="0"), dict(HDRNET_TEX_CHUNKS="4"),
-                                 dict(HDRNET_TEX_CHUNKS="3"), dict(HDRNET_TEX_CHUNKS="6"),
-                                 dict(HDRNET_ASYNC_LEAN="0", HDRNET_TEX_CHUNKS="4"),
-                                 dict(HDRNET_ASYNC_STORE="1"), dict(HDRNET_ASYNC_SLAB="1"),
-                                 dict(HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1"),
-                                 dict(HDRNET_ASYNC_STORE="0", HDRNET_ASYNC_SLAB="0"),
-                                 dict(HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1", HDRNET_TEX_CHUNKS="4"),
-                                 dict(HDRNET_ASYNC_STORE="1", HDRNET_ASYNC_SLAB="1", HDRNET_TEX_CHUNKS="6"),
-                                 dict(HDRNET_ASYNC_SLAB="1", HDRNET_TEX_CHUNKS="4")],
+def _knob_sha(env, *args):
+    """SHA-256 of a seeded case's output computed by tests/knob_runner.py in a process of its own
+    (the library reads its tuning record once per process)."""
+    import subprocess, sys
+    e = {k: v for k, v in os.environ.items() if not k.startswith("HDRNET_")}
+    e.update(env)
+    runner = os.path.join(os.path.dirname(os.path.abspath(__file__)), "knob_runner.py")
+    out = subprocess.run([sys.executable, runner, *map(str, args)], env=e, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    return [l for l in out.stdout.splitlines() if l.startswith("SHA256")][-1]
+
+
+@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_THREADS="512"), dict(HDRNET_ASYNC_THREADS="352"),
+                                 dict(HDRNET_TEX_CHUNKS="4"), dict(HDRNET_ASYNC_THREADS="512", HDRNET_TEX_CHUNKS="4")],
                          ids=lambda e: ",".join(f"{k[7:].lower()}={v}" for k, v in e.items()))
-def test_issuer_warp_kernel_knobs_are_bitwise_equal(env, monkeypatch):
-    """The issuer-warp form with per-pixel instead of per-quad index arithmetic, and with 3 / 5 / 6
-    of a pixel's 12 corner chunks on the texture pipe, with results stored straight from the
-    registers (ASYNC_STORE) and with the slab rows blended by the issuer warp (ASYNC_SLAB: the
-    pre-pass then writes only the texture-fetched parts): identical bits; also on narrow x cells
-    (W < 4 gw: the kernel must fall back to per-pixel indices by itself), many rows per CTA, a
-    ragged last segment and out-of-range guides."""
-    cases = [rand_case(5, 2, 64, 3840, 16, 16, 8, signed=True),
-             rand_case(6, 1, 700, 1028, 5, 7, 3, signed=True),
-             rand_case(7, 3, 9, 128, 8, 64, 4, signed=True)]
-    cases[1][1][0, :, ::5] = 1.75
-    cases[1][1][0, :, 1::5] = -0.6
-    for grid, guide, inp in cases:
-        for k in ("HDRNET_ASYNC_LEAN", "HDRNET_TEX_CHUNKS", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB"):
-            monkeypatch.delenv(k, raising=False)
-        want = run_apply(grid, guide, inp, True, "tex")
-        assert np.array_equal(want, run_apply(grid, guide, inp, True, "tex_async"))
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        if "HDRNET_TEX_CHUNKS" in env:   # the block-synchronous form honours the same knob
-            want_k = run_apply(grid, guide, inp, True, "tex")
-            assert np.array_equal(want, want_k)
-        assert np.array_equal(want, run_apply(grid, guide, inp, True, "tex_async"))
+def test_issuer_warp_kernel_knobs_are_bitwise_equal(env):
+    """Both CTA shapes of the issuer-warp form and 4 / 5 of a pixel's 12 corner chunks on the
+    texture pipe: identical bits; also on narrow x cells (W < 4 gw: per-pixel indices), many rows
+    per CTA, a ragged last segment and out-of-range guides."""
+    import hashlib
+    cases = [(5, 2, 64, 3840, 16, 16, 8, False), (6, 1, 700, 1028, 5, 7, 3, True), (7, 3, 9, 128, 8, 64, 4, False)]
+    for seed, B, H, W, gh, gw, gd, edge in cases:
+        grid, guide, inp = rand_case(seed, B, H, W, gh, gw, gd, signed=True)
+        if edge:
+            guide[0, :, ::5] = 1.75
+            guide[0, :, 1::5] = -0.6
+        want = "SHA256 " + hashlib.sha256(run_apply(grid, guide, inp, True, "tex").tobytes()).hexdigest()
+        args = ["apply", _lib.VARIANT_TEX_ASYNC, seed, B, H, W, gh, gw, gd] + (["edge"] if edge else [])
+        assert _knob_sha(env, *args) == want, (env, seed)
 
 
 def test_empty_batch_is_a_no_op():
@@ -295,7 +281,7 @@ def test_4k_frame_against_full_oracle():
     """One 3840x2160 frame, grid 16x16x8 (config 3's per-image shape), full oracle compare."""
     grid, guide, inp = rand_case(1234, 1, 2160, 3840, 16, 16, 8)
     expected = checker().bilateral_slice_apply(grid, guide, inp, True)
-    for v in ("tma", "generic", "zsort", "tex", "tex_ws", "tex_in", "tex_async"):
+    for v in ("tma", "generic", "tex", "tex_async"):
         got = run_apply(grid, guide, inp, True, v)
         assert_parity(got, expected, what=f"4K [{v}]")
     gidx = hdrnet_ops.slice_indices(cuda(guide), (16, 16, 8)).cpu().numpy()
@@ -335,68 +321,3 @@ def test_4k_batch8_properties():
     outp = hdrnet_ops.bilateral_slice_apply(grid[perm].contiguous(), guide[perm].contiguous(),
                                             inp[perm].contiguous(), True)
     assert torch.equal(outp, out[perm])
-
-
-# ---- experimental: depth interpolation on the tensor cores (csrc/slice_apply_tc.cu) -----------
-TC_SHAPES = [
-    (1, 6, 512, 4, 4, 8),        # one 512-pixel segment, four tiles, cells exactly one tile wide
-    (2, 9, 1156, 5, 7, 8),       # ragged last tile (1156 = 9 * 128 + 4), three-cell window at both borders
-    (1, 40, 3840, 16, 16, 8),    # the headline row shape: three 1280-pixel segments, ten tiles each
-    (3, 70, 1920, 8, 3, 8),      # gw = 3: the window never moves; more rows than fit one wave of CTAs
-]
-
-
-@experimental
-@pytest.mark.parametrize("variant", ["tc", "tc_gather"])
-@pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_tensor_core_form_matches_oracle(shape, variant):
-    B, H, W, gh, gw, gd = shape
-    grid, guide, inp = rand_case(99, B, H, W, gh, gw, gd, signed=True)
-    guide[0, 0, :6] = [0.0, 1.0, -0.3, 1.7, 0.0625, 0.9375]
-    expected = checker().bilateral_slice_apply(grid, guide, inp, True)
-    assert_parity(run_apply(grid, guide, inp, True, variant), expected, what=f"{shape} [{variant}]")
-
-
-@experimental
-def test_tensor_core_form_4k_batch_against_row_kernel():
-    """8 x 4K: against the issuer-warp form (different summation order: 1e-5, not bitwise), twice
-    (the second launch reuses every barrier phase and TMEM column of a fresh CTA set)."""
-    gen = torch.Generator(device="cuda").manual_seed(5)
-    grid = torch.randn(8, 16, 16, 8, 12, device="cuda", generator=gen)
-    guide = torch.rand(8, 2160, 3840, device="cuda", generator=gen)
-    inp = torch.randn(8, 2160, 3840, 3, device="cuda", generator=gen)
-    ref = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=_lib.VARIANT_TEX_ASYNC)
-    scale = ref.abs().max().item()
-    for variant in (_lib.VARIANT_TC, _lib.VARIANT_TC, _lib.VARIANT_TC_GATHER, _lib.VARIANT_TC_GATHER):
-        out = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True, variant=variant)
-        assert (out - ref).abs().max().item() / scale <= RTOL, variant
-
-
-@experimental
-def test_tensor_core_form_rejects_shapes_it_cannot_take():
-    for shape in [(1, 8, 512, 4, 4, 4), (1, 8, 512, 4, 2, 8), (1, 8, 256, 4, 4, 8)]:   # gd != 8, gw < 3, narrow cells
-        B, H, W, gh, gw, gd = shape
-        grid, guide, inp = rand_case(3, B, H, W, gh, gw, gd)
-        with pytest.raises(ValueError):
-            run_apply(grid, guide, inp, True, "tc")
-
-
-@experimental
-@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_PIPE="1"), dict(HDRNET_ASYNC_PIPE="1", HDRNET_TEX_CHUNKS="4"),
-                                 dict(HDRNET_ASYNC_PIPE="1", HDRNET_ASYNC_THREADS="352"),
-                                 dict(HDRNET_ASYNC_PIPE="1", HDRNET_ASYNC_THREADS="352", HDRNET_TEX_CHUNKS="4")],
-                         ids=lambda e: ",".join(f"{k[7:].lower()}={v}" for k, v in e.items()))
-def test_issuer_warp_kernel_pipelined_texture_fetches_are_bitwise_equal(env, monkeypatch):
-    """HDRNET_ASYNC_PIPE=1 (texture fetches issued one pixel ahead; written after the round's GPU
-    budget was spent): same operations in the same order per pixel, so identical bits."""
-    cases = [rand_case(5, 2, 64, 3840, 16, 16, 8, signed=True),
-             rand_case(6, 1, 700, 1028, 5, 7, 3, signed=True)]
-    cases[1][1][0, :, ::5] = 1.75
-    cases[1][1][0, :, 1::5] = -0.6
-    for grid, guide, inp in cases:
-        for k in ("HDRNET_ASYNC_PIPE", "HDRNET_ASYNC_THREADS", "HDRNET_TEX_CHUNKS"):
-            monkeypatch.delenv(k, raising=False)
-        want = run_apply(grid, guide, inp, True, "tex")
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        assert np.array_equal(want, run_apply(grid, guide, inp, True, "tex_async"))

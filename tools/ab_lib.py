@@ -3,8 +3,10 @@ spread is +-4 %, larger than most kernel changes).
     python tools/ab_lib.py SPEC [SPEC ...]      SPEC = path.so[:variant[:KEY=VAL,KEY=VAL...]]
 Every configuration is driven directly through the C-ABI (hdrnet_slice_apply_f32_ws) in
 interleaved bursts; all burst times and the SM clock sampled after each burst are printed, the
-median is reported.  Outputs of all configurations must be bitwise equal."""
-import ctypes, os, statistics, sys, torch
+median is reported.  Outputs of all configurations must be bitwise equal.
+The library reads its tuning record (HDRNET_ASYNC_THREADS, HDRNET_TEX_CHUNKS) ONCE per loaded copy,
+on its first call: every SPEC gets a private copy of the .so, first called under its own settings."""
+import ctypes, os, shutil, statistics, sys, tempfile, torch
 try:
     import pynvml
     pynvml.nvmlInit()
@@ -18,23 +20,24 @@ gen = torch.Generator(device="cuda").manual_seed(1234)
 grid = torch.rand(B, GH, GW, GD, 12, device="cuda", generator=gen)
 guide = torch.rand(B, H, W, device="cuda", generator=gen)
 inp = torch.rand(B, H, W, 3, device="cuda", generator=gen)
-KNOBS = ("HDRNET_TMA_THREADS", "HDRNET_TEX_CHUNKS", "HDRNET_TMA_STAGES", "HDRNET_TMA_OCC", "HDRNET_TEXIN_OCC",
-         "HDRNET_ASYNC_LEAN", "HDRNET_ASYNC_STORE", "HDRNET_ASYNC_SLAB", "HDRNET_ASYNC_THREADS", "HDRNET_ASYNC_OCC",
-         "HDRNET_ASYNC_PDL", "HDRNET_ASYNC_PIPE")
+KNOBS = ("HDRNET_TEX_CHUNKS", "HDRNET_ASYNC_THREADS", "HDRNET_FUSED_ASYNC")
 libs, cfgs = {}, []
+_tmp = tempfile.mkdtemp(prefix="ab_lib_")
 for spec in sys.argv[1:]:
     parts = spec.split(":")
     path = parts[0]
     variant = int(parts[1]) if len(parts) > 1 and parts[1] else 0
     env = dict(kv.split("=") for kv in parts[2].split(",")) if len(parts) > 2 and parts[2] else {}
-    if path not in libs:
-        lib = ctypes.CDLL(os.path.abspath(path))
+    if spec not in libs:
+        private = os.path.join(_tmp, f"lib{len(libs)}.so")
+        shutil.copy(os.path.abspath(path), private)
+        lib = ctypes.CDLL(private)
         lib.hdrnet_slice_apply_workspace_bytes.restype = ctypes.c_size_t
         lib.hdrnet_slice_apply_workspace_bytes.argtypes = [ctypes.c_int] * 4
         lib.hdrnet_slice_apply_f32_ws.restype = ctypes.c_int
         lib.hdrnet_slice_apply_f32_ws.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 10 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-        libs[path] = lib
-    cfgs.append((spec, libs[path], variant, env))
+        libs[spec] = lib
+    cfgs.append((spec, libs[spec], variant, env))
 n_ws = next(iter(libs.values())).hdrnet_slice_apply_workspace_bytes(B, H, GW, GD)
 ws = torch.empty(n_ws, dtype=torch.uint8, device="cuda")
 out = torch.empty_like(inp)

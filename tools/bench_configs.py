@@ -138,9 +138,6 @@ def main():
     slice_apply_case("C3 4K x8 (headline shape)", 8, 2160, 3840, 16, 16, 8)
     slice_apply_case("C3 4K x8 texture-assisted kernel (incl. y-blend pre-pass)", 8, 2160, 3840, 16, 16, 8, variant=_lib.VARIANT_TEX)
     slice_apply_case("C2 1080p x1 texture-assisted", 1, 1080, 1920, 16, 16, 8, variant=_lib.VARIANT_TEX)
-    slice_apply_case("C3 4K x8 z-bucketed kernel", 8, 2160, 3840, 16, 16, 8, variant=_lib.VARIANT_ZSORT)
-    slice_apply_case("C2 1080p x1 z-bucketed", 1, 1080, 1920, 16, 16, 8, variant=_lib.VARIANT_ZSORT)
-    slice_apply_case("C4 12MP x8 z-bucketed", 8, 3024, 4032, 16, 16, 8, iters=20, variant=_lib.VARIANT_ZSORT)
     slice_apply_case("C3 4K x8 generic kernel", 8, 2160, 3840, 16, 16, 8, iters=10, variant=_lib.VARIANT_GENERIC)
     slice_apply_case("C2 1080p x1", 1, 1080, 1920, 16, 16, 8)
     slice_apply_case("C4 12MP x8 (one GPU's share of batch 64)", 8, 3024, 4032, 16, 16, 8, iters=20)

@@ -54,7 +54,7 @@ namespace hdrnet_b200 {
 constexpr int kMmWgs = 4;
 constexpr int kMmMathWarps = kMmWgs * 4;
 constexpr int kMmSlabWarps = 2;
-constexpr int kMmThreads = (kMmMathWarps + 1 + kMmSlabWarps) * 32;   // + issuer warp + slab warps = 608
+constexpr int kMmThreads = (kMmMathWarps + 2 + kMmSlabWarps) * 32;   // + issuer, scheduler, slab warps = 640
 constexpr int kMmMaxStages = 4;
 constexpr int kMmTile = 128;
 constexpr int kMmWgCols = 128;      // per warpgroup: D of two tiles [0, 96), A operands [96, 128)
@@ -73,7 +73,7 @@ struct MmArgs {
   int row_floats;           // gw * gd * 12
   int bsplit_bytes;         // one operand split of one row's B'
   int max_tiles;            // capacity of a segment's tile list
-  int off_tab, off_raw, off_b, off_stage, smem_bytes, ctas;
+  int off_wx, off_raw, off_b, off_stage, smem_bytes, ctas;
 };
 
 // instruction descriptor: D f32, A / B tf32, both K-major, N = 48, M = 128
@@ -186,6 +186,91 @@ __host__ __device__ constexpr uint32_t mm_pack_tile(int start, int n, int cellp)
   return static_cast<uint32_t>(start) | (static_cast<uint32_t>(n) << 16) | (static_cast<uint32_t>(cellp) << 24);
 }
 
+// ---- shared-memory header of the kernel (byte offsets) -------------------------------------------
+constexpr uint32_t kOffFull = 0;         // [4]   pixel segment landed (TMA)
+constexpr uint32_t kOffDone = 32;        // [4]   every math warp is through the segment
+constexpr uint32_t kOffRawFull = 64;     // [2]   grid row landed
+constexpr uint32_t kOffBFull = 80;       // [2]   B' of a row built
+constexpr uint32_t kOffBFree = 96;       // [2]   B' of a row no longer read by any MMA
+constexpr uint32_t kOffDReady = 112;     // [4]   a warpgroup's MMAs complete
+constexpr uint32_t kOffDescReady = 144;  // [4][4] round descriptor published
+constexpr uint32_t kOffDescFree = 272;   // [4][4] round descriptor consumed
+constexpr uint32_t kOffTmem = 400;
+constexpr uint32_t kOffACnt = 416;       // [4]   warps done with a round's A rows
+constexpr uint32_t kOffDesc = 512;       // [4][4][8 words] round descriptors
+constexpr uint32_t kOffTab = 1024;       // run boundaries, tile lists, x weights (MmArgs::off_tab)
+
+// A ROUND descriptor (8 words), written by the scheduler warp, read by a warpgroup's math warps:
+//   0 stage address | 1 tile A (start | n << 16) | 2 tile B | 3 B' window of A | 4 B' window of B |
+//   5 first pixel of the segment in the row | 6 flags | 7 first pixel of the segment in the image
+constexpr uint32_t kDescEnd = 1u, kDescDone = 2u, kDescFree = 16u;   // flags: | stage << 2 | rb << 5
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void mm_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mm_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+__device__ __forceinline__ bool mm_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mm_wait_sleepy_a(uint32_t bar, uint32_t parity) {
+  while (!mm_test(bar, parity)) __nanosleep(200);
+}
+// one pixel of a staged tile, by shared-memory address
+template <int kFmt>
+__device__ __forceinline__ void mm_load_px_a(uint32_t tile, int p, float& r, float& g, float& b) {
+  if constexpr (kFmt == kPxF32) {
+    const uint32_t a = tile + 12u * p;
+    r = lds_f32(a); g = lds_f32(a + 4); b = lds_f32(a + 8);
+  } else if constexpr (kFmt == kPxU8) {
+    const uint32_t a = tile + 3u * p;
+    uint32_t x, y, z;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(x) : "r"(a));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(y) : "r"(a + 1));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(z) : "r"(a + 2));
+    r = px_to_float<kPxU8>(x); g = px_to_float<kPxU8>(y); b = px_to_float<kPxU8>(z);
+  } else {
+    const uint32_t a = tile + 6u * p;
+    uint32_t x, y, z;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(x) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(y) : "r"(a + 2));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(z) : "r"(a + 4));
+    r = px_to_float<kPxU16>(x); g = px_to_float<kPxU16>(y); b = px_to_float<kPxU16>(z);
+  }
+}
+template <int kFmt>
+__device__ __forceinline__ void mm_store_px_a(uint32_t tile, int p, float r, float g, float b) {
+  if constexpr (kFmt == kPxF32) {
+    const uint32_t a = tile + 12u * p;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(r) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 4), "f"(g) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 8), "f"(b) : "memory");
+  } else {
+    static_assert(kFmt == kPxU8, "results leave as float32 or uint8");
+    const uint32_t a = tile + 3u * p;
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(float_to_u8(r)) : "memory");
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + 1), "r"(float_to_u8(g)) : "memory");
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + 2), "r"(float_to_u8(b)) : "memory");
+  }
+}
+
 template <class GuideFn, int kIn, int kOut, int kNSplit, int kKSteps>
 __global__ void __launch_bounds__(kMmThreads, 1)
 slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
@@ -197,22 +282,18 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
   constexpr uint32_t kCellBytes = 3u * kSbo; // a cell = 24 n = three groups
   const SliceGeom& g = args.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sm0 = smem_u32(smem);
 
-  // ---- shared-memory map -------------------------------------------------------------------
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);     // [4]  pixel segment landed
-  uint64_t* done = full + kMmMaxStages;                    // [4]  every math warp is through it
-  uint64_t* raw_full = done + kMmMaxStages;                // [2]  grid row landed
-  uint64_t* b_full = raw_full + 2;                         // [2]  B' of a row ready
-  uint64_t* b_free = b_full + 2;                           // [2]  B' of a row no longer read
-  uint64_t* d_ready = b_free + 2;                          // [8]  a tile's MMAs complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
-  uint32_t* a_cnt = reinterpret_cast<uint32_t*>(smem + 200);   // [8]  warps done with a tile's A rows
-  int* bnd = reinterpret_cast<int*>(smem + args.off_tab);      // [gw + 2] run boundaries
+  int* bnd = reinterpret_cast<int*>(smem + kOffTab);          // [gw + 2] run boundaries
   int* seg_nt = bnd + 40;                                      // [nseg]   tiles per segment
   uint32_t* tiles = reinterpret_cast<uint32_t*>(seg_nt + 24);  // [nseg][max_tiles]
+  float* wx = reinterpret_cast<float*>(smem + args.off_wx);    // [W] x fraction of every pixel column
   float* raw = reinterpret_cast<float*>(smem + args.off_raw);  // two grid rows
   unsigned char* bt = smem + args.off_b;                       // [2 rows][kNSplit][bsplit_bytes]
-  unsigned char* stage_base = smem + args.off_stage;
+  const uint32_t bt_addr = sm0 + args.off_b;
+  const uint32_t stage_addr = sm0 + args.off_stage;
+  const uint32_t tiles_addr = smem_u32(tiles);
+  const uint32_t wx_addr = sm0 + args.off_wx;
 
   const long long total_items = static_cast<long long>(g.B) * g.rows * args.nseg;
   const long long i_begin = total_items * blockIdx.x / gridDim.x;
@@ -226,14 +307,19 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
 
   // ---- start-up ---------------------------------------------------------------------------
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm0 + kOffTmem),
                  "r"(static_cast<uint32_t>(kMmTmemCols)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 32) {
-    for (int s = 0; s < kMmMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kMmMathWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&b_full[i], kMmSlabWarps); mbar_init(&b_free[i], kMmMathWarps); }
-    for (int i = 0; i < kMmWgs; ++i) { mbar_init(&d_ready[i], 1); a_cnt[i] = 0u; }
+    auto init = [&](uint32_t off, int n, uint32_t count) {
+      for (int i = 0; i < n; ++i)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm0 + off + 8u * i), "r"(count));
+    };
+    init(kOffFull, kMmMaxStages, 1); init(kOffDone, kMmMaxStages, kMmMathWarps);
+    init(kOffRawFull, 2, 1); init(kOffBFull, 2, kMmSlabWarps); init(kOffBFree, 2, kMmMathWarps);
+    init(kOffDReady, kMmWgs, 1); init(kOffDescReady, 16, 1); init(kOffDescFree, 16, 4);
+    for (int i = 0; i < kMmWgs; ++i) reinterpret_cast<uint32_t*>(smem + kOffACnt)[i] = 0u;
     fence_mbar_init();
   }
   // run boundaries: bnd[k] = first pixel whose lower x cell is >= k - 1 (k = 0: 0; k = gw + 1: W),
@@ -249,6 +335,8 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
     }
     bnd[k] = lo;
   }
+  // x fractions: the same for every row (the reference's roundings; wx1 = f, wx0 = 1 - f)
+  for (int x = tid; x < g.W; x += kMmThreads) wx[x] = spatial_axis(x, g.scale_x).f;
   __syncthreads();
   // tile lists: (run ^ segment) cut into pieces of <= 128 pixels
   if (tid >= 64 && tid < 64 + args.nseg) {
@@ -271,11 +359,12 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
   mm_fence_before();
   __syncthreads();
   mm_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem + kOffTmem);
   const int NS = args.stages;
 
   if (warp == kMmMathWarps) {
     // =============================== issuer warp =============================================
+    // one lane issues every bulk copy of pixel segments: TMA ring in, one bulk store per segment out
     if (lane == 0) {
       long long l_row = r_begin;
       int l_seg = seg_first, l_s = 0;
@@ -283,12 +372,13 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
         if (l_row >= r_end) return;
         const int x0 = l_seg * args.seg_px;
         const int npx = min(args.seg_px, g.W - x0);
-        unsigned char* st = stage_base + static_cast<size_t>(l_s) * args.stage_bytes;
+        unsigned char* st = smem + args.off_stage + static_cast<size_t>(l_s) * args.stage_bytes;
         const size_t pix = static_cast<size_t>(l_row) * g.W + x0;
         const uint32_t in_bytes = static_cast<uint32_t>(npx) * args.in_bpp;
-        mbar_expect_tx(&full[l_s], in_bytes + (kGuideIn ? static_cast<uint32_t>(npx) * 4u : 0u));
-        tma_load_1d(st, args.input + pix * args.in_bpp, in_bytes, &full[l_s]);
-        if (kGuideIn) tma_load_1d(st + args.off_guide, args.guide + pix, static_cast<uint32_t>(npx) * 4u, &full[l_s]);
+        uint64_t* fb = reinterpret_cast<uint64_t*>(smem + kOffFull) + l_s;
+        mbar_expect_tx(fb, in_bytes + (kGuideIn ? static_cast<uint32_t>(npx) * 4u : 0u));
+        tma_load_1d(st, args.input + pix * args.in_bpp, in_bytes, fb);
+        if (kGuideIn) tma_load_1d(st + args.off_guide, args.guide + pix, static_cast<uint32_t>(npx) * 4u, fb);
         if (++l_s == NS) l_s = 0;
         if (++l_seg >= row_seg1(l_row)) { l_seg = 0; ++l_row; }
       };
@@ -298,10 +388,10 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
       for (long long row = r_begin; row < r_end; ++row) {
         const int sg1 = row_seg1(row);
         for (int sg = row_seg0(row); sg < sg1; ++sg) {
-          mm_wait_sleepy(&done[s], ph);   // every math warp has written (and proxy-fenced) its results
+          mm_wait_sleepy_a(sm0 + kOffDone + 8u * s, ph);   // every math warp has written (and proxy-fenced) its results
           const int x0 = sg * args.seg_px;
           const int npx = min(args.seg_px, g.W - x0);
-          unsigned char* st = stage_base + static_cast<size_t>(s) * args.stage_bytes;
+          unsigned char* st = smem + args.off_stage + static_cast<size_t>(s) * args.stage_bytes;
           const size_t pix = static_cast<size_t>(row) * g.W + x0;
           tma_store_1d(args.out + pix * args.out_bpp, st + args.off_out, static_cast<uint32_t>(npx) * args.out_bpp);
           tma_store_commit();
@@ -314,12 +404,63 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
       }
       tma_store_wait_all<0>();
     }
-  } else if (warp > kMmMathWarps) {
+  } else if (warp == kMmMathWarps + 1) {
+    // ============================== scheduler warp ===========================================
+    // One lane walks the CTA's rows / segments / tile pairs in order and publishes ROUND
+    // descriptors, round-robin to the four warpgroups (round i belongs to warpgroup i & 3 and is
+    // that warpgroup's (i >> 2)-th): the math warps never touch full[] / b_full[] themselves, a
+    // descriptor only appears once its segment has landed and its row's B' is built.
+    if (lane == 0) {
+      int s = 0;
+      uint32_t fph = 0u, gp = 0u;
+      auto publish = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                         uint32_t w6, uint32_t w7, uint32_t wg_, uint32_t n) {
+        const uint32_t slot = n & 3u, idx = wg_ * 4u + slot;
+        if (n >= 4u) mm_wait_sleepy_a(sm0 + kOffDescFree + 8u * idx, ((n >> 2) - 1u) & 1u);
+        const uint32_t da = sm0 + kOffDesc + 32u * idx;
+        sts_v4(da, w0, w1, w2, w3);
+        sts_v4(da + 16, w4, w5, w6, w7);
+        mm_arrive_a(sm0 + kOffDescReady + 8u * idx);   // release: the descriptor is visible to the waiters
+      };
+      for (long long row = r_begin; row < r_end; ++row) {
+        const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
+        mm_wait_sleepy_a(sm0 + kOffBFull + 8u * rb, static_cast<uint32_t>(rowk >> 1) & 1u);
+        const uint32_t b_row = bt_addr + static_cast<uint32_t>(rb) * kNSplit * static_cast<uint32_t>(args.bsplit_bytes);
+        const int sg0 = row_seg0(row), sg1 = row_seg1(row);
+        int row_left = 0;   // rounds of this row not yet published
+        for (int sg = sg0; sg < sg1; ++sg) row_left += (seg_nt[sg] + 1) >> 1;
+        const int row_rounds = row_left;
+        for (int sg = sg0; sg < sg1; ++sg) {
+          mm_wait_sleepy_a(sm0 + kOffFull + 8u * s, fph);
+          const int np = (seg_nt[sg] + 1) >> 1;
+          const uint32_t st = stage_addr + static_cast<uint32_t>(s) * static_cast<uint32_t>(args.stage_bytes);
+          const uint32_t tl = tiles_addr + 4u * static_cast<uint32_t>(sg * args.max_tiles);
+          const uint32_t xs = static_cast<uint32_t>(sg * args.seg_px);
+          const uint32_t pixbase = static_cast<uint32_t>(static_cast<unsigned long long>(row) * g.W + xs);
+          for (int j = 0; j < np; ++j) {
+            const uint32_t twA = lds_u32(tl + 8u * j), twB = lds_u32(tl + 8u * j + 4u);
+            --row_left;
+            uint32_t flags = (static_cast<uint32_t>(s) << 2) | (static_cast<uint32_t>(rb) << 5);
+            if (j + 4 >= np) flags |= kDescDone;        // this warpgroup's last round of the segment
+            if (row_left < 4) flags |= kDescFree;       // ... and of the row
+            publish(st, twA & 0xffffffu, twB & 0xffffffu, b_row + (twA >> 24) * kCellBytes,
+                    b_row + (twB >> 24) * kCellBytes, xs, flags, pixbase, gp & 3u, gp >> 2);
+            ++gp;
+          }
+          // warpgroups without a round in this segment / row: acknowledge on their behalf
+          if (np < 4) mm_arrive_n(sm0 + kOffDone + 8u * s, 4u * static_cast<uint32_t>(4 - np));
+          if (++s == NS) { s = 0; fph ^= 1u; }
+        }
+        if (row_rounds < 4) mm_arrive_n(sm0 + kOffBFree + 8u * rb, 4u * static_cast<uint32_t>(4 - row_rounds));
+      }
+      for (uint32_t w = 0; w < 4u; ++w) publish(0u, 0u, 0u, 0u, 0u, 0u, kDescEnd, 0u, w, (gp + 3u - w) >> 2);
+    }
+  } else if (warp > kMmMathWarps + 1) {
     // ================================ slab warps =============================================
     // Both warps walk the rows together (a named barrier keeps the shared grid-row slots
     // consistent); slab warp 0 issues the grid-row loads, each warp builds half of B'.
-    const int sw = warp - kMmMathWarps - 1;
-    // raw[slot] holds grid row key (b * gh + gy); -1 = empty
+    const int sw = warp - kMmMathWarps - 2;
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem + kOffRawFull);
     int key0 = -1, key1 = -1;          // grid row held by raw slot 0 / 1
     uint32_t rpar0 = 0u, rpar1 = 0u;   // parity of the next completion of raw_full[0 / 1]
     const uint32_t raw_bytes = static_cast<uint32_t>(args.row_floats) * 4u;
@@ -331,9 +472,9 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
       const Axis ay = spatial_axis(y, g.scale_y);
       const int k0 = b * g.gh + clampi(ay.i0, 0, g.gh - 1);
       const int k1 = b * g.gh + clampi(ay.i0 + 1, 0, g.gh - 1);
-      // which slots hold k0 / k1; load what is missing into the slot the other does not use
       // nobody still reads the grid-row slot a load below may overwrite
       asm volatile("bar.sync 1, %0;" ::"n"(kMmSlabWarps * 32) : "memory");
+      // which slots hold k0 / k1; load what is missing into the slot the other does not use
       int s0 = (key0 == k0) ? 0 : ((key1 == k0) ? 1 : -1);
       int s1 = (key0 == k1) ? 0 : ((key1 == k1) ? 1 : -1);
       auto fetch = [&](int slot, int k) {   // grid row k -> raw slot (warp-uniform)
@@ -348,7 +489,7 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
       if (s0 < 0) { s0 = (s1 == 0) ? 1 : 0; fetch(s0, k0); if (k1 == k0) s1 = s0; }
       if (s1 < 0) { s1 = s0 ^ 1; fetch(s1, k1); }
       // the row buffer is free once every math warp is through row - 2
-      if (rowk >= 2) mm_wait_sleepy(&b_free[rb], static_cast<uint32_t>((rowk >> 1) - 1) & 1u);
+      if (rowk >= 2) mm_wait_sleepy_a(sm0 + kOffBFree + 8u * rb, static_cast<uint32_t>((rowk >> 1) - 1) & 1u);
       const float wy1 = ay.f, wy0 = 1.0f - ay.f;
       const float* g0 = raw + static_cast<size_t>(s0) * args.row_floats;
       const float* g1 = raw + static_cast<size_t>(s1) * args.row_floats;
@@ -403,29 +544,25 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
       }
       fence_proxy_async_smem();   // generic writes -> the tensor core's (async-proxy) operand reads
       __syncwarp();
-      if (lane == 0) mm_arrive(&b_full[rb]);
+      if (lane == 0) mm_arrive_a(sm0 + kOffBFull + 8u * rb);
     }
   } else {
     // ================================ math warpgroups ========================================
-    const int wg = static_cast<int>(mm_uniform(static_cast<uint32_t>(warp >> 2))), t = tid & 127;
+    const uint32_t wg = mm_uniform(static_cast<uint32_t>(warp >> 2));
+    const int t = tid & 127;
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;   // this warp's TMEM lanes
-    const uint32_t tm_wg = tmem_base + static_cast<uint32_t>(wg) * kMmWgCols;
-    const uint32_t bt_addr = smem_u32(bt);
+    const uint32_t tm_wg = tmem_base + wg * kMmWgCols;
+    const uint32_t dbar = sm0 + kOffDReady + 8u * wg;
+    const uint32_t acnt = sm0 + kOffACnt + 4u * wg;
+    const uint32_t descr = sm0 + kOffDescReady + 32u * wg, descf = sm0 + kOffDescFree + 32u * wg;
+    const uint32_t descb = sm0 + kOffDesc + 128u * wg;
     const float gd_f = static_cast<float>(g.gd);
-
-    const uint32_t stage_addr = smem_u32(stage_base);
-    const uint32_t tiles_addr = smem_u32(tiles);
-    const uint32_t dbar = smem_u32(&d_ready[wg]);
-    const uint32_t acnt = smem_u32(&a_cnt[wg]);
-    const uint32_t done_addr = smem_u32(done);
-    const uint32_t bfree_addr = smem_u32(b_free);
     // tensor memory of this warpgroup (128 columns): D of the round's two tiles at [0, 48) and
     // [48, 96); A operands at [96, 128): kKSteps == 1 -- two BUFFERS of two tiles x 8 columns, so
     // that the one-hot rows of round r + 2 are written while the MMAs of round r + 1 run;
     // kKSteps == 2 -- one buffer of two tiles x 16 columns (the set-up then waits for the MMAs).
     constexpr bool kPipeA = (kKSteps == 1);
     const uint32_t tD0 = tm_wg, tD1 = tm_wg + 48u, tA0 = tm_wg + 96u;
-    uint32_t dpar = 0u;
 
     // One pixel's depth axis: guide -> lower depth cell (as a float, for the one-hot compare) and
     // the two smoothed weights (both on the first row when the two cells clamp to cell 0, whose
@@ -457,21 +594,18 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
         }
       }
     };
-    // read a pixel's 4 corner vectors back from tensor memory, blend, apply, store in place
-    auto finish_px = [&](uint32_t td, unsigned char* st, int x, uint32_t tw, float wz0, float wz1) {
+    // a pixel's 4 corner vectors back from tensor memory, blend, affine apply, store in place
+    auto finish_px = [&](uint32_t td, uint32_t st, uint32_t tw, uint32_t wxs, float wz0, float wz1) {
       float d[48];
       const uint32_t taddr = td + lane_sel;
       mm_ld16(taddr, d);
       mm_ld16(taddr + 16, d + 16);
       mm_ld16(taddr + 32, d + 32);
-      const int n = static_cast<int>((tw >> 16) & 0xffu), cellp = static_cast<int>(tw >> 24);
-      const bool valid = t < n;
+      const bool valid = t < static_cast<int>(tw >> 16);
       const int p = static_cast<int>(tw & 0xffffu) + (valid ? t : 0);
       float r, gg, bb;
-      mm_load_px<kIn>(st, p, r, gg, bb);
-      // x fraction with the reference's roundings; floor(tx) is the tile's x0 by construction
-      const float tx = __fsub_rn(__fmul_rn(__fadd_rn(static_cast<float>(x + p), 0.5f), g.scale_x), 0.5f);
-      const float wx1 = tx - static_cast<float>(cellp - 1), wx0 = 1.0f - wx1;
+      mm_load_px_a<kIn>(st, p, r, gg, bb);
+      const float wx1 = lds_f32(wxs + 4u * p), wx0 = 1.0f - wx1;
       const float w00 = wx0 * wz0, w01 = wx0 * wz1, w10 = wx1 * wz0, w11 = wx1 * wz1;
       const unsigned long long W00 = pack2(w00, w00), W01 = pack2(w01, w01);
       const unsigned long long W10 = pack2(w10, w10), W11 = pack2(w11, w11);
@@ -488,58 +622,39 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
       const float o_r = fmaf(v[2], bb, fmaf(v[1], gg, fmaf(v[0], r, v[3])));
       const float o_g = fmaf(v[6], bb, fmaf(v[5], gg, fmaf(v[4], r, v[7])));
       const float o_b = fmaf(v[10], bb, fmaf(v[9], gg, fmaf(v[8], r, v[11])));
-      if (valid) mm_store_px<kOut>(st + args.off_out, p, o_r, o_g, o_b);
+      if (valid) mm_store_px_a<kOut>(st + args.off_out, p, o_r, o_g, o_b);
     };
 
-    // A ROUND = a pair of tiles (one pixel of each per thread).  What is kept of it between its
-    // set-up (A written), the issue of its MMAs and its epilogue:
-    struct Round {
-      float wzA0, wzA1, wzB0, wzB1;   // per thread
-      uint32_t twA, twB;              // the tile words
-      unsigned char* st;              // stage of its segment
-      int xs;                         // first pixel of the segment
-      uint32_t b_row;                 // B' of its row
-      uint32_t abuf;                  // TMEM column of its A operands
-      uint32_t done_bar, free_bar;    // != 0: arrive there after the epilogue
-      int segc, rowk;                 // segment / row counters (look-ahead bounds)
-    };
-    Round cur, nxt;                   // cur: MMAs issued; nxt: A written
-    bool have_cur = false, have_nxt = false;
-
-    // ---- cursor over the tile pairs of this CTA's segments; every fourth pair is this warpgroup's.
-    // A warp observes full[] / b_full[] of every segment / row it passes, also those it has no
-    // tile in: that bounds how far it can run ahead of the others (it must never arrive on
-    // done[] / b_free[] for a later use of the same barrier).
-    long long c_row = r_begin;
-    int c_sg = seg_first, c_s = 0, c_gp = 0, c_segc = 0;
-    uint32_t c_fph = 0;
-    bool c_row_open = false, c_seg_open = false;   // b_full[] / full[] of the current row / segment observed
-    int c_np = 0, c_j = 0;
-    int nfetch = 0;
-    // marks on the most recently fetched round that is still pending (nxt, else cur)
-    auto newest = [&]() -> Round* { return have_nxt ? &nxt : (have_cur ? &cur : nullptr); };
-
+    // Per iteration: epilogue of round r (its MMAs were issued one iteration ago) -> MMAs of round
+    // r + 1 (its A rows were written one iteration ago; D is free now) -> set-up of round r + 2
+    // (overlaps those MMAs).  `cur` = MMAs issued, `nxt` = A written.
+    float cw0 = 0.f, cw1 = 0.f, cw2 = 0.f, cw3 = 0.f, nw0 = 0.f, nw1 = 0.f, nw2 = 0.f, nw3 = 0.f;
+    uint32_t cslot = 0u, nslot = 0u, nab = tA0;
+    bool have_cur = false, have_nxt = false, ended = false;
+    uint32_t nfetch = 0u, nsetup = 0u, dpar = 0u;
     for (;;) {
-      // ---- 1. epilogue of the round whose MMAs were issued one iteration ago ------------------
+      // ---- 1. epilogue ---------------------------------------------------------------------
       if (have_cur) {
         mbar_wait_addr(dbar, dpar);
         dpar ^= 1u;
         mm_fence_after();
-        finish_px(tD0, cur.st, cur.xs, cur.twA, cur.wzA0, cur.wzA1);
-        finish_px(tD1, cur.st, cur.xs, cur.twB, cur.wzB0, cur.wzB1);
+        const uint32_t da = descb + 32u * cslot;
+        const uint4 d0 = lds_v4(da);
+        const uint32_t xs = lds_u32(da + 20u), flags = lds_u32(da + 24u);
+        const uint32_t wxs = wx_addr + 4u * xs;
+        finish_px(tD0, d0.x, d0.y, wxs, cw0, cw1);
+        finish_px(tD1, d0.x, d0.z, wxs, cw2, cw3);
         mm_fence_before();   // D is read: order it before the MMAs of the next round
-        if (cur.done_bar != 0u) {
-          fence_proxy_async_smem();   // results (generic writes) -> the issuer's bulk store
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cur.done_bar) : "memory");
-        }
-        if (cur.free_bar != 0u) {
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cur.free_bar) : "memory");
+        if (flags & kDescDone) fence_proxy_async_smem();   // results (generic writes) -> the issuer's bulk store
+        __syncwarp();
+        if (lane == 0) {
+          mm_arrive_a(descf + 8u * cslot);
+          if (flags & kDescDone) mm_arrive_a(sm0 + kOffDone + 8u * ((flags >> 2) & 3u));
+          if (flags & kDescFree) mm_arrive_a(sm0 + kOffBFree + 8u * ((flags >> 5) & 1u));
         }
         have_cur = false;
       }
-      // ---- 2. MMAs of the next round: its A rows are written, D is free ----------------------
+      // ---- 2. MMAs of the next round --------------------------------------------------------
       if (have_nxt) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         mm_fence_before();
@@ -548,9 +663,9 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
         old = mm_uniform(old);
         if ((old & 3u) == 3u) {   // the last of the four warps: a warp-uniform branch
           mm_fence_after();
-          const uint32_t bA = mm_uniform(nxt.b_row + (nxt.twA >> 24) * kCellBytes);
-          const uint32_t bB = mm_uniform(nxt.b_row + (nxt.twB >> 24) * kCellBytes);
-          const uint32_t ab = mm_uniform(nxt.abuf);
+          const uint32_t da = descb + 32u * nslot;
+          const uint32_t bA = mm_uniform(lds_u32(da + 12u)), bB = mm_uniform(lds_u32(da + 16u));
+          const uint32_t ab = mm_uniform(nab);
           if (mm_elect_one()) {
             issue_mmas(tD0, ab, bA);
             issue_mmas(tD1, ab + 8u * kKSteps, bB);
@@ -558,94 +673,62 @@ slice_apply_rows_mma_kernel(const MmArgs args, const GuideFn guide_fn) {
           }
           __syncwarp();
         }
-        cur = nxt;
+        cw0 = nw0; cw1 = nw1; cw2 = nw2; cw3 = nw3;
+        cslot = nslot;
         have_cur = true;
         have_nxt = false;
       }
-      // ---- 3. fetch + set-up of one more round (overlaps the MMAs just issued) ---------------
-      bool fetched = false;
-      while (c_row < r_end) {
-        const int rowk = static_cast<int>(c_row - r_begin), rb = rowk & 1;
-        // look-ahead bounds: B' has two row buffers, the ring NS stages
-        if (have_cur && (rowk - cur.rowk > 1 || c_segc - cur.segc > NS - 2)) break;
-        if (!c_row_open) { mbar_wait(&b_full[rb], static_cast<uint32_t>(rowk >> 1) & 1u); c_row_open = true; }
-        if (!c_seg_open) {
-          mbar_wait(&full[c_s], c_fph);
-          c_seg_open = true;
-          c_np = (seg_nt[c_sg] + 1) >> 1;
-          c_j = (wg - c_gp) & 3;
-          if (c_j >= c_np) { __syncwarp(); if (lane == 0) mm_arrive(&done[c_s]); }   // no pair of ours here
-        }
-        if (c_j < c_np) {
-          // ---- set-up: guide -> depth cell, weights, one-hot rows of A ------------------------
-          unsigned char* st = stage_base + static_cast<size_t>(c_s) * args.stage_bytes;
-          const uint32_t st_a = stage_addr + static_cast<uint32_t>(c_s) * static_cast<uint32_t>(args.stage_bytes);
-          uint32_t twA, twB;
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(twA), "=r"(twB)
-                       : "r"(tiles_addr + 4u * static_cast<uint32_t>(c_sg * args.max_tiles) + 8u * c_j));
-          const int nA = static_cast<int>((twA >> 16) & 0xffu), nB = static_cast<int>((twB >> 16) & 0xffu);
-          const int pA = static_cast<int>(twA & 0xffffu) + (t < nA ? t : 0);
-          const int pB = static_cast<int>(twB & 0xffffu) + (t < nB ? t : 0);
-          const int xs = c_sg * args.seg_px;
-          float gvA, gvB;
-          if constexpr (kGuideIn) {
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gvA) : "r"(st_a + args.off_guide + 4u * pA));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gvB) : "r"(st_a + args.off_guide + 4u * pB));
-          } else {
-            float rA, gA, bA, rB, gB, bB;
-            mm_load_px<kIn>(st, pA, rA, gA, bA);
-            mm_load_px<kIn>(st, pB, rB, gB, bB);
-            gvA = guide_fn(rA, gA, bA);
-            gvB = guide_fn(rB, gB, bB);
-            if (args.guide_out != nullptr) {
-              float* go = args.guide_out + static_cast<size_t>(c_row) * g.W + xs;
-              if (t < nA) go[pA] = gvA;
-              if (t < nB) go[pB] = gvB;
-            }
-          }
-          float zfA, zfB;
-          depth_axis(gvA, zfA, nxt.wzA0, nxt.wzA1);
-          depth_axis(gvB, zfB, nxt.wzB0, nxt.wzB1);
-          const uint32_t abuf = tA0 + (kPipeA ? (static_cast<uint32_t>(nfetch) & 1u) * 16u : 0u);
-          if constexpr (!kPipeA) {
-            // one A buffer: the MMAs of `cur` (issued in step 2) read it -- wait for them first
-            if (have_cur) mbar_wait_addr(dbar, dpar);
-          }
-          put_onehot(abuf, zfA);
-          put_onehot(abuf + 8u * kKSteps, zfB);
+      // ---- 3. fetch + set-up of one more round ---------------------------------------------
+      if (!ended) {
+        const uint32_t slot = nfetch & 3u, par = (nfetch >> 2) & 1u;
+        bool ready = true;
+        // with MMAs in flight do not block here: their epilogue may be what the next descriptor waits for
+        if (have_cur) ready = mm_test(descr + 8u * slot, par);
+        else mbar_wait_addr(descr + 8u * slot, par);
+        if (ready) {
           ++nfetch;
-          nxt.twA = twA; nxt.twB = twB;
-          nxt.st = st; nxt.xs = xs;
-          nxt.b_row = bt_addr + static_cast<uint32_t>(rb) * kNSplit * static_cast<uint32_t>(args.bsplit_bytes);
-          nxt.abuf = abuf;
-          nxt.done_bar = 0u; nxt.free_bar = 0u;
-          nxt.segc = c_segc; nxt.rowk = rowk;
-          have_nxt = true;
-          fetched = true;
-          c_j += 4;
-          if (c_j < c_np) break;       // more pairs of ours in this segment: come back next iteration
+          const uint32_t da = descb + 32u * slot;
+          const uint4 d0 = lds_v4(da);
+          const uint32_t flags = lds_u32(da + 24u);
+          if (flags & kDescEnd) {
+            ended = true;
+          } else {
+            const uint32_t st = d0.x, twA = d0.y, twB = d0.z;
+            const int pA = static_cast<int>(twA & 0xffffu) + (t < static_cast<int>(twA >> 16) ? t : 0);
+            const int pB = static_cast<int>(twB & 0xffffu) + (t < static_cast<int>(twB >> 16) ? t : 0);
+            float gvA, gvB;
+            if constexpr (kGuideIn) {
+              gvA = lds_f32(st + args.off_guide + 4u * pA);
+              gvB = lds_f32(st + args.off_guide + 4u * pB);
+            } else {
+              float rA, gA, bA, rB, gB, bB;
+              mm_load_px_a<kIn>(st, pA, rA, gA, bA);
+              mm_load_px_a<kIn>(st, pB, rB, gB, bB);
+              gvA = guide_fn(rA, gA, bA);
+              gvB = guide_fn(rB, gB, bB);
+              if (args.guide_out != nullptr) {
+                float* go = args.guide_out + lds_u32(da + 28u);
+                if (t < static_cast<int>(twA >> 16)) go[pA] = gvA;
+                if (t < static_cast<int>(twB >> 16)) go[pB] = gvB;
+              }
+            }
+            float zfA, zfB;
+            depth_axis(gvA, zfA, nw0, nw1);
+            depth_axis(gvB, zfB, nw2, nw3);
+            nab = tA0 + (kPipeA ? (nsetup & 1u) * 16u : 0u);
+            if constexpr (!kPipeA) {
+              // one A buffer: the MMAs of `cur` (issued in step 2) read it -- wait for them first
+              if (have_cur) mbar_wait_addr(dbar, dpar);
+            }
+            put_onehot(nab, zfA);
+            put_onehot(nab + 8u * kKSteps, zfB);
+            ++nsetup;
+            nslot = slot;
+            have_nxt = true;
+          }
         }
-        // ---- leave the segment (all our pairs of it are fetched) -------------------------------
-        {
-          Round* nw = newest();
-          if (nw != nullptr && nw->segc == c_segc) nw->done_bar = done_addr + 8u * c_s;
-          // (a segment without a pair of ours was acknowledged when it was opened)
-        }
-        c_gp = (c_gp + c_np) & 3;
-        ++c_segc;
-        if (++c_s == NS) { c_s = 0; c_fph ^= 1u; }
-        c_seg_open = false;
-        if (++c_sg >= row_seg1(c_row)) {
-          Round* nw = newest();
-          if (nw != nullptr && nw->rowk == rowk) nw->free_bar = bfree_addr + 8u * rb;
-          else { __syncwarp(); if (lane == 0) mm_arrive(&b_free[rb]); }
-          c_sg = 0;
-          ++c_row;
-          c_row_open = false;
-        }
-        if (fetched) break;
       }
-      if (!have_cur && !have_nxt) break;
+      if (ended && !have_cur && !have_nxt) break;
     }
   }
   mm_fence_before();
@@ -690,8 +773,9 @@ bool make_mma_plan(const SliceGeom& g, int in_fmt, int out_fmt, bool guide_from_
   const int after_in = guide_from_input ? a.off_guide + a.seg_px * 4 : a.off_guide;
   a.off_out = (out_bpp == in_bpp) ? 0 : mm_round_up(after_in, 16);
   a.stage_bytes = mm_round_up(a.off_out ? a.off_out + a.seg_px * out_bpp : after_in, 128);
-  a.off_tab = 256;
-  a.off_raw = mm_round_up(a.off_tab + (40 + 24 + a.nseg * a.max_tiles) * 4, 128);
+  a.off_wx = mm_round_up(1024 + (40 + 24 + a.nseg * a.max_tiles) * 4, 16);   // after the header and the tables (kOffTab)
+  a.off_raw = mm_round_up(a.off_wx + g.W * 4, 128);
+  if (static_cast<long long>(g.B) * g.rows * g.W >= (1LL << 32)) return false;   // 32-bit pixel offsets in descriptors
   a.off_b = mm_round_up(a.off_raw + 2 * a.row_floats * 4, 1024);
   a.off_stage = mm_round_up(a.off_b + 2 * nsplit * a.bsplit_bytes, 128);
   a.stages = 0;

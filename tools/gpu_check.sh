@@ -1,23 +1,9 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, smoke, bench, ncu launch list + full capture of the top kernel.
-# Usage (from the repo root on the GPU box):  bash tools/gpu_check.sh [quick]
+# One gpurun call: GPU test suite, smoke, bench line, same-box A/B of the issuer-warp CTA shapes.
 set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.csv 2>&1
-nproc > gpurun_out/nproc.txt; lscpu | grep -E "Model name|^CPU\(s\)" >> gpurun_out/nproc.txt
-timeout 1500 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
-tail -25 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 300 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-if [ "${1:-}" != "quick" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launches.log 2>&1
-  echo "ncu launches exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:slice_apply_rows_async -s 3 -c 2 \
-      -f -o gpurun_out/prof_main python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
-  echo "ncu full exit $?"
-fi
-if [ "${1:-}" = "configs" ] || [ "${2:-}" = "configs" ]; then
-  timeout 300 python tools/bench_configs.py > gpurun_out/bench_configs.jsonl 2> gpurun_out/bench_configs.err; echo "bench_configs exit $?"; tail -12 gpurun_out/bench_configs.jsonl
-fi
+timeout 1500 python -m pytest tests -x -q -m gpu --timeout 600 -p no:cacheprovider 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 2500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+L=hdrnet_b200/lib/libhdrnet_b200.so
+AB_ROUNDS=5 timeout 300 python tools/ab_lib.py $L:7:HDRNET_ASYNC_THREADS=512 $L:7:HDRNET_ASYNC_THREADS=352 $L:7:HDRNET_ASYNC_THREADS=352,HDRNET_TEX_CHUNKS=4 $L:4 $L:2 > gpurun_out/ab_lib.txt 2>&1; grep -v bursts gpurun_out/ab_lib.txt | tail -8
