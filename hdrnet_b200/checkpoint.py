@@ -405,13 +405,23 @@ def legacy_name_map() -> dict:
 
 def upgrade_legacy_names(variables: dict) -> dict:
     """Old variable names -> the ``inference/...`` names (scripts/upgrade.py:29-61); the two old
-    biases that fed the fusion sum are ADDED into the single fc3 bias (upgrade.py:63-67)."""
+    biases that fed the fusion sum are ADDED into the single fc3 bias (upgrade.py:63-67).
+
+    The new graph is a batch-norm graph: the old biases become ``BatchNorm/beta``.  The reference
+    builds that graph and runs its initialiser before assigning the transferred tensors, so every
+    batch-normed layer also has ``moving_mean`` = 0 and ``moving_variance`` = 1 (the
+    tf.contrib.layers.batch_norm initial values) -- emitted here, or the upgraded weights would not
+    load (models._fold needs them; load the result with params['batch_norm'] = True)."""
     m = legacy_name_map()
     out = {}
     for name, val in variables.items():
         name = name[:-2] if name.endswith(":0") else name
         if name in m:
             out[m[name]] = np.asarray(val, np.float32)
+            if m[name].endswith("/BatchNorm/beta"):
+                scope = m[name][:-len("/beta")]
+                out[scope + "/moving_mean"] = np.zeros_like(out[m[name]])
+                out[scope + "/moving_variance"] = np.ones_like(out[m[name]])
     fused = [np.asarray(variables[k], np.float32) for k in ("grid_conv2/biases", "global_fc3/biases")
              if k in variables]
     if fused:

@@ -321,13 +321,16 @@ __global__ void __launch_bounds__(kFpThreads)
 fuse_predict_kernel(const float* __restrict__ local, const float* __restrict__ global_feat,
                     const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ grid, int B, int cells_per_image, int C, int gd,
-                    int n_out, int n_in) {
-  extern __shared__ __align__(16) float sm[];  // w[C][O] then f[kFpCells][C]
+                    int n_out, int n_in, int stage_w) {
+  extern __shared__ __align__(16) float sm[];  // [w[C][O] when stage_w] then f[kFpCells][C]
   const int O = gd * n_out * n_in;
-  float* wsm = sm;
-  float* fsm = sm + static_cast<size_t>(C) * O;
+  // stage_w == 0: the prediction weights do not fit shared memory next to the features (e.g.
+  // HDRNetGaussianPyrNN with channel_multiplier 4: C = 256, O = 288, 295 KB): read them through L1
+  float* fsm = sm + (stage_w ? static_cast<size_t>(C) * O : 0);
+  const float* wsm = stage_w ? sm : w;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int e = tid; e < C * O; e += kFpThreads) wsm[e] = __ldg(w + e);
+  if (stage_w)
+    for (int e = tid; e < C * O; e += kFpThreads) sm[e] = __ldg(w + e);
   const long long total = static_cast<long long>(B) * cells_per_image;
   const long long cell = static_cast<long long>(blockIdx.x) * kFpCells + warp;
   const bool valid = cell < total;
@@ -465,7 +468,9 @@ int hdrnet_fuse_predict_f32(const float* local, const float* global_feat, const 
   if (B == 0) return HDRNET_OK;
   if (!local || !global_feat || !w || !grid) return HDRNET_E_NULL_POINTER;
   const int O = gd * n_out * n_in;
-  const size_t smem = (static_cast<size_t>(C) * O + static_cast<size_t>(kFpCells) * C) * sizeof(float);
+  size_t smem = (static_cast<size_t>(C) * O + static_cast<size_t>(kFpCells) * C) * sizeof(float);
+  const int stage_w = smem <= 200 * 1024;
+  if (!stage_w) smem = static_cast<size_t>(kFpCells) * C * sizeof(float);
   if (smem > 200 * 1024) return HDRNET_E_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(fuse_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
@@ -473,7 +478,7 @@ int hdrnet_fuse_predict_f32(const float* local, const float* global_feat, const 
   const long long cells = static_cast<long long>(B) * gh * gw;
   fuse_predict_kernel<<<static_cast<unsigned>((cells + kFpCells - 1) / kFpCells), kFpThreads, smem,
                         static_cast<cudaStream_t>(stream)>>>(local, global_feat, w, bias, grid, B,
-                                                             gh * gw, C, gd, n_out, n_in);
+                                                             gh * gw, C, gd, n_out, n_in, stage_w);
   return static_cast<int>(cudaGetLastError());
 }
 

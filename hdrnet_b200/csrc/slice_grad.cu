@@ -305,7 +305,14 @@ int hdrnet_slice_apply_grad_f32(const float* grid, const float* guide, const flo
                                 int n_in, int n_out, int has_offset, void* stream) {
   if (B < 0 || H < 0 || W < 0 || gh < 1 || gw < 1 || gd < 1 || n_in < 1 || n_out < 1)
     return HDRNET_E_BAD_SHAPE;
-  if (static_cast<long long>(B) * H * W == 0) return HDRNET_OK;
+  if (static_cast<long long>(B) * H * W == 0) {
+    // no pixels: the pixel-shaped VJPs are empty, but the grid VJP is a full tensor of zeros when
+    // B > 0 (the reference's kernels write 0 for a cell without a footprint)
+    const size_t n = static_cast<size_t>(B) * gh * gw * gd * n_out * (n_in + (has_offset ? 1 : 0));
+    if (n == 0) return HDRNET_OK;
+    if (!grid_vjp) return HDRNET_E_NULL_POINTER;
+    return static_cast<int>(cudaMemsetAsync(grid_vjp, 0, n * sizeof(float), static_cast<cudaStream_t>(stream)));
+  }
   if (!grid || !guide || !input || !codomain_tangent || !grid_vjp || !guide_vjp || !input_vjp)
     return HDRNET_E_NULL_POINTER;
   GradGeom g{B, H, W, gh, gw, gd, n_in, n_out, n_in + (has_offset ? 1 : 0), 1};
@@ -317,7 +324,12 @@ int hdrnet_slice_grad_f32(const float* grid, const float* guide, const float* co
                           float* grid_vjp, float* guide_vjp, int B, int H, int W, int gh, int gw,
                           int gd, int gc, void* stream) {
   if (B < 0 || H < 0 || W < 0 || gh < 1 || gw < 1 || gd < 1 || gc < 1) return HDRNET_E_BAD_SHAPE;
-  if (static_cast<long long>(B) * H * W == 0) return HDRNET_OK;
+  if (static_cast<long long>(B) * H * W == 0) {
+    const size_t n = static_cast<size_t>(B) * gh * gw * gd * gc;
+    if (n == 0) return HDRNET_OK;
+    if (!grid_vjp) return HDRNET_E_NULL_POINTER;
+    return static_cast<int>(cudaMemsetAsync(grid_vjp, 0, n * sizeof(float), static_cast<cudaStream_t>(stream)));
+  }
   if (!grid || !guide || !codomain_tangent || !grid_vjp || !guide_vjp) return HDRNET_E_NULL_POINTER;
   GradGeom g{B, H, W, gh, gw, gd, 0, gc, 1, 0};
   return launch_grads(grid, guide, nullptr, codomain_tangent, grid_vjp, guide_vjp, nullptr, g,

@@ -112,7 +112,31 @@ def test_legacy_name_upgrade():
     old["global_fc3/biases"] = np.array([10.0, 20.0], np.float32)
     new = C.upgrade_legacy_names(old)
     assert np.array_equal(new["inference/coefficients/global/fc3/biases"], [11.0, 22.0])  # upgrade.py:63-67
-    assert len(new) == 29 and all(k.startswith("inference/") for k in new)
+    # 28 transferred + the summed fc3 bias + (moving_mean, moving_variance) for the 8 batch-normed layers
+    assert len(new) == 29 + 16 and all(k.startswith("inference/") for k in new)
+
+
+def test_upgraded_legacy_weights_load_into_the_model():
+    """the upgraded dict must be a complete batch-norm checkpoint -- every layer whose
+    old bias became BatchNorm/beta needs moving_mean = 0 / moving_variance = 1 (what the reference's
+    freshly initialised graph holds, scripts/upgrade.py:88-100) or models._fold raises KeyError."""
+    p = dict(M.DEFAULT_PARAMS, batch_norm=True)
+    ref = models.init_weights(p, seed=1)
+    inv = {v: k for k, v in C.legacy_name_map().items()}
+    old = {inv[k]: v for k, v in ref.items() if k in inv}
+    old["grid_conv2/biases"] = np.zeros_like(ref["inference/coefficients/global/fc3/biases"])
+    old["global_fc3/biases"] = np.asarray(ref["inference/coefficients/global/fc3/biases"])
+    new = C.upgrade_legacy_names(old)
+    assert sorted(new) == sorted(ref)                      # exactly the variables the BN graph has
+    pre = "inference/coefficients"
+    for scope, bn in ((f"{pre}/splat/conv1", False), (f"{pre}/splat/conv2", True), (f"{pre}/global/fc1", True),
+                      (f"{pre}/local/conv1", True), (f"{pre}/global/fc3", False)):
+        w, b = models._fold(new, scope, bn, not bn)
+        assert w.shape == np.asarray(ref[scope + "/weights"]).shape and b is not None
+    # the fresh statistics fold to (x / sqrt(1 + eps) + beta): no NaNs, scale just under 1
+    w, b = models._fold(new, f"{pre}/splat/conv2", True, False)
+    ratio = w / np.asarray(ref[f"{pre}/splat/conv2/weights"])
+    assert np.allclose(ratio[np.isfinite(ratio)], 1.0 / np.sqrt(1.0 + 1e-3), rtol=1e-6)
 
 
 @pytest.mark.parametrize("model_name", ["HDRNetCurves", "HDRNetPointwiseNNGuide", "HDRNetGaussianPyrNN"])
@@ -244,3 +268,46 @@ def test_run_py_reads_a_tensorflow_directory_and_debug_pictures(tmp_path):
     assert mosaic[z * 16 + y, (o * 4 + i) * 16 + x] == want
     assert pics["_guide_0.png"].max() == 255 and pics["_guide_0.png"].min() >= 127   # guide >= 0
     assert np.array_equal(pics["_input.png"], im[:, :, ::-1])
+
+
+# ---- a checkpoint assembled byte by byte from the format specifications ---------------------------
+BUNDLE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_bundle")
+INDEX_SHA = "ff14f7a6014e328bf5ef23e6f1a8fa2a2a66b4cb3da8491bc22d5f4b93fcaa4e"
+DATA_SHA = "82e81f7c01f0ab8f0b4d08920d53698ac4ffa77d25d2457f1c51e62c1a28f71b"
+
+
+def test_reads_the_hand_assembled_tensor_bundle():
+    """tests/golden/tf_bundle/ is written by tests/golden/make_tf_bundle_fixture.py, an independent
+    statement of the LevelDB table + tensor-bundle formats (bit-wise CRC-32C, literal protobuf bytes,
+    prefix-compressed keys, two data blocks) that shares no code with hdrnet_b200/checkpoint.py.
+    The committed bytes are pinned by their SHA-256; the reader must return exactly the values the
+    generator lists, with every block and tensor checksum verified."""
+    import hashlib
+    with open(os.path.join(BUNDLE_DIR, "model.ckpt-7.index"), "rb") as f:
+        index = f.read()
+    with open(os.path.join(BUNDLE_DIR, "model.ckpt-7.data-00000-of-00001"), "rb") as f:
+        data = f.read()
+    assert len(index) == 272 and len(data) == 76
+    assert index[-8:] == bytes.fromhex("57fb808b247547db")                    # table magic, little-endian
+    assert hashlib.sha256(index).hexdigest() == INDEX_SHA and hashlib.sha256(data).hexdigest() == DATA_SHA
+    v = C.read_tf_checkpoint(BUNDLE_DIR, verify=True)                         # via the `checkpoint` state file
+    assert sorted(v) == ["global_step", "inference/coefficients/splat/conv1/biases", "inference/guide/ccm"]
+    assert v["global_step"].dtype == np.int64 and v["global_step"].shape == () and int(v["global_step"]) == 1234567
+    assert v["inference/coefficients/splat/conv1/biases"].tolist() == [0.5, -0.25, 1.0, 2.0, -3.5, 0.125, 100.0, -0.0078125]
+    assert v["inference/guide/ccm"].dtype == np.float32
+    assert v["inference/guide/ccm"].tolist() == [[1.0, 0.0625, -0.0625], [0.03125, 0.96875, 0.0], [-0.015625, 0.25, 0.75]]
+    w = C.model_weights(v)                                                     # run.py:92 scope filter
+    assert sorted(w) == ["inference/coefficients/splat/conv1/biases", "inference/guide/ccm"]
+
+
+def test_hand_assembled_bundle_corruption_is_detected(tmp_path):
+    import shutil
+    for victim, offset, what in (("model.ckpt-7.data-00000-of-00001", 20, "tensor checksum"),
+                                 ("model.ckpt-7.index", 30, "checksum")):
+        d = tmp_path / victim.replace(".", "_")
+        shutil.copytree(BUNDLE_DIR, d)
+        raw = bytearray((d / victim).read_bytes())
+        raw[offset] ^= 0x40
+        (d / victim).write_bytes(bytes(raw))
+        with pytest.raises(ValueError, match=what):
+            C.read_tf_checkpoint(str(d), verify=True)

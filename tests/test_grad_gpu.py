@@ -110,3 +110,19 @@ def test_backward_is_deterministic():
         grads.append((g.grad.clone(), u.grad.clone(), i.grad.clone()))
     for a, b in zip(*grads):
         assert torch.equal(a, b)
+
+
+def test_grid_vjp_is_zero_when_there_are_no_pixels():
+    """B > 0 with H == 0 (or W == 0): no pixel contributes, the grid VJP is a tensor of
+    zeros (the reference's kernels write 0 for every cell) -- not uninitialised memory."""
+    for H, W in ((0, 8), (8, 0)):
+        grid = torch.randn(2, 4, 4, 8, 12, device="cuda", requires_grad=True)
+        guide = torch.rand(2, H, W, device="cuda", requires_grad=True)
+        inp = torch.randn(2, H, W, 3, device="cuda", requires_grad=True)
+        out = hdrnet_ops.bilateral_slice_apply(grid, guide, inp, True)
+        assert out.shape == (2, H, W, 3)
+        out.sum().backward()
+        assert grid.grad is not None and not grid.grad.any()
+        g2 = torch.randn(2, 4, 4, 8, 12, device="cuda", requires_grad=True)
+        hdrnet_ops.bilateral_slice(g2, guide.detach()).sum().backward()
+        assert not g2.grad.any()

@@ -2,9 +2,18 @@
 
 CPU part: host logic only (weight naming / shapes / batch-norm folding / error paths).
 GPU part (-m gpu): the CUDA layers and the full models against oracle/model_np.py, the
-float64-accumulated numpy restatement of hdrnet/models.py + layers.py.  That restatement is
-"parity unpinned" (the reference has no test or golden vector for models.py and TF cannot
-run here); tolerances are float32 round-off bounds and are written next to each check.
+float64-accumulated numpy restatement of hdrnet/models.py + layers.py, which is pinned by an
+independent torch restatement and hand-computed known answers (tests/test_model_kats.py; the
+reference has no test or golden vector for models.py and TF cannot run here).
+
+How the 1e-5 bar of BASELINE.json is applied to a whole model: stage by stage.
+  * coefficient CNN vs oracle: 2e-5 of range (9-11 float32 layers deep);
+  * guide vs oracle: 2e-6 absolute on [0, 1];
+  * full-resolution stage: the CUDA output against the pinned SLICE oracle (the compiled reference
+    loops) fed the CUDA stage's own coefficients and guide -- 1e-5, the bar itself.  This separates
+    the kernel's error from the sensitivity of the op to its inputs (a guide that differs by 1e-7
+    moves a pixel's depth coordinate by gd * 1e-7, which alone can exceed 1e-5 of the output);
+  * end to end vs the all-oracle pipeline: 1e-4, as a sanity bound on that sensitivity.
 """
 import numpy as np
 import pytest
@@ -165,10 +174,15 @@ def test_full_inference_matches_oracle(name, H, W):
     ref, ref_coeffs, ref_guide = M.inference(low, full, wts, p, oracle.best().bilateral_slice_apply)
     cls = getattr(models, p["model_name"])
     got = cls.inference(cuda(low), cuda(full), dict(p, weights=wts, debug=True))
-    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what=f"{name} output")
+    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what=f"{name} output", elem_rtol=None)
     dbg = cls.last_debug
-    assert_parity(dbg["bilateral_coefficients"].cpu().numpy(), ref_coeffs, rtol=2e-5)
+    assert_parity(dbg["bilateral_coefficients"].cpu().numpy(), ref_coeffs, rtol=2e-5, elem_rtol=None)
     assert np.abs(dbg["guide"].cpu().numpy() - ref_guide).max() < 2e-6
+    # the full-resolution stage itself, at the bar: pinned slice oracle on the CUDA stage's inputs
+    c = dbg["bilateral_coefficients"].cpu().numpy()
+    stage = oracle.best().bilateral_slice_apply(np.ascontiguousarray(c.reshape(c.shape[:4] + (12,))),
+                                                dbg["guide"].cpu().numpy(), full, True)
+    assert_parity(got.cpu().numpy(), stage, rtol=1e-5, what=f"{name} full-resolution stage")
     # same call without the debug dump takes the guide-fused kernel when W allows it
     got2 = cls.inference(cuda(low), cuda(full), dict(p, weights=wts))
     assert torch.equal(got2, got)
@@ -206,7 +220,7 @@ def test_run_py_identity_sample_plumbing(tmp_path):
     im = run.img_as_float(im8)[None]
     low = run.nearest_resize(im[0], 256)[None]
     ref, _, _ = M.inference(low, im, loaded, params, oracle.best().bilateral_slice_apply)
-    assert_parity(out.cpu().numpy(), ref, rtol=1e-4)
+    assert_parity(out.cpu().numpy(), ref, rtol=1e-4, elem_rtol=None)
     ref8 = (255.0 * np.clip(ref, 0, 1)).astype(np.uint8)[0]
     assert np.abs(out8.astype(int) - ref8.astype(int)).max() <= 1
 
@@ -285,13 +299,26 @@ def test_gaussian_pyramid_model_matches_oracle(H, W):
     ref, ref_coeffs, ref_guides = M.gaussian_pyr_inference(low, full, wts, p,
                                                            oracle.best().bilateral_slice_apply)
     got = models.HDRNetGaussianPyrNN.inference(cuda(low), cuda(full), dict(p, weights=wts, debug=True))
-    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what="pyramid output")
+    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what="pyramid output", elem_rtol=None)
     dbg = models.HDRNetGaussianPyrNN.last_debug
-    assert_parity(dbg["bilateral_coefficients"].cpu().numpy(), ref_coeffs, rtol=2e-5)
+    assert_parity(dbg["bilateral_coefficients"].cpu().numpy(), ref_coeffs, rtol=2e-5, elem_rtol=None)
     for g, r in zip(dbg["guide"], ref_guides):
         assert np.abs(g.cpu().numpy() - r).max() < 2e-6
     fast = models.HDRNetGaussianPyrNN.inference(cuda(low), cuda(full), dict(p, weights=wts))
-    assert_parity(fast.cpu().numpy(), ref, rtol=1e-4, what="pyramid output (guide-fused)")
+    assert_parity(fast.cpu().numpy(), ref, rtol=1e-4, what="pyramid output (guide-fused)", elem_rtol=None)
+    # the full-resolution stages at the bar: the oracle's own pyramid / upsample-add around the
+    # pinned slice oracle, fed the CUDA stage's coefficients and per-level guides
+    c = dbg["bilateral_coefficients"].cpu().numpy()
+    lvls = [full]
+    for _ in range(2):
+        lvls.append(M.resize_bilinear_ac(lvls[-1], lvls[-1].shape[1] // 2, lvls[-1].shape[2] // 2))
+    cur = None
+    for il in range(3):
+        src = 2 - il
+        ci = np.ascontiguousarray(c[:, :, :, :, il * 3:(il + 1) * 3, :]).reshape(c.shape[:4] + (12,))
+        o = oracle.best().bilateral_slice_apply(ci, dbg["guide"][src].cpu().numpy(), lvls[src], True)
+        cur = o if il == 0 else M.resize_bilinear_ac(cur, o.shape[1], o.shape[2]) + o
+    assert_parity(got.cpu().numpy(), cur, rtol=1e-5, what="pyramid full-resolution stages", elem_rtol=None)
 
 
 @pytest.mark.gpu
@@ -308,4 +335,27 @@ def test_full_inference_large_image_takes_texture_assisted_kernel(name):
     ref, _, _ = M.inference(low, full, wts, p, oracle.best().bilateral_slice_apply)
     cls = getattr(models, p["model_name"])
     got = cls.inference(cuda(low), cuda(full), dict(p, weights=wts))
-    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what=f"{name} 2 MP output")
+    assert_parity(got.cpu().numpy(), ref, rtol=1e-4, what=f"{name} 2 MP output", elem_rtol=None)
+
+
+@pytest.mark.gpu
+def test_fuse_predict_with_weights_larger_than_shared_memory():
+    """HDRNetGaussianPyrNN at channel_multiplier 4 (scripts/*/train_gpyrnn_cm4.sh) has
+    a 256 x 288 prediction conv (295 KB): the fused fusion + prediction + unroll kernel must read
+    the weights through the cache instead of refusing the model."""
+    rng = np.random.RandomState(3)
+    B, gh, gw, C, gd, n_out, n_in = 2, 4, 4, 256, 8, 9, 4
+    O = gd * n_out * n_in
+    loc = rng.randn(B, gh, gw, C).astype(np.float32)
+    glob = rng.randn(B, C).astype(np.float32)
+    w = (rng.randn(C, O) / np.sqrt(C)).astype(np.float32)
+    b = rng.randn(O).astype(np.float32)
+    out = torch.empty(B, gh, gw, gd, n_out, n_in, device="cuda")
+    rc = _lib.load().hdrnet_fuse_predict_f32(cuda(loc).data_ptr(), cuda(glob).data_ptr(), cuda(w).data_ptr(),
+                                             cuda(b).data_ptr(), out.data_ptr(), B, gh, gw, C, gd, n_out, n_in,
+                                             torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    f = np.maximum(loc + glob[:, None, None, :], 0).astype(np.float64)
+    pred = f @ w.astype(np.float64) + b                                   # [B, gh, gw, O], o = (j*n_out + i)*gd + z
+    ref = pred.reshape(B, gh, gw, n_in, n_out, gd).transpose(0, 1, 2, 5, 4, 3)
+    assert_parity(out.cpu().numpy(), ref.astype(np.float32), rtol=2e-6)

@@ -276,6 +276,31 @@ def test_non_default_stream_and_repeatability():
         assert torch.equal(o, ref)
 
 
+def test_two_streams_on_large_images_do_not_share_a_workspace():
+    """>= 2 Mi-pixel calls take the texture-assisted kernel, whose pre-pass writes the slab rows of
+    THIS call into a lent workspace: two streams (and two threads -- ctypes releases the GIL) with
+    different grids must not see each other's rows (round 1 kept one workspace per device)."""
+    import threading
+    cases = [rand_case(50 + k, 1, 1100, 2048, 16, 16, 8, signed=True) for k in range(2)]
+    dev = [tuple(cuda(a) for a in c) for c in cases]
+    want = [hdrnet_ops.bilateral_slice_apply(*d, True) for d in dev]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in dev]
+    got = [[] for _ in dev]
+
+    def work(k):
+        with torch.cuda.stream(streams[k]):
+            for _ in range(12):
+                got[k].append(hdrnet_ops.bilateral_slice_apply(*dev[k], True))
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(dev))]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    torch.cuda.synchronize()
+    for k in range(len(dev)):
+        for o in got[k]:
+            assert torch.equal(o, want[k]), f"stream {k}: result changed under a concurrent call"
+
+
 # ---- BASELINE.json full size: 4K ------------------------------------------------------------
 def test_4k_frame_against_full_oracle():
     """One 3840x2160 frame, grid 16x16x8 (config 3's per-image shape), full oracle compare."""
@@ -286,6 +311,26 @@ def test_4k_frame_against_full_oracle():
         assert_parity(got, expected, what=f"4K [{v}]")
     gidx = hdrnet_ops.slice_indices(cuda(guide), (16, 16, 8)).cpu().numpy()
     assert np.array_equal(gidx, oracle.port().slice_indices(guide, 16, 16, 8))
+
+
+def test_benchmarked_call_against_the_full_oracle():
+    """The call bench.py times -- 8 x 3840 x 2160, grid 16x16x8, AUTO with a lent workspace --
+    compared element by element with the compiled reference loops (oracle/_ref), all 66 MP."""
+    grid, guide, inp = rand_case(1234, 8, 2160, 3840, 16, 16, 8)
+    expected = checker().bilateral_slice_apply(grid, guide, inp, True)
+    got = run_apply(grid, guide, inp, True, "auto")
+    assert_parity(got, expected, what="8 x 4K [auto]")
+    del got, expected
+
+
+def test_12mp_frame_and_largest_grid_against_the_full_oracle():
+    """Config 4's frame size (3024 x 4032) and config 5's largest grid (32x32x16) through AUTO."""
+    grid, guide, inp = rand_case(7, 1, 3024, 4032, 16, 16, 8, signed=True)
+    assert_parity(run_apply(grid, guide, inp, True, "auto"),
+                  checker().bilateral_slice_apply(grid, guide, inp, True), what="12 MP [auto]")
+    grid, guide, inp = rand_case(8, 1, 2160, 3840, 32, 32, 16, signed=True)
+    assert_parity(run_apply(grid, guide, inp, True, "auto"),
+                  checker().bilateral_slice_apply(grid, guide, inp, True), what="4K 32x32x16 [auto]")
 
 
 def test_4k_batch8_properties():

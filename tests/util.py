@@ -23,13 +23,35 @@ def rel_err(actual, expected):
     return float(np.abs(actual - expected).max()) / scale
 
 
-def assert_parity(actual, expected, rtol=RTOL, what=""):
+def elem_err(actual, expected, floor=1e-3):
+    """Worst PER-ELEMENT relative error, |diff| / max(|ref|, floor * max|ref|): the global metric
+    above lets a pixel whose terms cancel be wrong by all of its own value; this one holds every
+    element that is not itself below `floor` of the tensor's range to its own magnitude."""
+    actual = np.asarray(actual, np.float64)
+    expected = np.asarray(expected, np.float64)
+    scale = max(float(np.abs(expected).max()), 1e-30)
+    return float((np.abs(actual - expected) / np.maximum(np.abs(expected), floor * scale)).max())
+
+
+# Per-element bar: an output is a sum of ~60 float32 products of magnitude up to max|grid| * max|in|;
+# with signed inputs the sum may cancel to `floor` of the range, so its float32 round-off is up to
+# ~1e-7 / floor = 1e-4 of ITS OWN value.  2e-3 leaves an order of magnitude and still catches any
+# wrong cell, weight or channel (those are errors of order 1).
+ELEM_RTOL = 2e-3
+
+
+def assert_parity(actual, expected, rtol=RTOL, what="", elem_rtol=ELEM_RTOL):
     actual = np.asarray(actual)
     expected = np.asarray(expected)
     assert actual.shape == expected.shape, f"{what}: shape {actual.shape} != {expected.shape}"
     assert np.isfinite(actual).all(), f"{what}: non-finite values"
     err = rel_err(actual, expected)
-    assert err <= rtol, f"{what}: max |diff| / max |ref| = {err:.3e} > {rtol:.1e}"
+    per_elem = elem_err(actual, expected)
+    assert err <= rtol, (f"{what}: max |diff| / max |ref| = {err:.3e} > {rtol:.1e} "
+                         f"(worst per-element {per_elem:.3e})")
+    if elem_rtol is not None:
+        assert per_elem <= elem_rtol, (f"{what}: worst per-element |diff| / max(|ref|, 1e-3 max|ref|) = "
+                                       f"{per_elem:.3e} > {elem_rtol:.1e} (global {err:.3e})")
 
 
 def rand_case(seed, B, H, W, gh, gw, gd, n_in=3, n_out=3, has_offset=True, signed=False):
