@@ -454,7 +454,11 @@ def run_b200_arm(args):
     e2e8_s = float(te.item())
     del h_im8, h_out8
 
-    # ---- sustained: the same step for >= 2 s (the boxes power-cap under sustained load) ----
+    peak, peak_src = measured_peaks()
+    extra = {} if args.no_extra else extra_records(torch, dist, lib, _lib, dev, stream, world, rank, peak, args)
+
+    # ---- sustained: the same step for >= 2 s, LAST (the boxes power-cap under sustained load and
+    # take a second to recover: anything timed right after it would carry the capped clock) ----
     sus_steps = max(args.steps, int(2200.0 / max(own_launch_ms, 1e-3)))
     sus = ClockSampler(local_rank)
     sus.start()
@@ -475,8 +479,6 @@ def run_b200_arm(args):
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
     sus_ms = float(ts.item()) / sus_steps
 
-    peak, peak_src = measured_peaks()
-    extra = {} if args.no_extra else extra_records(torch, dist, lib, _lib, dev, stream, world, rank, peak, args)
 
     sampler.stop_flag.set()
     sampler.join(timeout=2)

@@ -6,9 +6,10 @@
   hdrnet/bin/freeze_graph.py:36-85).  TensorFlow is not installed here and the reference ships
   no checkpoint, so this follows the published on-disk format (tensorflow/core/util/
   tensor_bundle: an SSTable of BundleEntryProto records keyed by variable name, LevelDB table
-  format, no block compression) and is **parity unpinned**: it round-trips against
-  ``write_tf_checkpoint`` below and verifies every CRC-32C the format carries, but has not met
-  a file produced by TensorFlow itself.
+  format, no block compression).  Pinned by a bundle assembled byte by byte from the format
+  specifications by an independent script (tests/golden/make_tf_bundle_fixture.py), by the round
+  trip against ``write_tf_checkpoint`` below and by every CRC-32C the format carries; it has not
+  met a file produced by TensorFlow itself.
 * ``model_weights`` -- variable-name filter: the reference's graph variables under
   ``inference/`` (run.py:92), optimiser slots and counters dropped.
 * ``upgrade_legacy_names`` -- the old-checkpoint name map of scripts/upgrade.py:29-67.

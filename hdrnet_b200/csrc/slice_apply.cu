@@ -124,6 +124,113 @@ slice_generic_kernel(const float* __restrict__ grid, const float* __restrict__ g
   }
 }
 
+// =========================================================================================
+// Any-shape ROW kernel: the row kernels' organisation without their alignment contract.
+// =========================================================================================
+// The TMA row kernels take the 3 -> 3 affine op with offset on 16-byte aligned rows (W % 4 == 0);
+// everything else -- has_offset = False (ops_test.py:345-365), other n_in / n_out
+// (HDRNetGaussianPyrNN's 9 x 4 grids sliced directly, hdrnet_ops_test.py:91-100), odd widths,
+// unaligned views, and the un-fused slice with gc != 12 -- used to fall to slice_generic_kernel:
+// 8 corners x gc scalar L2 loads per pixel, 16.7 % of the HBM roofline at 4K.
+// This kernel keeps what makes the row kernels fast and drops only the bulk copies: a persistent
+// CTA owns contiguous rows; the two grid rows a pixel row touches are staged in shared memory
+// (plain loads, reloaded only when the row pair changes) and pre-blended along y into a slab
+// [gw][gd][gc], so a pixel gathers 4 corners from shared memory instead of 8 from L2; pixels are
+// one per thread with plain (coalesced, any alignment) global loads / stores.
+constexpr int kAnyThreads = 256;
+
+struct AnyArgs {
+  const float* grid;
+  const float* guide;
+  const float* input;   // kApply only
+  float* out;
+  SliceGeom g;
+  int n_in, n_out, J, gc;   // kApply: gc = n_out * J;  slice: gc channels, n_out = gc
+  int row_floats;           // gw * gd * gc
+};
+
+template <bool kApply>
+__global__ void __launch_bounds__(kAnyThreads, 4)
+slice_rows_any_kernel(const AnyArgs a) {
+  extern __shared__ __align__(16) float sm_any[];
+  const SliceGeom& g = a.g;
+  float* raw0 = sm_any;
+  float* raw1 = raw0 + a.row_floats;
+  float* slab = raw1 + a.row_floats;
+  const int tid = threadIdx.x;
+  const long long total_rows = static_cast<long long>(g.B) * g.rows;
+  const long long r_begin = total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
+  const float gd_f = static_cast<float>(g.gd);
+  const int x_stride = g.gd * a.gc;
+  int cur_b = -1, cur_gy0 = INT_MIN;
+  for (long long row = r_begin; row < r_end; ++row) {
+    const int b = static_cast<int>(row / g.rows);
+    const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
+    const Axis ay = spatial_axis(y, g.scale_y);
+    __syncthreads();   // the previous row's pixels are done with the slab
+    if (b != cur_b || ay.i0 != cur_gy0) {
+      const float* gb = a.grid + static_cast<size_t>(b) * g.gh * a.row_floats;
+      const float* r0 = gb + static_cast<size_t>(clampi(ay.i0, 0, g.gh - 1)) * a.row_floats;
+      const float* r1 = gb + static_cast<size_t>(clampi(ay.i0 + 1, 0, g.gh - 1)) * a.row_floats;
+      for (int e = tid; e < a.row_floats; e += kAnyThreads) { raw0[e] = __ldg(r0 + e); raw1[e] = __ldg(r1 + e); }
+      cur_b = b;
+      cur_gy0 = ay.i0;
+      __syncthreads();
+    }
+    const float wy1 = ay.f, wy0 = 1.0f - ay.f;
+    for (int e = tid; e < a.row_floats; e += kAnyThreads) slab[e] = fmaf(wy1, raw1[e], wy0 * raw0[e]);   // lerp4's order
+    __syncthreads();
+    const size_t pix0 = static_cast<size_t>(row) * g.W;
+    for (int x = tid; x < g.W; x += kAnyThreads) {
+      const size_t p = pix0 + x;
+      const Axis ax = spatial_axis(x, g.scale_x);
+      const Axis az = range_axis(__ldg(a.guide + p), gd_f);
+      const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride, xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
+      const int zo0 = clampi(az.i0, 0, g.gd - 1) * a.gc, zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * a.gc;
+      float wz0, wz1;
+      smoothed_weights(az.f, wz0, wz1);
+      const float wx1 = ax.f, wx0 = 1.0f - ax.f;
+      const float w00 = wx0 * wz0, w01 = wx0 * wz1, w10 = wx1 * wz0, w11 = wx1 * wz1;
+      const float* c00 = slab + xo0 + zo0;
+      const float* c01 = slab + xo0 + zo1;
+      const float* c10 = slab + xo1 + zo0;
+      const float* c11 = slab + xo1 + zo1;
+      auto coef = [&](int ch) {   // the row kernels' order of operations
+        return fmaf(w11, c11[ch], fmaf(w10, c10[ch], fmaf(w01, c01[ch], w00 * c00[ch])));
+      };
+      if constexpr (kApply) {
+        for (int i = 0; i < a.n_out; ++i) {
+          float value = 0.0f;
+          for (int j = 0; j < a.J; ++j) {
+            const float sv = coef(i * a.J + j);
+            value = (j < a.n_in) ? fmaf(sv, __ldg(a.input + p * a.n_in + j), value) : value + sv;
+          }
+          a.out[p * a.n_out + i] = value;
+        }
+      } else {
+        for (int ch = 0; ch < a.gc; ++ch) a.out[p * a.gc + ch] = coef(ch);
+      }
+    }
+  }
+}
+
+// false when the shape does not suit it (slab rows larger than a quarter SM's shared memory,
+// images too narrow to fill a CTA): the caller then runs slice_generic_kernel.
+template <bool kApply>
+static bool launch_rows_any(const AnyArgs& a, int max_smem, int sms, cudaStream_t stream, int* rc) {
+  const size_t smem = 3u * static_cast<size_t>(a.row_floats) * sizeof(float);
+  if (a.g.W < 64 || smem > static_cast<size_t>((max_smem + 1024) / 4 - 1024)) return false;
+  auto kern = slice_rows_any_kernel<kApply>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) { *rc = static_cast<int>(e); return true; }
+  const long long rows = static_cast<long long>(a.g.B) * a.g.rows;
+  const int ctas = static_cast<int>(std::min<long long>(rows, static_cast<long long>(sms) * 4));
+  kern<<<ctas, kAnyThreads, smem, stream>>>(a);
+  *rc = static_cast<int>(cudaGetLastError());
+  return true;
+}
+
 __global__ void __launch_bounds__(256)
 slice_indices_kernel(const float* __restrict__ guide, int32_t* __restrict__ idx, SliceGeom g,
                      long long npix) {
@@ -865,6 +972,7 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
                                             gs.in_fmt, gs.out_fmt, 2) &&
                               fplan.resident == 2 && fplan.stages >= 3;
 
+  const bool auto_generic = variant == HDRNET_VARIANT_AUTO;   // GENERIC on request = the one-thread-per-pixel L2 gather
   if (variant == HDRNET_VARIANT_AUTO) {
     // the texture-assisted forms pay a pre-pass launch: large images only
     if (tex_ok && W >= 128 && npix >= (1LL << 21))
@@ -945,6 +1053,10 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   // The float32 fused-guide forms exist only in the row kernels; other shapes run the standalone
   // guide kernel first (the caller does that: see hdrnet_slice_apply_{curves,nn}_f32).
   if (gs.mode != 0) return HDRNET_E_UNSUPPORTED;
+  if (auto_generic) {   // AUTO on a shape the TMA kernels cannot take: the any-shape row kernel
+    AnyArgs aa{grid, gs.guide, input, out, g, n_in, n_out, J, n_out * J, gw * gd * n_out * J};
+    if (launch_rows_any<true>(aa, max_smem, sms, stream, &rc)) return rc;
+  }
   slice_generic_kernel<true><<<generic_grid(npix, sms), 256, 0, stream>>>(
       grid, gs.guide, input, out, g, n_in, n_out, J, npix);
   return static_cast<int>(cudaGetLastError());
@@ -995,6 +1107,11 @@ int launch_slice(const float* grid, const float* guide, float* out, int B, int H
     a.grid = grid; a.guide = guide; a.out = out; a.g = g; a.p = plan;
     slice_rows_tma_kernel<<<plan.ctas, kSliceThreads, plan.smem_bytes, stream>>>(a);
   } else {
+    if (variant == HDRNET_VARIANT_AUTO) {
+      AnyArgs aa{grid, guide, nullptr, out, g, 0, gc, 1, gc, gw * gd * gc};
+      int rc2 = 0;
+      if (launch_rows_any<false>(aa, device_max_smem_optin(), sms, stream, &rc2)) return rc2;
+    }
     slice_generic_kernel<false><<<generic_grid(npix, sms), 256, 0, stream>>>(
         grid, guide, nullptr, out, g, 0, 0, gc, npix);
   }

@@ -13,9 +13,11 @@ Follows hdrnet/models.py (HDRNetCurves, HDRNetPointwiseNNGuide) and hdrnet/layer
   without a gamma).
 * flatten  -> tf.reshape(NHWC -> [bs, h*w*c]) (models.py:94-95): channel fastest.
 
-Parity status: PARITY UNPINNED for this module.  The reference has no test that exercises
-models.py and TensorFlow cannot run here, so there is no golden vector to pin the CNN /
-guide numerics to; they are defined by this restatement (last row).
+Parity status: the reference has no test that exercises models.py and TensorFlow cannot run
+here, so there is no reference-side golden vector for the CNN / guide numerics.  This restatement
+is pinned instead by (i) oracle/model_torch.py, an independently written torch.nn.functional
+restatement that must agree with it to 1e-6 of range on every graph, and (ii) hand-computed known
+answers for the TensorFlow conventions a restatement can get wrong (tests/test_model_kats.py).
 All sums accumulate in float64 and the result is rounded to float32 once, so this file is
 the "exact" answer a float32 kernel is compared against with a stated tolerance.
 

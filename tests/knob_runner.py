@@ -2,8 +2,9 @@
 HDRNET_TEX_CHUNKS, HDRNET_FUSED_ASYNC) ONCE per process, so a knob setting needs a process of its
 own: this script runs one seeded case under the environment it was started with and prints the
 SHA-256 of the result bytes.
-    python tests/knob_runner.py apply <variant> <seed> <B> <H> <W> <gh> <gw> <gd> [edge]
-    python tests/knob_runner.py fused <curves|nn> <float32|uint8|uint16>
+    python tests/knob_runner.py apply <variant>     # the APPLY_CASES below, one "SHA256 <case> <hex>" line each
+    python tests/knob_runner.py fused               # curves / nn x float32 / uint8 / uint16
+One process per knob setting (not per case): a Python + torch start-up costs ~15 s on the GPU box.
 """
 import hashlib
 import os
@@ -15,6 +16,12 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
+
+
+# (seed, B, H, W, gh, gw, gd, out-of-range guides)
+APPLY_CASES = [(5, 2, 64, 3840, 16, 16, 8, False),     # headline row shape
+               (6, 1, 700, 1028, 5, 7, 3, True),       # many rows per CTA, ragged last segment, edge guides
+               (7, 3, 9, 128, 8, 64, 4, False)]        # W < 4 gw: per-pixel indices
 
 
 def apply_case(variant, seed, B, H, W, gh, gw, gd, edge):
@@ -55,10 +62,15 @@ def fused_case(kind, dtype):
     return out.cpu().numpy()
 
 
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "apply":
-        v, seed, B, H, W, gh, gw, gd = (int(a) for a in sys.argv[2:10])
-        res = apply_case(v, seed, B, H, W, gh, gw, gd, len(sys.argv) > 10)
+        for k, case in enumerate(APPLY_CASES):
+            print("SHA256", f"apply{k}", sha(apply_case(int(sys.argv[2]), *case)), flush=True)
     else:
-        res = fused_case(sys.argv[2], sys.argv[3])
-    print("SHA256", hashlib.sha256(np.ascontiguousarray(res).tobytes()).hexdigest())
+        for kind in ("curves", "nn"):
+            for dtype in ("float32", "uint8", "uint16"):
+                print("SHA256", f"{kind}-{dtype}", sha(fused_case(kind, dtype)), flush=True)

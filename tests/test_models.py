@@ -351,9 +351,11 @@ def test_fuse_predict_with_weights_larger_than_shared_memory():
     w = (rng.randn(C, O) / np.sqrt(C)).astype(np.float32)
     b = rng.randn(O).astype(np.float32)
     out = torch.empty(B, gh, gw, gd, n_out, n_in, device="cuda")
-    rc = _lib.load().hdrnet_fuse_predict_f32(cuda(loc).data_ptr(), cuda(glob).data_ptr(), cuda(w).data_ptr(),
-                                             cuda(b).data_ptr(), out.data_ptr(), B, gh, gw, C, gd, n_out, n_in,
+    d_loc, d_glob, d_w, d_b = cuda(loc), cuda(glob), cuda(w), cuda(b)     # keep the device buffers alive
+    rc = _lib.load().hdrnet_fuse_predict_f32(d_loc.data_ptr(), d_glob.data_ptr(), d_w.data_ptr(),
+                                             d_b.data_ptr(), out.data_ptr(), B, gh, gw, C, gd, n_out, n_in,
                                              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
     assert rc == 0
     f = np.maximum(loc + glob[:, None, None, :], 0).astype(np.float64)
     pred = f @ w.astype(np.float64) + b                                   # [B, gh, gw, O], o = (j*n_out + i)*gd + z

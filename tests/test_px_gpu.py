@@ -171,21 +171,18 @@ def test_unsupported_formats_are_refused():
 
 
 # ---- fused-guide forms under the issuer-warp control flow ------------------------------------------
-@pytest.mark.parametrize("kind", ["curves", "nn"])
-@pytest.mark.parametrize("dtype", ["float32", "uint8", "uint16"])
-def test_fused_guide_issuer_warp_form_is_bitwise_equal(kind, dtype):
+def test_fused_guide_issuer_warp_form_is_bitwise_equal():
     """HDRNET_FUSED_ASYNC=1 / 0 force the issuer-warp / the block-synchronous control flow around
     the same per-pixel code (process_quad): the output of the model's full-resolution stage must
-    not change by a bit (AUTO picks one of them per guide type).  One process per setting: the
-    library reads its tuning record once."""
+    not change by a bit, for both guides and all three pixel formats (AUTO picks one form per guide
+    type).  One process per setting: the library reads its tuning record once."""
     import subprocess, sys
     runner = os.path.join(os.path.dirname(os.path.abspath(__file__)), "knob_runner.py")
     shas = []
     for flag in ("0", "1"):
         env = {k: v for k, v in os.environ.items() if not k.startswith("HDRNET_")}
         env["HDRNET_FUSED_ASYNC"] = flag
-        out = subprocess.run([sys.executable, runner, "fused", kind, dtype], env=env, capture_output=True,
-                             text=True, timeout=300)
+        out = subprocess.run([sys.executable, runner, "fused"], env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
-        shas.append([l for l in out.stdout.splitlines() if l.startswith("SHA256")][-1])
-    assert shas[0] == shas[1]
+        shas.append(dict(l.split()[1:3] for l in out.stdout.splitlines() if l.startswith("SHA256")))
+    assert len(shas[0]) == 6 and shas[0] == shas[1]

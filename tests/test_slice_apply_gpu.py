@@ -123,6 +123,24 @@ def test_slice_apply_general_channels(n_in, n_out, has_offset):
     assert_parity(got, expected)
 
 
+@pytest.mark.parametrize("n_in,n_out,has_offset,W", [(3, 3, False, 1000), (3, 4, True, 1026), (2, 5, False, 777),
+                                                      (3, 3, True, 1023), (3, 9, True, 640), (1, 1, True, 65)])
+def test_any_shape_row_kernel_matches_oracle(n_in, n_out, has_offset, W):
+    """What AUTO runs where the TMA kernels' contract does not hold (has_offset False, other channel
+    counts, odd widths; ops_test.py:345-365, hdrnet_ops_test.py:91-100, models.py:221-223): the
+    any-shape row kernel (y-pre-blended slab in shared memory, plain loads) against the oracle,
+    and against the one-thread-per-pixel kernel it replaces; grid-row pairs change inside a CTA's rows."""
+    grid, guide, inp = rand_case(23, 2, 157, W, 7, 9, 5, n_in, n_out, has_offset, signed=True)
+    guide[0, :, ::7] = 1.6
+    guide[1, :, 3::11] = -0.4
+    expected = checker().bilateral_slice_apply(grid, guide, inp, has_offset)
+    got = run_apply(grid, guide, inp, has_offset)
+    assert_parity(got, expected, what=f"any-shape rows {n_in}->{n_out} offset={has_offset} W={W}")
+    assert_parity(got, run_apply(grid, guide, inp, has_offset, "generic"), rtol=2e-6, what="vs per-pixel kernel")
+    sl = run_slice(grid, guide)                                             # un-fused slice, gc = n_out * J
+    assert_parity(sl, checker().bilateral_slice(grid, guide), what="any-shape slice")
+
+
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("variant", ["auto", "generic", "tma"])
 def test_slice_matches_oracle(shape, variant):
@@ -194,16 +212,16 @@ def test_row_kernels_are_bitwise_equal():
         assert np.array_equal(a, run_apply(grid, gu, inp, True, "tex_async"))
 
 
-def _knob_sha(env, *args):
-    """SHA-256 of a seeded case's output computed by tests/knob_runner.py in a process of its own
+def _knob_shas(env, *args):
+    """{case: sha256} of the seeded cases of tests/knob_runner.py, computed in a process of its own
     (the library reads its tuning record once per process)."""
     import subprocess, sys
     e = {k: v for k, v in os.environ.items() if not k.startswith("HDRNET_")}
     e.update(env)
     runner = os.path.join(os.path.dirname(os.path.abspath(__file__)), "knob_runner.py")
-    out = subprocess.run([sys.executable, runner, *map(str, args)], env=e, capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, runner, *map(str, args)], env=e, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    return [l for l in out.stdout.splitlines() if l.startswith("SHA256")][-1]
+    return dict(l.split()[1:3] for l in out.stdout.splitlines() if l.startswith("SHA256"))
 
 
 @pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_THREADS="512"), dict(HDRNET_ASYNC_THREADS="352"),
@@ -214,15 +232,15 @@ def test_issuer_warp_kernel_knobs_are_bitwise_equal(env):
     texture pipe: identical bits; also on narrow x cells (W < 4 gw: per-pixel indices), many rows
     per CTA, a ragged last segment and out-of-range guides."""
     import hashlib
-    cases = [(5, 2, 64, 3840, 16, 16, 8, False), (6, 1, 700, 1028, 5, 7, 3, True), (7, 3, 9, 128, 8, 64, 4, False)]
-    for seed, B, H, W, gh, gw, gd, edge in cases:
+    import knob_runner
+    got = _knob_shas(env, "apply", _lib.VARIANT_TEX_ASYNC)
+    for k, (seed, B, H, W, gh, gw, gd, edge) in enumerate(knob_runner.APPLY_CASES):
         grid, guide, inp = rand_case(seed, B, H, W, gh, gw, gd, signed=True)
         if edge:
             guide[0, :, ::5] = 1.75
             guide[0, :, 1::5] = -0.6
-        want = "SHA256 " + hashlib.sha256(run_apply(grid, guide, inp, True, "tex").tobytes()).hexdigest()
-        args = ["apply", _lib.VARIANT_TEX_ASYNC, seed, B, H, W, gh, gw, gd] + (["edge"] if edge else [])
-        assert _knob_sha(env, *args) == want, (env, seed)
+        want = hashlib.sha256(run_apply(grid, guide, inp, True, "tex").tobytes()).hexdigest()
+        assert got[f"apply{k}"] == want, (env, k)
 
 
 def test_empty_batch_is_a_no_op():

@@ -49,6 +49,24 @@ def slice_apply_case(name, B, H, W, gh, gw, gd, iters=50, variant=_lib.VARIANT_A
                       "frac_of_measured_hbm": round(gbs / PEAK, 4)}), flush=True)
 
 
+def any_shape_case(name, B, H, W, gh, gw, gd, n_in, n_out, has_offset, iters=10):
+    """Shapes outside the TMA kernels' contract: AUTO (any-shape row kernel) vs the per-pixel kernel."""
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    J = n_in + (1 if has_offset else 0)
+    grid = torch.rand(B, gh, gw, gd, n_out * J, device="cuda", generator=gen)
+    guide = torch.rand(B, H, W, device="cuda", generator=gen)
+    inp = torch.rand(B, H, W, n_in, device="cuda", generator=gen)
+    out = torch.empty(B, H, W, n_out, device="cuda")
+    npx = B * H * W
+    nbytes = npx * 4 * (n_in + 1 + n_out) + grid.numel() * 4
+    rec = {"case": name, "shape": [B, H, W], "grid": [gh, gw, gd], "n_in": n_in, "n_out": n_out, "has_offset": has_offset,
+           "bytes_per_px": 4 * (n_in + 1 + n_out)}
+    for label, v in (("auto_rows_any", _lib.VARIANT_AUTO), ("per_pixel_generic", _lib.VARIANT_GENERIC)):
+        ms = timeit(lambda: hdrnet_ops.bilateral_slice_apply(grid, guide, inp, has_offset, out=out, variant=v), iters=iters)
+        rec[label] = {"ms": round(ms, 4), "MP/s": round(npx / ms / 1e3, 1), "frac_of_measured_hbm": round(nbytes / ms / 1e6 / PEAK, 4)}
+    print(json.dumps(rec), flush=True)
+
+
 def slice_case(name, B, H, W, gh, gw, gd, iters=30, variant=_lib.VARIANT_AUTO):
     gen = torch.Generator(device="cuda").manual_seed(1234)
     grid = torch.rand(B, gh, gw, gd, 12, device="cuda", generator=gen)
@@ -143,6 +161,9 @@ def main():
     slice_apply_case("C4 12MP x8 (one GPU's share of batch 64)", 8, 3024, 4032, 16, 16, 8, iters=20)
     for gh, gw, gd in [(8, 8, 4), (16, 16, 4), (16, 16, 8), (32, 32, 8), (32, 32, 16)]:
         slice_apply_case(f"C5 sweep 4K x8 grid {gh}x{gw}x{gd}", 8, 2160, 3840, gh, gw, gd, iters=20)
+    any_shape_case("4K x8 has_offset=False (3 -> 4, gc 12)", 8, 2160, 3840, 16, 16, 8, 3, 4, False)
+    any_shape_case("4K x8 odd width 3841 (3 -> 3 + offset)", 8, 2160, 3841, 16, 16, 8, 3, 3, True)
+    any_shape_case("4K x4 pyramid grid (3 -> 9 + offset, gc 36)", 4, 2160, 3840, 16, 16, 8, 3, 9, True)
     slice_case("un-fused bilateral_slice 4K x8 (TMA kernel)", 8, 2160, 3840, 16, 16, 8)
     slice_case("un-fused bilateral_slice 4K x8 (generic kernel)", 8, 2160, 3840, 16, 16, 8, iters=5,
                variant=_lib.VARIANT_GENERIC)
