@@ -62,6 +62,8 @@ SIGNATURES = {
     "hdrnet_fc_f32": (_c_int, [_vp] * 4 + [_c_int] * 4 + [_vp]),
     "hdrnet_fuse_predict_f32": (_c_int, [_vp] * 5 + [_c_int] * 7 + [_vp]),
     "hdrnet_resize_bilinear_f32": (_c_int, [_vp] * 3 + [_c_int] * 6 + [_vp]),
+    "hdrnet_coefficients_scratch_bytes": (ctypes.c_size_t, [_c_int] * 7),
+    "hdrnet_coefficients_f32": (_c_int, [_vp] * 4 + [_c_int, _vp, ctypes.c_size_t] + [_c_int] * 7 + [_vp]),
     "hdrnet_host_ctx_create": (_c_int, [ctypes.POINTER(_vp), ctypes.c_size_t]),
     "hdrnet_host_ctx_destroy": (_c_int, [_vp]),
     "hdrnet_slice_apply_host_f32": (_c_int, [_vp] * 5 + [_c_int] * 9),

@@ -144,6 +144,13 @@ def init_weights(params, seed: int = 0, model_name: str | None = None) -> dict:
     return w
 
 
+# Batches up to this size run the coefficient network as one persistent cooperative kernel
+# (csrc/cnn_persistent.cu) instead of twelve per-layer launches.  0 = never: the first version of
+# that kernel (one warp task = 32 outputs, operands straight from L1 / L2) is correct but no
+# faster -- 190 us against 177 us per layer at batch 1, 293 / 185 at batch 2 (tools/time_cnn.py) --
+# so it is not the default.  Tests set this to force either path.
+PERSISTENT_CNN_MAX_BATCH = 0
+
 # ---- prepared (device-resident, BN-folded) weights ---------------------------------------------
 # Keyed by the identity of the weights dict: an entry keeps a reference to its dict (so the id
 # cannot be recycled while the entry lives), the cache holds the most recent kPreparedMax entries,
@@ -447,6 +454,11 @@ class HDRNetCurves(object):
         p = "inference/coefficients"
         n_ds = int(np.log2(params["net_input_size"] / params["spatial_bin"]))
         bs = x.shape[0]
+        # small batches: the whole network as ONE persistent cooperative kernel (csrc/cnn_persistent.cu)
+        if bs <= PERSISTENT_CNN_MAX_BATCH:
+            grid = cls._coefficients_persistent(x, prep, params, n_ds)
+            if grid is not None:
+                return grid
         with torch.cuda.device(x.device):
             for i in range(n_ds):                                   # splat, :69-82
                 x = _conv(x, L[f"{p}/splat/conv{i + 1}"], stride=2)
@@ -468,6 +480,39 @@ class HDRNetCurves(object):
                 grid.data_ptr(), bs, gh, gw, C, gd, cls.n_out(), cls.n_in(),
                 torch.cuda.current_stream(x.device).cuda_stream)
         _lib.check(rc, "fuse_predict")
+        return grid
+
+    @classmethod
+    def _coefficients_persistent(cls, x, prep, params, n_ds):
+        """One launch for all layers; None when the library does not take the shape."""
+        lib = _lib.load()
+        bs, S = x.shape[0], x.shape[1]
+        gd, cm, sb = params["luma_bins"], params["channel_multiplier"], params["spatial_bin"]
+        nbytes = lib.hdrnet_coefficients_scratch_bytes(bs, S, sb, gd, cm, cls.n_out(), cls.n_in())
+        if nbytes == 0 or x.shape[2] != S:
+            return None
+        p = "inference/coefficients"
+        order = [f"{p}/splat/conv{i + 1}" for i in range(n_ds)] + \
+                [f"{p}/global/conv1", f"{p}/global/conv2", f"{p}/global/fc1", f"{p}/global/fc2",
+                 f"{p}/global/fc3", f"{p}/local/conv1", f"{p}/local/conv2", f"{p}/prediction/conv1"]
+        ptrs = getattr(prep, "_pc_ptrs", None)
+        if ptrs is None:     # host arrays of device pointers, built once per prepared model
+            n = len(order)
+            wa, ba = (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)()
+            for i, scope in enumerate(order):
+                w, b = prep.layers[scope][:2]
+                wa[i] = w.data_ptr()
+                ba[i] = None if b is None else b.data_ptr()
+            ptrs = prep._pc_ptrs = (wa, ba)
+        scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+        grid = torch.empty((bs, sb, sb, gd, cls.n_out(), cls.n_in()), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.hdrnet_coefficients_f32(x.data_ptr(), grid.data_ptr(), ptrs[0], ptrs[1], len(order),
+                                             scratch.data_ptr(), nbytes, bs, S, sb, gd, cm, cls.n_out(),
+                                             cls.n_in(), torch.cuda.current_stream(x.device).cuda_stream)
+        if rc == _lib.E_UNSUPPORTED:
+            return None
+        _lib.check(rc, "coefficients (persistent kernel)")
         return grid
 
     @classmethod

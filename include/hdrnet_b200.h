@@ -249,6 +249,29 @@ HDRNET_API int hdrnet_fuse_predict_f32(const float* local, const float* global_f
                                        void* stream);
 
 /*
+ * The WHOLE coefficient network (splat convs, global convs + fcs, local convs, fusion, prediction,
+ * unroll_grid) as one persistent cooperative kernel -- for small batches, where twelve separate
+ * launches are latency-bound (177 us at batch 1; this: one launch).  Replaces
+ * HDRNetCurves._coefficients, hdrnet/models.py:62-142, with batch norm folded by the caller.
+ *   lowres [B, S, S, 3] float32 -> grid [B, sb, sb, gd, n_out, n_in] float32
+ *   weights / biases: HOST arrays of n_layers = n_ds + 8 DEVICE pointers (n_ds = log2(S / sb)), in
+ *     the order splat conv1..n_ds, global conv1, conv2, fc1, fc2, fc3, local conv1, conv2,
+ *     prediction conv1; conv weights HWIO, fc / prediction weights [in][out]; a bias may be NULL;
+ *   scratch: hdrnet_coefficients_scratch_bytes(...) bytes of device memory, 16-byte aligned (every
+ *     layer's activations; the library never allocates).  0 bytes = shape not supported (channel
+ *     counts that are not powers of two, S / sb not a power of two): use the per-layer kernels.
+ * Returns HDRNET_E_UNSUPPORTED for such shapes or when the device cannot launch cooperatively.
+ */
+HDRNET_API size_t hdrnet_coefficients_scratch_bytes(int B, int net_input_size, int spatial_bin,
+                                                    int luma_bins, int channel_multiplier, int n_out,
+                                                    int n_in);
+HDRNET_API int hdrnet_coefficients_f32(const float* lowres, float* grid, const float* const* weights,
+                                       const float* const* biases, int n_layers, void* scratch,
+                                       size_t scratch_bytes, int B, int net_input_size,
+                                       int spatial_bin, int luma_bins, int channel_multiplier,
+                                       int n_out, int n_in, void* stream);
+
+/*
  * Bilinear resize, align_corners=True, NHWC, with an optional fused add (`add` has the output's
  * shape, or NULL).  Replaces tf.image.resize_images(BILINEAR, align_corners=True) in
  * HDRNetGaussianPyrNN._multiscale_input / ._output (hdrnet/models.py:249-289).

@@ -141,6 +141,52 @@ def test_coefficients_match_oracle(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", list(PARAM_SETS))
+@pytest.mark.parametrize("B", [1, 4])
+def test_coefficients_persistent_and_per_layer_paths_agree(name, B, monkeypatch):
+    """Small batches run the whole network as one persistent cooperative kernel
+    (csrc/cnn_persistent.cu), larger ones layer by layer: both against the oracle, and against each
+    other (same summation order per output: agreement to float32 round-off)."""
+    p = PARAM_SETS[name]
+    wts = M.make_weights(p, seed=3)
+    S = p["net_input_size"]
+    low = np.random.RandomState(40 + B).rand(B, S, S, 3).astype(np.float32)
+    cls = getattr(models, p["model_name"])
+    ref = M.coefficients(low, wts, p, n_out=cls.n_out())
+    lib = _lib.load()
+    assert lib.hdrnet_coefficients_scratch_bytes(B, S, p["spatial_bin"], p["luma_bins"], p["channel_multiplier"],
+                                                 cls.n_out(), cls.n_in()) > 0
+    monkeypatch.setattr(models, "PERSISTENT_CNN_MAX_BATCH", 64)
+    one = cls._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
+    monkeypatch.setattr(models, "PERSISTENT_CNN_MAX_BATCH", 0)
+    many = cls._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
+    assert_parity(one, ref, rtol=2e-5, what=f"{name} persistent", elem_rtol=None)
+    assert_parity(many, ref, rtol=2e-5, what=f"{name} per layer", elem_rtol=None)
+    assert_parity(one, many, rtol=5e-6, what=f"{name} persistent vs per layer", elem_rtol=None)
+
+
+@pytest.mark.gpu
+def test_persistent_coefficient_kernel_refuses_shapes_it_cannot_take():
+    lib = _lib.load()
+    assert lib.hdrnet_coefficients_scratch_bytes(1, 256, 16, 6, 1, 3, 4) == 0      # 6 depth bins: channels not a power of two
+    assert lib.hdrnet_coefficients_scratch_bytes(1, 240, 16, 8, 1, 3, 4) == 0      # 240 / 16 not a power of two
+    assert lib.hdrnet_coefficients_scratch_bytes(0, 256, 16, 8, 1, 3, 4) == 0
+    z = torch.zeros(64, device="cuda")
+    import ctypes
+    arr = (ctypes.c_void_p * 12)(*([z.data_ptr()] * 12))
+    rc = lib.hdrnet_coefficients_f32(z.data_ptr(), z.data_ptr(), arr, arr, 12, z.data_ptr(), 256, 1, 256, 16, 6, 1, 3, 4, 0)
+    assert rc == _lib.E_UNSUPPORTED
+    rc = lib.hdrnet_coefficients_f32(z.data_ptr(), z.data_ptr(), arr, arr, 11, z.data_ptr(), 1 << 30, 1, 256, 16, 8, 1, 3, 4, 0)
+    assert rc == _lib.E_BAD_SHAPE                                                  # n_layers must be n_ds + 8
+    # a model with 6 depth bins still runs (per-layer kernels)
+    p = dict(M.DEFAULT_PARAMS, luma_bins=6, net_input_size=64, spatial_bin=16)
+    wts = M.make_weights(p, seed=1)
+    low = np.random.RandomState(2).rand(1, 64, 64, 3).astype(np.float32)
+    got = models.HDRNetCurves._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
+    assert_parity(got, M.coefficients(low, wts, p), rtol=2e-5, elem_rtol=None)
+
+
+@pytest.mark.gpu
 def test_guides_match_oracle():
     rng = np.random.RandomState(5)
     full = rng.rand(2, 37, 53, 3).astype(np.float32)        # odd size: scalar tail path too
@@ -229,6 +275,7 @@ def test_run_py_identity_sample_plumbing(tmp_path):
 @pytest.fixture
 def tcgen05_convs(monkeypatch):
     monkeypatch.setenv("HDRNET_CONV_TCGEN05", "1")
+    monkeypatch.setattr(models, "PERSISTENT_CNN_MAX_BATCH", 0)    # per-layer kernels, not the persistent one
     yield
 
 

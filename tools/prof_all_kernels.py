@@ -56,5 +56,17 @@ hdrnet_ops.bilateral_slice_apply(g1, u1, i1, True).sum().backward()          # s
 g2 = grid[:1].clone().requires_grad_(True)
 hdrnet_ops.bilateral_slice(g2, u1.detach()).sum().backward()
 hdrnet_ops.slice_indices(guide[:1, :270].contiguous(), (16, 16, 8))
+# ---- standalone guide kernels, any-shape row kernels, per-pixel integer-I/O kernel, plain fc kernel
+models.HDRNetCurves._guide(im[:2].contiguous(), pc)
+pn = params("HDRNetPointwiseNNGuide", batch_norm=True)
+models.HDRNetPointwiseNNGuide._guide(im[:2].contiguous(), pn)
+g4 = torch.rand(4, 16, 16, 8, 12, device=dev, generator=gen)
+hdrnet_ops.bilateral_slice_apply(g4, guide[:4].contiguous(), im[:4].contiguous(), False)      # 3 -> 4, no offset
+g7 = torch.rand(2, 16, 16, 8, 7, device=dev, generator=gen)
+hdrnet_ops.bilateral_slice(g7, guide[:2].contiguous())                                        # slice, gc = 7
+odd = torch.randint(0, 256, (1, 1080, 1921, 3), device=dev, generator=gen, dtype=torch.uint8)
+models.HDRNetCurves.inference_image(odd, pc)                                                  # W % 16 != 0
+x = torch.rand(64, 1024, device=dev, generator=gen); w = torch.rand(1024, 256, device=dev, generator=gen)
+models._fc(x, (w, torch.zeros(256, device=dev)), relu=True)
 torch.cuda.synchronize()
 print("done")
