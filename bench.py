@@ -515,6 +515,8 @@ def run_b200_arm(args):
                     "path": "hdrnet_ops.bilateral_slice_apply on pinned CPU tensors -> "
                             "hdrnet_slice_apply_host_f32 (row-band H2D/kernel/D2H pipeline)",
                     "matches_device_result": e2e_ok,
+                    # what bounds this leg at N > 1: every byte crosses host DRAM and the root complexes
+                    "host_traffic_gb_s_all_gpus": round(world * (e2e_h2d + e2e_d2h) * e2e_steps / e2e_s / 1e9, 1),
                     "u8_image_path": {
                         "value": round(world * npix * e2e_steps / e2e8_s / 1e6, 1), "unit": UNIT,
                         "h2d_bytes_per_step": int(npix * 3), "d2h_bytes_per_step": int(npix * 3),
