@@ -41,9 +41,10 @@ WORKLOAD = (f"4K ({W4K}x{H4K}) batch={B_PER_GPU} per GPU, fused slice-apply, "
 
 
 KERNEL_TEXT = {
-    7: "tex_async (AUTO with workspace): yblend_rows_kernel pre-pass + "
-       "slice_apply_rows_async_kernel<5 texture chunks, per-quad indices, math warps + issuer warp> "
-       "(threads: see `threads`), both inside every timed step",
+    7: "tex_async (AUTO with workspace): slice_apply_rows_async_kernel<5 texture chunks, per-quad indices, "
+       "math warps + issuer warp + slab warp> -- 384 threads: the slab warp blends every row's slab inside "
+       "the kernel (no pre-pass launch); 352 / 512 threads: yblend_rows_kernel pre-pass + row kernel, both "
+       "inside every timed step",
     4: "tex (AUTO with workspace): yblend_rows_kernel pre-pass + "
        "slice_apply_rows_tma_kernel<GuideFromInput,4,2,512,f32,f32>, both inside every timed step",
     2: "tma: slice_apply_rows_tma_kernel (all-LSU form)",
@@ -507,8 +508,7 @@ def run_b200_arm(args):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "launch_ms": round(own_launch_ms, 5),
-                         "note": "duration = whole step (pre-pass + main kernel); the main kernel "
-                                 "alone is ~5 % shorter (profiles/)"},
+                         "note": "duration = the whole step the caller pays for (every launch of the call)"},
             "e2e": {"value": round(world * npix * e2e_steps / e2e_s / 1e6, 1), "unit": UNIT,
                     "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h, "steps": e2e_steps,
                     "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3),
@@ -524,7 +524,7 @@ def run_b200_arm(args):
                         "path": "pinned uint8 frames -> models.HDRNetCurves.inference_image (lowres gather + "
                                 "coefficient CNN + fused-guide slice-apply, uint8 in / out) -> pinned uint8"},
                     "numa_cpus_bound": len(numa_cpus)},
-            "gpu_launches": 2 * args.steps * world,
+            "gpu_launches": (1 if threads.value == 384 else 2) * args.steps * world,
             "clocks": sampler.summary(),
             "sustained": {"steps": sus_steps, "ms_per_step": round(sus_ms, 5),
                           "value": round(world * npix / sus_ms / 1e3, 1), "unit": UNIT,

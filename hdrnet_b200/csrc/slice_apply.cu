@@ -698,7 +698,7 @@ static int device_max_smem_optin() {
 // separate slab region (lets 32x32x16 grids keep two CTAs per SM).
 static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* out,
                           bool tex_mode = false, int threads = kTmaThreads, int in_fmt = kPxF32,
-                          int out_fmt = kPxF32, int occ_override = 0) {
+                          int out_fmt = kPxF32, int occ_override = 0, int grid_rows = 0) {
   // Bulk copies move 16-byte units: a row and every segment must start on one.  float32 pixels
   // need W % 4 == 0, uint16 W % 8 == 0, uint8 W % 16 == 0 (12 / 6 / 3 bytes per pixel).
   const int in_bpp = 3 * px_bytes_per_channel(in_fmt), out_bpp = 3 * px_bytes_per_channel(out_fmt);
@@ -718,7 +718,9 @@ static bool make_tma_plan(const SliceGeom& g, int max_smem, int sms, TmaPlan* ou
   p.stage_bytes = round_up((p.off_out ? p.off_out + p.seg_px * out_bpp : p.off_guide + p.seg_px * 4), 128);
   p.off_raw = 256;  // barriers: up to 2 * kMaxStages + 4 (warp-specialised form) = 160 bytes
   p.off_slab = p.off_raw + round_up(2 * p.row_floats * 4, 128);
-  p.off_stage = p.off_slab + (tex_mode ? 0 : round_up(p.row_floats * 4, 128));
+  // grid_rows: grid rows staged next to the slab rows (the slab warp of the issuer-warp form)
+  p.off_grid = p.off_slab;
+  p.off_stage = p.off_slab + (tex_mode ? grid_rows * round_up(p.row_floats * 4, 128) : round_up(p.row_floats * 4, 128));
   // Residency: two CTAs per SM with a 4-stage ring; shrink the ring before giving up residency.
   const int want_occ = occ_override > 0 ? occ_override : 2;
   const int per_cta_3 = (max_smem + 1024) / 3 - 1024;
@@ -898,10 +900,12 @@ static int launch_px_generic(const float* grid, const void* input, void* out, fl
 //   HDRNET_ASYNC_THREADS = 512 | 352   CTA shape of the issuer-warp kernel (15 / 10 math warps)
 //   HDRNET_TEX_CHUNKS    = 4 | 5       corner chunks per pixel served by the texture pipe there
 //   HDRNET_FUSED_ASYNC   = 0 | 1       force the block-synchronous / issuer-warp fused-guide form
-struct Tuning { int async_threads, async_chunks, fused_async; };
+//   HDRNET_ASYNC_SLAB    = 0 | 1       slab rows from the pre-pass / blended by a slab warp in the kernel
+struct Tuning { int async_threads, async_chunks, fused_async, async_slab; };
 static const Tuning& tuning() {
   static const Tuning t = [] {
-    Tuning v{kAsyncThreadsDefault, kAsyncTexChunksDefault, -1};
+    Tuning v{kAsyncThreadsDefault, kAsyncTexChunksDefault, -1, kAsyncSlabWarpDefault};
+    if (const char* e = std::getenv("HDRNET_ASYNC_SLAB")) v.async_slab = std::atoi(e) != 0 ? 1 : 0;
     if (const char* e = std::getenv("HDRNET_ASYNC_THREADS")) { const int x = std::atoi(e); if (x == 512 || x == 352) v.async_threads = x; }
     if (const char* e = std::getenv("HDRNET_TEX_CHUNKS")) { const int x = std::atoi(e); if (x == 4 || x == 5) v.async_chunks = x; }
     if (const char* e = std::getenv("HDRNET_FUSED_ASYNC")) v.fused_async = std::atoi(e) != 0 ? 1 : 0;
@@ -958,10 +962,24 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
                       aligned16(gs.workspace) && gs.workspace_bytes / 16 <= (1u << 27);
   // Issuer-warp form: float32 pixels, guide as an input, a ring of >= 3 stages at two CTAs per SM.
   TmaPlan aplan;
-  const bool async_ok = tex_ok && gs.mode == 0 && !px &&
-                        make_tma_plan(g, max_smem, sms, &aplan, /*tex_mode=*/true, tune.async_threads - 32,
-                                      kPxF32, kPxF32, 2) &&
-                        aplan.resident == 2 && aplan.seg_px <= aplan.threads * 4;
+  bool async_ok = tex_ok && gs.mode == 0 && !px &&
+                  make_tma_plan(g, max_smem, sms, &aplan, /*tex_mode=*/true, tune.async_threads - 32,
+                                kPxF32, kPxF32, 2) &&
+                  aplan.resident == 2 && aplan.seg_px <= aplan.threads * 4;
+  // ... with a SLAB WARP that blends each row's slab inside the kernel (no pre-pass launch): needs
+  // two more grid rows of shared memory next to the two slab rows, and still a ring of >= 3 stages
+  TmaPlan splan;
+  // ... and workspace rows that are whole 128-byte cache lines (row bytes and base): a CTA fetches a
+  // workspace row through the texture path only after its own slab warp wrote it in THIS launch, and
+  // the caches start a launch invalid -- but a line shared by rows r and r + 1 would be cached,
+  // with row r + 1's bytes of the previous call, when row r is fetched (seen: 252-float rows)
+  const bool slab_lines = (static_cast<size_t>(plan.row_floats) * sizeof(float)) % 128 == 0 &&
+                          (reinterpret_cast<uintptr_t>(gs.workspace) & 127u) == 0;
+  const bool slab_warp = async_ok && tune.async_slab && tune.async_threads == 352 && slab_lines &&
+                         make_tma_plan(g, max_smem, sms, &splan, /*tex_mode=*/true, tune.async_threads - 32,
+                                       kPxF32, kPxF32, 2, /*grid_rows=*/2) &&
+                         splan.resident == 2 && splan.seg_px <= splan.threads * 4 && splan.stages >= kAsyncAutoMinStages;
+  if (slab_warp) aplan = splan;
   // ... and its fused-guide forms (8 math warps + the issuer).  Measured at 4K x 8
   // (profiles/r02_ab_fused_issuer_warp.txt): curves 0.628 ms against 0.700 block-synchronous (u8:
   // 0.668 / 0.729); pointwise NN 0.628 / 0.625 (u8: 0.694 / 0.654) -- AUTO takes it for the
@@ -991,13 +1009,16 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
     cudaEvent_t tex_use = nullptr;
     rc = get_slab_texture(gs.workspace, gs.workspace_bytes, &a.slab_tex, &tex_use);
     if (rc != 0) return rc;
-    rc = launch_yblend(grid, gs.workspace, g, plan.row_floats, stream);
-    if (rc != 0) return rc;
+    const bool in_kernel_slab = variant == HDRNET_VARIANT_TEX_ASYNC && slab_warp;
+    if (!in_kernel_slab) {   // pre-pass: every row's y-pre-blended slab into the workspace
+      rc = launch_yblend(grid, gs.workspace, g, plan.row_floats, stream);
+      if (rc != 0) return rc;
+    }
     if (variant == HDRNET_VARIANT_TEX_ASYNC) {
       a.p = aplan;
       a.guide_out = nullptr;
       const bool lean = static_cast<long long>(W) >= 4LL * gw;   // x cells at least 4 pixels wide
-      rc = launch_async_form(a, tune.async_chunks, lean, tune.async_threads, stream);
+      rc = launch_async_form(a, tune.async_chunks, lean, tune.async_threads, in_kernel_slab, stream);
     } else {
       bool fused_async = gs.mode == 1;
       if (tune.fused_async >= 0) fused_async = tune.fused_async != 0;
@@ -1332,7 +1353,17 @@ int hdrnet_slice_apply_plan_ws(int B, int H, int W, int gh, int gw, int gd, int 
                           make_tma_plan(g, device_max_smem_optin(), sms, &ap, true, tuning().async_threads - 32,
                                         kPxF32, kPxF32, 2) && ap.resident == 2 &&
                           ap.seg_px <= ap.threads * 4 && ap.stages >= kAsyncAutoMinStages;
-  if (async_form) { plan = ap; plan.threads = tuning().async_threads; }
+  if (async_form) {
+    plan = ap;
+    plan.threads = tuning().async_threads;
+    TmaPlan sp;   // the slab-warp form (no pre-pass) when two more grid rows leave a ring of >= 3 stages
+    if (tuning().async_slab && tuning().async_threads == 352 && (static_cast<size_t>(gw) * gd * kGc * 4) % 128 == 0 &&
+        make_tma_plan(g, device_max_smem_optin(), sms, &sp, true, tuning().async_threads - 32, kPxF32, kPxF32, 2, 2) &&
+        sp.resident == 2 && sp.seg_px <= sp.threads * 4 && sp.stages >= kAsyncAutoMinStages) {
+      plan = sp;
+      plan.threads = tuning().async_threads + 32;
+    }
+  }
   if (variant) *variant = tma ? (tex ? (async_form ? HDRNET_VARIANT_TEX_ASYNC : HDRNET_VARIANT_TEX) : HDRNET_VARIANT_TMA)
                               : HDRNET_VARIANT_GENERIC;
   if (ctas) *ctas = tma ? plan.ctas : generic_grid(npix, sms);

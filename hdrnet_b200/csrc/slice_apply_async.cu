@@ -157,11 +157,20 @@ __device__ __forceinline__ void process_quad_lean(const TmaArgs& args, const uns
   fence_proxy_async_smem();
 }
 
-template <int kTexChunks, bool kLean, int kThreads, int kMinBlocks>
+// kSlabWarp: one more warp blends each image row's slab INSIDE the kernel, two rows ahead of the math
+// warps -- from the two grid rows it keeps staged in shared memory (TMA, reloaded only when the pair
+// changes) into (i) the shared-memory slab buffer the LSU chunks are read from and (ii) the row's
+// place in the caller's workspace, from where the texture chunks are fetched a row later.  The
+// separate pre-pass launch (21 us, 5 % of the step at 8 x 4K) and the slab-row bulk loads
+// disappear.  A CTA only ever fetches workspace rows its own slab warp wrote earlier in this launch
+// (a row split between two CTAs is written by both, with identical bytes), after a device-scope
+// fence and the slab barrier; L1 / texture caches start a launch invalid, so no stale line of an
+// earlier call can be hit.
+template <int kTexChunks, bool kLean, int kThreads, int kMinBlocks, bool kSlabWarp>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 slice_apply_rows_async_kernel(const TmaArgs args) {
   static_assert(kTexChunks > 0, "the issuer-warp kernel serves part of the gather by texture");
-  constexpr int kMathWarps = kThreads / 32 - 1;
+  constexpr int kMathWarps = kThreads / 32 - 1 - (kSlabWarp ? 1 : 0);
   extern __shared__ __align__(128) unsigned char smem[];
   const SliceGeom& g = args.g;
   const TmaPlan& pl = args.p;
@@ -170,6 +179,8 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]  TMA landed
   uint64_t* done = full + kMaxStages;                    // [kMaxStages]  every math warp is through
   uint64_t* slab_full = done + kMaxStages;               // [2]
+  uint64_t* row_free = slab_full + 2;                    // [2]  kSlabWarp: the row's slab buffer may be rewritten
+  uint64_t* grid_full = row_free + 2;                    // [2]  kSlabWarp: a staged grid row landed
   unsigned char* raw0 = smem + pl.off_raw;               // two slab rows
   unsigned char* stage_base = smem + pl.off_stage;
 
@@ -190,8 +201,7 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
 
   if (tid == 0) {
     for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], kMathWarps); }
-    mbar_init(&slab_full[0], 1);
-    mbar_init(&slab_full[1], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&slab_full[i], 1); mbar_init(&row_free[i], 1); mbar_init(&grid_full[i], 1); }
     fence_mbar_init();
   }
   __syncthreads();  // the only block-wide barrier
@@ -202,11 +212,60 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
   };
 
+  if (kSlabWarp && warp == kMathWarps + 1) {
+    // -------------------------------- slab warp ---------------------------------------------
+    float* graw = reinterpret_cast<float*>(smem + pl.off_grid);   // two staged grid rows
+    const int gstride = (static_cast<int>(slab_bytes) + 127) / 128 * 32;   // floats between the two slots
+    int key0 = -1, key1 = -1;          // grid row (b * gh + gy) held by slot 0 / 1
+    uint32_t gpar0 = 0u, gpar1 = 0u;
+    const int n4 = pl.row_floats / 4;
+    float4* ws4 = reinterpret_cast<float4*>(const_cast<float*>(args.yslab));
+    for (long long row = r_begin; row < r_end; ++row) {
+      const int rowk = static_cast<int>(row - r_begin), rb = rowk & 1;
+      const int b = static_cast<int>(row / g.rows);
+      const int y = g.y_off + static_cast<int>(row - static_cast<long long>(b) * g.rows);
+      const Axis ay = spatial_axis(y, g.scale_y);
+      const int k0 = b * g.gh + clampi(ay.i0, 0, g.gh - 1);
+      const int k1 = b * g.gh + clampi(ay.i0 + 1, 0, g.gh - 1);
+      int s0 = (key0 == k0) ? 0 : ((key1 == k0) ? 1 : -1);
+      int s1 = (key0 == k1) ? 0 : ((key1 == k1) ? 1 : -1);
+      auto fetch = [&](int slot, int k) {   // grid row k -> slot (warp-uniform); the warp itself is the only reader
+        if (lane == 0) {
+          mbar_expect_tx(&grid_full[slot], slab_bytes);
+          tma_load_1d(graw + slot * gstride, args.grid + static_cast<size_t>(k) * pl.row_floats, slab_bytes,
+                      &grid_full[slot]);
+        }
+        if (slot == 0) { key0 = k; mbar_wait(&grid_full[0], gpar0); gpar0 ^= 1u; }
+        else { key1 = k; mbar_wait(&grid_full[1], gpar1); gpar1 ^= 1u; }
+      };
+      __syncwarp();   // every lane is done reading the slot a load may overwrite
+      if (s0 < 0) { s0 = (s1 == 0) ? 1 : 0; fetch(s0, k0); if (k1 == k0) s1 = s0; }
+      if (s1 < 0) { s1 = s0 ^ 1; fetch(s1, k1); }
+      // the slab buffer of row - 2 is free once the issuer has seen that row's last item done
+      if (rowk >= 2) mbar_wait(&row_free[rb], static_cast<uint32_t>((rowk >> 1) - 1) & 1u);
+      const float wy1 = ay.f, wy0 = 1.0f - ay.f;
+      const float4* a4 = reinterpret_cast<const float4*>(graw + s0 * gstride);
+      const float4* b4 = reinterpret_cast<const float4*>(graw + s1 * gstride);
+      float4* slab4 = reinterpret_cast<float4*>(raw0 + static_cast<size_t>(rb) * slab_bytes);
+      float4* wrow = ws4 + static_cast<size_t>(row) * n4;
+      for (int e = lane; e < n4; e += 32) {   // exactly yblend_rows_kernel's arithmetic
+        const float4 v = lerp4(wy0, a4[e], wy1, b4[e]);
+        slab4[e] = v;
+        wrow[e] = v;
+      }
+      __threadfence();   // the workspace row is visible device-wide before anyone is told it exists
+      __syncwarp();
+      if (lane == 0) arrive(&slab_full[rb]);
+    }
+    return;
+  }
+
   if (warp == kMathWarps) {
     // ------------------------------- issuer warp --------------------------------------------
     // Lane 0 issues every bulk copy.
     if (lane != 0) return;
     auto make_slab = [&](long long row) {   // the row's y-pre-blended slab, from the pre-pass workspace
+      if constexpr (kSlabWarp) return;
       const int rb = static_cast<int>(row - r_begin) & 1;
       mbar_expect_tx(&slab_full[rb], slab_bytes);
       tma_load_1d(raw0 + static_cast<size_t>(rb) * slab_bytes,
@@ -250,7 +309,8 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
       // the row's slab buffer is free: every math warp arrived after its last read of it
-      if (row + 2 < r_end) make_slab(row + 2);
+      if constexpr (kSlabWarp) arrive(&row_free[static_cast<int>(row - r_begin) & 1]);
+      else if (row + 2 < r_end) make_slab(row + 2);
     }
     tma_store_wait_all<0>();
     return;
@@ -286,12 +346,13 @@ slice_apply_rows_async_kernel(const TmaArgs args) {
   }
 }
 
-template <int kTexChunks, bool kLean, int kThreads>
+template <int kTexChunks, bool kLean, int kThreads, bool kSlabWarp>
 static int launch_async(const TmaArgs& a, cudaStream_t stream) {
-  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kThreads, 2>;
+  constexpr int kLaunchThreads = kThreads + (kSlabWarp ? 32 : 0);   // + the slab warp
+  auto kern = slice_apply_rows_async_kernel<kTexChunks, kLean, kLaunchThreads, 2, kSlabWarp>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.p.smem_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<a.p.ctas, kThreads, a.p.smem_bytes, stream>>>(a);
+  kern<<<a.p.ctas, kLaunchThreads, a.p.smem_bytes, stream>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -450,16 +511,22 @@ int launch_async_fused(const TmaArgs& a, int mode, const CurvesGuideParams* curv
   return HDRNET_E_UNSUPPORTED;
 }
 
-// chunks (4 | 5), per-quad index arithmetic or not, CTA shape (512 | 352 threads) -> instantiation
-int launch_async_form(const TmaArgs& a, int chunks, bool lean, int threads, cudaStream_t stream) {
-  if (threads == 352) {
-    if (lean) return chunks == 4 ? launch_async<4, true, 352>(a, stream) : launch_async<5, true, 352>(a, stream);
-    return chunks == 4 ? launch_async<4, false, 352>(a, stream) : launch_async<5, false, 352>(a, stream);
-  }
-  if (threads == 512) {
-    if (lean) return chunks == 4 ? launch_async<4, true, 512>(a, stream) : launch_async<5, true, 512>(a, stream);
-    return chunks == 4 ? launch_async<4, false, 512>(a, stream) : launch_async<5, false, 512>(a, stream);
-  }
+// chunks (4 | 5), per-quad index arithmetic or not, CTA shape (512 | 352 threads: math warps + the
+// issuer), slab warp or pre-pass -> instantiation
+template <int kThreads, bool kSlabWarp>
+static int launch_async_shape(const TmaArgs& a, int chunks, bool lean, cudaStream_t stream) {
+  if (lean) return chunks == 4 ? launch_async<4, true, kThreads, kSlabWarp>(a, stream)
+                               : launch_async<5, true, kThreads, kSlabWarp>(a, stream);
+  return chunks == 4 ? launch_async<4, false, kThreads, kSlabWarp>(a, stream)
+                     : launch_async<5, false, kThreads, kSlabWarp>(a, stream);
+}
+
+int launch_async_form(const TmaArgs& a, int chunks, bool lean, int threads, bool slab_warp, cudaStream_t stream) {
+  if (threads == 352)
+    return slab_warp ? launch_async_shape<352, true>(a, chunks, lean, stream)
+                     : launch_async_shape<352, false>(a, chunks, lean, stream);
+  if (threads == 512)   // 15 math warps + issuer + slab warp would be 544 threads: pre-pass only
+    return slab_warp ? HDRNET_E_UNSUPPORTED : launch_async_shape<512, false>(a, chunks, lean, stream);
   return HDRNET_E_UNSUPPORTED;
 }
 

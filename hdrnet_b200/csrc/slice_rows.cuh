@@ -112,6 +112,7 @@ constexpr int kAsyncThreadsDefault = 352; // issuer-warp form: 10 math warps + t
 // block-synchronous form (32x32x8: 46.9 % vs 53.2 % of HBM peak; 32x32x16: 31.1 % vs 37.5 %).
 constexpr int kAsyncAutoMinStages = 3;
 constexpr int kAsyncTexChunksDefault = 5; // corner chunks per pixel through the texture pipe (HDRNET_TEX_CHUNKS)
+constexpr int kAsyncSlabWarpDefault = 1;  // slab rows blended by a slab warp inside the kernel: no pre-pass (HDRNET_ASYNC_SLAB)
 constexpr int kMaxStages = 8;
 constexpr int kTexChunksDefault = 4;   // texture chunks of the block-synchronous and opt-in forms
 constexpr int kGc = 12;
@@ -129,6 +130,7 @@ struct TmaPlan {
   int smem_bytes;
   // byte offsets into dynamic shared memory
   int off_raw, off_slab, off_stage, stage_bytes;
+  int off_grid;    // issuer-warp form with a slab warp: two staged grid rows (else unused)
   // pixel formats: bytes per pixel of the staged input / output tiles, and where the guide and
   // output tiles sit inside a stage (off_out == 0: the result overwrites the input tile)
   int in_bpp, out_bpp, off_guide, off_out;
@@ -286,7 +288,7 @@ __device__ __forceinline__ void process_quad(const TmaArgs& args, const GuideFn&
 }
 
 // Entry points of slice_apply_async.cu (non-template: the arguments select the instantiation).
-int launch_async_form(const TmaArgs& a, int chunks, bool lean, int threads, cudaStream_t stream);
+int launch_async_form(const TmaArgs& a, int chunks, bool lean, int threads, bool slab_warp, cudaStream_t stream);
 int launch_async_fused(const TmaArgs& a, int mode, const CurvesGuideParams* curves, const NNGuideParams* nn,
                        int in_fmt, int out_fmt, cudaStream_t stream);
 constexpr int kFusedAsyncMathThreads = 256;   // 8 math warps (+ the issuer warp) of the fused-guide issuer-warp form

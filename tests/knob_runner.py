@@ -21,7 +21,8 @@ sys.path.insert(0, os.path.dirname(HERE))
 # (seed, B, H, W, gh, gw, gd, out-of-range guides)
 APPLY_CASES = [(5, 2, 64, 3840, 16, 16, 8, False),     # headline row shape
                (6, 1, 700, 1028, 5, 7, 3, True),       # many rows per CTA, ragged last segment, edge guides
-               (7, 3, 9, 128, 8, 64, 4, False)]        # W < 4 gw: per-pixel indices
+               (7, 3, 9, 128, 8, 64, 4, False),        # W < 4 gw: per-pixel indices
+               (8, 2, 300, 2048, 8, 8, 4, True)]       # small grid, 1536-byte slab rows, several rows per grid row
 
 
 def apply_case(variant, seed, B, H, W, gh, gw, gd, edge):
@@ -31,6 +32,11 @@ def apply_case(variant, seed, B, H, W, gh, gw, gd, edge):
     if edge:
         guide[0, :, ::5] = 1.75
         guide[0, :, 1::5] = -0.6
+    # a call with ANOTHER grid first: it leaves its slab rows in the workspace block the caching allocator
+    # hands to the next call -- a kernel that read stale rows (e.g. through a cache) would show it
+    other = torch.from_numpy(np.ascontiguousarray(grid[::-1, ::-1] * 1.5 + 0.25)).cuda()
+    hdrnet_ops.bilateral_slice_apply(other, torch.from_numpy(guide).cuda(), torch.from_numpy(inp).cuda(), True,
+                                     variant=variant)
     out = hdrnet_ops.bilateral_slice_apply(torch.from_numpy(grid).cuda(), torch.from_numpy(guide).cuda(),
                                            torch.from_numpy(inp).cuda(), True, variant=variant)
     torch.cuda.synchronize()

@@ -145,18 +145,19 @@ def test_kernel_selection_plan(built_lib):
     227 KB of opt-in shared memory): which form AUTO runs for BASELINE.json's shapes."""
     from hdrnet_b200 import _lib
     lib = built_lib
-    # config 3 (headline): issuer-warp texture-assisted form, 2 CTAs x 148 SMs, 10 math warps + issuer,
-    # 4-stage ring of 1280-pixel segments
-    assert _plan(lib, 8, 2160, 3840, 16, 16, 8, 1) == (_lib.VARIANT_TEX_ASYNC, 296, 352, 94464)
+    # config 3 (headline): issuer-warp texture-assisted form, 2 CTAs x 148 SMs, 10 math warps + issuer
+    # + slab warp (no pre-pass), 4-stage ring of 1280-pixel segments + 2 slab rows + 2 grid rows
+    assert _plan(lib, 8, 2160, 3840, 16, 16, 8, 1) == (_lib.VARIANT_TEX_ASYNC, 296, 384, 106752)
     # no workspace lent: the all-LSU TMA row kernel
     v, c, t, _ = _plan(lib, 8, 2160, 3840, 16, 16, 8, 0)
     assert (v, c, t) == (_lib.VARIANT_TMA, 296, 256)
     # config 4 (12 MP, 8 frames per GPU): three 1344-pixel segments per row, 4-stage ring
     v, c, t, sm = _plan(lib, 8, 3024, 4032, 16, 16, 8, 1)
-    assert (v, c, t) == (_lib.VARIANT_TEX_ASYNC, 296, 352) and sm <= 115712
-    # config 5's 32x32 grids (24 / 48 KB of slab rows) still leave the 20 KB stages a 3-stage ring
-    assert _plan(lib, 8, 2160, 3840, 32, 32, 8, 1)[0] == _lib.VARIANT_TEX_ASYNC
-    assert _plan(lib, 8, 2160, 3840, 32, 32, 16, 1)[0] == _lib.VARIANT_TEX_ASYNC
+    assert (v, c, t) == (_lib.VARIANT_TEX_ASYNC, 296, 384) and sm <= 115712
+    # config 5's 32x32 grids (24 / 48 KB of slab rows) still leave the 20 KB stages a 3-stage ring;
+    # 32x32x16 has no room for two more grid rows: pre-pass form (352 threads)
+    assert _plan(lib, 8, 2160, 3840, 32, 32, 8, 1)[:3] == (_lib.VARIANT_TEX_ASYNC, 296, 384)
+    assert _plan(lib, 8, 2160, 3840, 32, 32, 16, 1)[:3] == (_lib.VARIANT_TEX_ASYNC, 296, 352)
     assert _plan(lib, 8, 2160, 3840, 8, 8, 4, 1)[0] == _lib.VARIANT_TEX_ASYNC
     # config 2 (one 1080p frame, < 2 Mi px): no pre-pass, TMA row kernel
     assert _plan(lib, 1, 1080, 1920, 16, 16, 8, 1)[0] == _lib.VARIANT_TMA

@@ -224,12 +224,13 @@ def _knob_shas(env, *args):
     return dict(l.split()[1:3] for l in out.stdout.splitlines() if l.startswith("SHA256"))
 
 
-@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_THREADS="512"), dict(HDRNET_ASYNC_THREADS="352"),
-                                 dict(HDRNET_TEX_CHUNKS="4"), dict(HDRNET_ASYNC_THREADS="512", HDRNET_TEX_CHUNKS="4")],
+@pytest.mark.parametrize("env", [dict(HDRNET_ASYNC_THREADS="512"), dict(HDRNET_ASYNC_SLAB="0"),
+                                 dict(HDRNET_ASYNC_SLAB="1"), dict(HDRNET_ASYNC_SLAB="1", HDRNET_TEX_CHUNKS="4"),
+                                 dict(HDRNET_ASYNC_THREADS="512", HDRNET_TEX_CHUNKS="4")],
                          ids=lambda e: ",".join(f"{k[7:].lower()}={v}" for k, v in e.items()))
 def test_issuer_warp_kernel_knobs_are_bitwise_equal(env):
-    """Both CTA shapes of the issuer-warp form and 4 / 5 of a pixel's 12 corner chunks on the
-    texture pipe: identical bits; also on narrow x cells (W < 4 gw: per-pixel indices), many rows
+    """Both CTA shapes of the issuer-warp form, slab rows from the pre-pass or from the slab warp
+    inside the kernel, and 4 / 5 of a pixel's 12 corner chunks on the texture pipe: identical bits; also on narrow x cells (W < 4 gw: per-pixel indices), many rows
     per CTA, a ragged last segment and out-of-range guides."""
     import hashlib
     import knob_runner
