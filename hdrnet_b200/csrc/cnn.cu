@@ -16,6 +16,8 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 
@@ -119,6 +121,10 @@ conv2d_nhwc_kernel(const ConvArgs a) {
       }
       const float* wt = wsm + static_cast<size_t>(t) * cn * kConvTileCo + cg * kConvCo;
       if (vec_in && (cn % 4 == 0)) {
+        // unrolled so that several iterations' input loads are in flight at once: a late layer at
+        // batch 1 is a few dozen CTAs of 4 warps, and every new (tap, 4 channels) is an L2 round trip
+        // that nothing else on the SM hides (ncu: 31 us for 9.4 MMAC before; see tools/time_cnn.py)
+#pragma unroll(kConvPx == 1 ? 8 : 4)
         for (int ci = 0; ci < cn; ci += 4) {
           float xin[kConvPx][4];
 #pragma unroll
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(kFpThreads)
 fuse_predict_kernel(const float* __restrict__ local, const float* __restrict__ global_feat,
                     const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ grid, int B, int cells_per_image, int C, int gd,
-                    int n_out, int n_in, int stage_w) {
+                    int n_out, int n_in, int stage_w, int pdl) {
   extern __shared__ __align__(16) float sm[];  // [w[C][O] when stage_w] then f[kFpCells][C]
   const int O = gd * n_out * n_in;
   // stage_w == 0: the prediction weights do not fit shared memory next to the features (e.g.
@@ -329,8 +335,17 @@ fuse_predict_kernel(const float* __restrict__ local, const float* __restrict__ g
   float* fsm = sm + (stage_w ? static_cast<size_t>(C) * O : 0);
   const float* wsm = stage_w ? sm : w;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (stage_w)
-    for (int e = tid; e < C * O; e += kFpThreads) sm[e] = __ldg(w + e);
+  if (stage_w) {
+    if ((C * O) % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15u) == 0) {
+      for (int e = tid; e < C * O / 4; e += kFpThreads)
+        reinterpret_cast<float4*>(sm)[e] = __ldg(reinterpret_cast<const float4*>(w) + e);
+    } else {
+      for (int e = tid; e < C * O; e += kFpThreads) sm[e] = __ldg(w + e);
+    }
+  }
+  // launched with programmatic stream serialisation (hdrnet_coefficients_f32): the weights above do
+  // not depend on the previous kernels, the features below do
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long total = static_cast<long long>(B) * cells_per_image;
   const long long cell = static_cast<long long>(blockIdx.x) * kFpCells + warp;
   const bool valid = cell < total;
@@ -366,6 +381,239 @@ static void same_pad(int size, int k, int s, int* out, int* before) {
   *before = total / 2;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Latency form for the small late layers (batch 1-2: a few thousand output pixels at most).
+// conv2d_nhwc_kernel walks its k*k*Cin reduction with one dependent L2 round trip per 4 input
+// channels and 4 warps per SM: ncu showed 17-29 us per layer for 2-9 MMAC (12 % issue-active).
+// Here a CTA owns 32 output pixels (lane = pixel) x 4*kCoGroups output channels and
+//   1. copies every lane's k x k x Cin input patch and the CTA's weight columns into shared
+//      memory with 16-byte cp.async -- ALL of them in flight at once, one memory round trip;
+//   2. splits the reduction four ways across warps (kPatchSlices), each warp doing
+//      LDS.128 (its pixel's 4 inputs, conflict-free row stride) + 4 broadcast LDS.128 (weights)
+//      + 16 FFMA per step, no global access;
+//   3. adds the four partial sums through shared memory, bias + ReLU, 16-byte stores.
+// The patches overlap (9x redundant for stride 1), which is why this form is for SMALL layers
+// only: the redundancy is L2 -> shared traffic of tens of KB per CTA.
+// Input channels that are not a multiple of 4 (the first layer: 3) are staged with 4-byte copies and
+// the reduction is zero-padded to a multiple of 4; reductions of <= 64 terms are not split across
+// warps (kSlices = 1: the first layer is 27 terms).
+constexpr int kPatchPx = 32;
+
+__host__ __device__ inline int patch_k4(int K) { return (K + 3) / 4 * 4; }
+__host__ __device__ inline int patch_row_floats(int K) {
+  const int q = patch_k4(K) / 4;
+  return ((q & 1) ? q : q + 1) * 4;  // odd number of 16-byte chunks: lanes hit distinct banks
+}
+
+//
+// The kernel takes TWO layers: x-tiles [0, tiles0) belong to a0, the rest to a1 (a1.B == 0: none).
+// That is how the global and the local branch of the network (models.py:86-118: both read the
+// splat features, neither reads the other) share one launch.  kPdl: launched with programmatic
+// stream serialisation -- the weight copies (independent of the previous layer) are issued
+// BEFORE griddepcontrol.wait, the input patch after it, so the previous layer's tail and this
+// layer's launch + weight fetch overlap.
+template <int kCoGroups, int kPatchSlices>
+__global__ void __launch_bounds__(32 * kPatchSlices * kCoGroups)
+conv2d_patch_kernel(const ConvArgs a0, const ConvArgs a1, const int tiles0, const int pdl) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next layer's prologue start
+  const bool second = static_cast<int>(blockIdx.x) >= tiles0;
+  ConvArgs a;   // scalar selects: the structs are kernel parameters (constant bank)
+  a.in = second ? a1.in : a0.in;       a.w = second ? a1.w : a0.w;
+  a.bias = second ? a1.bias : a0.bias; a.out = second ? a1.out : a0.out;
+  a.B = second ? a1.B : a0.B;          a.H = second ? a1.H : a0.H;
+  a.W = second ? a1.W : a0.W;          a.Cin = second ? a1.Cin : a0.Cin;
+  a.OH = second ? a1.OH : a0.OH;       a.OW = second ? a1.OW : a0.OW;
+  a.Cout = second ? a1.Cout : a0.Cout; a.k = second ? a1.k : a0.k;
+  a.stride = second ? a1.stride : a0.stride;
+  a.pad_t = second ? a1.pad_t : a0.pad_t; a.pad_l = second ? a1.pad_l : a0.pad_l;
+  a.relu = second ? a1.relu : a0.relu;
+  const int tile_x = static_cast<int>(blockIdx.x) - (second ? tiles0 : 0);
+  constexpr int kTileCo = 4 * kCoGroups;
+  constexpr int kWarps = kPatchSlices * kCoGroups;
+  constexpr int kThreads = 32 * kWarps;
+  extern __shared__ __align__(16) float psm[];
+  const int kk = a.k * a.k;
+  const int K = kk * a.Cin;
+  const int K4 = patch_k4(K);
+  const int Kp = patch_row_floats(K);
+  float* in_s = psm;                                  // [32][Kp]
+  float* w_s = in_s + kPatchPx * Kp;                  // [K4][kTileCo]
+  float* red = w_s + static_cast<size_t>(K4) * kTileCo;  // [kPatchSlices-1][kCoGroups][32][4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int co0 = blockIdx.y * kTileCo;
+  const long long total_px = static_cast<long long>(a.B) * a.OH * a.OW;
+  const long long q = static_cast<long long>(tile_x) * kPatchPx + lane;
+  const bool pv = q < total_px;
+  const long long qq = pv ? q : 0;
+  const int px = static_cast<int>(qq % a.OW);
+  const int py = static_cast<int>((qq / a.OW) % a.OH);
+  const int pb = static_cast<int>(qq / (static_cast<long long>(a.OW) * a.OH));
+
+  // 1a. weights: row k of the CTA's column block = kCoGroups 16-byte chunks
+  for (int e = tid; e < K4 * kCoGroups; e += kThreads) {
+    const int krow = e / kCoGroups, g = e - krow * kCoGroups;
+    float* dst = w_s + static_cast<size_t>(krow) * kTileCo + g * 4;
+    if (krow < K && co0 + g * 4 < a.Cout) {  // Cout % 4 == 0 (launch precondition): whole chunk or nothing
+      const float* src = a.w + static_cast<size_t>(krow) * a.Cout + co0 + g * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                       static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                   "l"(src)
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // 1b. this lane's input patch: tap t -> Cin / 4 chunks, the warps interleave over the chunks
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous layer's output is complete
+  {
+    const bool vec = (a.Cin & 3) == 0;
+    const int cpr = vec ? a.Cin / 4 : a.Cin;   // copies per tap: 16-byte chunks, or single floats
+    float* row = in_s + static_cast<size_t>(lane) * Kp;
+    if (warp == 0)
+      for (int c = K; c < K4; ++c) row[c] = 0.0f;
+    for (int t = 0; t < kk; ++t) {
+      const int ky = t / a.k, kx = t - ky * a.k;
+      const int iy = py * a.stride - a.pad_t + ky;
+      const int ix = px * a.stride - a.pad_l + kx;
+      const bool ok = pv && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+      const float* src = a.in + ((static_cast<size_t>(pb) * a.H + (ok ? iy : 0)) * a.W +
+                                 (ok ? ix : 0)) * a.Cin;
+      float* dst = row + t * a.Cin;
+      for (int c4 = warp; c4 < cpr; c4 += kWarps) {
+        if (!vec) {
+          if (ok) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                             static_cast<uint32_t>(__cvta_generic_to_shared(dst + c4))),
+                         "l"(src + c4)
+                         : "memory");
+          } else {
+            dst[c4] = 0.0f;
+          }
+        } else if (ok) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                           static_cast<uint32_t>(__cvta_generic_to_shared(dst + c4 * 4))),
+                       "l"(src + c4 * 4)
+                       : "memory");
+        } else {
+          *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // 2. this warp's quarter of the reduction
+  const int ks = warp % kPatchSlices, cg = warp / kPatchSlices;
+  const int nq = K4 / 4;
+  const int q0 = (nq * ks) / kPatchSlices, q1 = (nq * (ks + 1)) / kPatchSlices;
+  const float* xs = in_s + static_cast<size_t>(lane) * Kp;
+  const float* ws = w_s + cg * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int i = q0; i < q1; ++i) {
+    const float4 x = *reinterpret_cast<const float4*>(xs + 4 * i);
+    const float4 w0 = *reinterpret_cast<const float4*>(ws + static_cast<size_t>(4 * i + 0) * kTileCo);
+    const float4 w1 = *reinterpret_cast<const float4*>(ws + static_cast<size_t>(4 * i + 1) * kTileCo);
+    const float4 w2 = *reinterpret_cast<const float4*>(ws + static_cast<size_t>(4 * i + 2) * kTileCo);
+    const float4 w3 = *reinterpret_cast<const float4*>(ws + static_cast<size_t>(4 * i + 3) * kTileCo);
+    acc.x = fmaf(x.x, w0.x, acc.x); acc.y = fmaf(x.x, w0.y, acc.y);
+    acc.z = fmaf(x.x, w0.z, acc.z); acc.w = fmaf(x.x, w0.w, acc.w);
+    acc.x = fmaf(x.y, w1.x, acc.x); acc.y = fmaf(x.y, w1.y, acc.y);
+    acc.z = fmaf(x.y, w1.z, acc.z); acc.w = fmaf(x.y, w1.w, acc.w);
+    acc.x = fmaf(x.z, w2.x, acc.x); acc.y = fmaf(x.z, w2.y, acc.y);
+    acc.z = fmaf(x.z, w2.z, acc.z); acc.w = fmaf(x.z, w2.w, acc.w);
+    acc.x = fmaf(x.w, w3.x, acc.x); acc.y = fmaf(x.w, w3.y, acc.y);
+    acc.z = fmaf(x.w, w3.z, acc.z); acc.w = fmaf(x.w, w3.w, acc.w);
+  }
+
+  // 3. partial sums -> slice 0, epilogue
+  if (kPatchSlices > 1) {
+    if (ks > 0)
+      *reinterpret_cast<float4*>(red + ((static_cast<size_t>(ks - 1) * kCoGroups + cg) * 32 + lane) * 4) = acc;
+    __syncthreads();
+  }
+  if (ks == 0 && pv) {
+#pragma unroll
+    for (int s = 0; s < kPatchSlices - 1; ++s) {
+      const float4 r = *reinterpret_cast<const float4*>(
+          red + ((static_cast<size_t>(s) * kCoGroups + cg) * 32 + lane) * 4);
+      acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+    }
+    const int gco = co0 + cg * 4;
+    if (gco < a.Cout) {
+      if (a.bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + gco));
+        acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+      }
+      if (a.relu) {
+        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+        acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+      }
+      float* dst = a.out + ((static_cast<size_t>(pb) * a.OH + py) * a.OW + px) * a.Cout + gco;
+      *reinterpret_cast<float4*>(dst) = acc;
+    }
+  }
+}
+
+inline int patch_slices(int K) { return patch_k4(K) <= 64 ? 1 : 4; }
+
+inline size_t patch_smem_bytes(int K, int co_groups) {
+  return (static_cast<size_t>(kPatchPx) * patch_row_floats(K) + static_cast<size_t>(patch_k4(K)) * 4 * co_groups +
+          static_cast<size_t>(patch_slices(K) - 1) * co_groups * 32 * 4) * sizeof(float);
+}
+
+// Preconditions for the patch form: float4 weights / outputs (Cout % 4, 16-byte bases); input
+// channels % 4 with a 16-byte base, or any count with 4-byte copies.
+inline bool patch_ok(const ConvArgs& a) {
+  const auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return (a.Cin % 4 != 0 || al(a.in)) && a.Cout % 4 == 0 && al(a.w) && al(a.out) &&
+         (!a.bias || al(a.bias)) && patch_smem_bytes(a.k * a.k * a.Cin, 1) <= 200 * 1024;
+}
+
+// One launch for one layer (b == nullptr) or two independent layers of equal Cout and equal
+// reduction split.
+template <int kCoGroups, int kSlices>
+static int launch_conv_patch_t(const ConvArgs& a, const ConvArgs* b, bool pdl, cudaStream_t stream) {
+  size_t smem = patch_smem_bytes(a.k * a.k * a.Cin, kCoGroups);
+  if (b) smem = std::max(smem, patch_smem_bytes(b->k * b->k * b->Cin, kCoGroups));
+  // the attribute is per function and sticky: raise it once, never lower it (threads may race
+  // here; every value written is a valid upper bound for every launch that follows)
+  static std::atomic<int> raised{0};
+  if (!raised.load(std::memory_order_relaxed)) {
+    cudaError_t e = cudaFuncSetAttribute(conv2d_patch_kernel<kCoGroups, kSlices>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    raised.store(1, std::memory_order_relaxed);
+  }
+  const auto tiles = [](const ConvArgs& c) {
+    return static_cast<int>((static_cast<long long>(c.B) * c.OH * c.OW + kPatchPx - 1) / kPatchPx);
+  };
+  const int tiles0 = tiles(a), tiles1 = b ? tiles(*b) : 0;
+  ConvArgs none = a;
+  none.B = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(tiles0 + tiles1),
+                     static_cast<unsigned>((a.Cout + 4 * kCoGroups - 1) / (4 * kCoGroups)));
+  cfg.blockDim = dim3(32 * kSlices * kCoGroups);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv2d_patch_kernel<kCoGroups, kSlices>, a, b ? *b : none, tiles0,
+                                     static_cast<int>(pdl));
+  return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+template <int kCoGroups>
+static int launch_conv_patch(const ConvArgs& a, const ConvArgs* b, bool pdl, cudaStream_t stream) {
+  return patch_slices(a.k * a.k * a.Cin) == 1 ? launch_conv_patch_t<kCoGroups, 1>(a, b, pdl, stream)
+                                              : launch_conv_patch_t<kCoGroups, 4>(a, b, pdl, stream);
+}
+
 template <int kPx, int kCo>
 static int launch_conv(ConvArgs a, cudaStream_t stream) {
   constexpr int kTilePx = 32 * kPx, kTileCo = 4 * kCo;
@@ -386,6 +634,276 @@ static int launch_conv(ConvArgs a, cudaStream_t stream) {
   return static_cast<int>(cudaGetLastError());
 }
 
+// ---- fc1 -> fc2 -> fc3 in ONE cluster (models.py:94-104) ------------------------------------
+// Three launches of 0.6 MFLOP cost 3 x 4 us.  Here one cluster of 8 CTAs runs all three: every
+// layer is split over K by cluster rank (rank r multiplies inputs [r*I/8, (r+1)*I/8) into ALL the
+// outputs: its 1/8 of the weight matrix, streamed once), the per-rank partial sums meet through
+// distributed shared memory, and rank r reduces outputs [r*O/8, (r+1)*O/8) -- which are exactly
+// the inputs of ITS K-slice of the next layer, so activations never leave shared memory.
+constexpr int kFcChainRanks = 8;
+constexpr int kFcChainThreads = 256;
+constexpr int kFcChainBatch = 4;
+
+struct FcChainArgs {
+  const float* x;      // [B][n[0]]
+  const float* w[3];   // [n[l]][n[l+1]]
+  const float* b[3];
+  float* out;          // [B][n[3]]
+  int B, n[4], max_slice, max_o, pdl;
+  int stage_w;   // this rank's three weight slices fit shared memory: copied there before the dependency wait
+};
+
+__global__ void __launch_bounds__(kFcChainThreads)
+fc_chain_kernel(const FcChainArgs a) {
+  namespace cg = cooperative_groups;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float fsm[];
+  float* xs = fsm;                                                  // [kFcChainBatch][max_slice]
+  float* partial = xs + kFcChainBatch * a.max_slice;                // [2][kFcChainBatch][max_o]
+  float* red = partial + 2 * kFcChainBatch * a.max_o;               // [krows][kFcChainBatch][O]: 256 float4 x batch
+  float* wsm = red + kFcChainThreads * 4 * kFcChainBatch;            // [3 layers][slice][O] when stage_w
+  const int tid = threadIdx.x;
+  const int rank = static_cast<int>(cluster.block_rank());
+  if (a.stage_w) {
+    // the weights do not depend on the previous kernel: every 16-byte copy of all three layers is
+    // in flight before the wait (one memory round trip, hidden behind the previous layer's tail)
+    float* dst = wsm;
+    for (int l = 0; l < 3; ++l) {
+      const int slice = a.n[l] / kFcChainRanks, O = a.n[l + 1];
+      const float* src = a.w[l] + static_cast<size_t>(rank) * slice * O;
+      for (int e = tid; e < slice * O / 4; e += kFcChainThreads)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                         static_cast<uint32_t>(__cvta_generic_to_shared(dst + e * 4))),
+                     "l"(src + e * 4)
+                     : "memory");
+      dst += slice * O;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  {
+    const int slice = a.n[0] / kFcChainRanks;
+    for (int e = tid; e < kFcChainBatch * slice; e += kFcChainThreads) {
+      const int b = e / slice, i = e - b * slice;
+      xs[b * a.max_slice + i] = (b < a.B) ? __ldg(a.x + static_cast<size_t>(b) * a.n[0] + rank * slice + i) : 0.0f;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const float* wstaged = wsm;
+#pragma unroll 1
+  for (int l = 0; l < 3; ++l) {
+    const int I = a.n[l], O = a.n[l + 1];
+    const int slice = I / kFcChainRanks, ncol = O / 4, krows = kFcChainThreads / ncol;
+    const int col = tid % ncol, kr = tid / ncol;
+    float acc[kFcChainBatch][4];
+#pragma unroll
+    for (int b = 0; b < kFcChainBatch; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0f;
+    const float* wp = a.stage_w ? wstaged + col * 4 : a.w[l] + (static_cast<size_t>(rank) * slice) * O + col * 4;
+    wstaged += slice * O;
+#pragma unroll 8
+    for (int i = kr; i < slice; i += krows) {
+      const float4 wv = a.stage_w ? *reinterpret_cast<const float4*>(wp + static_cast<size_t>(i) * O)
+                                  : __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(i) * O));
+#pragma unroll
+      for (int b = 0; b < kFcChainBatch; ++b) {
+        const float x = xs[b * a.max_slice + i];
+        acc[b][0] = fmaf(x, wv.x, acc[b][0]);
+        acc[b][1] = fmaf(x, wv.y, acc[b][1]);
+        acc[b][2] = fmaf(x, wv.z, acc[b][2]);
+        acc[b][3] = fmaf(x, wv.w, acc[b][3]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kFcChainBatch; ++b)
+      *reinterpret_cast<float4*>(red + (static_cast<size_t>(kr) * kFcChainBatch + b) * O + col * 4) =
+          make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+    __syncthreads();
+    float* mine = partial + static_cast<size_t>(l & 1) * kFcChainBatch * a.max_o;
+    for (int e = tid; e < kFcChainBatch * O; e += kFcChainThreads) {
+      const int b = e / O, o = e - b * O;
+      float sum = 0.0f;
+      for (int r = 0; r < krows; ++r) sum += red[(static_cast<size_t>(r) * kFcChainBatch + b) * O + o];
+      mine[b * a.max_o + o] = sum;
+    }
+    cluster.sync();   // every rank's partial of layer l is complete and visible cluster-wide
+    // (the buffer of layer l is rewritten by layer l + 2, behind the sync of layer l + 1: no rank
+    // can still be reading it then)
+    const int oslice = O / kFcChainRanks;
+    for (int e = tid; e < kFcChainBatch * oslice; e += kFcChainThreads) {
+      const int b = e / oslice, oo = e - b * oslice, o = rank * oslice + oo;
+      float sum = 0.0f;
+#pragma unroll
+      for (int r = 0; r < kFcChainRanks; ++r) sum += cluster.map_shared_rank(mine, r)[b * a.max_o + o];
+      sum += a.b[l] ? __ldg(a.b[l] + o) : 0.0f;
+      if (l < 2) {
+        xs[b * a.max_slice + oo] = fmaxf(sum, 0.0f);   // my K-slice of the next layer's input
+      } else if (b < a.B) {
+        a.out[static_cast<size_t>(b) * O + o] = sum;    // fc3: no activation (models.py:103)
+      }
+    }
+    __syncthreads();
+  }
+  cluster.sync();   // keep this CTA's shared memory alive until every rank has read it
+}
+
+// Shapes the cluster chain takes: each width a power of two in [32, 1024] (so that 256 threads
+// tile the float4 columns and every rank's slice is a multiple of 4), batch <= kFcChainBatch.
+static bool fc_chain_ok(int B, const int n[4], const float* const w[3]) {
+  if (B < 1 || B > kFcChainBatch) return false;
+  for (int l = 0; l < 4; ++l)
+    if (n[l] < 32 || (n[l] & (n[l] - 1))) return false;
+  for (int l = 1; l < 4; ++l)
+    if (n[l] > 1024) return false;
+  if (n[0] / kFcChainRanks > 1024) return false;
+  for (int l = 0; l < 3; ++l)
+    if (reinterpret_cast<uintptr_t>(w[l]) & 15u) return false;
+  return true;
+}
+
+static int launch_fc_chain(const float* x, const float* const w[3], const float* const b[3], float* out,
+                           int B, const int n[4], bool pdl, cudaStream_t stream) {
+  FcChainArgs a;
+  a.x = x; a.out = out; a.B = B; a.pdl = pdl;
+  a.max_slice = 0; a.max_o = 0;
+  for (int l = 0; l < 3; ++l) {
+    a.w[l] = w[l]; a.b[l] = b[l];
+    a.max_slice = std::max(a.max_slice, n[l] / kFcChainRanks);
+    a.max_o = std::max(a.max_o, n[l + 1]);
+  }
+  for (int l = 0; l < 4; ++l) a.n[l] = n[l];
+  const size_t red_floats = static_cast<size_t>(kFcChainThreads) * 4 * kFcChainBatch;   // krows * (O / 4) = 256 float4 per image
+  size_t smem = (static_cast<size_t>(kFcChainBatch) * a.max_slice +
+                 2 * static_cast<size_t>(kFcChainBatch) * a.max_o + red_floats) * sizeof(float);
+  if (smem > 200 * 1024) return HDRNET_E_UNSUPPORTED;
+  size_t w_bytes = 0;
+  for (int l = 0; l < 3; ++l) w_bytes += static_cast<size_t>(n[l] / kFcChainRanks) * n[l + 1] * sizeof(float);
+  a.stage_w = smem + w_bytes <= 200 * 1024;
+  if (a.stage_w) smem += w_bytes;
+  static std::atomic<int> raised{0};
+  if (!raised.load(std::memory_order_relaxed)) {
+    cudaError_t e = cudaFuncSetAttribute(fc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    raised.store(1, std::memory_order_relaxed);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kFcChainRanks);
+  cfg.blockDim = dim3(kFcChainThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kFcChainRanks;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fc_chain_kernel, a);
+  return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+
+
+
+
+
+
+// Layer dispatch shared by hdrnet_conv2d_nhwc_f32 and the network chain (hdrnet_coefficients_f32).
+// pdl: the launch may overlap the tail of the previous kernel on the stream (patch form only; the
+// other forms are launched in plain stream order, which is always correct).
+static int conv_fill(ConvArgs* a, const float* in, const float* w, const float* bias, float* out, int B,
+                     int H, int W, int Cin, int Cout, int k, int stride, int relu) {
+  if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return HDRNET_E_BAD_SHAPE;
+  if ((k != 1 && k != 3) || (stride != 1 && stride != 2)) return HDRNET_E_UNSUPPORTED;
+  if (B > 0 && (!in || !w || !out)) return HDRNET_E_NULL_POINTER;
+  a->in = in; a->w = w; a->bias = bias; a->out = out;
+  a->B = B; a->H = H; a->W = W; a->Cin = Cin; a->Cout = Cout; a->k = k; a->stride = stride; a->relu = relu;
+  same_pad(H, k, stride, &a->OH, &a->pad_t);
+  same_pad(W, k, stride, &a->OW, &a->pad_l);
+  a->w_vec = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
+  a->ci_chunk = Cin;
+  return HDRNET_OK;
+}
+
+static int device_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+static int patch_mode() {   // HDRNET_CONV_PATCH: 0 off, 1 / 2 force 4 / 8 channels per CTA (A/B knob, read once)
+  static const int mode = [] {
+    const char* e = std::getenv("HDRNET_CONV_PATCH");
+    return e ? std::atoi(e) : -1;
+  }();
+  return mode;
+}
+
+// 4 or 8 output channels per CTA for `ctas1` CTAs of the 4-channel form (tools/time_conv_layers.py)
+static bool patch_two_groups(long long ctas1, int Cout, int K, int sms) {
+  const int mode = patch_mode();
+  const bool two = mode == 2 || (mode < 0 && ctas1 > sms);   // a second CTA on an SM doubles its staging time
+  return two && Cout % 8 == 0 && patch_smem_bytes(K, 2) <= 200 * 1024;
+}
+
+static int conv_dispatch(const ConvArgs& a, bool pdl, cudaStream_t stream) {
+  if (a.B == 0) return HDRNET_OK;
+  {  // Tensor-core path (conv_tcgen05.cu).  Each 128-pixel tile runs a fixed-latency chunk loop,
+     // so it wins once there are about as many tiles as SMs (measured on B200: 2x faster at 128
+     // tiles, 3x slower at 2); HDRNET_CONV_TCGEN05=1 / =0 forces it on / off.
+    const char* e = std::getenv("HDRNET_CONV_TCGEN05");   // per call: tests and smoke() flip it in-process
+    const long long tiles = (static_cast<long long>(a.B) * a.OH * a.OW + 127) / 128;
+    const bool want = e ? (e[0] == '1') : (tiles >= 96);
+    if (want) {
+      const int rc = launch_conv_tcgen05(a.in, a.w, a.bias, a.out, a.B, a.H, a.W, a.Cin, a.Cout, a.k, a.stride,
+                                         a.relu, a.OH, a.OW, a.pad_t, a.pad_l, stream);
+      if (rc != HDRNET_E_UNSUPPORTED) return rc;
+    }
+  }
+  const long long total_px = static_cast<long long>(a.B) * a.OH * a.OW;
+  const int sms = device_sms();
+  const long long big_ctas = ((total_px + 63) / 64) * ((a.Cout + 31) / 32);
+  // The shared-memory patch form: one memory round trip instead of one per 4 input channels.  It
+  // beats the register-tile kernels at every size measured (batch 1-8 of every layer of the
+  // network, tools/time_conv_layers.py: 2-3.5x at batch 1, 1.3-3x at batch 8); the bound below
+  // is where its 9x-redundant staging traffic was last measured, not a known crossover.
+  if (patch_mode() != 0 && patch_ok(a)) {
+    const long long tiles = (total_px + kPatchPx - 1) / kPatchPx;
+    const long long ctas1 = tiles * (a.Cout / 4);
+    const bool two = patch_two_groups(ctas1, a.Cout, a.k * a.k * a.Cin, sms);
+    if (patch_mode() > 0 || (two ? ctas1 / 2 : ctas1) <= 32LL * sms)
+      return two ? launch_conv_patch<2>(a, nullptr, pdl, stream) : launch_conv_patch<1>(a, nullptr, pdl, stream);
+  }
+  return (big_ctas >= 2LL * sms) ? launch_conv<2, 8>(a, stream) : launch_conv<1, 4>(a, stream);
+}
+
+// Two independent layers of equal Cout (the global and the local branch): one launch when both
+// take the patch form, else two.
+static int conv_dispatch_pair(const ConvArgs& a, const ConvArgs& b, bool pdl, cudaStream_t stream) {
+  const int sms = device_sms();
+  const auto small = [&](const ConvArgs& c) {   // not a tensor-core-sized layer, and the patch form takes it
+    const long long px = static_cast<long long>(c.B) * c.OH * c.OW;
+    return ((px + 127) / 128) < 96 && patch_ok(c);
+  };
+  if (patch_mode() != 0 && a.Cout == b.Cout && a.B > 0 && b.B > 0 && small(a) && small(b) &&
+      patch_slices(a.k * a.k * a.Cin) == patch_slices(b.k * b.k * b.Cin) &&
+      !std::getenv("HDRNET_CONV_TCGEN05")) {
+    const auto tiles = [](const ConvArgs& c) {
+      return (static_cast<long long>(c.B) * c.OH * c.OW + kPatchPx - 1) / kPatchPx;
+    };
+    const long long ctas1 = (tiles(a) + tiles(b)) * (a.Cout / 4);
+    const int K = std::max(a.k * a.k * a.Cin, b.k * b.k * b.Cin);
+    if (patch_two_groups(ctas1, a.Cout, K, sms)) return launch_conv_patch<2>(a, &b, pdl, stream);
+    return launch_conv_patch<1>(a, &b, pdl, stream);
+  }
+  const int rc = conv_dispatch(a, pdl, stream);
+  return rc ? rc : conv_dispatch(b, false, stream);
+}
+
 }  // namespace hdrnet_b200
 
 using namespace hdrnet_b200;
@@ -395,36 +913,9 @@ extern "C" {
 int hdrnet_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, float* out, int B,
                            int H, int W, int Cin, int Cout, int k, int stride, int relu,
                            void* stream) {
-  if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return HDRNET_E_BAD_SHAPE;
-  if ((k != 1 && k != 3) || (stride != 1 && stride != 2)) return HDRNET_E_UNSUPPORTED;
-  if (B == 0) return HDRNET_OK;
-  if (!in || !w || !out) return HDRNET_E_NULL_POINTER;
   ConvArgs a;
-  a.in = in; a.w = w; a.bias = bias; a.out = out;
-  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = k; a.stride = stride; a.relu = relu;
-  same_pad(H, k, stride, &a.OH, &a.pad_t);
-  same_pad(W, k, stride, &a.OW, &a.pad_l);
-  a.w_vec = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15u) == 0);
-  {  // Tensor-core path (conv_tcgen05.cu).  Each 128-pixel tile runs a fixed-latency chunk loop,
-     // so it wins once there are about as many tiles as SMs (measured on B200: 2x faster at 128
-     // tiles, 3x slower at 2); HDRNET_CONV_TCGEN05=1 / =0 forces it on / off.
-    const char* e = std::getenv("HDRNET_CONV_TCGEN05");
-    const long long tiles = (static_cast<long long>(B) * a.OH * a.OW + 127) / 128;
-    const bool want = e ? (e[0] == '1') : (tiles >= 96);
-    if (want) {
-      const int rc = launch_conv_tcgen05(in, w, bias, out, B, H, W, Cin, Cout, k, stride, relu,
-                                         a.OH, a.OW, a.pad_t, a.pad_l,
-                                         static_cast<cudaStream_t>(stream));
-      if (rc != HDRNET_E_UNSUPPORTED) return rc;
-    }
-  }
-  const long long total_px = static_cast<long long>(B) * a.OH * a.OW;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long big_ctas = ((total_px + 63) / 64) * ((Cout + 31) / 32);
-  return (big_ctas >= 2LL * sms) ? launch_conv<2, 8>(a, static_cast<cudaStream_t>(stream))
-                                 : launch_conv<1, 4>(a, static_cast<cudaStream_t>(stream));
+  const int rc = conv_fill(&a, in, w, bias, out, B, H, W, Cin, Cout, k, stride, relu);
+  return rc ? rc : conv_dispatch(a, false, static_cast<cudaStream_t>(stream));
 }
 
 int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out, int B, int I,
@@ -437,8 +928,10 @@ int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out
   int ksplit = 1;
   while (ksplit < 8 && I / (ksplit * 2) >= 64) ksplit *= 2;
   const int slice = (I + ksplit - 1) / ksplit;
-  const char* env = std::getenv("HDRNET_FC_CLUSTER");
-  const bool allow = !(env && env[0] == '0');
+  static const bool allow = [] {   // read once per process
+    const char* env = std::getenv("HDRNET_FC_CLUSTER");
+    return !(env && env[0] == '0');
+  }();
   if (allow && O % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15u) == 0 && ksplit >= 2 &&
       slice <= kFcCMaxSlice) {
     cudaLaunchConfig_t cfg = {};
@@ -461,9 +954,9 @@ int hdrnet_fc_f32(const float* in, const float* w, const float* bias, float* out
   return static_cast<int>(cudaGetLastError());
 }
 
-int hdrnet_fuse_predict_f32(const float* local, const float* global_feat, const float* w,
-                            const float* bias, float* grid, int B, int gh, int gw, int C, int gd,
-                            int n_out, int n_in, void* stream) {
+static int fuse_predict_launch(const float* local, const float* global_feat, const float* w,
+                               const float* bias, float* grid, int B, int gh, int gw, int C, int gd,
+                               int n_out, int n_in, bool pdl, cudaStream_t stream) {
   if (B < 0 || gh < 1 || gw < 1 || C < 1 || gd < 1 || n_out < 1 || n_in < 1) return HDRNET_E_BAD_SHAPE;
   if (B == 0) return HDRNET_OK;
   if (!local || !global_feat || !w || !grid) return HDRNET_E_NULL_POINTER;
@@ -472,14 +965,150 @@ int hdrnet_fuse_predict_f32(const float* local, const float* global_feat, const 
   const int stage_w = smem <= 200 * 1024;
   if (!stage_w) smem = static_cast<size_t>(kFpCells) * C * sizeof(float);
   if (smem > 200 * 1024) return HDRNET_E_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(fuse_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return static_cast<int>(e);
+  static std::atomic<int> raised{0};   // sticky per-function attribute: raise once, never lower
+  if (!raised.load(std::memory_order_relaxed)) {
+    cudaError_t e = cudaFuncSetAttribute(fuse_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    raised.store(1, std::memory_order_relaxed);
+  }
   const long long cells = static_cast<long long>(B) * gh * gw;
-  fuse_predict_kernel<<<static_cast<unsigned>((cells + kFpCells - 1) / kFpCells), kFpThreads, smem,
-                        static_cast<cudaStream_t>(stream)>>>(local, global_feat, w, bias, grid, B,
-                                                             gh * gw, C, gd, n_out, n_in, stage_w);
-  return static_cast<int>(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((cells + kFpCells - 1) / kFpCells));
+  cfg.blockDim = dim3(kFpThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fuse_predict_kernel, local, global_feat, w, bias, grid, B, gh * gw, C,
+                                     gd, n_out, n_in, stage_w, static_cast<int>(pdl));
+  return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+int hdrnet_fuse_predict_f32(const float* local, const float* global_feat, const float* w,
+                            const float* bias, float* grid, int B, int gh, int gw, int C, int gd,
+                            int n_out, int n_in, void* stream) {
+  return fuse_predict_launch(local, global_feat, w, bias, grid, B, gh, gw, C, gd, n_out, n_in, false,
+                             static_cast<cudaStream_t>(stream));
+}
+
+// ---- the whole coefficient network behind one call ------------------------------------------
+// HDRNetCurves._coefficients (hdrnet/models.py:62-142): splat convs, global convs + 3 fc, local
+// convs, fusion + prediction + unroll_grid.  One FFI crossing and 8 launches at small batch
+// (n_ds splat + [global conv1 || local conv1] + [global conv2 || local conv2] + fc cluster chain
+// + fuse/predict), each launched with programmatic stream serialisation so that a layer's launch
+// latency and weight fetch hide behind the previous layer.  Layer i of the network writes buffer i
+// of the caller's scratch: nothing is written twice inside a call.
+namespace {
+
+struct CoefPlan {
+  int n_ds, c_splat[8], c8, f1, f2, g1, g2;   // g1, g2: spatial extent after global conv1 / conv2
+  size_t act_floats;
+};
+
+bool coef_plan(int S, int sb, int gd, int cm, int B, CoefPlan* d) {
+  if (S < 1 || sb < 1 || gd < 1 || cm < 1 || B < 1 || S % sb) return false;
+  int n_ds = 0;
+  for (int s = S; s > sb; s >>= 1) {
+    if (s & 1) return false;
+    ++n_ds;
+  }
+  if (n_ds < 1 || n_ds > 8 || (sb << n_ds) != S) return false;   // models.py:69: int(log2(S / sb)) halvings
+  d->n_ds = n_ds;
+  size_t fl = 0;
+  const auto take = [&](size_t n) { fl += (n + 3) & ~static_cast<size_t>(3); };
+  for (int i = 0; i < n_ds; ++i) {
+    d->c_splat[i] = cm * (1 << i) * gd;
+    const size_t sp = static_cast<size_t>(S >> (i + 1));
+    take(static_cast<size_t>(B) * sp * sp * d->c_splat[i]);
+  }
+  d->c8 = 8 * cm * gd; d->f1 = 32 * cm * gd; d->f2 = 16 * cm * gd;
+  d->g1 = (sb + 1) / 2; d->g2 = (d->g1 + 1) / 2;
+  take(static_cast<size_t>(B) * d->g1 * d->g1 * d->c8);
+  take(static_cast<size_t>(B) * d->g2 * d->g2 * d->c8);
+  take(static_cast<size_t>(B) * sb * sb * d->c8);
+  take(static_cast<size_t>(B) * sb * sb * d->c8);
+  take(static_cast<size_t>(B) * d->f1);
+  take(static_cast<size_t>(B) * d->f2);
+  take(static_cast<size_t>(B) * d->c8);
+  d->act_floats = fl;
+  return true;
+}
+
+}  // namespace
+
+size_t hdrnet_coefficients_scratch_bytes(int B, int net_input_size, int spatial_bin, int luma_bins,
+                                         int channel_multiplier, int n_out, int n_in) {
+  CoefPlan d;
+  if (n_out < 1 || n_in < 1 || !coef_plan(net_input_size, spatial_bin, luma_bins, channel_multiplier, B, &d))
+    return 0;
+  return d.act_floats * sizeof(float);
+}
+
+int hdrnet_coefficients_f32(const float* lowres, float* grid, const float* const* weights,
+                            const float* const* biases, int n_layers, void* scratch, size_t scratch_bytes,
+                            int B, int net_input_size, int spatial_bin, int luma_bins,
+                            int channel_multiplier, int n_out, int n_in, void* stream) {
+  if (B < 0 || n_out < 1 || n_in < 1) return HDRNET_E_BAD_SHAPE;
+  if (B == 0) return HDRNET_OK;
+  if (!lowres || !grid || !weights || !biases || !scratch) return HDRNET_E_NULL_POINTER;
+  CoefPlan d;
+  if (!coef_plan(net_input_size, spatial_bin, luma_bins, channel_multiplier, B, &d)) return HDRNET_E_UNSUPPORTED;
+  if (n_layers != d.n_ds + 8) return HDRNET_E_BAD_SHAPE;
+  if (scratch_bytes < d.act_floats * sizeof(float)) return HDRNET_E_BAD_SHAPE;
+  for (int i = 0; i < n_layers; ++i)
+    if (!weights[i]) return HDRNET_E_NULL_POINTER;
+  if (reinterpret_cast<uintptr_t>(scratch) & 15u) return HDRNET_E_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* cur = static_cast<float*>(scratch);
+  const auto take = [&](size_t n) { float* p = cur; cur += (n + 3) & ~static_cast<size_t>(3); return p; };
+  int rc = HDRNET_OK;
+  // layer order of `weights` / `biases`: splat conv1..n_ds, global conv1, conv2, fc1, fc2, fc3,
+  // local conv1, conv2, prediction conv1
+  const float* in = lowres;
+  int H = net_input_size, C = 3, li = 0;
+  for (int i = 0; i < d.n_ds; ++i, ++li) {
+    const int OH = H / 2;
+    float* out = take(static_cast<size_t>(B) * OH * OH * d.c_splat[i]);
+    ConvArgs a;
+    rc = conv_fill(&a, in, weights[li], biases[li], out, B, H, H, C, d.c_splat[i], 3, 2, 1);
+    if (!rc) rc = conv_dispatch(a, /*pdl=*/i > 0, st);
+    if (rc) return rc;
+    in = out; H = OH; C = d.c_splat[i];
+  }
+  const float* splat = in;   // [B, sb, sb, C]
+  const int sb = spatial_bin, c8 = d.c8;
+  float* g1 = take(static_cast<size_t>(B) * d.g1 * d.g1 * c8);
+  float* g2 = take(static_cast<size_t>(B) * d.g2 * d.g2 * c8);
+  float* l1 = take(static_cast<size_t>(B) * sb * sb * c8);
+  float* l2 = take(static_cast<size_t>(B) * sb * sb * c8);
+  float* f1 = take(static_cast<size_t>(B) * d.f1);
+  float* f2 = take(static_cast<size_t>(B) * d.f2);
+  float* f3 = take(static_cast<size_t>(B) * c8);
+  const int gi = li, fi = li + 2, lci = li + 5, pi = li + 7;
+  ConvArgs ga, la;
+  rc = conv_fill(&ga, splat, weights[gi], biases[gi], g1, B, sb, sb, C, c8, 3, 2, 1);
+  if (!rc) rc = conv_fill(&la, splat, weights[lci], biases[lci], l1, B, sb, sb, C, c8, 3, 1, 1);
+  if (!rc) rc = conv_dispatch_pair(la, ga, true, st);
+  if (rc) return rc;
+  rc = conv_fill(&ga, g1, weights[gi + 1], biases[gi + 1], g2, B, d.g1, d.g1, c8, c8, 3, 2, 1);
+  if (!rc) rc = conv_fill(&la, l1, weights[lci + 1], biases[lci + 1], l2, B, sb, sb, c8, c8, 3, 1, 0);
+  if (!rc) rc = conv_dispatch_pair(la, ga, true, st);
+  if (rc) return rc;
+  const int n[4] = {d.g2 * d.g2 * c8, d.f1, d.f2, c8};   // NHWC flatten = the buffer as it lies (models.py:94-95)
+  const float* fw[3] = {weights[fi], weights[fi + 1], weights[fi + 2]};
+  const float* fb[3] = {biases[fi], biases[fi + 1], biases[fi + 2]};
+  if (fc_chain_ok(B, n, fw)) {
+    rc = launch_fc_chain(g2, fw, fb, f3, B, n, true, st);
+  } else {
+    rc = hdrnet_fc_f32(g2, fw[0], fb[0], f1, B, n[0], n[1], 1, stream);
+    if (!rc) rc = hdrnet_fc_f32(f1, fw[1], fb[1], f2, B, n[1], n[2], 1, stream);
+    if (!rc) rc = hdrnet_fc_f32(f2, fw[2], fb[2], f3, B, n[2], n[3], 0, stream);
+  }
+  if (rc) return rc;
+  return fuse_predict_launch(l2, f3, weights[pi], biases[pi], grid, B, sb, sb, c8, luma_bins, n_out, n_in, true, st);
 }
 
 }  // extern "C"

@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import collections
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -144,12 +145,12 @@ def init_weights(params, seed: int = 0, model_name: str | None = None) -> dict:
     return w
 
 
-# Batches up to this size run the coefficient network as one persistent cooperative kernel
-# (csrc/cnn_persistent.cu) instead of twelve per-layer launches.  0 = never: the first version of
-# that kernel (one warp task = 32 outputs, operands straight from L1 / L2) is correct but no
-# faster -- 190 us against 177 us per layer at batch 1, 293 / 185 at batch 2 (tools/time_cnn.py) --
-# so it is not the default.  Tests set this to force either path.
-PERSISTENT_CNN_MAX_BATCH = 0
+# Batches up to this size run the coefficient network through ONE library call
+# (hdrnet_coefficients_f32, csrc/cnn.cu: 8 launches chained with programmatic dependent launch, the
+# global and local branches sharing launches, fc1-fc3 in one cluster) instead of twelve per-layer
+# calls from Python; larger batches go layer by layer so that the convs can use the packed
+# tensor-core weights.  Measured crossover: tools/time_cnn.py.  Tests set this to force either path.
+CHAIN_CNN_MAX_BATCH = 4
 
 # ---- prepared (device-resident, BN-folded) weights ---------------------------------------------
 # Keyed by the identity of the weights dict: an entry keeps a reference to its dict (so the id
@@ -454,9 +455,9 @@ class HDRNetCurves(object):
         p = "inference/coefficients"
         n_ds = int(np.log2(params["net_input_size"] / params["spatial_bin"]))
         bs = x.shape[0]
-        # small batches: the whole network as ONE persistent cooperative kernel (csrc/cnn_persistent.cu)
-        if bs <= PERSISTENT_CNN_MAX_BATCH:
-            grid = cls._coefficients_persistent(x, prep, params, n_ds)
+        # small batches: the whole network behind one library call (launch chain, csrc/cnn.cu)
+        if bs <= CHAIN_CNN_MAX_BATCH and os.environ.get("HDRNET_CONV_TCGEN05") != "1":
+            grid = cls._coefficients_chain(x, prep, params, n_ds)
             if grid is not None:
                 return grid
         with torch.cuda.device(x.device):
@@ -483,8 +484,8 @@ class HDRNetCurves(object):
         return grid
 
     @classmethod
-    def _coefficients_persistent(cls, x, prep, params, n_ds):
-        """One launch for all layers; None when the library does not take the shape."""
+    def _coefficients_chain(cls, x, prep, params, n_ds):
+        """One library call for all layers; None when the library does not take the shape."""
         lib = _lib.load()
         bs, S = x.shape[0], x.shape[1]
         gd, cm, sb = params["luma_bins"], params["channel_multiplier"], params["spatial_bin"]
@@ -512,7 +513,7 @@ class HDRNetCurves(object):
                                              cls.n_in(), torch.cuda.current_stream(x.device).cuda_stream)
         if rc == _lib.E_UNSUPPORTED:
             return None
-        _lib.check(rc, "coefficients (persistent kernel)")
+        _lib.check(rc, "coefficients (launch chain)")
         return grid
 
     @classmethod

@@ -250,17 +250,21 @@ HDRNET_API int hdrnet_fuse_predict_f32(const float* local, const float* global_f
 
 /*
  * The WHOLE coefficient network (splat convs, global convs + fcs, local convs, fusion, prediction,
- * unroll_grid) as one persistent cooperative kernel -- for small batches, where twelve separate
- * launches are latency-bound (177 us at batch 1; this: one launch).  Replaces
- * HDRNetCurves._coefficients, hdrnet/models.py:62-142, with batch norm folded by the caller.
+ * unroll_grid) behind one call: replaces HDRNetCurves._coefficients, hdrnet/models.py:62-142, with
+ * batch norm folded by the caller.  At small batch the twelve layers are 8 launches -- the global
+ * and the local branch (both read the splat features) share a launch per depth, fc1-fc3 run in one
+ * 8-CTA cluster with activations in distributed shared memory -- chained with programmatic
+ * dependent launch so that each layer's launch and weight fetch overlap the previous layer's tail
+ * (batch 1: 65 us against 150 us for twelve per-layer calls, tools/time_cnn.py).
  *   lowres [B, S, S, 3] float32 -> grid [B, sb, sb, gd, n_out, n_in] float32
  *   weights / biases: HOST arrays of n_layers = n_ds + 8 DEVICE pointers (n_ds = log2(S / sb)), in
  *     the order splat conv1..n_ds, global conv1, conv2, fc1, fc2, fc3, local conv1, conv2,
  *     prediction conv1; conv weights HWIO, fc / prediction weights [in][out]; a bias may be NULL;
  *   scratch: hdrnet_coefficients_scratch_bytes(...) bytes of device memory, 16-byte aligned (every
- *     layer's activations; the library never allocates).  0 bytes = shape not supported (channel
- *     counts that are not powers of two, S / sb not a power of two): use the per-layer kernels.
- * Returns HDRNET_E_UNSUPPORTED for such shapes or when the device cannot launch cooperatively.
+ *     layer's activations, each in a buffer of its own; the library never allocates).  0 bytes =
+ *     S / sb is not a power of two >= 2 (HDRNET_E_UNSUPPORTED from the call).
+ * Layers whose shape a fast form does not take (channels % 4, fc widths not powers of two, large
+ * batches) run the general kernels inside the same call.
  */
 HDRNET_API size_t hdrnet_coefficients_scratch_bytes(int B, int net_input_size, int spatial_bin,
                                                     int luma_bins, int channel_multiplier, int n_out,

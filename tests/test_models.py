@@ -143,10 +143,10 @@ def test_coefficients_match_oracle(name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(PARAM_SETS))
 @pytest.mark.parametrize("B", [1, 4])
-def test_coefficients_persistent_and_per_layer_paths_agree(name, B, monkeypatch):
-    """Small batches run the whole network as one persistent cooperative kernel
-    (csrc/cnn_persistent.cu), larger ones layer by layer: both against the oracle, and against each
-    other (same summation order per output: agreement to float32 round-off)."""
+def test_coefficients_chain_and_per_layer_paths_agree(name, B, monkeypatch):
+    """Small batches run the whole network behind one library call (hdrnet_coefficients_f32: launch
+    chain with paired branches and the fc cluster chain), larger ones layer by layer: both against
+    the oracle, and against each other (float32 round-off: the reductions are split differently)."""
     p = PARAM_SETS[name]
     wts = M.make_weights(p, seed=3)
     S = p["net_input_size"]
@@ -156,34 +156,65 @@ def test_coefficients_persistent_and_per_layer_paths_agree(name, B, monkeypatch)
     lib = _lib.load()
     assert lib.hdrnet_coefficients_scratch_bytes(B, S, p["spatial_bin"], p["luma_bins"], p["channel_multiplier"],
                                                  cls.n_out(), cls.n_in()) > 0
-    monkeypatch.setattr(models, "PERSISTENT_CNN_MAX_BATCH", 64)
+    monkeypatch.delenv("HDRNET_CONV_TCGEN05", raising=False)
+    monkeypatch.setattr(models, "CHAIN_CNN_MAX_BATCH", 64)
     one = cls._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
-    monkeypatch.setattr(models, "PERSISTENT_CNN_MAX_BATCH", 0)
+    monkeypatch.setattr(models, "CHAIN_CNN_MAX_BATCH", 0)
     many = cls._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
-    assert_parity(one, ref, rtol=2e-5, what=f"{name} persistent", elem_rtol=None)
+    assert_parity(one, ref, rtol=2e-5, what=f"{name} chain", elem_rtol=None)
     assert_parity(many, ref, rtol=2e-5, what=f"{name} per layer", elem_rtol=None)
-    assert_parity(one, many, rtol=5e-6, what=f"{name} persistent vs per layer", elem_rtol=None)
+    assert_parity(one, many, rtol=5e-6, what=f"{name} chain vs per layer", elem_rtol=None)
 
 
 @pytest.mark.gpu
-def test_persistent_coefficient_kernel_refuses_shapes_it_cannot_take():
+def test_coefficient_chain_argument_checks_and_odd_channel_counts(monkeypatch):
     lib = _lib.load()
-    assert lib.hdrnet_coefficients_scratch_bytes(1, 256, 16, 6, 1, 3, 4) == 0      # 6 depth bins: channels not a power of two
     assert lib.hdrnet_coefficients_scratch_bytes(1, 240, 16, 8, 1, 3, 4) == 0      # 240 / 16 not a power of two
     assert lib.hdrnet_coefficients_scratch_bytes(0, 256, 16, 8, 1, 3, 4) == 0
+    assert lib.hdrnet_coefficients_scratch_bytes(1, 256, 16, 8, 1, 3, 4) > 0
     z = torch.zeros(64, device="cuda")
     import ctypes
     arr = (ctypes.c_void_p * 12)(*([z.data_ptr()] * 12))
-    rc = lib.hdrnet_coefficients_f32(z.data_ptr(), z.data_ptr(), arr, arr, 12, z.data_ptr(), 256, 1, 256, 16, 6, 1, 3, 4, 0)
+    rc = lib.hdrnet_coefficients_f32(z.data_ptr(), z.data_ptr(), arr, arr, 12, z.data_ptr(), 256, 1, 240, 16, 8, 1, 3, 4, 0)
     assert rc == _lib.E_UNSUPPORTED
     rc = lib.hdrnet_coefficients_f32(z.data_ptr(), z.data_ptr(), arr, arr, 11, z.data_ptr(), 1 << 30, 1, 256, 16, 8, 1, 3, 4, 0)
     assert rc == _lib.E_BAD_SHAPE                                                  # n_layers must be n_ds + 8
-    # a model with 6 depth bins still runs (per-layer kernels)
+    rc = lib.hdrnet_coefficients_f32(z.data_ptr(), z.data_ptr(), arr, arr, 12, z.data_ptr(), 256, 1, 256, 16, 8, 1, 3, 4, 0)
+    assert rc == _lib.E_BAD_SHAPE                                                  # scratch too small
+    # 6 depth bins: channel counts 6 / 12 / 24 / 48 -- not multiples of 4 early on, fc widths not
+    # powers of two: the chain falls back layer by layer to the general kernels, same result
     p = dict(M.DEFAULT_PARAMS, luma_bins=6, net_input_size=64, spatial_bin=16)
     wts = M.make_weights(p, seed=1)
     low = np.random.RandomState(2).rand(1, 64, 64, 3).astype(np.float32)
-    got = models.HDRNetCurves._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
-    assert_parity(got, M.coefficients(low, wts, p), rtol=2e-5, elem_rtol=None)
+    monkeypatch.delenv("HDRNET_CONV_TCGEN05", raising=False)
+    for mb in (64, 0):
+        monkeypatch.setattr(models, "CHAIN_CNN_MAX_BATCH", mb)
+        got = models.HDRNetCurves._coefficients(cuda(low), dict(p, weights=wts)).cpu().numpy()
+        assert_parity(got, M.coefficients(low, wts, p), rtol=2e-5, elem_rtol=None, what=f"chain max batch {mb}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,cin,cout,stride,relu,bias", [
+    (1, 16, 64, 64, 1, True, True),      # local conv1 at batch 1: 4 output channels per CTA
+    (2, 16, 64, 64, 1, False, False),    # local conv2 at batch 2: 8 per CTA
+    (1, 16, 64, 64, 2, True, True),      # global conv1
+    (1, 8, 64, 64, 2, True, True),       # global conv2: 16 pixels, half a tile
+    (1, 128, 8, 16, 2, True, True),      # splat conv2: 2 chunks per tap
+    (3, 9, 12, 20, 2, True, True),       # odd extents (asymmetric SAME pads), 3 chunks per tap, Cout % 8 != 0
+    (1, 7, 4, 4, 1, False, True),        # one chunk per tap, one channel group
+])
+def test_small_conv_layers_patch_form_against_oracle(B, H, cin, cout, stride, relu, bias):
+    """conv2d_patch_kernel (the shared-memory patch form AUTO takes for small layers, csrc/cnn.cu)
+    against the float64-accumulating oracle conv (hdrnet/layers.py:25-59 semantics)."""
+    rng = np.random.RandomState(B * 100 + H)
+    x = rng.randn(B, H, H, cin).astype(np.float32)
+    w = (rng.randn(3, 3, cin, cout) * 0.2).astype(np.float32)
+    b = rng.randn(cout).astype(np.float32) if bias else None
+    ref = M.conv2d_same(x, w, stride) + (0 if b is None else b)
+    if relu:
+        ref = np.maximum(ref, 0)
+    got = models._conv(cuda(x), (cuda(w), None if b is None else cuda(b)), stride=stride, relu=relu).cpu().numpy()
+    assert_parity(got, ref.astype(np.float32), rtol=5e-6, elem_rtol=None)
 
 
 @pytest.mark.gpu
@@ -275,7 +306,7 @@ def test_run_py_identity_sample_plumbing(tmp_path):
 @pytest.fixture
 def tcgen05_convs(monkeypatch):
     monkeypatch.setenv("HDRNET_CONV_TCGEN05", "1")
-    monkeypatch.setattr(models, "PERSISTENT_CNN_MAX_BATCH", 0)    # per-layer kernels, not the persistent one
+    monkeypatch.setattr(models, "CHAIN_CNN_MAX_BATCH", 0)    # per-layer calls from Python, not the chain
     yield
 
 

@@ -1,4 +1,4 @@
-"""Coefficient network: one persistent cooperative kernel vs the per-layer kernels, by batch size."""
+"""Coefficient network: one-call launch chain vs the per-layer kernels, by batch size."""
 import os, sys, statistics, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hdrnet_b200 import models
@@ -16,11 +16,11 @@ def t(fn, iters=50):
     return a.elapsed_time(b) / iters * 1e3
 
 
-for B in (1, 2, 4, 8):
+for B in (1, 2, 4, 8, 16, 64):
     low = torch.rand(B, 256, 256, 3, device="cuda")
     res = {}
-    for label, mb in (("persistent", 64), ("per-layer", 0)):
-        models.PERSISTENT_CNN_MAX_BATCH = mb
+    for label, mb in (("chain", 64), ("per-layer", 0)):
+        models.CHAIN_CNN_MAX_BATCH = mb
         f = lambda: models.HDRNetCurves._coefficients(low, p)
         res[label] = statistics.median(t(f) for _ in range(3))
         g = torch.cuda.CUDAGraph()      # launch overhead out: the kernels' own time
