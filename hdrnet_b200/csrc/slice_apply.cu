@@ -35,6 +35,8 @@
 // gather forms) live in tools/experiments/ with their profiles; they are not part of the library.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <algorithm>
 #include <climits>
 #include <cstdint>
@@ -149,20 +151,30 @@ struct AnyArgs {
   int row_floats;           // gw * gd * gc
 };
 
-template <bool kApply>
+// kGc > 0: the channel counts are compile-time (kGc grid channels; kApply: kIn inputs, kOut
+// outputs, offset when kGc == kOut * (kIn + 1)).  The slab then pads each cell to a multiple of 4
+// floats, a corner is kGc / 4 128-bit shared loads instead of kGc scalar ones, and the affine
+// apply runs out of registers.  kGc == 0: any counts at run time (scalar loads).  Same order of
+// floating-point operations in both.
+template <bool kApply, int kGc, int kIn, int kOut>
 __global__ void __launch_bounds__(kAnyThreads, 4)
 slice_rows_any_kernel(const AnyArgs a) {
   extern __shared__ __align__(16) float sm_any[];
   const SliceGeom& g = a.g;
+  constexpr int kGcp = (kGc + 3) / 4 * 4;            // padded cell stride of the slab (kGc > 0)
+  const int gc = kGc > 0 ? kGc : a.gc;
+  const int cell_stride = kGc > 0 ? kGcp : a.gc;
+  const int cells = g.gw * g.gd;
   float* raw0 = sm_any;
-  float* raw1 = raw0 + a.row_floats;
-  float* slab = raw1 + a.row_floats;
+  float* raw1 = raw0 + ((a.row_floats + 3) & ~3);
+  float* slab = raw1 + ((a.row_floats + 3) & ~3);
   const int tid = threadIdx.x;
   const long long total_rows = static_cast<long long>(g.B) * g.rows;
   const long long r_begin = total_rows * blockIdx.x / gridDim.x;
   const long long r_end = total_rows * (blockIdx.x + 1) / gridDim.x;
   const float gd_f = static_cast<float>(g.gd);
-  const int x_stride = g.gd * a.gc;
+  const int x_stride = g.gd * cell_stride;
+  const bool out_vec = (reinterpret_cast<uintptr_t>(a.out) & 15u) == 0;
   int cur_b = -1, cur_gy0 = INT_MIN;
   for (long long row = r_begin; row < r_end; ++row) {
     const int b = static_cast<int>(row / g.rows);
@@ -179,7 +191,14 @@ slice_rows_any_kernel(const AnyArgs a) {
       __syncthreads();
     }
     const float wy1 = ay.f, wy0 = 1.0f - ay.f;
-    for (int e = tid; e < a.row_floats; e += kAnyThreads) slab[e] = fmaf(wy1, raw1[e], wy0 * raw0[e]);   // lerp4's order
+    if constexpr (kGc > 0 && kGcp != kGc) {
+      for (int e = tid; e < cells * kGcp; e += kAnyThreads) {
+        const int cell = e / kGcp, ch = e - cell * kGcp;
+        slab[e] = ch < kGc ? fmaf(wy1, raw1[cell * kGc + ch], wy0 * raw0[cell * kGc + ch]) : 0.0f;
+      }
+    } else {
+      for (int e = tid; e < a.row_floats; e += kAnyThreads) slab[e] = fmaf(wy1, raw1[e], wy0 * raw0[e]);   // lerp4's order
+    }
     __syncthreads();
     const size_t pix0 = static_cast<size_t>(row) * g.W;
     for (int x = tid; x < g.W; x += kAnyThreads) {
@@ -187,7 +206,7 @@ slice_rows_any_kernel(const AnyArgs a) {
       const Axis ax = spatial_axis(x, g.scale_x);
       const Axis az = range_axis(__ldg(a.guide + p), gd_f);
       const int xo0 = clampi(ax.i0, 0, g.gw - 1) * x_stride, xo1 = clampi(ax.i0 + 1, 0, g.gw - 1) * x_stride;
-      const int zo0 = clampi(az.i0, 0, g.gd - 1) * a.gc, zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * a.gc;
+      const int zo0 = clampi(az.i0, 0, g.gd - 1) * cell_stride, zo1 = clampi(az.i0 + 1, 0, g.gd - 1) * cell_stride;
       float wz0, wz1;
       smoothed_weights(az.f, wz0, wz1);
       const float wx1 = ax.f, wx0 = 1.0f - ax.f;
@@ -196,20 +215,57 @@ slice_rows_any_kernel(const AnyArgs a) {
       const float* c01 = slab + xo0 + zo1;
       const float* c10 = slab + xo1 + zo0;
       const float* c11 = slab + xo1 + zo1;
-      auto coef = [&](int ch) {   // the row kernels' order of operations
-        return fmaf(w11, c11[ch], fmaf(w10, c10[ch], fmaf(w01, c01[ch], w00 * c00[ch])));
-      };
-      if constexpr (kApply) {
-        for (int i = 0; i < a.n_out; ++i) {
-          float value = 0.0f;
-          for (int j = 0; j < a.J; ++j) {
-            const float sv = coef(i * a.J + j);
-            value = (j < a.n_in) ? fmaf(sv, __ldg(a.input + p * a.n_in + j), value) : value + sv;
+      if constexpr (kGc > 0) {
+        float cf[kGcp];
+#pragma unroll
+        for (int q4 = 0; q4 < kGcp / 4; ++q4) {
+          const float4 v00 = *reinterpret_cast<const float4*>(c00 + 4 * q4);
+          const float4 v01 = *reinterpret_cast<const float4*>(c01 + 4 * q4);
+          const float4 v10 = *reinterpret_cast<const float4*>(c10 + 4 * q4);
+          const float4 v11 = *reinterpret_cast<const float4*>(c11 + 4 * q4);
+          cf[4 * q4 + 0] = fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, w00 * v00.x)));
+          cf[4 * q4 + 1] = fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, w00 * v00.y)));
+          cf[4 * q4 + 2] = fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, w00 * v00.z)));
+          cf[4 * q4 + 3] = fmaf(w11, v11.w, fmaf(w10, v10.w, fmaf(w01, v01.w, w00 * v00.w)));
+        }
+        if constexpr (kApply) {
+          constexpr int kJ = kGc / kOut;
+          float in[kIn];
+#pragma unroll
+          for (int j = 0; j < kIn; ++j) in[j] = __ldg(a.input + p * kIn + j);
+#pragma unroll
+          for (int i = 0; i < kOut; ++i) {
+            float value = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kJ; ++j)
+              value = (j < kIn) ? fmaf(cf[i * kJ + j], in[j], value) : value + cf[i * kJ + j];
+            a.out[p * kOut + i] = value;
           }
-          a.out[p * a.n_out + i] = value;
+        } else if ((kGc % 4 == 0) && out_vec) {   // a pixel is kGc * 4 bytes: 16-byte aligned whenever the base is
+#pragma unroll
+          for (int q4 = 0; q4 < kGc / 4; ++q4)
+            *reinterpret_cast<float4*>(a.out + p * kGc + 4 * q4) =
+                make_float4(cf[4 * q4], cf[4 * q4 + 1], cf[4 * q4 + 2], cf[4 * q4 + 3]);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < kGc; ++ch) a.out[p * kGc + ch] = cf[ch];
         }
       } else {
-        for (int ch = 0; ch < a.gc; ++ch) a.out[p * a.gc + ch] = coef(ch);
+        auto coef = [&](int ch) {   // the row kernels' order of operations
+          return fmaf(w11, c11[ch], fmaf(w10, c10[ch], fmaf(w01, c01[ch], w00 * c00[ch])));
+        };
+        if constexpr (kApply) {
+          for (int i = 0; i < a.n_out; ++i) {
+            float value = 0.0f;
+            for (int j = 0; j < a.J; ++j) {
+              const float sv = coef(i * a.J + j);
+              value = (j < a.n_in) ? fmaf(sv, __ldg(a.input + p * a.n_in + j), value) : value + sv;
+            }
+            a.out[p * a.n_out + i] = value;
+          }
+        } else {
+          for (int ch = 0; ch < gc; ++ch) a.out[p * gc + ch] = coef(ch);
+        }
       }
     }
   }
@@ -217,18 +273,41 @@ slice_rows_any_kernel(const AnyArgs a) {
 
 // false when the shape does not suit it (slab rows larger than a quarter SM's shared memory,
 // images too narrow to fill a CTA): the caller then runs slice_generic_kernel.
-template <bool kApply>
-static bool launch_rows_any(const AnyArgs& a, int max_smem, int sms, cudaStream_t stream, int* rc) {
-  const size_t smem = 3u * static_cast<size_t>(a.row_floats) * sizeof(float);
+template <bool kApply, int kGc, int kIn, int kOut>
+static bool launch_rows_any_t(const AnyArgs& a, int max_smem, int sms, cudaStream_t stream, int* rc) {
+  constexpr int kGcp = (kGc + 3) / 4 * 4;
+  const size_t raw = (static_cast<size_t>(a.row_floats) + 3) & ~static_cast<size_t>(3);
+  const size_t slab = kGc > 0 ? static_cast<size_t>(a.g.gw) * a.g.gd * kGcp : raw;
+  const size_t smem = (2 * raw + slab) * sizeof(float);
   if (a.g.W < 64 || smem > static_cast<size_t>((max_smem + 1024) / 4 - 1024)) return false;
-  auto kern = slice_rows_any_kernel<kApply>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) { *rc = static_cast<int>(e); return true; }
+  auto kern = slice_rows_any_kernel<kApply, kGc, kIn, kOut>;
+  static std::atomic<int> granted{0};   // sticky per-function attribute: only ever raise it
+  if (granted.load(std::memory_order_relaxed) < static_cast<int>(smem)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (max_smem + 1024) / 4 - 1024);
+    if (e != cudaSuccess) { *rc = static_cast<int>(e); return true; }
+    granted.store((max_smem + 1024) / 4 - 1024, std::memory_order_relaxed);
+  }
   const long long rows = static_cast<long long>(a.g.B) * a.g.rows;
   const int ctas = static_cast<int>(std::min<long long>(rows, static_cast<long long>(sms) * 4));
   kern<<<ctas, kAnyThreads, smem, stream>>>(a);
   *rc = static_cast<int>(cudaGetLastError());
   return true;
+}
+
+// The common shapes get compile-time channel counts: the 3 -> 3 affine op with and without offset
+// (what the TMA kernels take, at widths / alignments they do not; ops_test.py:345-365), and the
+// un-fused slice of a 12-channel grid.
+template <bool kApply>
+static bool launch_rows_any(const AnyArgs& a, int max_smem, int sms, cudaStream_t stream, int* rc) {
+  if constexpr (kApply) {
+    if (a.n_in == 3 && a.n_out == 3 && a.J == 4) return launch_rows_any_t<true, 12, 3, 3>(a, max_smem, sms, stream, rc);
+    if (a.n_in == 3 && a.n_out == 3 && a.J == 3) return launch_rows_any_t<true, 9, 3, 3>(a, max_smem, sms, stream, rc);
+    if (a.n_in == 3 && a.n_out == 9 && a.J == 4) return launch_rows_any_t<true, 36, 3, 9>(a, max_smem, sms, stream, rc);   // pyramid grid, hdrnet_ops_test.py:91-100
+    return launch_rows_any_t<true, 0, 0, 0>(a, max_smem, sms, stream, rc);
+  } else {
+    if (a.gc == 12) return launch_rows_any_t<false, 12, 0, 0>(a, max_smem, sms, stream, rc);
+    return launch_rows_any_t<false, 0, 0, 0>(a, max_smem, sms, stream, rc);
+  }
 }
 
 __global__ void __launch_bounds__(256)

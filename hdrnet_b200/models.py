@@ -149,8 +149,9 @@ def init_weights(params, seed: int = 0, model_name: str | None = None) -> dict:
 # (hdrnet_coefficients_f32, csrc/cnn.cu: 8 launches chained with programmatic dependent launch, the
 # global and local branches sharing launches, fc1-fc3 in one cluster) instead of twelve per-layer
 # calls from Python; larger batches go layer by layer so that the convs can use the packed
-# tensor-core weights.  Measured crossover: tools/time_cnn.py.  Tests set this to force either path.
-CHAIN_CNN_MAX_BATCH = 4
+# tensor-core weights.  Measured (tools/time_cnn.py): the chain wins up to batch 16 (221 vs 234 us),
+# loses at 64 (596 vs 487 us).  Tests set this to force either path.
+CHAIN_CNN_MAX_BATCH = 16
 
 # ---- prepared (device-resident, BN-folded) weights ---------------------------------------------
 # Keyed by the identity of the weights dict: an entry keeps a reference to its dict (so the id
