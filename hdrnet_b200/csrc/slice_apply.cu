@@ -1066,8 +1066,8 @@ static int launch_slice_apply_impl(const float* grid, const GuideSpec& gs, const
   TmaPlan fplan;
   const bool fused_async_ok = tex_ok && gs.mode != 0 &&
                               make_tma_plan(g, max_smem, sms, &fplan, /*tex_mode=*/true, kFusedAsyncMathThreads,
-                                            gs.in_fmt, gs.out_fmt, 2) &&
-                              fplan.resident == 2 && fplan.stages >= 3;
+                                            gs.in_fmt, gs.out_fmt, kFusedAsyncResident) &&
+                              fplan.resident == kFusedAsyncResident && fplan.stages >= 3;
 
   const bool auto_generic = variant == HDRNET_VARIANT_AUTO;   // GENERIC on request = the one-thread-per-pixel L2 gather
   if (variant == HDRNET_VARIANT_AUTO) {

@@ -3,7 +3,9 @@ the CURRENT environment (HDRNET_FUSED_ASYNC = unset / 0 / 1 is read once per pro
     for f in "" 0 1; do HDRNET_FUSED_ASYNC=$f python tools/time_fused.py; done"""
 import os, sys, statistics, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from hdrnet_b200 import models
+from hdrnet_b200 import models, _lib
+if os.environ.get("HDRNET_LIB_OVERRIDE"):      # an experimental build (tools/experiments/lib_alt*)
+    _lib.LIB_PATH = os.path.abspath(os.environ["HDRNET_LIB_OVERRIDE"])
 if os.environ.get("HDRNET_FUSED_ASYNC") == "":
     del os.environ["HDRNET_FUSED_ASYNC"]
 B, H, W = 8, 2160, 3840
@@ -28,4 +30,6 @@ for kind, name in (("curves", "HDRNetCurves"), ("nn", "HDRNetPointwiseNNGuide"))
             b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) / 20)
         out[f"{kind} {px}"] = statistics.median(ts)
-print("HDRNET_FUSED_ASYNC=%s  " % os.environ.get("HDRNET_FUSED_ASYNC", "unset") + "  ".join(f"{k}: {v:.4f} ms" for k, v in out.items()))
+import hashlib
+sha = hashlib.sha1(cls._fullres(coeffs, im8, p, torch.uint8).cpu().numpy().tobytes()).hexdigest()[:10]
+print("lib=%s FUSED_ASYNC=%s  u8-sha=%s  " % (os.environ.get("HDRNET_LIB_OVERRIDE", "product"), os.environ.get("HDRNET_FUSED_ASYNC", "unset"), sha) + "  ".join(f"{k}: {v:.4f} ms" for k, v in out.items()))
