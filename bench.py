@@ -438,9 +438,8 @@ def run_b200_arm(args):
     h_im8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8).pin_memory()
     h_out8 = torch.empty(B, H, W, 3, dtype=torch.uint8).pin_memory()
 
-    def e2e_u8_step():
-        d_im = h_im8.to(dev, non_blocking=True)
-        h_out8.copy_(models.HDRNetCurves.inference_image(d_im, mp), non_blocking=True)
+    def e2e_u8_step():   # frame-pipelined: upload i + 1 | model i | download i - 1 (host_pipeline.py)
+        models.HDRNetCurves.inference_image_host(h_im8, mp, out=h_out8, device=dev)
     e2e_u8_step()
     torch.cuda.synchronize()
     barrier()
@@ -521,8 +520,9 @@ def run_b200_arm(args):
                         "value": round(world * npix * e2e_steps / e2e8_s / 1e6, 1), "unit": UNIT,
                         "h2d_bytes_per_step": int(npix * 3), "d2h_bytes_per_step": int(npix * 3),
                         "ms_per_step": round(e2e8_s / e2e_steps * 1e3, 3),
-                        "path": "pinned uint8 frames -> models.HDRNetCurves.inference_image (lowres gather + "
-                                "coefficient CNN + fused-guide slice-apply, uint8 in / out) -> pinned uint8"},
+                        "path": "pinned uint8 frames -> models.HDRNetCurves.inference_image_host: per frame upload | "
+                                "inference_image (lowres gather + coefficient CNN chain + fused-guide slice-apply, "
+                                "uint8 in / out) | download on three streams -> pinned uint8"},
                     "numa_cpus_bound": len(numa_cpus)},
             "gpu_launches": (1 if threads.value == 384 else 2) * args.steps * world,
             "clocks": sampler.summary(),

@@ -153,6 +153,8 @@ def init_weights(params, seed: int = 0, model_name: str | None = None) -> dict:
 # loses at 64 (596 vs 487 us).  Tests set this to force either path.
 CHAIN_CNN_MAX_BATCH = 16
 
+_host_pipelines = {}   # (model class, device, out dtype) -> HostImagePipeline (inference_image_host)
+
 # ---- prepared (device-resident, BN-folded) weights ---------------------------------------------
 # Keyed by the identity of the weights dict: an entry keeps a reference to its dict (so the id
 # cannot be recycled while the entry lives), the cache holds the most recent kPreparedMax entries,
@@ -402,6 +404,22 @@ class HDRNetCurves(object):
         lowres = lowres_from_image(src, int(params["net_input_size"]))
         coeffs = cls._coefficients(lowres, params, False)
         return cls._fullres(coeffs, image, params, out_dtype)
+
+    @classmethod
+    def inference_image_host(cls, frames, params, out=None, device=None, out_dtype=torch.uint8):
+        """``inference_image`` for frames that live in HOST memory (what hdrnet/bin/run.py does per
+        file: load, ``sess.run``, save): uploads, the model and downloads of consecutive frames
+        overlap on three streams (hdrnet_b200/host_pipeline.py).  ``frames`` [N,H,W,3] uint8 /
+        uint16 / float32 CPU tensor (pinned for asynchronous copies) -> CPU tensor of ``out_dtype``.
+        One pipeline (streams + two frame buffers) is kept per (class, device, out_dtype)."""
+        from .host_pipeline import HostImagePipeline
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        key = (cls, dev, out_dtype)
+        pipe = _host_pipelines.get(key)
+        if pipe is None:
+            pipe = _host_pipelines.setdefault(key, HostImagePipeline(cls, params, dev, out_dtype=out_dtype))
+        pipe.params = params
+        return pipe(frames, out)
 
     @classmethod
     def _fullres(cls, coeffs, fullres_input, params, out_dtype):

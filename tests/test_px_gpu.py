@@ -186,3 +186,30 @@ def test_fused_guide_issuer_warp_form_is_bitwise_equal():
         assert out.returncode == 0, out.stdout + out.stderr
         shas.append(dict(l.split()[1:3] for l in out.stdout.splitlines() if l.startswith("SHA256")))
     assert len(shas[0]) == 6 and shas[0] == shas[1]
+
+
+@pytest.mark.parametrize("kind,dtype,pinned", [("curves", torch.uint8, True), ("nn", torch.uint16, True),
+                                              ("curves", torch.uint8, False), ("pyramid", torch.uint8, True)])
+def test_host_frame_pipeline_equals_inference_image(kind, dtype, pinned):
+    """inference_image_host (upload | model | download of consecutive frames on three streams,
+    host_pipeline.py) against inference_image on the same frames, frame by frame: bitwise.  Five
+    frames through two device buffers exercise the buffer-reuse events; a second call with
+    different content reuses the pipeline object."""
+    p = params_for(kind)
+    wts = M.make_weights(p, seed=5)
+    cls = getattr(models, p["model_name"])
+    prm = dict(p, weights=wts)
+    g = torch.Generator().manual_seed(11)
+    hi = 256 if dtype == torch.uint8 else 65536
+    for rep in range(2):
+        frames = torch.randint(0, hi, (5, 48, 192, 3), generator=g, dtype=torch.int32).to(dtype)
+        if pinned:
+            frames = frames.pin_memory()
+        got = cls.inference_image_host(frames, prm)
+        assert got.dtype == torch.uint8 and not got.is_cuda and tuple(got.shape) == tuple(frames.shape)
+        for i in range(frames.shape[0]):
+            want = cls.inference_image(frames[i:i + 1].cuda(), prm).cpu()
+            assert torch.equal(got[i:i + 1], want), f"{kind}: frame {i} of call {rep} differs"
+    with pytest.raises(TypeError):
+        cls.inference_image_host(frames.cuda(), prm)
+    assert cls.inference_image_host(frames[:0], prm).shape[0] == 0
