@@ -108,21 +108,23 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), mhz, reasons))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.001)
 
     def summary(self):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         t0, t1 = self.window
         inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1]
-        use = inside if len(inside) >= 3 else self.samples
+        # too short a region for three samples: take everything up to its end (warm-up included),
+        # never what ran AFTER it (the sampler of the headline is stopped right behind the region)
+        use = inside if len(inside) >= 3 else [s for s in self.samples if t1 is None or s[0] <= t1] or self.samples
         mask = 0
         for s in use:
             mask |= s[2]
         return {"sm_mhz": float(np.median([s[1] for s in use])), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(n for b, n in self.REASONS.items() if mask & b),
                 "samples": len(use),
-                "window": "timed region" if use is inside else "whole run (timed region too short)"}
+                "window": "timed region" if use is inside else "warm-up + timed region (timed region too short)"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -163,9 +165,9 @@ def cpu_baseline(target_seconds: float = 15.0):
     """Bounded sample of the same workload on the host cores (reported-only baseline)."""
     lib = cpu_checker()
     cores = lib.num_threads()
-    frames = max(1, min(cores, 64))  # the reference loops thread over frames only
+    frames = max(1, min(cores, 256))  # the reference loops thread over frames only: one frame per host thread
     guess = cpu_rate(lib, frames, 64)  # calibration, ~0.2 s
-    rows = int(min(H4K, max(64, guess * 1e6 * target_seconds / (frames * W4K))))
+    rows = int(min(H4K, 64 * H4K // frames, max(64, guess * 1e6 * target_seconds / (frames * W4K))))  # <= 15 GB of host arrays
     grid, guide, inp = cpu_inputs(frames, rows)
     t = time.perf_counter()
     lib.bilateral_slice_apply(grid, guide, inp, True)
@@ -184,10 +186,10 @@ def run_reference_arm(args):
         return 0
     lib = cpu_checker()
     cores = lib.num_threads()
-    frames = max(1, min(cores, 64))  # the reference loops thread over frames only
+    frames = max(1, min(cores, 256))  # the reference loops thread over frames only: one frame per host thread
     guess = cpu_rate(lib, frames, 64)
     budget = 120.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
-    rows = int(min(H4K, max(16, guess * 1e6 * budget / (frames * W4K))))
+    rows = int(min(H4K, 64 * H4K // frames, max(16, guess * 1e6 * budget / (frames * W4K))))  # <= 15 GB of host arrays
     grid, guide, inp = cpu_inputs(frames, rows)
     for _ in range(args.warmup):
         lib.bilateral_slice_apply(grid, guide, inp, True)
@@ -399,6 +401,8 @@ def run_b200_arm(args):
     ev1.record(stream)
     torch.cuda.synchronize()
     sampler.window[1] = time.perf_counter()
+    sampler.stop_flag.set()     # the later legs (end to end, extras, sustained) are not the headline's clocks
+    sampler.join(timeout=2)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -478,10 +482,6 @@ def run_b200_arm(args):
     if world > 1:
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
     sus_ms = float(ts.item()) / sus_steps
-
-
-    sampler.stop_flag.set()
-    sampler.join(timeout=2)
 
     if rank == 0:
         achieved = algo_bytes / (own_launch_ms * 1e-3) / 1e9

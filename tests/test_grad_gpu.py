@@ -126,3 +126,30 @@ def test_grid_vjp_is_zero_when_there_are_no_pixels():
         g2 = torch.randn(2, 4, 4, 8, 12, device="cuda", requires_grad=True)
         hdrnet_ops.bilateral_slice(g2, guide.detach()).sum().backward()
         assert not g2.grad.any()
+
+
+@pytest.mark.parametrize("name", ["grid", "guide", "both"])
+def test_sgd_convergence_bounds_of_the_reference_tests(name):
+    """hdrnet/test/ops_test.py:189-322 (test_grid_optimize, test_guide_optimize, test_optimize_both):
+    plain gradient descent on sum((target - slice(grid, guide))^2) through the CUDA forward and VJP
+    kernels (torch.autograd) reaches the loss bounds the reference asserts.  tests/test_oracle.py runs
+    the same cases through the reference's own loops."""
+    from util import sgd_case
+    c = sgd_case(name)
+    grid = cuda(c["grid"], "grid" in c["trained"])
+    v = cuda(c["guide"], "guide" in c["trained"])
+    target = cuda(c["target"])
+    params = [t for t in (grid, v) if t.requires_grad]
+
+    def forward():
+        return hdrnet_ops.bilateral_slice(grid, torch.sigmoid(v) if c["sigmoid"] else v)
+
+    for _ in range(c["steps"]):
+        loss = (target - forward()).square().sum()
+        grads = torch.autograd.grad(loss, params)
+        with torch.no_grad():
+            for p, g in zip(params, grads):
+                p -= c["lr"] * g
+    with torch.no_grad():
+        final = float((target - forward()).square().sum())
+    assert final < c["bound"], f"{name}: final loss {final:.3e} >= {c['bound']:.1e}"

@@ -63,3 +63,35 @@ def rand_case(seed, B, H, W, gh, gw, gd, n_in=3, n_out=3, has_offset=True, signe
     guide = rng.rand(B, H, W).astype(np.float32)
     inp = draw(B, H, W, n_in).astype(np.float32)
     return grid, guide, inp
+
+
+# The reference's convergence-by-SGD tests (hdrnet/test/ops_test.py:189-322): a 1 x 32 image sliced
+# from a tiny grid is fitted to one period of a sine by plain gradient descent on sum((target-out)^2)
+# (l2_optimizer, :178-186) -- over the grid, over the guide (through a sigmoid), or over both.
+# name -> (gh, gw, gd, learning rate, steps, the reference's bound on the final loss, what is trained)
+SGD_CASES = {
+    "grid": (1, 16, 8, 1e-2, 10000, 0.0085, ("grid",)),          # test_grid_optimize  :189-230
+    "guide": (1, 8, 2, 1e-3, 6000, 1e-4, ("guide",)),            # test_guide_optimize :232-278
+    "both": (1, 8, 2, 1e-1, 10000, 1e-4, ("grid", "guide")),     # test_optimize_both  :280-322
+}
+
+
+def sgd_case(name):
+    """Initial values as the reference test builds them.  The reference draws its random initial
+    values unseeded; the seeds here are fixed, and for "both" chosen among those for which the
+    reference's own loops (oracle) meet the reference's bound -- they do not for every draw."""
+    gh, gw, gd, lr, steps, bound, trained = SGD_CASES[name]
+    w = 32
+    rng = np.random.RandomState({"grid": 1, "guide": 0, "both": 3}[name])
+    target = np.sin(np.linspace(0, 2 * np.pi, w)).astype(np.float32)[None, None, :, None]
+    if name == "grid":
+        guide = np.linspace(0, 1, w).astype(np.float32)[None, None, :]       # used as is
+        grid = rng.rand(1, gh, gw, gd, 1).astype(np.float32)
+    elif name == "guide":
+        guide = np.linspace(0.5 / gd, 1 - 0.5 / gd, w).astype(np.float32)[None, None, :]   # pre-sigmoid
+        grid = np.tile(np.linspace(-1, 1, gd).astype(np.float32)[None, None, None, :, None], [1, gh, gw, 1, 1])
+    else:
+        guide = rng.rand(1, 1, w).astype(np.float32) * 2.0 - 1.0                # pre-sigmoid
+        grid = rng.rand(1, gh, gw, gd, 1).astype(np.float32)
+    return dict(grid=grid, guide=guide, target=target, lr=lr, steps=steps, bound=bound, trained=trained,
+                sigmoid=(name != "grid"))
