@@ -236,11 +236,18 @@ def _time_ms(torch, stream, fn, iters, warm=3):
     return a.elapsed_time(b) / iters
 
 
-def _op_case(torch, lib, _lib, dev, stream, B, H, W, gh, gw, gd, iters, peak):
-    """Device-resident op-API call (guide as an input, f32) through the C-ABI with a lent workspace."""
+def _op_case(torch, lib, _lib, dev, stream, B, H, W, gh, gw, gd, iters, peak, smooth_guide=False):
+    """Device-resident op-API call (guide as an input, f32) through the C-ABI with a lent workspace.
+    smooth_guide: a low-frequency guide plus 1 % noise (a natural image's luminance varies slowly:
+    neighbouring pixels share a depth cell) instead of the headline's uniformly random one."""
     gen = torch.Generator(device=dev).manual_seed(7)
     grid = torch.rand(B, gh, gw, gd, GC, device=dev, generator=gen)
     guide = torch.rand(B, H, W, device=dev, generator=gen)
+    if smooth_guide:
+        yy = torch.linspace(0, 1, H, device=dev)[None, :, None]
+        xx = torch.linspace(0, 1, W, device=dev)[None, None, :]
+        bb = torch.arange(B, device=dev, dtype=torch.float32)[:, None, None] / max(B, 1)
+        guide = (0.5 + 0.45 * torch.sin(6.2831853 * (3 * xx + 2 * yy + bb)) + 0.01 * (guide - 0.5)).clamp_(0, 1)
     inp = torch.rand(B, H, W, N_IN, device=dev, generator=gen)
     out = torch.empty(B, H, W, N_OUT, device=dev)
     nws = int(lib.hdrnet_slice_apply_workspace_bytes(B, H, gw, gd))
@@ -328,6 +335,12 @@ def extra_records(torch, dist, lib, _lib, dev, stream, world, rank, peak, args):
         for gh, gw, gd in ((8, 8, 4), (16, 16, 4), (16, 16, 8), (32, 32, 8), (32, 32, 16)):
             sweep[f"{gh}x{gw}x{gd}"] = _op_case(torch, lib, _lib, dev, stream, B_PER_GPU, H4K, W4K, gh, gw, gd, 30, peak)
         ex["C5_grid_sweep_4k_x8"] = sweep
+        # the same shapes with a natural-image-like guide (the random one is the worst case for the
+        # shared-memory bank groups at 16 depth cells)
+        ex["C5_smooth_guide_4k_x8"] = {
+            f"{gh}x{gw}x{gd}": _op_case(torch, lib, _lib, dev, stream, B_PER_GPU, H4K, W4K, gh, gw, gd, 30, peak,
+                                        smooth_guide=True)
+            for gh, gw, gd in ((16, 16, 8), (32, 32, 16))}
     return ex
 
 # ------------------------------------------------------------------------------------------
