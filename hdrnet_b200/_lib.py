@@ -34,6 +34,8 @@ SIGNATURES = {
     "hdrnet_slice_apply_f32_variant": (_c_int, [_vp] * 4 + [_c_int] * 10 + [_vp]),
     "hdrnet_slice_apply_workspace_bytes": (ctypes.c_size_t, [_c_int] * 4),
     "hdrnet_slice_apply_f32_ws": (_c_int, [_vp] * 4 + [_c_int] * 10 + [_vp, ctypes.c_size_t, _vp]),
+    # (grid, guide, input, out, B,H,W, rows,y_off, gh,gw,gd, n_in,n_out,has_offset, variant, ws, bytes, stream)
+    "hdrnet_slice_apply_rows_f32_ws": (_c_int, [_vp] * 4 + [_c_int] * 12 + [_vp, ctypes.c_size_t, _vp]),
     "hdrnet_slice_f32": (_c_int, [_vp] * 3 + [_c_int] * 7 + [_vp]),
     "hdrnet_slice_f32_variant": (_c_int, [_vp] * 3 + [_c_int] * 8 + [_vp]),
     "hdrnet_slice_apply_grad_f32": (_c_int, [_vp] * 7 + [_c_int] * 9 + [_vp]),

@@ -1268,6 +1268,17 @@ int hdrnet_slice_apply_f32_ws(const float* grid, const float* guide, const float
                                  has_offset, variant, static_cast<cudaStream_t>(stream));
 }
 
+int hdrnet_slice_apply_rows_f32_ws(const float* grid, const float* guide, const float* input,
+                                   float* out, int B, int H, int W, int rows, int y_off, int gh,
+                                   int gw, int gd, int n_in, int n_out, int has_offset, int variant,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  GuideSpec gs{0, guide, nullptr, nullptr, nullptr};
+  gs.workspace = static_cast<float*>(workspace);
+  gs.workspace_bytes = workspace_bytes;
+  return launch_slice_apply_impl(grid, gs, input, out, B, H, W, rows, y_off, gh, gw, gd, n_in, n_out,
+                                 has_offset, variant, static_cast<cudaStream_t>(stream));
+}
+
 int hdrnet_slice_apply_f32(const float* grid, const float* guide, const float* input,
                            float* out, int B, int H, int W, int gh, int gw, int gd, int n_in,
                            int n_out, int has_offset, void* stream) {

@@ -27,7 +27,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["bilateral_slice", "bilateral_slice_apply", "slice_indices"]
+__all__ = ["bilateral_slice", "bilateral_slice_apply", "bilateral_slice_apply_rows", "slice_indices"]
 
 _ctx_lock = threading.Lock()
 _host_ctx = {}  # device index -> hdrnet_host_ctx*
@@ -254,6 +254,70 @@ def bilateral_slice_apply(grid: torch.Tensor, guide: torch.Tensor, input: torch.
                                              input.data_ptr(), out.data_ptr(), B, H, W, gh, gw,
                                              gd, n_in, n_out, int(has_offset))
     _lib.check(rc, "BilateralSliceApply(host)")
+    return out
+
+
+def bilateral_slice_apply_rows(grid: torch.Tensor, guide: torch.Tensor, input: torch.Tensor,  # noqa: A002
+                               has_offset: bool, y_off: int, height: int, *,
+                               out: torch.Tensor | None = None,
+                               variant: int = _lib.VARIANT_AUTO) -> torch.Tensor:
+    """A ROW BAND of ``bilateral_slice_apply``: ``guide`` [B, rows, W] and ``input`` [B, rows, W, n_in]
+    hold image rows ``y_off .. y_off + rows - 1`` of images that are ``height`` rows tall; the grid is
+    whole.  The op is pointwise in (x, y) (hdrnet/ops/bilateral_slice_apply.cu.cc:75, :80), so bands
+    need no halo and equal the rows of the whole-image call bit for bit (same kernel).  Beyond the
+    reference: it is the multi-GPU fallback for fewer images than GPUs (SURVEY.md section 8e,
+    ``parallel.slice_apply_sharded``).  Inference only (no gradient registration); CUDA tensors."""
+    lib = _lib.load()
+    grid = _f32c(grid, "grid")
+    guide = _f32c(guide, "guide")
+    input = _f32c(input, "input")  # noqa: A001
+    if grid.dim() != 5:
+        raise ValueError("Input grid should be 5D (batch_size, height, width, depth, "
+                         "output_channels * input_channels)")
+    if guide.dim() != 3:
+        raise ValueError("Guide image should be 3D (batch_size, height, width)")
+    if input.dim() != 4:
+        raise ValueError("Input image should be 4D (batch_size, height, width, input_channels)")
+    if tuple(input.shape[:3]) != tuple(guide.shape):
+        raise ValueError("Input and guide size should match.")
+    if guide.shape[0] != grid.shape[0]:
+        raise ValueError("Batch sizes should match.")
+    has_offset = bool(has_offset)
+    B, gh, gw, gd, gc = grid.shape
+    _, rows, W, n_in = input.shape
+    y_off, height = int(y_off), int(height)
+    if y_off < 0 or y_off + rows > height:
+        raise ValueError(f"row band [{y_off}, {y_off + rows}) does not fit an image of {height} rows")
+    J = n_in + (1 if has_offset else 0)
+    if gc % J != 0:
+        raise ValueError("Slicing with affine offset, grid should have output_channels * (input_channels + 1) "
+                         "channels." if has_offset else
+                         "Slicing without affine offset, grid should have output_channels * input_channels channels.")
+    n_out = gc // J
+    dev = _same_device(grid, guide, input)
+    _require_cuda()
+    if dev.type != "cuda":
+        raise _lib.HdrnetLibraryError("bilateral_slice_apply_rows: tensors must be CUDA tensors")
+    if _wants_grad(grid, guide, input):
+        raise ValueError("bilateral_slice_apply_rows is an inference path: call it under torch.no_grad() "
+                         "or use bilateral_slice_apply for gradients")
+    shape = (B, rows, W, n_out)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or out.device != dev or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 tensor of shape {shape} on {dev}")
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws_ptr, ws_bytes = 0, 0
+        explicit_tex = int(variant) in (_lib.VARIANT_TEX, _lib.VARIANT_TEX_ASYNC)
+        if (int(variant) == _lib.VARIANT_AUTO or explicit_tex) and n_in == 3 and n_out == 3 \
+                and has_offset and W % 4 == 0 and (explicit_tex or B * rows * W >= (1 << 21)):
+            ws = _workspace(dev, lib.hdrnet_slice_apply_workspace_bytes(B, rows, gw, gd))
+            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel() * 4
+        rc = lib.hdrnet_slice_apply_rows_f32_ws(
+            grid.data_ptr(), guide.data_ptr(), input.data_ptr(), out.data_ptr(), B, height, W, rows, y_off,
+            gh, gw, gd, n_in, n_out, int(has_offset), int(variant), ws_ptr, ws_bytes, stream)
+    _lib.check(rc, "BilateralSliceApply(rows)")
     return out
 
 

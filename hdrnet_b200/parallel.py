@@ -16,8 +16,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["init_distributed", "shard_batch", "shard_rows", "broadcast_weights",
-           "max_over_ranks", "finalize", "bind_to_gpu_numa", "gpu_cpu_affinity"]
+__all__ = ["init_distributed", "shard_batch", "shard_rows", "shard_plan", "slice_apply_sharded",
+           "broadcast_weights", "max_over_ranks", "finalize", "bind_to_gpu_numa", "gpu_cpu_affinity"]
 
 
 def gpu_cpu_affinity(device_index: int) -> list[int]:
@@ -88,6 +88,32 @@ def shard_rows(height: int, rank: int, world: int):
     images than GPUs.  Every band needs the whole (98 KB) grid; no halo is needed because the
     gather is pointwise in x, y (the kernels take the band's y offset and the full height)."""
     return shard_batch(height, rank, world)
+
+
+def shard_plan(n_images: int, height: int, rank: int, world: int):
+    """What rank `rank` of `world` computes of a job of `n_images` images of `height` rows:
+    ("batch", lo, hi) -- whole images [lo, hi) -- when every rank gets at least one image, else
+    ("rows", y0, y1) -- rows [y0, y1) of EVERY image (fewer images than GPUs).
+    The parts of all ranks tile the job exactly; a part may be empty (more ranks than rows)."""
+    if n_images >= world:
+        return ("batch",) + shard_batch(n_images, rank, world)
+    return ("rows",) + shard_rows(height, rank, world)
+
+
+def slice_apply_sharded(grid, guide, input, has_offset, rank: int, world: int):  # noqa: A002
+    """This rank's part of ``hdrnet_ops.bilateral_slice_apply(grid, guide, input, has_offset)`` over
+    the whole job's CUDA tensors (replicated or rank-local views): returns (plan, out_part) with
+    plan = shard_plan(...) and out_part = out[lo:hi] ("batch") or out[:, y0:y1] ("rows").  No
+    communication: the caller places the parts (they tile the output)."""
+    from . import hdrnet_ops
+    B, H = int(guide.shape[0]), int(guide.shape[1])
+    plan = shard_plan(B, H, rank, world)
+    kind, lo, hi = plan
+    with torch.no_grad():
+        if kind == "batch":
+            return plan, hdrnet_ops.bilateral_slice_apply(grid[lo:hi], guide[lo:hi], input[lo:hi], has_offset)
+        return plan, hdrnet_ops.bilateral_slice_apply_rows(grid, guide[:, lo:hi], input[:, lo:hi], has_offset,
+                                                           y_off=lo, height=H)
 
 
 def broadcast_weights(weights: dict | None, src: int = 0, device=None) -> dict:

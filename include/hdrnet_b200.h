@@ -103,6 +103,23 @@ HDRNET_API int hdrnet_slice_apply_f32_ws(const float* grid, const float* guide,
                                          size_t workspace_bytes, void* stream);
 
 /*
+ * Row band of the same op: guide / input / out hold `rows` image rows per image, starting at
+ * image row `y_off` of images that are H rows tall ([B, rows, W(, c)] dense); the grid is whole.
+ * The op is pointwise in (x, y) -- the kernel's only use of y is the grid coordinate
+ * (y + 0.5) * gh / H, hdrnet/ops/bilateral_slice_apply.cu.cc:52, :75, :80, :88-90 -- so bands need no halo
+ * and the bands of an image, computed anywhere, are bit for bit the rows of the whole-image call
+ * by the same kernel.  This is the multi-GPU fallback when there are fewer images than GPUs
+ * (each rank takes a row band and a copy of the 98 KB grid) and what the
+ * host path streams.  workspace (optional, may be NULL / 0): hdrnet_slice_apply_workspace_bytes(B,
+ * rows, gw, gd) bytes.  rows == H, y_off == 0 is hdrnet_slice_apply_f32_ws.
+ */
+HDRNET_API int hdrnet_slice_apply_rows_f32_ws(const float* grid, const float* guide,
+                                              const float* input, float* out, int B, int H, int W,
+                                              int rows, int y_off, int gh, int gw, int gd, int n_in,
+                                              int n_out, int has_offset, int variant,
+                                              void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Un-fused slice.  Replaces the BilateralSlice op:
  *   Python   hdrnet/hdrnet_ops.py:30          hdrnet_ops.bilateral_slice
  *   OpKernel hdrnet/ops/bilateral_slice_op.cc:120-174

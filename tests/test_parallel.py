@@ -22,6 +22,21 @@ def test_shard_batch_partitions_exactly():
     assert parallel.shard_rows(2160, 1, 8) == (270, 540)
 
 
+def test_shard_plan_tiles_the_job_exactly():
+    """whole images per rank while there are enough of them, else row bands of
+    every image; either way the parts of all ranks tile the job with nothing shared or left out."""
+    for n, H, world in ((8, 2160, 8), (64, 3024, 8), (9, 100, 4), (1, 2160, 8), (3, 37, 8), (2, 5, 8), (1, 1, 2)):
+        plans = [parallel.shard_plan(n, H, r, world) for r in range(world)]
+        kinds = {p[0] for p in plans}
+        assert kinds == ({"batch"} if n >= world else {"rows"})
+        extent = n if n >= world else H
+        assert plans[0][1] == 0 and plans[-1][2] == extent
+        for a, b in zip(plans, plans[1:]):
+            assert a[2] == b[1] and a[2] >= a[1]
+        sizes = [p[2] - p[1] for p in plans]
+        assert sum(sizes) == extent and max(sizes) - min(sizes) <= 1
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -320,6 +320,48 @@ def test_two_streams_on_large_images_do_not_share_a_workspace():
             assert torch.equal(o, want[k]), f"stream {k}: result changed under a concurrent call"
 
 
+# ---- row bands: the multi-GPU fallback for fewer images than GPUs ---------
+@pytest.mark.parametrize("B,H,W,world", [(1, 67, 256, 4), (3, 50, 384, 8), (2, 5, 128, 8)])
+def test_row_bands_tile_the_whole_image_call(B, H, W, world):
+    """Every rank's part (parallel.slice_apply_sharded, ranks emulated one after the other on this
+    GPU) placed into the output equals the whole-image call: against the oracle through AUTO, and bit
+    for bit when band and whole image run the same row kernel."""
+    from hdrnet_b200 import parallel
+    grid, guide, inp = rand_case(77, B, H, W, 16, 16, 8, signed=True)
+    g, u, i = cuda(grid), cuda(guide), cuda(inp)
+    out = torch.full((B, H, W, 3), float("nan"), device="cuda")
+    for rank in range(world):
+        (kind, lo, hi), part = parallel.slice_apply_sharded(g, u, i, True, rank, world)
+        assert kind == ("batch" if B >= world else "rows")
+        if kind == "batch":
+            out[lo:hi] = part
+        else:
+            out[:, lo:hi] = part
+    assert_parity(out.cpu().numpy(), checker().bilateral_slice_apply(grid, guide, inp, True),
+                  what=f"row bands {B}x{H}x{W} over {world} ranks")
+    whole = hdrnet_ops.bilateral_slice_apply(g, u, i, True, variant=_lib.VARIANT_TMA)
+    bands = torch.cat([hdrnet_ops.bilateral_slice_apply_rows(g, u[:, y0:y1], i[:, y0:y1], True, y0, H,
+                                                            variant=_lib.VARIANT_TMA)
+                       for y0, y1 in (parallel.shard_rows(H, r, world) for r in range(world)) if y1 > y0], dim=1)
+    assert torch.equal(bands, whole)
+
+
+def test_row_bands_of_a_4k_frame_take_the_workspace_kernels():
+    """One 4K frame over two ranks: each band (1080 rows = 4.1 MP) is large enough for AUTO to lend a
+    workspace and run the issuer-warp kernel with a non-zero row offset; the bands equal the rows of
+    the whole-frame call bit for bit (every row-kernel form produces the same bits)."""
+    from hdrnet_b200 import parallel
+    grid, guide, inp = rand_case(78, 1, 2160, 3840, 16, 16, 8)
+    g, u, i = cuda(grid), cuda(guide), cuda(inp)
+    whole = hdrnet_ops.bilateral_slice_apply(g, u, i, True)
+    for rank in range(2):
+        (kind, y0, y1), part = parallel.slice_apply_sharded(g, u, i, True, rank, 2)
+        assert kind == "rows" and (y0, y1) == (1080 * rank, 1080 * (rank + 1))
+        assert torch.equal(part, whole[:, y0:y1]), f"band of rank {rank} differs from the whole-frame call"
+    with pytest.raises(ValueError):
+        hdrnet_ops.bilateral_slice_apply_rows(g, u[:, :100], i[:, :100], True, y_off=2100, height=2160)
+
+
 # ---- BASELINE.json full size: 4K ------------------------------------------------------------
 def test_4k_frame_against_full_oracle():
     """One 3840x2160 frame, grid 16x16x8 (config 3's per-image shape), full oracle compare."""
