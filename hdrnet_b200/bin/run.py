@@ -129,10 +129,12 @@ def _to_png(x01: np.ndarray) -> np.ndarray:
     return np.clip(np.rint(x01 * 255.0), 0, 255).astype(np.uint8)
 
 
-def debug_images(im_rgb: np.ndarray, coeffs: np.ndarray, guides: list) -> dict:
+def debug_images(im_rgb: np.ndarray, coeffs: np.ndarray, guides: list, multiscale=()) -> dict:
     """The --debug pictures of the reference (run.py:98-133, :192-215) as {file suffix: image}:
     the input, the coefficient mosaic ([gh*gd, gw*n_in*n_out], symmetric normalisation
-    (x + m) / 2m with m = max |x|) and one normalised picture per guide map."""
+    (x + m) / 2m with m = max |x|), one normalised picture per guide map and -- for the pyramid
+    model's 'multiscale' collection (run.py:108-117, :201-205) -- one picture per level with its
+    channels side by side ([H, C*W])."""
     out = {"_input.png": np.ascontiguousarray(im_rgb[:, :, ::-1])}
     gh, gw, gd, no, ni = coeffs.shape
     c = np.transpose(coeffs, (2, 0, 3, 4, 1)).reshape(gh * gd, gw * ni * no)   # tf.transpose [0,3,1,4,5,2]
@@ -141,6 +143,10 @@ def debug_images(im_rgb: np.ndarray, coeffs: np.ndarray, guides: list) -> dict:
     for i, g in enumerate(guides):
         mg = float(np.abs(g).max()) or 1.0
         out[f"_guide_{i}.png"] = _to_png(np.clip((g + mg) / (2 * mg), 0, 1))
+    for i, m in enumerate(multiscale):                               # [H, W, C] -> [H, C * W]
+        mm = float(np.abs(m).max()) or 1.0
+        m = np.clip((m + mm) / (2 * mm), 0, 1)
+        out[f"_ms_{i}.png"] = _to_png(np.transpose(m, (0, 2, 1)).reshape(m.shape[0], -1))
     return out
 
 
@@ -174,7 +180,8 @@ def main(args):
             coeffs = dbg["bilateral_coefficients"][0].cpu().numpy()
             np.save(os.path.join(args.output, name + "_guide.npy"), guides[0][0].cpu().numpy())
             np.save(os.path.join(args.output, name + "_coefficients.npy"), coeffs)
-            for fname, img in debug_images(rgb, coeffs, [g[0].cpu().numpy() for g in guides]).items():
+            ms = [m[0].cpu().numpy() for m in dbg.get("multiscale", ())]
+            for fname, img in debug_images(rgb, coeffs, [g[0].cpu().numpy() for g in guides], ms).items():
                 cv2.imwrite(os.path.join(args.output, name + fname), img)
 
 
@@ -184,7 +191,8 @@ if __name__ == "__main__":
     parser.add_argument("input", type=str, help="image, directory of images, or filelist.txt")
     parser.add_argument("output", type=str, help="output directory")
     parser.add_argument("--lowres_input", default=None, type=str)
-    parser.add_argument("--hdrp", dest="hdrp", action="store_true")
+    parser.add_argument("--hdrp", dest="hdrp", action="store_true", help="HDR+ inputs: 16-bit linear, white level 32767")
+    parser.add_argument("--nohdrp", dest="hdrp", action="store_false")
     parser.add_argument("--debug", dest="debug", action="store_true")
     parser.add_argument("--limit", type=int)
     parser.set_defaults(hdrp=False, debug=False)

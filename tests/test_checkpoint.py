@@ -268,6 +268,12 @@ def test_run_py_reads_a_tensorflow_directory_and_debug_pictures(tmp_path):
     assert mosaic[z * 16 + y, (o * 4 + i) * 16 + x] == want
     assert pics["_guide_0.png"].max() == 255 and pics["_guide_0.png"].min() >= 127   # guide >= 0
     assert np.array_equal(pics["_input.png"], im[:, :, ::-1])
+    # the pyramid model's 'multiscale' pictures (run.py:108-117): channels side by side, [H, C * W]
+    level = rng.rand(10, 15, 3).astype(np.float32)
+    pics = run.debug_images(im, coeffs, [guide], [level])
+    assert "_ms_0.png" in pics and pics["_ms_0.png"].shape == (10, 45)
+    mm = np.abs(level).max()
+    assert pics["_ms_0.png"][4, 2 * 15 + 7] == np.rint(np.clip((level[4, 7, 2] + mm) / (2 * mm), 0, 1) * 255)
 
 
 # ---- a checkpoint assembled byte by byte from the format specifications ---------------------------
