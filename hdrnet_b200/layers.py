@@ -7,8 +7,15 @@ Same names, argument order and shapes as the reference (hdrnet/layers.py:99-198)
     bilateral_slice_apply(grid, guide, input_image, has_offset)    layers.py:125-148
     apply(sliced, input_image, has_affine_term)                    layers.py:153-198
 
-``conv`` / ``fc`` (layers.py:25-93) live in ``hdrnet_b200.models`` next to the coefficient
-network's kernels.
+    conv(inputs, num_outputs, kernel_size, stride, ..., scope)     layers.py:25-59
+    fc(inputs, num_outputs, ..., scope)                            layers.py:62-93
+
+``conv`` / ``fc`` are the INFERENCE form of the reference's layer constructors: TensorFlow creates
+the layer's variables under ``scope``; here the variables already exist -- a dict keyed by the
+reference's variable names (``<scope>/weights``, ``<scope>/biases``, ``<scope>/BatchNorm/beta`` ...;
+``weights=`` or the dict given to ``models.set_weights``) -- and ``scope`` is the full variable scope
+(e.g. ``inference/coefficients/splat/conv1``).  The models call the same kernels through
+``hdrnet_b200.models`` with device-resident, pre-folded weights.
 """
 from __future__ import annotations
 
@@ -16,7 +23,86 @@ import torch
 
 from . import hdrnet_ops
 
-__all__ = ["bilateral_slice", "bilateral_slice_apply", "apply"]
+__all__ = ["conv", "fc", "bilateral_slice", "bilateral_slice_apply", "apply", "relu"]
+
+
+def relu(x: torch.Tensor) -> torch.Tensor:
+    """``tf.nn.relu``: the default ``activation_fn`` of conv / fc (fused into the layer's kernel)."""
+    return torch.relu(x)
+
+
+def _layer_variables(scope, weights, use_bias, batch_norm, device):
+    """(weights, bias-or-None) on `device`, inference batch norm folded in (models._fold)."""
+    from . import models
+    if scope is None:
+        raise ValueError("scope is required: it names the layer's variables (<scope>/weights, ...)")
+    wts = weights if weights is not None else models._resolve_weights({})
+    w, b = models._fold(wts, scope, bool(batch_norm), bool(use_bias))
+    wd = torch.from_numpy(w).contiguous().to(device)
+    return wd, (None if b is None else torch.from_numpy(b).contiguous().to(device))
+
+
+def _activation(activation_fn):
+    """(fused_relu, post_fn): tf.nn.relu / torch.relu / layers.relu fuse into the kernel, None is
+    linear, any other callable runs on the layer's output."""
+    if activation_fn is None:
+        return False, None
+    if activation_fn in (relu, torch.relu, torch.nn.functional.relu) or activation_fn == "relu":
+        return True, None
+    if not callable(activation_fn):
+        raise TypeError("activation_fn must be None or a callable")
+    return False, activation_fn
+
+
+def conv(inputs: torch.Tensor, num_outputs: int, kernel_size: int, stride: int = 1, rate: int = 1,
+         use_bias: bool = True, batch_norm: bool = False, is_training: bool = False,
+         activation_fn=relu, scope: str | None = None, reuse: bool = False, *,
+         weights: dict | None = None) -> torch.Tensor:
+    """hdrnet/layers.py:25-59 (``tf.contrib.layers.convolution2d``, padding='SAME' incl. the
+    asymmetric stride-2 padding, HWIO weights, batch norm with center and no scale; with
+    ``batch_norm`` the layer has no bias of its own, :30-32).  inputs [B, H, W, Cin] float32 CUDA;
+    returns [B, ceil(H / stride), ceil(W / stride), num_outputs]."""
+    del reuse
+    from . import models
+    if is_training:
+        raise NotImplementedError("hdrnet_b200 implements the inference path only")
+    if rate != 1:
+        raise NotImplementedError("dilated convolutions (rate != 1) are not used by the reference models")
+    if not isinstance(inputs, torch.Tensor) or inputs.dtype != torch.float32 or inputs.dim() != 4:
+        raise ValueError("inputs must be a float32 tensor [B, H, W, C]")
+    if inputs.device.type != "cuda":
+        from . import _lib
+        raise _lib.HdrnetLibraryError("inputs must be a CUDA tensor; hdrnet_b200 has no CPU path")
+    w, b = _layer_variables(scope, weights, use_bias, batch_norm, inputs.device)
+    if w.dim() != 4 or w.shape[0] != kernel_size or w.shape[1] != kernel_size or w.shape[3] != num_outputs:
+        raise ValueError(f"{scope}/weights has shape {tuple(w.shape)}, expected "
+                         f"[{kernel_size}, {kernel_size}, Cin, {num_outputs}]")
+    fused, post = _activation(activation_fn)
+    with torch.cuda.device(inputs.device):
+        out = models._conv(inputs.contiguous(), (w, b), stride=stride, relu=fused)
+    return out if post is None else post(out)
+
+
+def fc(inputs: torch.Tensor, num_outputs: int, use_bias: bool = True, batch_norm: bool = False,
+       is_training: bool = False, activation_fn=relu, scope: str | None = None, *,
+       weights: dict | None = None) -> torch.Tensor:
+    """hdrnet/layers.py:62-93 (``tf.contrib.layers.fully_connected``).  inputs [B, I] float32 CUDA;
+    returns [B, num_outputs]."""
+    from . import models
+    if is_training:
+        raise NotImplementedError("hdrnet_b200 implements the inference path only")
+    if not isinstance(inputs, torch.Tensor) or inputs.dtype != torch.float32 or inputs.dim() != 2:
+        raise ValueError("inputs must be a float32 tensor [B, I]")
+    if inputs.device.type != "cuda":
+        from . import _lib
+        raise _lib.HdrnetLibraryError("inputs must be a CUDA tensor; hdrnet_b200 has no CPU path")
+    w, b = _layer_variables(scope, weights, use_bias, batch_norm, inputs.device)
+    if w.dim() != 2 or w.shape[1] != num_outputs:
+        raise ValueError(f"{scope}/weights has shape {tuple(w.shape)}, expected [I, {num_outputs}]")
+    fused, post = _activation(activation_fn)
+    with torch.cuda.device(inputs.device):
+        out = models._fc(inputs.contiguous(), (w, b), relu=fused)
+    return out if post is None else post(out)
 
 
 # pylint: disable=redefined-builtin

@@ -70,8 +70,15 @@ def test_product_never_imports_the_oracle():
 def test_python_surface_mirrors_reference_names():
     # hdrnet/hdrnet_ops.py:30-31, hdrnet/layers.py:99-198
     assert callable(hdrnet_ops.bilateral_slice) and callable(hdrnet_ops.bilateral_slice_apply)
-    for name in ("bilateral_slice", "bilateral_slice_apply", "apply"):
+    for name in ("bilateral_slice", "bilateral_slice_apply", "apply", "conv", "fc"):
         assert callable(getattr(layers, name))
+    import inspect
+    # positional order of the reference's constructors (hdrnet/layers.py:25-29, :62-66)
+    assert list(inspect.signature(layers.conv).parameters)[:11] == [
+        "inputs", "num_outputs", "kernel_size", "stride", "rate", "use_bias", "batch_norm", "is_training",
+        "activation_fn", "scope", "reuse"]
+    assert list(inspect.signature(layers.fc).parameters)[:7] == [
+        "inputs", "num_outputs", "use_bias", "batch_norm", "is_training", "activation_fn", "scope"]
 
 
 def _t(*shape):

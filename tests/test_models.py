@@ -125,6 +125,42 @@ def test_fc_matches(B, I, O, relu):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("batch_norm,use_bias,stride,act", [(False, True, 2, "relu"), (True, True, 1, "relu"),
+                                                            (False, False, 1, None), (False, True, 1, "tanh")])
+def test_layers_conv_and_fc_follow_the_reference_constructors(batch_norm, use_bias, stride, act):
+    """hdrnet/layers.py:25-93 through the public layers.conv / layers.fc: variables found under
+    `scope` by the reference's names, batch norm (center, no scale) instead of the bias, SAME
+    padding, fused relu / no activation / an arbitrary activation applied on the output."""
+    from hdrnet_b200 import layers
+    rng = np.random.RandomState(5)
+    wts = {"net/c/weights": (rng.randn(3, 3, 6, 12) / 7).astype(np.float32),
+           "net/c/biases": rng.randn(12).astype(np.float32),
+           "net/c/BatchNorm/beta": rng.randn(12).astype(np.float32),
+           "net/c/BatchNorm/moving_mean": rng.randn(12).astype(np.float32),
+           "net/c/BatchNorm/moving_variance": (0.5 + rng.rand(12)).astype(np.float32),
+           "net/f/weights": (rng.randn(40, 10) / 6).astype(np.float32),
+           "net/f/biases": rng.randn(10).astype(np.float32),
+           "net/f/BatchNorm/beta": rng.randn(10).astype(np.float32),
+           "net/f/BatchNorm/moving_mean": rng.randn(10).astype(np.float32),
+           "net/f/BatchNorm/moving_variance": (0.5 + rng.rand(10)).astype(np.float32)}
+    fn = {"relu": layers.relu, None: None, "tanh": torch.tanh}[act]
+    post = (lambda a: a) if act != "tanh" else np.tanh
+    x = rng.randn(2, 9, 14, 6).astype(np.float32)
+    got = layers.conv(cuda(x), 12, 3, stride=stride, use_bias=use_bias, batch_norm=batch_norm,
+                      activation_fn=fn, scope="net/c", weights=wts)
+    ref = post(M.conv(x, wts, "net/c", stride=stride, use_bias=use_bias, batch_norm=batch_norm, relu=act == "relu"))
+    assert_parity(got.cpu().numpy(), ref.astype(np.float32), rtol=2e-6)
+    v = rng.randn(5, 40).astype(np.float32)
+    got = layers.fc(cuda(v), 10, use_bias=use_bias, batch_norm=batch_norm, activation_fn=fn, scope="net/f", weights=wts)
+    ref = post(M.fc(v, wts, "net/f", use_bias=use_bias, batch_norm=batch_norm, relu=act == "relu"))
+    assert_parity(got.cpu().numpy(), ref.astype(np.float32), rtol=2e-6)
+    with pytest.raises(ValueError):
+        layers.conv(cuda(x), 16, 3, scope="net/c", weights=wts)          # num_outputs does not match the variables
+    with pytest.raises(NotImplementedError):
+        layers.conv(cuda(x), 12, 3, scope="net/c", weights=wts, is_training=True)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", list(PARAM_SETS))
 def test_coefficients_match_oracle(name):
     p = PARAM_SETS[name]
