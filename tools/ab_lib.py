@@ -16,11 +16,13 @@ except Exception:
     sm_clock = lambda: 0
 
 B, H, W, GH, GW, GD = 8, 2160, 3840, 16, 16, 8
+if os.environ.get("AB_GRID"):   # e.g. AB_GRID=32,32,16
+    GH, GW, GD = (int(v) for v in os.environ["AB_GRID"].split(","))
 gen = torch.Generator(device="cuda").manual_seed(1234)
 grid = torch.rand(B, GH, GW, GD, 12, device="cuda", generator=gen)
 guide = torch.rand(B, H, W, device="cuda", generator=gen)
 inp = torch.rand(B, H, W, 3, device="cuda", generator=gen)
-KNOBS = ("HDRNET_TEX_CHUNKS", "HDRNET_ASYNC_THREADS", "HDRNET_FUSED_ASYNC")
+KNOBS = ("HDRNET_TEX_CHUNKS", "HDRNET_ASYNC_THREADS", "HDRNET_FUSED_ASYNC", "HDRNET_ASYNC_SLAB")
 libs, cfgs = {}, []
 _tmp = tempfile.mkdtemp(prefix="ab_lib_")
 for spec in sys.argv[1:]:
