@@ -523,7 +523,10 @@ def load_guide_bins(bin_dir: str, model_name: str, feats: int = 16) -> dict:
 # The messages involved (public .proto definitions): MetaGraphDef{graph_def=2, collection_def=4},
 # GraphDef{node=1}, NodeDef{name=1, op=2, attr=5}, AttrValue{tensor=8}, TensorProto{dtype=1,
 # tensor_content=4, float_val=5, double_val=6, int_val=7, string_val=8, int64_val=10,
-# bool_val=11}, CollectionDef{node_list=1}, NodeList{value=1}.  Parity unpinned, as above.
+# bool_val=11}, CollectionDef{node_list=1}, NodeList{value=1}.  Pinned like the bundle reader: by a
+# MetaGraphDef assembled from the .proto definitions by an independent script
+# (tests/golden/make_tf_meta_fixture.py: packed scalars, tensor_content, negative varints, other
+# nodes / collections to skip); it has not met a file produced by TensorFlow itself.
 def _map_entry(buf: bytes):
     key = val = b""
     for field, _, v in _pb_fields(buf):

@@ -306,6 +306,37 @@ def test_reads_the_hand_assembled_tensor_bundle():
     assert sorted(w) == ["inference/coefficients/splat/conv1/biases", "inference/guide/ccm"]
 
 
+META_SHA = "b1eccc63d615d9eb5f7d37487fdc6dc1a891a102cc98dcc914a2721879f06a4b"
+
+
+def test_reads_the_hand_assembled_meta_graph():
+    """tests/golden/tf_bundle/model.ckpt-7.meta is written by tests/golden/make_tf_meta_fixture.py from
+    the public .proto definitions (its own varint / tag arithmetic; no code shared with the module):
+    train.py's model_params (hdrnet/bin/train.py:60-63, :224-252) as Const nodes the way
+    tensor_util.make_tensor_proto encodes python values -- PACKED int_val / float_val / bool_val,
+    string_val, an empty shape message for scalars, tensor_content for the 2-vector, a negative int32
+    as a ten-byte varint, a False flag -- between a placeholder, other constants, an op with inputs,
+    meta_info_def, saver_def and two other collections.  The reader must return exactly these
+    values with these python types (what utils.get_model_params returns, hdrnet/utils.py:19-23)."""
+    import hashlib
+    path = os.path.join(BUNDLE_DIR, "model.ckpt-7.meta")
+    with open(path, "rb") as f:
+        raw = f.read()
+    assert len(raw) == 1414 and hashlib.sha256(raw).hexdigest() == META_SHA
+    got = C.read_meta_model_params(path)
+    want = {"model_name": "HDRNetPointwiseNNGuide", "data_pipeline": "ImageFilesDataPipeline",
+            "net_input_size": 256, "output_resolution": [512, 768], "batch_norm": True,
+            "channel_multiplier": 1, "guide_complexity": 16, "luma_bins": 8, "spatial_bin": 16,
+            "learning_rate": float(np.float32(0.0001)), "crop_offset": -3, "use_hdrp": False}
+    assert list(got) == list(want)                                  # collection order
+    for k, v in want.items():
+        assert got[k] == v and type(got[k]) is type(v), (k, got[k])
+    params, weights = C.import_checkpoint(BUNDLE_DIR, verify=True)  # the directory as run.py takes it (:70-85)
+    assert params == want and sorted(weights) == ["inference/coefficients/splat/conv1/biases", "inference/guide/ccm"]
+    from hdrnet_b200 import models
+    assert hasattr(models, params["model_name"])                    # run.py:82-85
+
+
 def test_hand_assembled_bundle_corruption_is_detected(tmp_path):
     import shutil
     for victim, offset, what in (("model.ckpt-7.data-00000-of-00001", 20, "tensor checksum"),
