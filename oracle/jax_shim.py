@@ -87,7 +87,10 @@ def _make_jnp() -> types.ModuleType:
         return np.arange(*a, **k).astype(np.int32).view(_F32Int)
 
     def meshgrid(*xs, **k):
-        return [m.astype(np.int32).view(_F32Int) for m in np.meshgrid(*[np.asarray(x) for x in xs], **k)]
+        # integer coordinates stay weak-typed int32; float arguments (the VJP helpers mesh float grid
+        # coordinates with integer cell indices, bilateral_slice.py:153-154) keep their values
+        return [m.astype(np.int32).view(_F32Int) if m.dtype.kind in "iu" else m
+                for m in np.meshgrid(*[np.asarray(x) for x in xs], **k)]
 
     def zeros(shape, dtype=np.float32):
         return np.zeros(shape, dtype).view(_Arr)
@@ -172,6 +175,20 @@ def bilateral_slice(grid, guide) -> np.ndarray:
     guide = np.asarray(guide, np.float32)
     outs = [np.asarray(mod.bilateral_slice(grid[b], guide[b])) for b in range(grid.shape[0])]
     return np.stack(outs).astype(np.float32)
+
+
+def bilateral_slice_vjp(grid, guide, codomain_tangent):
+    """Batched reference VJPs of the slice: (grid_vjp, guide_vjp) from the reference's own
+    ``bilateral_slice_grid_vjp`` (jax/bilateral_slice.py:257-295: mirror-padded footprint, einsum of
+    the spatial and range weights) and ``bilateral_slice_guide_vjp`` (:26-108), one image at a time
+    -- what ``_bilateral_slice_bwd`` (:387-392) returns under ``jax.vmap``."""
+    mod = load()
+    grid = np.asarray(grid, np.float32)
+    guide = np.asarray(guide, np.float32)
+    ct = np.asarray(codomain_tangent, np.float32)
+    gv = [np.asarray(mod.bilateral_slice_grid_vjp(guide[b], ct[b], grid.shape[1:])) for b in range(grid.shape[0])]
+    uv = [np.asarray(mod.bilateral_slice_guide_vjp(grid[b], guide[b], ct[b])) for b in range(grid.shape[0])]
+    return np.stack(gv).astype(np.float32), np.stack(uv).astype(np.float32)
 
 
 def bilateral_slice_apply(grid, guide, inp, has_offset: bool) -> np.ndarray:

@@ -13,6 +13,9 @@ reference's tests:
                      from 640x480x4 to 2x96x128 to keep the fixture small)
   interpolate_kat    hdrnet/test/ops_test.py:61-86 (grid value = depth index)
   edge_cases         guide exactly 0 / 1 / out of [0,1], 1-pixel-wide image, gd = 1
+  vjp_*              the reference's own VJPs of the slice (jax/bilateral_slice.py:26-108, :257-295) at
+                     the extents of its gradient tests (hdrnet_ops_test.py:91-100, :185-195) and on a
+                     grid coarser / finer than the image; `python make_golden.py vjp` writes only these
 Each .npz stores inputs, outputs and the reference's cell indices.
 """
 import os
@@ -91,5 +94,23 @@ def main():
     save("wide_rows", **case(grid, guide, inp))
 
 
+def main_vjp():
+    # (B, H, W, gh, gw, gd, gc): default test extents; hdrnet_ops_test.py:185-195; a coarse grid; an
+    # image narrower than the grid (cells without a pixel centre).  Guides are generic random values:
+    # where guide * gd - 0.5 is EXACTLY an integer the JAX helpers take floor == ceil as two corners
+    # (the grid VJP counts the pixel twice, the guide VJP returns 0) while the C++ op -- which the
+    # library and the oracle port follow -- uses cells k and k + 1; tests/test_oracle.py pins that corner.
+    for k, (B, H, W, gh, gw, gd, gc) in enumerate([(3, 30, 25, 16, 12, 8, 12), (3, 8, 5, 6, 3, 7, 4),
+                                                   (2, 21, 36, 5, 4, 6, 2), (1, 9, 7, 3, 12, 9, 5)]):
+        rng = np.random.RandomState(900 + k)
+        grid = rng.randn(B, gh, gw, gd, gc).astype(np.float32)
+        guide = rng.rand(B, H, W).astype(np.float32)
+        ct = rng.randn(B, H, W, gc).astype(np.float32)
+        gv, uv = jax_shim.bilateral_slice_vjp(grid, guide, ct)
+        save(f"vjp_{k}", grid=grid, guide=guide, codomain_tangent=ct, grid_vjp=gv, guide_vjp=uv)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] != ["vjp"]:
+        main()
+    main_vjp()

@@ -64,6 +64,19 @@ def test_slice_vjps_match_reference(case):
     assert_parity(u.grad.cpu().numpy(), want[1], rtol=2e-5, what="guide VJP")
 
 
+@pytest.mark.parametrize("name", ["vjp_0", "vjp_2"])
+def test_slice_vjps_match_reference_jax_golden(name):
+    """tests/golden/vjp_*.npz: the reference's own JAX VJP functions (jax/bilateral_slice.py:26-108,
+    :257-295; tests/golden/make_golden.py) at the reference's default test extents and on a coarse
+    grid -- the same bar as against the C++ loops above."""
+    from util import load_golden
+    z = load_golden(name)
+    g, u = cuda(z["grid"], True), cuda(z["guide"], True)
+    hdrnet_ops.bilateral_slice(g, u).backward(cuda(z["codomain_tangent"]))
+    assert_parity(g.grad.cpu().numpy(), z["grid_vjp"], rtol=2e-5, what=f"{name} grid VJP")
+    assert_parity(u.grad.cpu().numpy(), z["guide_vjp"], rtol=2e-5, what=f"{name} guide VJP", elem_rtol=None)
+
+
 def test_grad_shapes_follow_reference_contract():
     """hdrnet_ops_test.py:125-135, :304-315 (test_grad_shape)."""
     grid, guide, inp = rand_case(1, 3, 30, 25, 16, 12, 8)
