@@ -126,6 +126,27 @@ def test_fails_loudly_without_a_gpu(built_lib):
                                          has_offset=True)
 
 
+def test_row_band_argument_checks(built_lib):
+    """bilateral_slice_apply_rows: the reference op's messages for rank / size / batch / channel
+    errors, a band that does not fit the image, and no CPU path."""
+    f = hdrnet_ops.bilateral_slice_apply_rows
+    grid, guide, inp = _t(1, 4, 4, 8, 12), _t(1, 6, 16), _t(1, 6, 16, 3)
+    with pytest.raises(ValueError, match="Input grid should be 5D"):
+        f(_t(4, 4, 8, 12), guide, inp, True, 0, 6)
+    with pytest.raises(ValueError, match="Input and guide size should match"):
+        f(grid, _t(1, 5, 16), inp, True, 0, 6)
+    with pytest.raises(ValueError, match="Batch sizes should match"):
+        f(_t(2, 4, 4, 8, 12), guide, inp, True, 0, 6)
+    with pytest.raises(ValueError, match="output_channels \\* \\(input_channels \\+ 1\\)"):
+        f(_t(1, 4, 4, 8, 10), guide, inp, True, 0, 6)
+    for y_off, height in ((-1, 10), (5, 10), (0, 5)):
+        with pytest.raises(ValueError, match="does not fit an image"):
+            f(grid, guide, inp, True, y_off, height)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.HdrnetLibraryError):
+            f(grid, guide, inp, True, 2, 10)
+
+
 def test_layers_apply_matches_reference_semantics():
     """hdrnet/layers.py:153-198 on CPU tensors (pure torch ops, no kernel)."""
     torch.manual_seed(0)
