@@ -49,17 +49,42 @@ def wavefronts(gw, gd, guide_row, rng):
     return total / count
 
 
+def tex_lines(gw, gd, guide_row):
+    """mean number of distinct 128-byte lines one warp-wide texture fetch of a corner chunk touches
+    (32 lanes; the texture path has no banks, its cost grows with the lines a request spreads over)"""
+    x = np.arange(W)
+    xcell = np.floor((x + 0.5) * (gw / W) - 0.5).astype(np.int64)
+    zcell = np.floor(guide_row * gd - 0.5).astype(np.int64)
+    quads = W // 4
+    total, count = 0.0, 0
+    for i in range(4):
+        px = 4 * np.arange(quads) + i
+        for dx in (0, 1):
+            xc = np.clip(xcell[px] + dx, 0, gw - 1)
+            for dz in (0, 1):
+                zc = np.clip(zcell[px] + dz, 0, gd - 1)
+                line = (xc * gd * 48 + zc * 48) // 128          # part p shifts all lanes alike
+                a = np.sort(line[: quads // 32 * 32].reshape(-1, 32), axis=1)
+                total += ((np.diff(a, axis=1) != 0).sum(1) + 1).mean()
+                count += 1
+    return total / count
+
+
 def main():
     rng = np.random.RandomState(0)
     rows = 64
-    print("| grid | random guide: wavefronts per LDS.128 | smooth guide | ideal |")
-    print("|---|---|---|---|")
+    xx = np.linspace(0, 1, W)
+    smooth_rows = [np.clip(0.5 + 0.45 * np.sin(6.2831853 * (3 * xx + ph)) + 0.01 * (rng.rand(W) - 0.5), 0, 1)
+                   for ph in np.linspace(0, 1, 16, endpoint=False)]
+    print("| grid | random guide: wavefronts per LDS.128 | smooth guide | ideal | random guide: 128-byte lines per warp-wide texture fetch | smooth guide |")
+    print("|---|---|---|---|---|---|")
     for gh, gw, gd in ((8, 8, 4), (16, 16, 4), (16, 16, 8), (32, 32, 8), (16, 16, 16), (32, 32, 16)):
-        rnd = np.mean([wavefronts(gw, gd, rng.rand(W), rng) for _ in range(rows)])
-        xx = np.linspace(0, 1, W)
-        smooth = np.mean([wavefronts(gw, gd, np.clip(0.5 + 0.45 * np.sin(6.2831853 * (3 * xx + ph)) + 0.01 * (rng.rand(W) - 0.5), 0, 1), rng)
-                          for ph in np.linspace(0, 1, 16, endpoint=False)])
-        print(f"| {gh}x{gw}x{gd} | {rnd:.2f} | {smooth:.2f} | 4.00 |")
+        rand_rows = [rng.rand(W) for _ in range(rows)]
+        rnd = np.mean([wavefronts(gw, gd, r, rng) for r in rand_rows])
+        smooth = np.mean([wavefronts(gw, gd, r, rng) for r in smooth_rows])
+        tl_r = np.mean([tex_lines(gw, gd, r) for r in rand_rows])
+        tl_s = np.mean([tex_lines(gw, gd, r) for r in smooth_rows])
+        print(f"| {gh}x{gw}x{gd} | {rnd:.2f} | {smooth:.2f} | 4.00 | {tl_r:.2f} | {tl_s:.2f} |")
 
 
 if __name__ == "__main__":
